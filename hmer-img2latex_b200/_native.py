@@ -1,0 +1,146 @@
+"""ctypes binding of ``libi2l_b200.so`` (C-ABI declared in ``include/i2l_b200.h``).
+
+The library is built in-tree by ``hmer-img2latex_b200/csrc/Makefile`` with nvcc for
+sm_100a.  There is NO fallback: if the shared object is missing or an entry point
+fails, a ``RuntimeError`` is raised (the message comes from ``i2l_last_error``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libi2l_b200.so")
+
+MAX_CONV = 8
+MAX_LSTM = 8
+MAX_RESNET_CONVS = 160
+
+FP32, BF16 = 0, 1
+STOP_NONE, STOP_ALL_END_SAME_STEP, STOP_ALL_FINISHED_STICKY = 0, 1, 2
+PRECISIONS = {"fp32": FP32, "bf16": BF16}
+
+_fp = C.c_void_p  # all device pointers travel as void*
+
+
+class CnnDesc(C.Structure):
+    _fields_ = [("img_height", C.c_int32), ("img_width", C.c_int32), ("channels", C.c_int32),
+                ("n_conv", C.c_int32), ("filters", C.c_int32 * MAX_CONV), ("kernel_size", C.c_int32),
+                ("pool_size", C.c_int32), ("embedding_dim", C.c_int32), ("precision", C.c_int32)]
+
+
+class CnnParams(C.Structure):
+    _fields_ = [("conv_w", _fp * MAX_CONV), ("conv_b", _fp * MAX_CONV), ("fc_w", _fp), ("fc_b", _fp)]
+
+
+class ResnetDesc(C.Structure):
+    _fields_ = [("depth", C.c_int32), ("img_height", C.c_int32), ("embedding_dim", C.c_int32),
+                ("precision", C.c_int32)]
+
+
+class ResnetParams(C.Structure):
+    _fields_ = [("n_convs", C.c_int32), ("conv_w", _fp * MAX_RESNET_CONVS), ("bn_weight", _fp * MAX_RESNET_CONVS),
+                ("bn_bias", _fp * MAX_RESNET_CONVS), ("bn_mean", _fp * MAX_RESNET_CONVS),
+                ("bn_var", _fp * MAX_RESNET_CONVS), ("fc_w", _fp), ("fc_b", _fp)]
+
+
+class DecDesc(C.Structure):
+    _fields_ = [("vocab_size", C.c_int32), ("embedding_dim", C.c_int32), ("hidden_dim", C.c_int32),
+                ("lstm_layers", C.c_int32), ("attention", C.c_int32), ("precision", C.c_int32)]
+
+
+class DecParams(C.Structure):
+    _fields_ = [("embedding", _fp), ("w_ih", _fp * MAX_LSTM), ("w_hh", _fp * MAX_LSTM), ("b_ih", _fp * MAX_LSTM),
+                ("b_hh", _fp * MAX_LSTM), ("out_w", _fp), ("out_b", _fp)]
+
+
+# name -> (restype, argtypes); mirrors include/i2l_b200.h one to one.
+SIGNATURES = {
+    "i2l_version": (C.c_char_p, []),
+    "i2l_last_error": (C.c_char_p, []),
+    "i2l_device_check": (C.c_int, []),
+    "i2l_cnn_packed_bytes": (C.c_size_t, [C.POINTER(CnnDesc)]),
+    "i2l_cnn_pack": (C.c_int, [C.POINTER(CnnDesc), C.POINTER(CnnParams), _fp, C.c_size_t, _fp]),
+    "i2l_cnn_workspace_bytes": (C.c_size_t, [C.POINTER(CnnDesc), C.c_int32]),
+    "i2l_cnn_encoder_fwd": (C.c_int, [C.POINTER(CnnDesc), _fp, _fp, C.c_int32, _fp, _fp, C.c_size_t, _fp]),
+    "i2l_resnet_num_convs": (C.c_int32, [C.c_int32]),
+    "i2l_resnet_packed_bytes": (C.c_size_t, [C.POINTER(ResnetDesc)]),
+    "i2l_resnet_pack": (C.c_int, [C.POINTER(ResnetDesc), C.POINTER(ResnetParams), _fp, C.c_size_t, _fp]),
+    "i2l_resnet_workspace_bytes": (C.c_size_t, [C.POINTER(ResnetDesc), C.c_int32, C.c_int32]),
+    "i2l_resnet_encoder_fwd": (C.c_int, [C.POINTER(ResnetDesc), _fp, _fp, C.c_int32, C.c_int32, _fp, _fp,
+                                         C.c_size_t, _fp]),
+    "i2l_attention_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "i2l_attention_fwd": (C.c_int, [C.c_int32, C.c_int32, _fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp,
+                                    C.c_size_t, _fp]),
+    "i2l_dec_packed_bytes": (C.c_size_t, [C.POINTER(DecDesc)]),
+    "i2l_dec_pack": (C.c_int, [C.POINTER(DecDesc), C.POINTER(DecParams), _fp, C.c_size_t, _fp]),
+    "i2l_dec_workspace_bytes": (C.c_size_t, [C.POINTER(DecDesc), C.c_int32, C.c_int32]),
+    "i2l_decode_step": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp,
+                                  C.c_size_t, _fp]),
+    "i2l_decode_greedy": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_float, C.c_int32, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "i2l_decode_sample": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_float, C.c_int32, C.c_float, C.c_uint64, C.c_uint64, _fp, _fp, _fp, _fp,
+                                    _fp, _fp, C.c_size_t, _fp]),
+    "i2l_decode_beam": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("building libi2l_b200.so failed (see output above)")
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load the native library; raises loudly when it is missing (no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} not found: the sm_100a CUDA library is required and there is no CPU / "
+                    f"PyTorch fallback.  Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    f"or `make -C {CSRC}`.")
+            l = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(l, name)  # AttributeError if the symbol is not exported
+                fn.restype = res
+                fn.argtypes = args
+            _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    return lib().i2l_last_error().decode("utf-8", "replace")
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise RuntimeError(f"{what} failed with status {status}: {last_error()}")
+
+
+def ptr(t) -> C.c_void_p:
+    """Device pointer of a torch tensor (or NULL for None)."""
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None) -> C.c_void_p:
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,40 @@
+// Device-side bookkeeping of the decode loops (shared by the general fp32 path and
+// the persistent bf16 path): LSTM cell update, token selection (argmax / filtered
+// sampling / beam expansion), EOS masking and loop-exit flags.  No host sync.
+#pragma once
+#include "common.cuh"
+
+namespace i2l {
+
+// Loop-global device state (one per decode call, lives in the workspace).
+struct LoopState {
+  int done;            // != 0 once the reference loop would have executed `break`
+  int steps_run;       // loop iterations the reference executes
+  int finished_count;  // sticky rule: rows that have emitted END
+  int ticket;          // block completion ticket of the current select kernel
+  int end_count;       // ALL_END_SAME_STEP rule: rows emitting END in the current step
+};
+
+struct PackedDec {     // offsets (in floats) into the packed decoder buffer, fp32 section
+  size_t emb, gtok, w_ih0, bsum[I2L_MAX_LSTM_LAYERS], w_hh[I2L_MAX_LSTM_LAYERS],
+      w_ih[I2L_MAX_LSTM_LAYERS], out_w, out_b, end_f32;
+  size_t bf16_section;  // byte offset of the persistent-kernel section (0 if absent)
+  size_t total_bytes;
+};
+PackedDec dec_layout(const i2l_dec_desc& d);
+
+int lstm_cell_f32(const float* gates, float* h, float* c, int rows, int H, const int* skip_flag,
+                  cudaStream_t s);
+
+// persistent bf16 greedy decode (decode_persistent.cu); returns I2L_ERR_UNSUPPORTED for
+// shapes it does not cover so that the caller can take the general path.
+bool persistent_supported(const i2l_dec_desc& d);
+size_t persistent_packed_bytes(const i2l_dec_desc& d);
+int persistent_pack(const i2l_dec_desc& d, const i2l_dec_params& p, void* section, cudaStream_t s);
+size_t persistent_workspace_bytes(const i2l_dec_desc& d, int rows, int max_length);
+int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* packed_f32,
+                      const PackedDec& lay, const float* enc, int batch, int start_id, int end_id,
+                      int max_length, float temperature, int stop_rule, int64_t* tokens, int32_t* lengths,
+                      int32_t* steps_run, void* ws, size_t ws_bytes, cudaStream_t s);
+
+}  // namespace i2l

@@ -1,0 +1,348 @@
+// Encoder entry points: CNNEncoder.forward (model/encoder.py:111-129) and
+// ResNetEncoder.forward (model/encoder.py:231-249).  fp32 path = NCHW implicit-GEMM
+// convs on CUDA cores; the bf16 CNN path (tcgen05 implicit GEMM, NHWC) is in cnn_bf16.cu.
+#include "common.cuh"
+#include "encoder_bf16.cuh"
+#include <vector>
+
+namespace i2l {
+namespace {
+
+// ---------------------------------------------------------------- CNN
+struct CnnLayout {
+  size_t conv_w[I2L_MAX_CONV], conv_b[I2L_MAX_CONV], fc_w, fc_b, end_f32;
+  int ci[I2L_MAX_CONV], h[I2L_MAX_CONV + 1], w[I2L_MAX_CONV + 1];   // input geometry of layer i
+  size_t flat;
+  size_t bf16_section, total_bytes;
+};
+
+int cnn_check(const i2l_cnn_desc* d) {
+  I2L_REQUIRE(d != nullptr, "cnn: null descriptor");
+  I2L_REQUIRE(d->n_conv >= 1 && d->n_conv <= I2L_MAX_CONV, "cnn: n_conv out of range");
+  I2L_REQUIRE(d->kernel_size >= 1 && (d->kernel_size & 1), "cnn: kernel_size must be odd");
+  I2L_REQUIRE(d->pool_size >= 1 && d->img_height > 0 && d->img_width > 0 && d->channels > 0 && d->embedding_dim > 0,
+              "cnn: invalid geometry");
+  return I2L_OK;
+}
+
+CnnLayout cnn_layout(const i2l_cnn_desc& d) {
+  CnnLayout L{};
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
+  int ci = d.channels, h = d.img_height, w = d.img_width;
+  for (int i = 0; i < d.n_conv; ++i) {
+    L.ci[i] = ci; L.h[i] = h; L.w[i] = w;
+    L.conv_w[i] = take((size_t)d.filters[i] * ci * d.kernel_size * d.kernel_size);
+    L.conv_b[i] = take(d.filters[i]);
+    ci = d.filters[i];
+    h /= d.pool_size; w /= d.pool_size;            // MaxPool2d floor semantics (encoder.py:91)
+  }
+  L.h[d.n_conv] = h; L.w[d.n_conv] = w;
+  L.flat = (size_t)ci * h * w;
+  L.fc_w = take((size_t)d.embedding_dim * L.flat);
+  L.fc_b = take(d.embedding_dim);
+  L.end_f32 = o;
+  size_t bytes = o * 4;
+  L.bf16_section = 0;
+  if (d.precision == I2L_BF16 && cnn_bf16_supported(d)) {
+    bytes = align_up(bytes, 1024);
+    L.bf16_section = bytes;
+    bytes += cnn_bf16_packed_bytes(d);
+  }
+  L.total_bytes = bytes;
+  return L;
+}
+
+int fc_splitk(int M, int N, int K) {
+  int tiles = cdiv(M, 64) * cdiv(N, 64);
+  int sk = cdiv(2 * num_sms(), tiles);
+  int maxk = K / 512;
+  if (sk > maxk) sk = maxk;
+  if (sk > 64) sk = 64;
+  if (sk < 1) sk = 1;
+  return sk;
+}
+
+struct CnnWs { float* a; float* b[2]; float* sk; size_t bytes; int splitk; };
+CnnWs cnn_carve(const i2l_cnn_desc& d, const CnnLayout& L, int B, void* ws) {
+  Arena ar(ws, (size_t)-1);
+  size_t max_conv = 0, max_pool = 0;
+  for (int i = 0; i < d.n_conv; ++i) {
+    max_conv = std::max(max_conv, (size_t)d.filters[i] * L.h[i] * L.w[i]);
+    max_pool = std::max(max_pool, (size_t)d.filters[i] * L.h[i + 1] * L.w[i + 1]);
+  }
+  CnnWs w{};
+  w.a = ar.take<float>((size_t)B * max_conv);
+  w.b[0] = ar.take<float>((size_t)B * max_pool);
+  w.b[1] = ar.take<float>((size_t)B * max_pool);
+  w.splitk = fc_splitk(B, d.embedding_dim, (int)L.flat);
+  w.sk = ar.take<float>(gemm_f32_splitk_ws_bytes(B, d.embedding_dim, w.splitk) / 4);
+  w.bytes = align_up(ar.off, 256);
+  return w;
+}
+
+// ---------------------------------------------------------------- ResNet
+struct RConv { int ci, co, k, stride, pad; size_t w_off, b_off; };
+struct RBlock { int c1, c2, c3, ds; };
+struct RNet { std::vector<RConv> convs; std::vector<RBlock> blocks; int feat; bool ok; };
+
+RNet build_resnet(int depth) {
+  RNet n; n.ok = true; n.feat = 0;
+  bool bottleneck; int layers[4];
+  switch (depth) {
+    case 18: bottleneck = false; layers[0] = 2; layers[1] = 2; layers[2] = 2; layers[3] = 2; break;
+    case 34: bottleneck = false; layers[0] = 3; layers[1] = 4; layers[2] = 6; layers[3] = 3; break;
+    case 50: bottleneck = true; layers[0] = 3; layers[1] = 4; layers[2] = 6; layers[3] = 3; break;
+    case 101: bottleneck = true; layers[0] = 3; layers[1] = 4; layers[2] = 23; layers[3] = 3; break;
+    case 152: bottleneck = true; layers[0] = 3; layers[1] = 8; layers[2] = 36; layers[3] = 3; break;
+    default: n.ok = false; return n;
+  }
+  auto add = [&](int ci, int co, int k, int s, int p) { n.convs.push_back(RConv{ci, co, k, s, p, 0, 0}); return (int)n.convs.size() - 1; };
+  add(3, 64, 7, 2, 3);
+  int inpl = 64, exp = bottleneck ? 4 : 1;
+  for (int li = 0; li < 4; ++li) {
+    int planes = 64 << li;
+    for (int b = 0; b < layers[li]; ++b) {
+      int stride = (li > 0 && b == 0) ? 2 : 1;
+      RBlock blk{-1, -1, -1, -1};
+      if (!bottleneck) {
+        blk.c1 = add(inpl, planes, 3, stride, 1);
+        blk.c2 = add(planes, planes, 3, 1, 1);
+      } else {
+        blk.c1 = add(inpl, planes, 1, 1, 0);
+        blk.c2 = add(planes, planes, 3, stride, 1);
+        blk.c3 = add(planes, planes * 4, 1, 1, 0);
+      }
+      if (stride != 1 || inpl != planes * exp) blk.ds = add(inpl, planes * exp, 1, stride, 0);
+      inpl = planes * exp;
+      n.blocks.push_back(blk);
+    }
+  }
+  n.feat = inpl;
+  size_t o = 0;
+  auto take = [&](size_t c) { size_t r = o; o += (c + 63) / 64 * 64; return r; };
+  for (auto& c : n.convs) { c.w_off = take((size_t)c.co * c.ci * c.k * c.k); c.b_off = take(c.co); }
+  return n;
+}
+
+struct RLayout { size_t fc_w, fc_b, end_f32; };
+RLayout resnet_layout(const RNet& n, int E) {
+  size_t o = n.convs.back().b_off + (n.convs.back().co + 63) / 64 * 64;
+  RLayout L{};
+  L.fc_w = o; o += ((size_t)E * n.feat + 63) / 64 * 64;
+  L.fc_b = o; o += (E + 63) / 64 * 64;
+  L.end_f32 = o;
+  return L;
+}
+
+__global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ b,
+                               const float* __restrict__ m, const float* __restrict__ v, float* __restrict__ wo,
+                               float* __restrict__ bo, int co, int per) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)co * per) return;
+  int c = (int)(i / per);
+  float sc = g[c] / sqrtf(v[c] + 1e-5f);
+  wo[i] = w[i] * sc;
+  if (i % per == 0) bo[c] = b[c] - m[c] * sc;
+}
+
+size_t resnet_max_act(const RNet& n, int H, int W) {
+  // per-image float count of the largest activation
+  auto o = [](int x, int k, int s, int p) { return (x + 2 * p - k) / s + 1; };
+  int h = o(H, 7, 2, 3), w = o(W, 7, 2, 3);
+  size_t mx = (size_t)64 * h * w;
+  h = o(h, 3, 2, 1); w = o(w, 3, 2, 1);
+  for (auto& b : n.blocks) {
+    const RConv& c1 = n.convs[b.c1];
+    const RConv& c2 = n.convs[b.c2];
+    int h1 = o(h, c1.k, c1.stride, c1.pad), w1 = o(w, c1.k, c1.stride, c1.pad);
+    mx = std::max(mx, (size_t)c1.co * h1 * w1);
+    int h2 = o(h1, c2.k, c2.stride, c2.pad), w2 = o(w1, c2.k, c2.stride, c2.pad);
+    mx = std::max(mx, (size_t)c2.co * h2 * w2);
+    if (b.c3 >= 0) mx = std::max(mx, (size_t)n.convs[b.c3].co * h2 * w2);
+    h = h2; w = w2;
+  }
+  return mx;
+}
+
+}  // namespace
+}  // namespace i2l
+
+using namespace i2l;
+
+// ====================================================================== CNN C ABI
+extern "C" size_t i2l_cnn_packed_bytes(const i2l_cnn_desc* d) {
+  if (cnn_check(d) != I2L_OK) return 0;
+  return cnn_layout(*d).total_bytes;
+}
+
+extern "C" int i2l_cnn_pack(const i2l_cnn_desc* d, const i2l_cnn_params* p, void* packed, size_t packed_bytes,
+                            void* stream) {
+  I2L_TRY(device_check());
+  I2L_TRY(cnn_check(d));
+  I2L_REQUIRE(p && packed, "i2l_cnn_pack: null argument");
+  CnnLayout L = cnn_layout(*d);
+  if (packed_bytes < L.total_bytes) { set_error("i2l_cnn_pack: packed buffer too small"); return I2L_ERR_WORKSPACE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  float* pk = reinterpret_cast<float*>(packed);
+  const int ks = d->kernel_size;
+  for (int i = 0; i < d->n_conv; ++i) {
+    I2L_REQUIRE(p->conv_w[i] && p->conv_b[i], "i2l_cnn_pack: missing conv layer %d", i);
+    I2L_CUDA_OK(cudaMemcpyAsync(pk + L.conv_w[i], p->conv_w[i], (size_t)d->filters[i] * L.ci[i] * ks * ks * 4,
+                                cudaMemcpyDeviceToDevice, s));
+    I2L_CUDA_OK(cudaMemcpyAsync(pk + L.conv_b[i], p->conv_b[i], (size_t)d->filters[i] * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  I2L_REQUIRE(p->fc_w && p->fc_b, "i2l_cnn_pack: missing embedding layer");
+  I2L_CUDA_OK(cudaMemcpyAsync(pk + L.fc_w, p->fc_w, (size_t)d->embedding_dim * L.flat * 4, cudaMemcpyDeviceToDevice, s));
+  I2L_CUDA_OK(cudaMemcpyAsync(pk + L.fc_b, p->fc_b, (size_t)d->embedding_dim * 4, cudaMemcpyDeviceToDevice, s));
+  if (L.bf16_section) I2L_TRY(cnn_bf16_pack(*d, *p, reinterpret_cast<char*>(packed) + L.bf16_section, s));
+  return I2L_OK;
+}
+
+extern "C" size_t i2l_cnn_workspace_bytes(const i2l_cnn_desc* d, int32_t batch) {
+  if (cnn_check(d) != I2L_OK || batch <= 0) return 0;
+  CnnLayout L = cnn_layout(*d);
+  if (L.bf16_section) return cnn_bf16_workspace_bytes(*d, batch);
+  return cnn_carve(*d, L, batch, nullptr).bytes;
+}
+
+extern "C" int i2l_cnn_encoder_fwd(const i2l_cnn_desc* d, const void* packed, const float* x, int32_t batch,
+                                   float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  I2L_TRY(device_check());
+  I2L_TRY(cnn_check(d));
+  I2L_REQUIRE(packed && batch >= 0, "i2l_cnn_encoder_fwd: invalid argument");
+  if (batch == 0) return I2L_OK;
+  I2L_REQUIRE(x && out && workspace, "i2l_cnn_encoder_fwd: null buffer");
+  cudaStream_t s = (cudaStream_t)stream;
+  CnnLayout L = cnn_layout(*d);
+  if (L.bf16_section)
+    return cnn_bf16_fwd(*d, reinterpret_cast<const char*>(packed) + L.bf16_section, x, batch, out, workspace,
+                        workspace_bytes, s);
+  CnnWs w = cnn_carve(*d, L, batch, workspace);
+  if (workspace_bytes < w.bytes) { set_error("i2l_cnn_encoder_fwd: workspace too small (%zu < %zu)", workspace_bytes, w.bytes); return I2L_ERR_WORKSPACE; }
+  const float* pk = reinterpret_cast<const float*>(packed);
+  const float* cur = x;
+  for (int i = 0; i < d->n_conv; ++i) {
+    ConvF32 c;
+    c.x = cur; c.w = pk + L.conv_w[i]; c.bias = pk + L.conv_b[i]; c.y = w.a;
+    c.B = batch; c.Ci = L.ci[i]; c.Hi = L.h[i]; c.Wi = L.w[i]; c.Co = d->filters[i];
+    c.KH = c.KW = d->kernel_size; c.stride = 1; c.pad = d->kernel_size / 2; c.relu = 1;
+    I2L_TRY(conv2d_f32(c, s));
+    // conv output -> w.a, pooled output -> w.b[i&1] (the next layer reads it while writing w.a)
+    I2L_TRY(maxpool2d_f32(w.a, w.b[i & 1], batch, d->filters[i], L.h[i], L.w[i], d->pool_size, d->pool_size, 0, s));
+    cur = w.b[i & 1];
+  }
+  GemmF32 g;
+  g.M = batch; g.N = d->embedding_dim; g.C = out; g.ldc = d->embedding_dim;
+  g.A1 = cur; g.lda1 = (int)L.flat; g.W1 = pk + L.fc_w; g.ldw1 = (int)L.flat; g.K1 = (int)L.flat;
+  g.bias = pk + L.fc_b; g.relu = 1; g.splitk = w.splitk; g.splitk_ws = w.sk;
+  return gemm_f32(g, s);
+}
+
+// ====================================================================== ResNet C ABI
+extern "C" int32_t i2l_resnet_num_convs(int32_t depth) {
+  RNet n = build_resnet(depth);
+  return n.ok ? (int32_t)n.convs.size() : -1;
+}
+
+extern "C" size_t i2l_resnet_packed_bytes(const i2l_resnet_desc* d) {
+  if (!d) return 0;
+  RNet n = build_resnet(d->depth);
+  if (!n.ok || d->embedding_dim <= 0) return 0;
+  return resnet_layout(n, d->embedding_dim).end_f32 * 4;
+}
+
+extern "C" int i2l_resnet_pack(const i2l_resnet_desc* d, const i2l_resnet_params* p, void* packed,
+                               size_t packed_bytes, void* stream) {
+  I2L_TRY(device_check());
+  I2L_REQUIRE(d && p && packed, "i2l_resnet_pack: null argument");
+  RNet n = build_resnet(d->depth);
+  I2L_REQUIRE(n.ok, "Invalid ResNet model name: resnet%d", d->depth);      // encoder.py:195-196
+  I2L_REQUIRE(p->n_convs == (int)n.convs.size(), "i2l_resnet_pack: expected %d convs, got %d", (int)n.convs.size(), p->n_convs);
+  RLayout L = resnet_layout(n, d->embedding_dim);
+  if (packed_bytes < L.end_f32 * 4) { set_error("i2l_resnet_pack: packed buffer too small"); return I2L_ERR_WORKSPACE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  float* pk = reinterpret_cast<float*>(packed);
+  for (size_t i = 0; i < n.convs.size(); ++i) {
+    const RConv& c = n.convs[i];
+    I2L_REQUIRE(p->conv_w[i] && p->bn_weight[i] && p->bn_bias[i] && p->bn_mean[i] && p->bn_var[i],
+                "i2l_resnet_pack: missing tensors for conv %d", (int)i);
+    int per = c.ci * c.k * c.k;
+    size_t tot = (size_t)c.co * per;
+    fold_bn_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(p->conv_w[i], p->bn_weight[i], p->bn_bias[i],
+                                                               p->bn_mean[i], p->bn_var[i], pk + c.w_off,
+                                                               pk + c.b_off, c.co, per);
+    I2L_LAUNCH_OK();
+  }
+  I2L_REQUIRE(p->fc_w && p->fc_b, "i2l_resnet_pack: missing embedding layer");
+  I2L_CUDA_OK(cudaMemcpyAsync(pk + L.fc_w, p->fc_w, (size_t)d->embedding_dim * n.feat * 4, cudaMemcpyDeviceToDevice, s));
+  I2L_CUDA_OK(cudaMemcpyAsync(pk + L.fc_b, p->fc_b, (size_t)d->embedding_dim * 4, cudaMemcpyDeviceToDevice, s));
+  return I2L_OK;
+}
+
+extern "C" size_t i2l_resnet_workspace_bytes(const i2l_resnet_desc* d, int32_t batch, int32_t img_width) {
+  if (!d || batch <= 0 || img_width <= 0) return 0;
+  RNet n = build_resnet(d->depth);
+  if (!n.ok) return 0;
+  size_t act = align_up(resnet_max_act(n, d->img_height, img_width) * (size_t)batch * 4, 256);
+  return 5 * act + align_up((size_t)batch * n.feat * 4, 256);
+}
+
+extern "C" int i2l_resnet_encoder_fwd(const i2l_resnet_desc* d, const void* packed, const float* x, int32_t batch,
+                                      int32_t img_width, float* out, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  I2L_TRY(device_check());
+  I2L_REQUIRE(d && packed && batch >= 0 && img_width > 0, "i2l_resnet_encoder_fwd: invalid argument");
+  if (batch == 0) return I2L_OK;
+  I2L_REQUIRE(x && out && workspace, "i2l_resnet_encoder_fwd: null buffer");
+  RNet n = build_resnet(d->depth);
+  I2L_REQUIRE(n.ok, "Invalid ResNet model name: resnet%d", d->depth);
+  size_t need = i2l_resnet_workspace_bytes(d, batch, img_width);
+  if (workspace_bytes < need) { set_error("i2l_resnet_encoder_fwd: workspace too small (%zu < %zu)", workspace_bytes, need); return I2L_ERR_WORKSPACE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  RLayout L = resnet_layout(n, d->embedding_dim);
+  const float* pk = reinterpret_cast<const float*>(packed);
+  size_t act = align_up(resnet_max_act(n, d->img_height, img_width) * (size_t)batch * 4, 256);
+  char* base = reinterpret_cast<char*>(workspace);
+  float* buf[5];
+  for (int i = 0; i < 5; ++i) buf[i] = reinterpret_cast<float*>(base + i * act);
+  float* pooled = reinterpret_cast<float*>(base + 5 * act);
+  auto osz = [](int v, int k, int st, int p) { return (v + 2 * p - k) / st + 1; };
+  auto run = [&](int idx, const float* in, float* o, int h, int w, const float* res, int relu) {
+    const RConv& c = n.convs[idx];
+    ConvF32 cv;
+    cv.x = in; cv.w = pk + c.w_off; cv.bias = pk + c.b_off; cv.residual = res; cv.y = o;
+    cv.B = batch; cv.Ci = c.ci; cv.Hi = h; cv.Wi = w; cv.Co = c.co; cv.KH = cv.KW = c.k; cv.stride = c.stride;
+    cv.pad = c.pad; cv.relu = relu;
+    return conv2d_f32(cv, s);
+  };
+  int h = d->img_height, w = img_width;
+  I2L_TRY(run(0, x, buf[1], h, w, nullptr, 1));                      // conv1 + bn1 + relu
+  h = osz(h, 7, 2, 3); w = osz(w, 7, 2, 3);
+  I2L_TRY(maxpool2d_f32(buf[1], buf[0], batch, 64, h, w, 3, 2, 1, s));
+  h = osz(h, 3, 2, 1); w = osz(w, 3, 2, 1);
+  float* cur = buf[0]; float* nxt = buf[1]; float* t1 = buf[2]; float* t2 = buf[3]; float* idt = buf[4];
+  for (const RBlock& b : n.blocks) {
+    const RConv& c1 = n.convs[b.c1];
+    const RConv& c2 = n.convs[b.c2];
+    int h1 = osz(h, c1.k, c1.stride, c1.pad), w1 = osz(w, c1.k, c1.stride, c1.pad);
+    int h2 = osz(h1, c2.k, c2.stride, c2.pad), w2 = osz(w1, c2.k, c2.stride, c2.pad);
+    const float* res = cur;
+    if (b.ds >= 0) { I2L_TRY(run(b.ds, cur, idt, h, w, nullptr, 0)); res = idt; }
+    I2L_TRY(run(b.c1, cur, t1, h, w, nullptr, 1));
+    if (b.c3 < 0) {
+      I2L_TRY(run(b.c2, t1, nxt, h1, w1, res, 1));
+    } else {
+      I2L_TRY(run(b.c2, t1, t2, h1, w1, nullptr, 1));
+      I2L_TRY(run(b.c3, t2, nxt, h2, w2, res, 1));
+    }
+    std::swap(cur, nxt);
+    h = h2; w = w2;
+  }
+  I2L_TRY(global_avgpool_f32(cur, pooled, batch, n.feat, h * w, s));   // AdaptiveAvgPool2d(1)
+  GemmF32 g;
+  g.M = batch; g.N = d->embedding_dim; g.C = out; g.ldc = d->embedding_dim;
+  g.A1 = pooled; g.lda1 = n.feat; g.W1 = pk + L.fc_w; g.ldw1 = n.feat; g.K1 = n.feat;
+  g.bias = pk + L.fc_b; g.relu = 1;
+  return gemm_f32(g, s);
+}

@@ -1,0 +1,12 @@
+// bf16 tcgen05 CNN encoder path (cnn_bf16.cu).
+#pragma once
+#include "common.cuh"
+
+namespace i2l {
+bool cnn_bf16_supported(const i2l_cnn_desc& d);
+size_t cnn_bf16_packed_bytes(const i2l_cnn_desc& d);
+int cnn_bf16_pack(const i2l_cnn_desc& d, const i2l_cnn_params& p, void* section, cudaStream_t s);
+size_t cnn_bf16_workspace_bytes(const i2l_cnn_desc& d, int batch);
+int cnn_bf16_fwd(const i2l_cnn_desc& d, const void* section, const float* x, int batch, float* out, void* ws,
+                 size_t ws_bytes, cudaStream_t s);
+}  // namespace i2l

@@ -1,0 +1,43 @@
+"""Batch-sharded data-parallel inference: images are independent through
+encoder and decode, so each rank takes a contiguous slice of the batch with a full weight
+replica and NO per-step communication.  The one exchange is an all-gather of the
+(B/G, T+1) token ids (+ lengths) at the end; the global stop step of the sticky rule
+composes as max over ranks.  Works with NCCL (GPU) and gloo (CPU tests)."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced slices; the first n % world_size ranks get one extra item."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_tokens(tokens: torch.Tensor, lengths: torch.Tensor, steps: torch.Tensor, n_total: int,
+                  pad_id: int = -1) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """All-gather ragged per-rank (b_r, T+1) token matrices into the (n_total, T+1) global
+    matrix in rank order.  Every rank receives the full result."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return tokens, lengths, steps
+    ws = dist.get_world_size()
+    T1 = tokens.shape[1]
+    cap = (n_total + ws - 1) // ws
+    buf = torch.full((cap, T1 + 1), pad_id, dtype=torch.int64, device=tokens.device)
+    b = tokens.shape[0]
+    buf[:b, :T1] = tokens
+    buf[:b, T1] = lengths.to(torch.int64)
+    out = torch.empty(ws * cap, T1 + 1, dtype=torch.int64, device=tokens.device)
+    dist.all_gather_into_tensor(out, buf)
+    rows: List[torch.Tensor] = []
+    for r in range(ws):
+        lo, hi = shard_bounds(n_total, ws, r)
+        rows.append(out[r * cap: r * cap + (hi - lo)])
+    full = torch.cat(rows, dim=0)
+    gsteps = steps.clone().to(torch.int32)
+    dist.all_reduce(gsteps, op=dist.ReduceOp.MAX)
+    return full[:, :T1].contiguous(), full[:, T1].to(torch.int32), gsteps

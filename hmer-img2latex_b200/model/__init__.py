@@ -1,0 +1,5 @@
+from .encoder import CNNEncoder, ResNetEncoder
+from .decoder import LSTMDecoder, Attention
+from .seq2seq import Seq2SeqModel
+
+__all__ = ["CNNEncoder", "ResNetEncoder", "LSTMDecoder", "Attention", "Seq2SeqModel"]

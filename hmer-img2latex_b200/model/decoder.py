@@ -1,0 +1,226 @@
+"""Drop-in decoder modules: same constructor signatures, attributes and ``state_dict``
+keys as the reference's ``img2latex/model/decoder.py`` (LSTMDecoder 16-284, Attention
+287-343).  ``decode_step`` / ``Attention.forward`` and the three device-resident
+decode loops run through the C-ABI; the torch sub-modules only own the parameters.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from ._common import Workspace, default_precision, f32c, params_key, require_cuda
+
+
+class Attention(nn.Module):
+    """reference: img2latex/model/decoder.py:287-343."""
+
+    def __init__(self, hidden_dim: int, encoder_dim: int):
+        super().__init__()
+        self.hidden_dim, self.encoder_dim = hidden_dim, encoder_dim
+        self.attn = nn.Linear(hidden_dim + encoder_dim, hidden_dim)
+        self.v = nn.Linear(hidden_dim, 1, bias=False)
+        self._ws = Workspace()
+
+    def forward(self, hidden: torch.Tensor, encoder_outputs: torch.Tensor) -> torch.Tensor:
+        """hidden (B,1,H), encoder_outputs (B,L,E) -> context (B,1,E); decoder.py:312-343."""
+        require_cuda(hidden, "Attention.forward")
+        if hidden.dim() != 3 or hidden.shape[1] != 1 or encoder_outputs.dim() != 3:
+            raise RuntimeError(f"Attention expects hidden (B,1,H) and encoder_outputs (B,L,E); got "
+                               f"{tuple(hidden.shape)}, {tuple(encoder_outputs.shape)}")
+        B, L, E = encoder_outputs.shape
+        with torch.cuda.device(hidden.device):
+            lib = N.lib()
+            hid, enc = f32c(hidden.reshape(B, self.hidden_dim)), f32c(encoder_outputs)
+            w, b, v = f32c(self.attn.weight), f32c(self.attn.bias), f32c(self.v.weight)
+            out = torch.empty(B, E, dtype=torch.float32, device=hidden.device)
+            wsb = lib.i2l_attention_workspace_bytes(self.hidden_dim, E, B, L)
+            ws = self._ws.get(wsb, hidden.device)
+            N.check(lib.i2l_attention_fwd(self.hidden_dim, E, N.ptr(w), N.ptr(b), N.ptr(v), N.ptr(hid), N.ptr(enc),
+                                          B, L, N.ptr(out), N.ptr(ws), ws.numel(), N.stream_ptr(hidden.device)),
+                    "i2l_attention_fwd")
+        return out.unsqueeze(1)
+
+
+class LSTMDecoder(nn.Module):
+    """reference: img2latex/model/decoder.py:16-284."""
+
+    def __init__(self, vocab_size: int, embedding_dim: int = None, hidden_dim: int = None,
+                 max_seq_length: int = None, lstm_layers: int = None, dropout: float = None,
+                 attention: bool = True, precision: Optional[str] = None):
+        super().__init__()
+        # defaults: decoder.py:48-58
+        embedding_dim = 256 if embedding_dim is None else embedding_dim
+        hidden_dim = 256 if hidden_dim is None else hidden_dim
+        max_seq_length = 141 if max_seq_length is None else max_seq_length
+        lstm_layers = 1 if lstm_layers is None else lstm_layers
+        dropout = 0.1 if dropout is None else dropout
+        if lstm_layers > N.MAX_LSTM:
+            raise ValueError(f"at most {N.MAX_LSTM} LSTM layers are supported")
+        self.vocab_size, self.embedding_dim, self.hidden_dim = vocab_size, embedding_dim, hidden_dim
+        self.max_seq_length, self.lstm_layers, self.dropout = max_seq_length, lstm_layers, dropout
+        self.use_attention = attention
+        self.precision = precision or default_precision()
+        self.embedding = nn.Embedding(vocab_size, embedding_dim)
+        self.lstm = nn.LSTM(input_size=2 * embedding_dim, hidden_size=hidden_dim, num_layers=lstm_layers,
+                            batch_first=True, dropout=dropout if lstm_layers > 1 else 0)
+        if attention:
+            self.attention = Attention(hidden_dim, embedding_dim)
+        self.output_layer = nn.Linear(hidden_dim, vocab_size)
+        self.dropout_layer = nn.Dropout(dropout)
+        self._packed = None
+        self._packed_key = None
+        self._ws = Workspace()
+
+    # -- native plumbing -------------------------------------------------
+    def _desc(self) -> N.DecDesc:
+        d = N.DecDesc()
+        d.vocab_size, d.embedding_dim, d.hidden_dim = self.vocab_size, self.embedding_dim, self.hidden_dim
+        d.lstm_layers, d.attention = self.lstm_layers, int(self.use_attention)
+        d.precision = N.PRECISIONS[self.precision]
+        return d
+
+    def _weights(self):
+        ts = [self.embedding.weight]
+        for l in range(self.lstm_layers):
+            ts += [getattr(self.lstm, f"weight_ih_l{l}"), getattr(self.lstm, f"weight_hh_l{l}"),
+                   getattr(self.lstm, f"bias_ih_l{l}"), getattr(self.lstm, f"bias_hh_l{l}")]
+        return ts + [self.output_layer.weight, self.output_layer.bias]
+
+    def _ensure_packed(self, device):
+        ts = self._weights()
+        key = params_key(ts, self.precision)
+        if self._packed is not None and key == self._packed_key:
+            return
+        lib = N.lib()
+        d = self._desc()
+        held = [f32c(t) for t in ts]
+        p = N.DecParams()
+        p.embedding = held[0].data_ptr()
+        for l in range(self.lstm_layers):
+            p.w_ih[l], p.w_hh[l], p.b_ih[l], p.b_hh[l] = (held[1 + 4 * l + j].data_ptr() for j in range(4))
+        p.out_w, p.out_b = held[-2].data_ptr(), held[-1].data_ptr()
+        nbytes = lib.i2l_dec_packed_bytes(C.byref(d))
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        N.check(lib.i2l_dec_pack(C.byref(d), C.byref(p), N.ptr(packed), nbytes, N.stream_ptr(device)), "i2l_dec_pack")
+        torch.cuda.current_stream(device).synchronize()
+        self._packed, self._packed_key = packed, key
+
+    def _workspace(self, rows: int, max_length: int, device) -> torch.Tensor:
+        d = self._desc()
+        return self._ws.get(N.lib().i2l_dec_workspace_bytes(C.byref(d), rows, max_length), device)
+
+    # -- reference API ---------------------------------------------------
+    def forward(self, encoder_output, target_sequence, hidden=None):
+        raise NotImplementedError(
+            "teacher-forced training forward (decoder.py:100-195) is outside the inference hot path "
+            "(SURVEY.md 8f-4); use decode_step / the decode loops")
+
+    def decode_step(self, encoder_output: torch.Tensor, input_token: torch.Tensor, hidden=None
+                    ) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+        """(B,E), (B,1) int64, None | ((L,B,H),(L,B,H)) -> logits (B,1,V), (h,c);
+        reference decoder.py:197-284."""
+        require_cuda(encoder_output, "LSTMDecoder.decode_step")
+        if input_token.dim() != 2 or input_token.shape[1] != 1:
+            raise RuntimeError(f"Shape mismatch: input_token must be (B,1), got {tuple(input_token.shape)}")
+        dev = encoder_output.device
+        with torch.cuda.device(dev):
+            self._ensure_packed(dev)
+            lib = N.lib()
+            d = self._desc()
+            B = input_token.shape[0]
+            enc = f32c(encoder_output)
+            tok = input_token.reshape(B).to(torch.int64).contiguous()
+            h_in = c_in = None
+            if hidden is not None:
+                h_in, c_in = f32c(hidden[0]), f32c(hidden[1])
+            logits = torch.empty(B, self.vocab_size, dtype=torch.float32, device=dev)
+            h_out = torch.empty(self.lstm_layers, B, self.hidden_dim, dtype=torch.float32, device=dev)
+            c_out = torch.empty_like(h_out)
+            ws = self._workspace(max(B, 1), 1, dev)
+            N.check(lib.i2l_decode_step(C.byref(d), N.ptr(self._packed), N.ptr(enc), N.ptr(tok), B, N.ptr(h_in),
+                                        N.ptr(c_in), N.ptr(logits), N.ptr(h_out), N.ptr(c_out), N.ptr(ws),
+                                        ws.numel(), N.stream_ptr(dev)), "i2l_decode_step")
+        return logits.unsqueeze(1), (h_out, c_out)
+
+    # -- device-resident loops (no host sync per token) ------------------
+    def greedy(self, encoder_output: torch.Tensor, start_token_id: int, end_token_id: int, max_length: int,
+               temperature: float = 1.0, stop_rule: int = N.STOP_ALL_END_SAME_STEP):
+        """Loop of Seq2SeqModel._greedy_search (seq2seq.py:192-232) on the device.
+        Returns tokens (B, max_length+1) int64, lengths (B) int32, steps_run (0-dim int32)."""
+        require_cuda(encoder_output, "LSTMDecoder.greedy")
+        dev = encoder_output.device
+        with torch.cuda.device(dev):
+            self._ensure_packed(dev)
+            lib, d = N.lib(), self._desc()
+            enc = f32c(encoder_output)
+            B = enc.shape[0]
+            tokens = torch.empty(B, max_length + 1, dtype=torch.int64, device=dev)
+            lengths = torch.empty(B, dtype=torch.int32, device=dev)
+            steps = torch.zeros((), dtype=torch.int32, device=dev)
+            ws = self._workspace(max(B, 1), max_length, dev)
+            N.check(lib.i2l_decode_greedy(C.byref(d), N.ptr(self._packed), N.ptr(enc), B, start_token_id,
+                                          end_token_id, max_length, float(temperature), stop_rule, N.ptr(tokens),
+                                          N.ptr(lengths), N.ptr(steps), N.ptr(ws), ws.numel(), N.stream_ptr(dev)),
+                    "i2l_decode_greedy")
+        return tokens, lengths, steps
+
+    def sample(self, encoder_output: torch.Tensor, start_token_id: int, end_token_id: int, max_length: int,
+               temperature: float = 1.0, top_k: int = 0, top_p: float = 0.0, seed: int = 0, offset: int = 0,
+               uniforms: Optional[torch.Tensor] = None, return_probs: bool = False):
+        """Loop of Predictor.predict_batch (predictor.py:283-347) on the device."""
+        require_cuda(encoder_output, "LSTMDecoder.sample")
+        dev = encoder_output.device
+        with torch.cuda.device(dev):
+            self._ensure_packed(dev)
+            lib, d = N.lib(), self._desc()
+            enc = f32c(encoder_output)
+            B = enc.shape[0]
+            tokens = torch.empty(B, max_length + 1, dtype=torch.int64, device=dev)
+            lengths = torch.empty(B, dtype=torch.int32, device=dev)
+            steps = torch.zeros((), dtype=torch.int32, device=dev)
+            probs = torch.zeros(max_length, B, self.vocab_size, dtype=torch.float32, device=dev) if return_probs else None
+            if uniforms is not None:
+                uniforms = f32c(uniforms.to(dev))
+                if tuple(uniforms.shape) != (max_length, B):
+                    raise RuntimeError(f"uniforms must be (max_length, B) = ({max_length}, {B})")
+            ws = self._workspace(max(B, 1), max_length, dev)
+            N.check(lib.i2l_decode_sample(C.byref(d), N.ptr(self._packed), N.ptr(enc), B, start_token_id,
+                                          end_token_id, max_length, float(temperature), int(top_k), float(top_p),
+                                          int(seed), int(offset), N.ptr(uniforms), N.ptr(tokens), N.ptr(lengths),
+                                          N.ptr(steps), N.ptr(probs), N.ptr(ws), ws.numel(), N.stream_ptr(dev)),
+                    "i2l_decode_sample")
+        if return_probs:
+            return tokens, lengths, steps, probs
+        return tokens, lengths, steps
+
+    def beam(self, encoder_output: torch.Tensor, start_token_id: int, end_token_id: int, max_length: int,
+             beam_size: int, return_trace: bool = False):
+        """Seq2SeqModel._beam_search (seq2seq.py:234-298) run independently per image, on the
+        device.  Returns out_tokens (B,max_length) int64 padded with -1, out_len (B), score (B) f64."""
+        require_cuda(encoder_output, "LSTMDecoder.beam")
+        dev = encoder_output.device
+        with torch.cuda.device(dev):
+            self._ensure_packed(dev)
+            lib, d = N.lib(), self._desc()
+            enc = f32c(encoder_output)
+            B, K = enc.shape[0], beam_size
+            out = torch.empty(B, max_length, dtype=torch.int64, device=dev)
+            olen = torch.empty(B, dtype=torch.int32, device=dev)
+            score = torch.empty(B, dtype=torch.float64, device=dev)
+            trp = trt = trs = None
+            if return_trace:
+                trp = torch.empty(max_length, B, K, dtype=torch.int32, device=dev)
+                trt = torch.empty(max_length, B, K, dtype=torch.int32, device=dev)
+                trs = torch.empty(max_length, B, K, dtype=torch.float64, device=dev)
+            ws = self._workspace(max(B * K, 1), max_length, dev)
+            N.check(lib.i2l_decode_beam(C.byref(d), N.ptr(self._packed), N.ptr(enc), B, K, start_token_id,
+                                        end_token_id, max_length, N.ptr(out), N.ptr(olen), N.ptr(score), N.ptr(trp),
+                                        N.ptr(trt), N.ptr(trs), N.ptr(ws), ws.numel(), N.stream_ptr(dev)),
+                    "i2l_decode_beam")
+        if return_trace:
+            return out, olen, score, (trp, trt, trs)
+        return out, olen, score

@@ -1,0 +1,225 @@
+"""Drop-in encoders: same constructor signatures, attributes and ``state_dict`` keys as
+the reference's ``img2latex/model/encoder.py`` (CNNEncoder 16-129, ResNetEncoder
+132-249); ``forward`` runs the sm_100a kernels through the C-ABI
+(``i2l_cnn_encoder_fwd`` / ``i2l_resnet_encoder_fwd``).  The torch sub-modules exist
+only to own the parameters under the reference's names -- they are never called.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from ._common import Workspace, default_precision, f32c, params_key, require_cuda
+
+_RESNET_DEPTH = {"resnet18": 18, "resnet34": 34, "resnet50": 50, "resnet101": 101, "resnet152": 152}
+
+
+class CNNEncoder(nn.Module):
+    """reference: img2latex/model/encoder.py:16-129."""
+
+    def __init__(self, img_height: int = None, img_width: int = None, channels: int = None,
+                 conv_filters: List[int] = None, kernel_size: int = None, pool_size: int = None,
+                 padding: str = "same", embedding_dim: int = None, precision: Optional[str] = None):
+        super().__init__()
+        # defaults: encoder.py:50-64
+        img_height = 64 if img_height is None else img_height
+        img_width = 800 if img_width is None else img_width
+        channels = 1 if channels is None else channels
+        conv_filters = [32, 64, 128] if conv_filters is None else list(conv_filters)
+        kernel_size = 3 if kernel_size is None else kernel_size
+        pool_size = 2 if pool_size is None else pool_size
+        embedding_dim = 256 if embedding_dim is None else embedding_dim
+        if padding != "same":
+            raise NotImplementedError("only padding='same' (the reference default, encoder.py:32) is implemented")
+        if kernel_size % 2 == 0 or len(conv_filters) > N.MAX_CONV:
+            raise ValueError("kernel_size must be odd and at most %d conv layers are supported" % N.MAX_CONV)
+        self.img_height, self.img_width, self.channels = img_height, img_width, channels
+        self.embedding_dim = embedding_dim
+        self.conv_filters, self.kernel_size, self.pool_size = conv_filters, kernel_size, pool_size
+        self.precision = precision or default_precision()
+
+        layers = []
+        cin, h, w = channels, img_height, img_width
+        for f in conv_filters:                                   # encoder.py:78-93
+            layers += [nn.Conv2d(cin, f, kernel_size, padding=kernel_size // 2), nn.ReLU(), nn.MaxPool2d(pool_size)]
+            cin, h, w = f, h // pool_size, w // pool_size
+        self.cnn_layers = nn.Sequential(*layers)
+        self.flatten = nn.Flatten()
+        self.embedding_layer = nn.Linear(cin * h * w, embedding_dim)   # encoder.py:97-106
+        self.activation = nn.ReLU()
+        self._packed = None
+        self._packed_key = None
+        self._ws = Workspace()
+
+    # -- native plumbing -------------------------------------------------
+    def _desc(self) -> N.CnnDesc:
+        d = N.CnnDesc()
+        d.img_height, d.img_width, d.channels = self.img_height, self.img_width, self.channels
+        d.n_conv = len(self.conv_filters)
+        for i, f in enumerate(self.conv_filters):
+            d.filters[i] = f
+        d.kernel_size, d.pool_size, d.embedding_dim = self.kernel_size, self.pool_size, self.embedding_dim
+        d.precision = N.PRECISIONS[self.precision]
+        return d
+
+    def _weights(self):
+        convs = [m for m in self.cnn_layers if isinstance(m, nn.Conv2d)]
+        ts = []
+        for c in convs:
+            ts += [c.weight, c.bias]
+        return ts + [self.embedding_layer.weight, self.embedding_layer.bias]
+
+    def _ensure_packed(self, device):
+        ts = self._weights()
+        key = params_key(ts, self.precision)
+        if self._packed is not None and key == self._packed_key:
+            return
+        lib = N.lib()
+        d = self._desc()
+        held = [f32c(t) for t in ts]
+        p = N.CnnParams()
+        n = len(self.conv_filters)
+        for i in range(n):
+            p.conv_w[i] = held[2 * i].data_ptr()
+            p.conv_b[i] = held[2 * i + 1].data_ptr()
+        p.fc_w, p.fc_b = held[2 * n].data_ptr(), held[2 * n + 1].data_ptr()
+        nbytes = lib.i2l_cnn_packed_bytes(C.byref(d))
+        if nbytes == 0:
+            raise RuntimeError("i2l_cnn_packed_bytes rejected the configuration: " + N.last_error())
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        N.check(lib.i2l_cnn_pack(C.byref(d), C.byref(p), N.ptr(packed), nbytes, N.stream_ptr(device)), "i2l_cnn_pack")
+        torch.cuda.current_stream(device).synchronize()   # `held` temporaries may be freed after this
+        self._packed, self._packed_key = packed, key
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """(B, C, H, W) -> (B, embedding_dim); reference encoder.py:111-129."""
+        require_cuda(x, "CNNEncoder.forward")
+        if x.dim() != 4 or tuple(x.shape[1:]) != (self.channels, self.img_height, self.img_width):
+            raise RuntimeError(f"CNNEncoder expected (B,{self.channels},{self.img_height},{self.img_width}), "
+                               f"got {tuple(x.shape)}")
+        with torch.cuda.device(x.device):
+            self._ensure_packed(x.device)
+            lib = N.lib()
+            d = self._desc()
+            x = f32c(x)
+            B = x.shape[0]
+            out = torch.empty(B, self.embedding_dim, dtype=torch.float32, device=x.device)
+            if B == 0:
+                return out
+            wsb = lib.i2l_cnn_workspace_bytes(C.byref(d), B)
+            ws = self._ws.get(wsb, x.device)
+            N.check(lib.i2l_cnn_encoder_fwd(C.byref(d), N.ptr(self._packed), N.ptr(x), B, N.ptr(out), N.ptr(ws),
+                                            ws.numel(), N.stream_ptr(x.device)), "i2l_cnn_encoder_fwd")
+        return out
+
+
+class ResNetEncoder(nn.Module):
+    """reference: img2latex/model/encoder.py:132-249.  The torchvision trunk is built with
+    ``weights=None`` unless ``pretrained=True`` (the reference always downloads ImageNet
+    weights, encoder.py:185-194, which needs a network)."""
+
+    def __init__(self, img_height: int = None, img_width: int = None, channels: int = None,
+                 model_name: str = "resnet50", embedding_dim: int = None, freeze_backbone: bool = True,
+                 pretrained: bool = False, precision: Optional[str] = None):
+        super().__init__()
+        import torchvision.models as models
+        img_height = 64 if img_height is None else img_height
+        img_width = 800 if img_width is None else img_width
+        channels = 3 if channels is None else channels
+        embedding_dim = 256 if embedding_dim is None else embedding_dim
+        if model_name not in _RESNET_DEPTH:
+            raise ValueError(f"Invalid ResNet model name: {model_name}")      # encoder.py:195-196
+        if channels != 3:
+            raise ValueError("ResNet expects 3-channel RGB images")
+        self.img_height, self.img_width, self.channels = img_height, img_width, channels
+        self.embedding_dim, self.model_name = embedding_dim, model_name
+        self.precision = precision or default_precision()
+        weights = "IMAGENET1K_V1" if pretrained else None
+        backbone = getattr(models, model_name)(weights=weights)
+        modules = list(backbone.children())[:-1]                              # encoder.py:198
+        self.resnet = nn.Sequential(*modules)
+        if freeze_backbone:                                                   # encoder.py:201-210
+            for p in self.resnet.parameters():
+                p.requires_grad = False
+            for p in modules[-2].parameters():
+                p.requires_grad = True
+        self.flatten = nn.Flatten()
+        feat = 512 if model_name in ("resnet18", "resnet34") else 2048        # encoder.py:219-222
+        self.embedding_layer = nn.Linear(feat, embedding_dim)
+        self.activation = nn.ReLU()
+        self._packed = None
+        self._packed_key = None
+        self._ws = Workspace()
+
+    def _desc(self) -> N.ResnetDesc:
+        d = N.ResnetDesc()
+        d.depth = _RESNET_DEPTH[self.model_name]
+        d.img_height, d.embedding_dim = self.img_height, self.embedding_dim
+        d.precision = N.PRECISIONS[self.precision]
+        return d
+
+    def _conv_bn_pairs(self):
+        """(conv, bn) in the canonical order of include/i2l_b200.h: stem, then per block
+        conv1, conv2[, conv3][, downsample]."""
+        pairs = [(self.resnet[0], self.resnet[1])]
+        for li in range(4, 8):
+            for blk in self.resnet[li]:
+                pairs.append((blk.conv1, blk.bn1))
+                pairs.append((blk.conv2, blk.bn2))
+                if hasattr(blk, "conv3"):
+                    pairs.append((blk.conv3, blk.bn3))
+                if blk.downsample is not None:
+                    pairs.append((blk.downsample[0], blk.downsample[1]))
+        return pairs
+
+    def _ensure_packed(self, device):
+        pairs = self._conv_bn_pairs()
+        ts = []
+        for c, b in pairs:
+            ts += [c.weight, b.weight, b.bias, b.running_mean, b.running_var]
+        ts += [self.embedding_layer.weight, self.embedding_layer.bias]
+        key = params_key(ts, self.precision)
+        if self._packed is not None and key == self._packed_key:
+            return
+        lib = N.lib()
+        d = self._desc()
+        held = [f32c(t) for t in ts]
+        p = N.ResnetParams()
+        p.n_convs = len(pairs)
+        assert p.n_convs == lib.i2l_resnet_num_convs(d.depth)
+        for i in range(len(pairs)):
+            p.conv_w[i], p.bn_weight[i], p.bn_bias[i], p.bn_mean[i], p.bn_var[i] = (
+                held[5 * i + j].data_ptr() for j in range(5))
+        p.fc_w, p.fc_b = held[-2].data_ptr(), held[-1].data_ptr()
+        nbytes = lib.i2l_resnet_packed_bytes(C.byref(d))
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        N.check(lib.i2l_resnet_pack(C.byref(d), C.byref(p), N.ptr(packed), nbytes, N.stream_ptr(device)),
+                "i2l_resnet_pack")
+        torch.cuda.current_stream(device).synchronize()
+        self._packed, self._packed_key = packed, key
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """(B, 3, H, W) -> (B, embedding_dim); any W (the trunk ends in adaptive average
+        pooling), which is what width bucketing relies on.  reference encoder.py:231-249."""
+        require_cuda(x, "ResNetEncoder.forward")
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.img_height:
+            raise RuntimeError(f"ResNetEncoder expected (B,3,{self.img_height},W), got {tuple(x.shape)}")
+        with torch.cuda.device(x.device):
+            self._ensure_packed(x.device)
+            lib = N.lib()
+            d = self._desc()
+            x = f32c(x)
+            B, W = x.shape[0], x.shape[3]
+            out = torch.empty(B, self.embedding_dim, dtype=torch.float32, device=x.device)
+            if B == 0:
+                return out
+            wsb = lib.i2l_resnet_workspace_bytes(C.byref(d), B, W)
+            ws = self._ws.get(wsb, x.device)
+            N.check(lib.i2l_resnet_encoder_fwd(C.byref(d), N.ptr(self._packed), N.ptr(x), B, W, N.ptr(out),
+                                               N.ptr(ws), ws.numel(), N.stream_ptr(x.device)),
+                    "i2l_resnet_encoder_fwd")
+        return out

@@ -1,0 +1,103 @@
+"""Drop-in ``Seq2SeqModel`` (reference: img2latex/model/seq2seq.py:17-298): same
+constructor, sub-module names (``encoder`` / ``decoder`` => same ``state_dict`` keys),
+``inference`` signature and return conventions.  The decode loops run on the device
+with no host sync per token; the host reads the token matrix back once at the end.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from .decoder import LSTMDecoder
+from .encoder import CNNEncoder, ResNetEncoder
+
+
+class Seq2SeqModel(nn.Module):
+    def __init__(self, model_type: str = "cnn_lstm", vocab_size: int = None, encoder_params: Dict = None,
+                 decoder_params: Dict = None, precision: Optional[str] = None):
+        super().__init__()
+        encoder_params = {} if encoder_params is None else encoder_params
+        decoder_params = {} if decoder_params is None else decoder_params
+        vocab_size = 100 if vocab_size is None else vocab_size              # seq2seq.py:50-51
+        embedding_dim = encoder_params.get("embedding_dim", 256)            # seq2seq.py:54
+        if model_type == "cnn_lstm":                                        # seq2seq.py:57-67
+            self.encoder = CNNEncoder(
+                img_height=encoder_params.get("img_height", 50), img_width=encoder_params.get("img_width", 200),
+                channels=encoder_params.get("channels", 1),
+                conv_filters=encoder_params.get("conv_filters", [32, 64, 128]),
+                kernel_size=encoder_params.get("kernel_size", 3), pool_size=encoder_params.get("pool_size", 2),
+                padding=encoder_params.get("padding", "same"), embedding_dim=embedding_dim, precision=precision)
+        elif model_type == "resnet_lstm":                                   # seq2seq.py:68-76
+            self.encoder = ResNetEncoder(
+                img_height=encoder_params.get("img_height", 224), img_width=encoder_params.get("img_width", 224),
+                channels=encoder_params.get("channels", 3), model_name=encoder_params.get("model_name", "resnet50"),
+                embedding_dim=embedding_dim, freeze_backbone=encoder_params.get("freeze_backbone", True),
+                pretrained=encoder_params.get("pretrained", False), precision=precision)
+        else:
+            raise ValueError(f"Invalid model type: {model_type}. Expected 'cnn_lstm' or 'resnet_lstm'.")
+        self.decoder = LSTMDecoder(                                         # seq2seq.py:83-91
+            vocab_size=vocab_size, embedding_dim=embedding_dim, hidden_dim=decoder_params.get("hidden_dim", 256),
+            max_seq_length=decoder_params.get("max_seq_length", 150), lstm_layers=decoder_params.get("lstm_layers", 1),
+            dropout=decoder_params.get("dropout", 0.1), attention=decoder_params.get("attention", False),
+            precision=precision)
+        self.model_type = model_type
+        self.vocab_size = vocab_size
+
+    def set_precision(self, precision: str) -> "Seq2SeqModel":
+        if precision not in N.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(N.PRECISIONS)}")
+        self.encoder.precision = precision
+        self.decoder.precision = precision
+        return self
+
+    def forward(self, images, target_sequences):
+        raise NotImplementedError("training forward (seq2seq.py:98-122) is outside the inference hot path")
+
+    @torch.no_grad()
+    def inference(self, image: torch.Tensor, start_token_id: int, end_token_id: int, max_length: int = None,
+                  temperature: float = None, top_k: int = None, top_p: float = None, beam_size: int = None):
+        """reference seq2seq.py:124-190.  B==1 -> List[int] (START stripped, cut at END);
+        B>1 -> raw List[List[int]] incl. START (seq2seq.py:223-232)."""
+        max_length = 150 if max_length is None else max_length
+        temperature = 1.0 if temperature is None else temperature
+        top_k = 0 if top_k is None else top_k
+        top_p = 0.0 if top_p is None else top_p
+        beam_size = 0 if beam_size is None else beam_size
+        encoder_output = self.encoder(image)
+        if encoder_output.dim() == 1:
+            encoder_output = encoder_output.unsqueeze(0)
+        if beam_size > 0:
+            return self._beam_search(encoder_output, start_token_id, end_token_id, max_length, beam_size)
+        return self._greedy_search(encoder_output, start_token_id, end_token_id, max_length, temperature, top_k, top_p)
+
+    def _greedy_search(self, encoder_output, start_token_id, end_token_id, max_length, temperature, top_k, top_p):
+        """reference seq2seq.py:192-232 (top_k / top_p are ignored there too)."""
+        tokens, _, steps = self.decoder.greedy(encoder_output, start_token_id, end_token_id, max_length,
+                                               temperature, N.STOP_ALL_END_SAME_STEP)
+        n = int(steps.item())                       # the one host sync of the decode
+        rows = tokens[:, : n + 1].tolist()
+        if len(rows) == 1:                          # seq2seq.py:224-231
+            seq = rows[0]
+            if seq and seq[0] == start_token_id:
+                seq = seq[1:]
+            if end_token_id in seq:
+                seq = seq[: seq.index(end_token_id)]
+            return seq
+        return rows
+
+    def _beam_search(self, encoder_output, start_token_id, end_token_id, max_length, beam_size):
+        """reference seq2seq.py:234-298: batch-size-1 only, B>1 falls back to greedy (244-247)."""
+        if encoder_output.size(0) != 1:
+            return self._greedy_search(encoder_output, start_token_id, end_token_id, max_length, 1.0, 0, 0.0)
+        return self.beam_search_batch(encoder_output, start_token_id, end_token_id, max_length, beam_size)[0]
+
+    @torch.no_grad()
+    def beam_search_batch(self, encoder_output, start_token_id, end_token_id, max_length, beam_size) -> List[List[int]]:
+        """Batched beam search = the reference's B==1 beam run independently per image
+        (BASELINE config 3); not present in the reference."""
+        out, olen, _ = self.decoder.beam(encoder_output, start_token_id, end_token_id, max_length, beam_size)
+        out, olen = out.tolist(), olen.tolist()
+        return [r[:n] for r, n in zip(out, olen)]

@@ -1,0 +1,201 @@
+/*
+ * i2l_b200.h -- C-ABI of the B200-native (sm_100a) img2latex inference hot path.
+ *
+ * This is the drop-in boundary for the reference's batched inference path
+ * (Jeremy-Cleland/hmer-img2latex).  The reference has no FFI of its own: its
+ * boundary is the Python nn.Module surface.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference root).
+ * The Python host side (hmer-img2latex_b200/) binds these with ctypes and keeps
+ * the reference's class / method signatures; see INTEGRATION.md for the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers + sizes only; all tensor pointers are DEVICE pointers unless
+ *    a parameter is documented as host; `stream` is a cudaStream_t passed as void*.
+ *  - the caller owns every buffer (weights, packed weights, workspace, outputs);
+ *    the library allocates nothing on the hot path and never synchronises the
+ *    host (all launches are asynchronous on `stream`).
+ *  - return value: 0 = I2L_OK, negative = i2l_status; a message for the calling
+ *    thread is available from i2l_last_error().  Nothing throws across the ABI.
+ *  - CUDA only, sm_100 only: no CPU fallback.  i2l_device_check() != 0 => every
+ *    compute entry point fails with I2L_ERR_NO_DEVICE.
+ *  - weights arrive in the reference's own state_dict layouts (fp32) and are
+ *    re-laid-out once by the *_pack calls into a caller-owned packed buffer.
+ */
+#ifndef I2L_B200_H_
+#define I2L_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I2L_MAX_CONV 8
+#define I2L_MAX_LSTM_LAYERS 8
+#define I2L_MAX_RESNET_CONVS 160
+
+typedef enum {
+  I2L_OK = 0,
+  I2L_ERR_INVALID = -1,     /* bad argument / unsupported shape combination        */
+  I2L_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed                 */
+  I2L_ERR_NO_DEVICE = -3,   /* no sm_100 device is current                         */
+  I2L_ERR_UNSUPPORTED = -4, /* valid request the library does not implement        */
+  I2L_ERR_WORKSPACE = -5    /* workspace / packed buffer too small                 */
+} i2l_status;
+
+typedef enum { I2L_FP32 = 0, I2L_BF16 = 1 } i2l_precision;
+
+/* Loop-exit rules of the reference's three decode loops. */
+typedef enum {
+  I2L_STOP_NONE = 0,
+  I2L_STOP_ALL_END_SAME_STEP = 1,   /* Seq2SeqModel._greedy_search, model/seq2seq.py:220      */
+  I2L_STOP_ALL_FINISHED_STICKY = 2  /* Predictor.predict_batch, training/predictor.py:343-347 */
+} i2l_stop_rule;
+
+const char* i2l_version(void);
+const char* i2l_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x, else I2L_ERR_NO_DEVICE. */
+int i2l_device_check(void);
+
+/* ------------------------------------------------------------------------- */
+/* CNN encoder -- replaces CNNEncoder.forward, model/encoder.py:111-129        */
+/* (layer stack built at model/encoder.py:74-107).                             */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t img_height, img_width, channels;
+  int32_t n_conv;                 /* len(conv_filters)                          */
+  int32_t filters[I2L_MAX_CONV];  /* conv_filters                               */
+  int32_t kernel_size;            /* odd; padding "same" = kernel_size/2        */
+  int32_t pool_size;
+  int32_t embedding_dim;
+  int32_t precision;              /* i2l_precision                              */
+} i2l_cnn_desc;
+
+typedef struct {                         /* state_dict tensors, fp32, device     */
+  const float* conv_w[I2L_MAX_CONV];     /* cnn_layers.{0,3,6..}.weight (Co,Ci,k,k) */
+  const float* conv_b[I2L_MAX_CONV];     /* cnn_layers.{0,3,6..}.bias              */
+  const float* fc_w;                     /* embedding_layer.weight (E, C*H*W) NCHW flatten order */
+  const float* fc_b;                     /* embedding_layer.bias                   */
+} i2l_cnn_params;
+
+size_t i2l_cnn_packed_bytes(const i2l_cnn_desc* d);
+int i2l_cnn_pack(const i2l_cnn_desc* d, const i2l_cnn_params* p, void* packed, size_t packed_bytes,
+                 void* stream);
+size_t i2l_cnn_workspace_bytes(const i2l_cnn_desc* d, int32_t batch);
+/* x: (B,C,H,W) fp32 NCHW;  out: (B,E) fp32. */
+int i2l_cnn_encoder_fwd(const i2l_cnn_desc* d, const void* packed, const float* x, int32_t batch,
+                        float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* ResNet encoder -- replaces ResNetEncoder.forward, model/encoder.py:231-249   */
+/* (torchvision trunk minus fc, model/encoder.py:184-199; eval-mode BN folded). */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t depth;                 /* 18, 34, 50, 101, 152  (model_name)          */
+  int32_t img_height;            /* width is a call-time argument (width buckets) */
+  int32_t embedding_dim;
+  int32_t precision;
+} i2l_resnet_desc;
+
+typedef struct {
+  int32_t n_convs;               /* convs in canonical order: stem, then per block conv1,conv2[,conv3][,downsample] */
+  const float* conv_w[I2L_MAX_RESNET_CONVS];
+  const float* bn_weight[I2L_MAX_RESNET_CONVS];
+  const float* bn_bias[I2L_MAX_RESNET_CONVS];
+  const float* bn_mean[I2L_MAX_RESNET_CONVS];
+  const float* bn_var[I2L_MAX_RESNET_CONVS];
+  const float* fc_w;             /* embedding_layer.weight (E, 512|2048)         */
+  const float* fc_b;
+} i2l_resnet_params;
+
+int32_t i2l_resnet_num_convs(int32_t depth);   /* <0 if depth is invalid */
+size_t i2l_resnet_packed_bytes(const i2l_resnet_desc* d);
+int i2l_resnet_pack(const i2l_resnet_desc* d, const i2l_resnet_params* p, void* packed,
+                    size_t packed_bytes, void* stream);
+size_t i2l_resnet_workspace_bytes(const i2l_resnet_desc* d, int32_t batch, int32_t img_width);
+/* x: (B,3,H,W) fp32 NCHW; out: (B,E) fp32. */
+int i2l_resnet_encoder_fwd(const i2l_resnet_desc* d, const void* packed, const float* x, int32_t batch,
+                           int32_t img_width, float* out, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Attention -- replaces Attention.forward, model/decoder.py:312-343            */
+/* hidden (B,H), encoder_outputs (B,L,E) -> context (B,E).  General L; the     */
+/* decode path always has L == 1 where the result is encoder_outputs itself.   */
+/* ------------------------------------------------------------------------- */
+size_t i2l_attention_workspace_bytes(int32_t hidden_dim, int32_t encoder_dim, int32_t batch, int32_t src_len);
+int i2l_attention_fwd(int32_t hidden_dim, int32_t encoder_dim, const float* attn_w /*(H,H+E)*/,
+                      const float* attn_b /*(H)*/, const float* v_w /*(1,H)*/, const float* hidden,
+                      const float* encoder_outputs, int32_t batch, int32_t src_len, float* context,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* LSTM decoder                                                                */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t vocab_size, embedding_dim, hidden_dim, lstm_layers;
+  int32_t attention;             /* LSTMDecoder(attention=...) -- src_len is 1 on this path */
+  int32_t precision;
+} i2l_dec_desc;
+
+typedef struct {                              /* state_dict tensors, fp32, device */
+  const float* embedding;                     /* decoder.embedding.weight (V,E)           */
+  const float* w_ih[I2L_MAX_LSTM_LAYERS];     /* decoder.lstm.weight_ih_l{k} (4H, 2E | H)   */
+  const float* w_hh[I2L_MAX_LSTM_LAYERS];     /* decoder.lstm.weight_hh_l{k} (4H, H)        */
+  const float* b_ih[I2L_MAX_LSTM_LAYERS];
+  const float* b_hh[I2L_MAX_LSTM_LAYERS];
+  const float* out_w;                         /* decoder.output_layer.weight (V,H)        */
+  const float* out_b;
+} i2l_dec_params;
+
+size_t i2l_dec_packed_bytes(const i2l_dec_desc* d);
+int i2l_dec_pack(const i2l_dec_desc* d, const i2l_dec_params* p, void* packed, size_t packed_bytes,
+                 void* stream);
+/* rows = batch (greedy / sample / step) or batch*beam (beam). */
+size_t i2l_dec_workspace_bytes(const i2l_dec_desc* d, int32_t rows, int32_t max_length);
+
+/* replaces LSTMDecoder.decode_step, model/decoder.py:197-284.
+ * enc (B,E) fp32; tok (B) int64; h_in/c_in (L,B,H) fp32 or NULL (= zeros, decoder.py:253-266);
+ * logits (B,V) fp32; h_out/c_out (L,B,H) fp32 (may not alias h_in/c_in). */
+int i2l_decode_step(const i2l_dec_desc* d, const void* packed, const float* enc, const int64_t* tok,
+                    int32_t batch, const float* h_in, const float* c_in, float* logits, float* h_out,
+                    float* c_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces Seq2SeqModel._greedy_search, model/seq2seq.py:192-232 (stop rule
+ * ALL_END_SAME_STEP) -- the whole loop runs on the device, no host sync per token.
+ * tokens (B, max_length+1) int64, column 0 = start; lengths (B) int32 = position
+ * of the first END (or steps_run+1 when none); steps_run: device int32 scalar =
+ * loop iterations the reference would have executed. */
+int i2l_decode_greedy(const i2l_dec_desc* d, const void* packed, const float* enc, int32_t batch,
+                      int32_t start_id, int32_t end_id, int32_t max_length, float temperature,
+                      int32_t stop_rule, int64_t* tokens, int32_t* lengths, int32_t* steps_run,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces the batched loop of Predictor.predict_batch, training/predictor.py:283-347
+ * (temperature / top-k / top-p filter 295-327, draw 330-335, sticky finished 343-347).
+ * uniforms: optional (max_length,B) fp32 in [0,1) used for the inverse-CDF draw;
+ * NULL => Philox4x32-10 keyed by (seed, offset + step*B + row).
+ * probs_trace: optional (max_length,B,V) fp32 dump of the filtered distribution. */
+int i2l_decode_sample(const i2l_dec_desc* d, const void* packed, const float* enc, int32_t batch,
+                      int32_t start_id, int32_t end_id, int32_t max_length, float temperature,
+                      int32_t top_k, float top_p, uint64_t seed, uint64_t offset, const float* uniforms,
+                      int64_t* tokens, int32_t* lengths, int32_t* steps_run, float* probs_trace,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces Seq2SeqModel._beam_search, model/seq2seq.py:234-298, run independently
+ * per image (the reference handles B==1 only).  out_tokens (B,max_length) int64:
+ * best sequence, START stripped, cut at END, padded with -1; out_len (B) int32;
+ * out_score (B) fp64.  Optional traces (max_length,B,K): parent slot / token /
+ * score of every kept beam per step (-1 / NaN where a slot is empty). */
+int i2l_decode_beam(const i2l_dec_desc* d, const void* packed, const float* enc, int32_t batch,
+                    int32_t beam_size, int32_t start_id, int32_t end_id, int32_t max_length,
+                    int64_t* out_tokens, int32_t* out_len, double* out_score, int32_t* trace_parent,
+                    int32_t* trace_token, double* trace_score, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2L_B200_H_ */

@@ -1,0 +1,229 @@
+"""fp32 parity of the CUDA path (through the C-ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances: logits / encodings within 1e-3 relative (BASELINE north_star);
+greedy tokens identical except at documented near-tie argmaxes; beam parents / tokens
+bit-exact given the scores agree."""
+import math
+
+import pytest
+import torch
+
+import helpers as H
+from helpers import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.mark.parametrize("cfg,batch", [(H.SMALL, 5), (H.HEADLINE, 3)])
+def test_cnn_encoder(pkg, cfg, batch):
+    p = oracle.make_params(cfg, 0)
+    m = H.build_model(pkg, cfg, p)
+    x = H.make_images(cfg, batch)
+    ref = oracle.cnn_encoder(p, x)
+    out = m.encoder(x.cuda())
+    assert out.shape == ref.shape
+    assert H.rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("cfg,width", [(H.R18, 128), (H.R18, 160), (H.R50, 96)])
+def test_resnet_encoder(pkg, cfg, width):
+    p = oracle.make_params(cfg, 0)
+    m = H.build_model(pkg, cfg, p)
+    x = H.make_images(cfg, 2, width=width)
+    ref = oracle.resnet_encoder(p, x, cfg["model_name"])
+    out = m.encoder(x.cuda())
+    assert H.rel_err(out, ref) < TOL
+
+
+def test_encoder_empty_batch(pkg):
+    p = oracle.make_params(H.SMALL, 0)
+    m = H.build_model(pkg, H.SMALL, p)
+    out = m.encoder(torch.zeros(0, 1, 16, 40, device="cuda"))
+    assert out.shape == (0, 32)
+
+
+@pytest.mark.parametrize("L", [1, 2, 7, 40])
+def test_attention_general_len(pkg, L):
+    g = torch.Generator().manual_seed(3)
+    Hd, E, B = 48, 32, 6
+    att = pkg.Attention(Hd, E).cuda()
+    hid = torch.randn(B, 1, Hd, generator=g)
+    enc = torch.randn(B, L, E, generator=g)
+    ref = oracle.attention(att.attn.weight.detach().cpu(), att.attn.bias.detach().cpu(), att.v.weight.detach().cpu(),
+                           hid, enc)
+    out = att(hid.cuda(), enc.cuda())
+    assert out.shape == (B, 1, E)
+    if L == 1:
+        assert torch.equal(out.cpu().squeeze(1), enc.squeeze(1))      # identity, bit for bit
+    assert H.rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("cfg", [H.SMALL, H.HEADLINE])
+def test_decode_step(pkg, cfg):
+    p = oracle.make_params(cfg, 0)
+    m = H.build_model(pkg, cfg, p)
+    B = 7
+    g = torch.Generator().manual_seed(5)
+    enc = torch.rand(B, cfg["embedding_dim"], generator=g)
+    tok = torch.randint(0, cfg["vocab_size"], (B, 1), generator=g)
+    ref_l, (ref_h, ref_c) = oracle.decode_step(p, enc, tok, None, cfg)
+    out_l, (h, c) = m.decoder.decode_step(enc.cuda(), tok.cuda(), None)
+    assert out_l.shape == ref_l.shape and h.shape == ref_h.shape
+    assert H.rel_err(out_l, ref_l) < TOL and H.rel_err(h, ref_h) < TOL and H.rel_err(c, ref_c) < TOL
+    # second step from a given hidden state
+    tok2 = torch.randint(0, cfg["vocab_size"], (B, 1), generator=g)
+    ref_l2, (ref_h2, ref_c2) = oracle.decode_step(p, enc, tok2, (ref_h, ref_c), cfg)
+    out_l2, (h2, c2) = m.decoder.decode_step(enc.cuda(), tok2.cuda(), (ref_h.cuda(), ref_c.cuda()))
+    assert H.rel_err(out_l2, ref_l2) < TOL and H.rel_err(h2, ref_h2) < TOL and H.rel_err(c2, ref_c2) < TOL
+
+
+def _near_tie_rows(tokens, ref_seqs, logit_trace, tol_rel=1e-4):
+    """Rows whose first divergence from the oracle happens at a step where the oracle's
+    top-1 / top-2 margin is below tol_rel * max|logit| (near-tie policy)."""
+    bad, ties = [], []
+    for b, ref in enumerate(ref_seqs):
+        got = tokens[b][: len(ref)]
+        if got == ref:
+            continue
+        t = next(i for i, (a, r) in enumerate(zip(got, ref)) if a != r) - 1   # loop step index
+        lg = logit_trace[t][b]
+        top2 = torch.topk(lg, 2).values
+        margin = float(top2[0] - top2[1])
+        (ties if margin < tol_rel * float(lg.abs().max()) else bad).append((b, t, margin))
+    return bad, ties
+
+
+@pytest.mark.parametrize("cfg,sharp,T", [(H.SMALL, True, 30), (H.HEADLINE, False, 40), (H.HEADLINE, True, 60)])
+def test_greedy_loop(pkg, cfg, sharp, T):
+    p = oracle.make_params(cfg, 1 if sharp else 0, sharp=sharp)
+    m = H.build_model(pkg, cfg, p)
+    B = 16
+    x = H.make_images(cfg, B)
+    enc_ref = oracle.encoder(p, x, cfg)
+    ref, steps_ref, trace = oracle.greedy_search(p, enc_ref, H.START, H.END, T, 1.0, cfg, return_logits=True)
+    enc = m.encoder(x.cuda())
+    tokens, lengths, steps = m.decoder.greedy(enc, H.START, H.END, T)
+    assert int(steps) == steps_ref
+    toks = tokens[:, : steps_ref + 1].tolist()
+    bad, ties = _near_tie_rows(toks, ref, trace)
+    assert not bad, f"rows diverging away from a near tie: {bad}"
+    assert len(ties) <= B // 4, f"too many near-tie divergences: {ties}"
+    # lengths = position of first END
+    for b in range(B):
+        if b not in [t[0] for t in ties]:
+            exp = ref[b].index(H.END) if H.END in ref[b][1:] else steps_ref + 1
+            assert int(lengths[b]) == exp
+    # full model API: raw lists incl. START for B>1 (seq2seq.py:223-232)
+    out = m.inference(x.cuda(), H.START, H.END, max_length=T)
+    assert out == toks
+
+
+def test_greedy_b1_postprocess_and_all_end_stop(pkg):
+    cfg = H.SMALL
+    p = oracle.make_params(cfg, 0, sharp=True)
+    p["decoder.output_layer.bias"][H.END] += 3.0      # make END likely so the loop exits early
+    m = H.build_model(pkg, cfg, p)
+    for seed in range(4):
+        x = H.make_images(cfg, 1, seed=seed)
+        enc_ref = oracle.encoder(p, x, cfg)
+        ref, steps_ref = oracle.greedy_search(p, enc_ref, H.START, H.END, 25, 1.0, cfg)
+        exp = oracle.inference_postprocess(ref, H.START, H.END)
+        got = m.inference(x.cuda(), H.START, H.END, max_length=25)
+        assert got == exp
+        _, _, steps = m.decoder.greedy(m.encoder(x.cuda()), H.START, H.END, 25)
+        assert int(steps) == steps_ref
+
+
+@pytest.mark.parametrize("temperature,top_k,top_p", [(1.0, 0, 0.0), (0.7, 0, 0.0), (0.8, 5, 0.0), (1.0, 0, 0.9),
+                                                     (0.8, 50, 0.9), (1.3, 3, 0.5)])
+def test_sampling_loop(pkg, temperature, top_k, top_p):
+    cfg = H.SMALL
+    T, B = 20, 12
+    p = oracle.make_params(cfg, 1, sharp=True)
+    m = H.build_model(pkg, cfg, p)
+    x = H.make_images(cfg, B)
+    enc_ref = oracle.encoder(p, x, cfg)
+    u = torch.rand(T, B, generator=torch.Generator().manual_seed(9))
+    seqs, trimmed, steps_ref, ptrace = oracle.sample_loop(p, enc_ref, H.START, H.END, T, temperature, top_k, top_p,
+                                                          cfg, uniforms=u, return_probs=True)
+    enc = m.encoder(x.cuda())
+    tokens, lengths, steps, probs = m.decoder.sample(enc, H.START, H.END, T, temperature, top_k, top_p, uniforms=u,
+                                                     return_probs=True)
+    tokens, probs = tokens.cpu(), probs.cpu()
+    # rows are compared up to their first divergence (a draw landing within 1e-5 of a cdf
+    # boundary may flip: documented near-tie policy); everything before must match.
+    n_div = 0
+    for b in range(B):
+        ref_row = seqs[b].tolist()
+        got_row = tokens[b, : len(ref_row)].tolist()
+        t_div = next((i for i, (a, r) in enumerate(zip(got_row, ref_row)) if a != r), None)
+        upto = len(ref_row) - 1 if t_div is None else t_div - 1
+        for t in range(min(upto, steps_ref)):
+            assert torch.allclose(probs[t, b], ptrace[t][b], rtol=1e-3, atol=1e-6), (b, t)
+        if t_div is not None:
+            n_div += 1
+            t = t_div - 1
+            cdf = torch.cumsum(ptrace[t][b].double(), 0)
+            tgt = float(u[t, b]) * float(cdf[-1])
+            assert float((cdf - tgt).abs().min()) < 1e-4, f"row {b} diverged at step {t} away from a cdf boundary"
+    assert n_div <= 1
+    if n_div == 0:
+        assert int(steps) == steps_ref
+        for b in range(B):
+            assert tokens[b, : int(lengths[b])].tolist() == trimmed[b]
+
+
+def test_predict_batch_strings(pkg):
+    cfg = H.SMALL
+    p = oracle.make_params(cfg, 1, sharp=True)
+    m = H.build_model(pkg, cfg, p)
+    tok = pkg.LaTeXTokenizer(); tok.default_init()
+    assert tok.vocab_size == 46
+    pred = pkg.Predictor(m, tok)
+    x = H.make_images(cfg, 6)
+    enc_ref = oracle.encoder(p, x, cfg)
+    _, trimmed, _ = oracle.sample_loop(p, enc_ref, H.START, H.END, 20, 1.0, 0, 0.0, cfg)
+    got = pred.predict_batch(list(x), max_length=20, batch_size=4, return_ids=True)
+    assert got == [t[1:] for t in trimmed]
+    strs = pred.predict_batch(list(x), max_length=20, batch_size=4, beam_size=5)   # beam clamped to greedy
+    assert strs == [tok.decode(t[1:]) for t in trimmed]
+    one = pred.predict(x[0], max_length=20)
+    assert one == strs[0]
+
+
+@pytest.mark.parametrize("cfg,K,T,sharp", [(H.SMALL, 3, 15, True), (H.SMALL, 5, 25, True), (H.HEADLINE, 5, 20, True),
+                                           (H.HEADLINE, 5, 12, False)])
+def test_beam_search(pkg, cfg, K, T, sharp):
+    p = oracle.make_params(cfg, 2, sharp=sharp)
+    if sharp:
+        p["decoder.output_layer.bias"][H.END] += 1.0
+    m = H.build_model(pkg, cfg, p)
+    B = 6
+    x = H.make_images(cfg, B)
+    enc_ref = oracle.encoder(p, x, cfg)
+    enc = m.encoder(x.cuda())
+    out, olen, score, (trp, trt, trs) = m.decoder.beam(enc, H.START, H.END, T, K, return_trace=True)
+    out, olen, score, trp, trt, trs = (t.cpu() for t in (out, olen, score, trp, trt, trs))
+    for b in range(B):
+        seq, sc, trace = oracle.beam_search(p, enc_ref[b:b + 1], H.START, H.END, T, K, cfg, return_trace=True)
+        # bit-exact bookkeeping as long as the scores agree (and are not near-tied)
+        ok = True
+        for t, beams in enumerate(trace):
+            ref_sc = torch.tensor([s for _, _, s in beams], dtype=torch.float64)
+            gaps = (ref_sc[:-1] - ref_sc[1:]).abs()
+            if len(gaps) and float(gaps.min()) < 1e-4:
+                ok = False          # near-tied candidates: ordering not pinned, stop comparing this image
+                break
+            n = len(beams)
+            assert trp[t, b, :n].tolist() == [pb for pb, _, _ in beams], (b, t)
+            assert trt[t, b, :n].tolist() == [tk for _, tk, _ in beams], (b, t)
+            assert torch.allclose(trs[t, b, :n], ref_sc, rtol=0, atol=2e-4), (b, t)
+        if ok:
+            assert out[b, : int(olen[b])].tolist() == seq, b
+            assert abs(float(score[b]) - sc) < 5e-4
+    # model-level API
+    one = m.inference(x[:1].cuda(), H.START, H.END, max_length=T, beam_size=K)
+    assert one == out[0, : int(olen[0])].tolist()
+    fallback = m.inference(x.cuda(), H.START, H.END, max_length=T, beam_size=K)      # B>1 -> greedy (244-247)
+    assert fallback == m.inference(x.cuda(), H.START, H.END, max_length=T)
