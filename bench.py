@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of CNN-LSTM greedy decode @ 3x64x320 (BASELINE.json
+configs[1]: batch 1024 per GPU, max_len 150, bf16, V=512, E=H=256, L=1, random init).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K --warmup W   # CPU oracle port of the reference
+
+A "step" = one pass of the hot path over one batch of synthetic images: encoder +
+150-step on-device greedy decode (+ the token all-gather when N > 1).  `value` is
+whole-job images/s with the inputs resident in HBM; `e2e` is the same metric through the
+public module API with pinned HOST buffers (H2D of the images and D2H of the token ids
+inside the timed region).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(model_type="cnn_lstm", vocab_size=512, embedding_dim=256, hidden_dim=256, lstm_layers=1,
+           attention=True, img_height=64, img_width=320, channels=3)
+START, END, MAX_LEN = 1, 2, 150
+METRIC = "images/sec greedy decode @320x64 (CNN-LSTM encoder + 150-step attention-LSTM greedy loop)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work of each named kernel (per launch), DESIGN.md section "Kernels and rooflines"
+# ---------------------------------------------------------------------------------------------
+def kernel_work(name, B, steps):
+    E = H = 256; V = 512
+    conv = {1: (3, 32, 64, 320), 2: (32, 64, 32, 160), 3: (64, 128, 16, 80)}
+    if name.startswith("cnn.conv"):
+        i = int(name[len("cnn.conv")])
+        ci, co, h, w = conv[i]
+        return "tensor", 2.0 * B * h * w * co * ci * 9
+    if name.startswith("cnn.fc"):
+        return "tensor", 2.0 * B * E * 40960
+    if name.startswith("cnn.pool"):
+        i = int(name[len("cnn.pool")])
+        ci, co, h, w = conv[i]
+        return "hbm", B * co * h * w * 4 * 1.25
+    if name.startswith("dec."):
+        W = 2 * (4 * H * (2 * E + H) + 8 * H + V * H + V)       # bf16 weights
+        S = 16 * H + 2 * E + 2 * E + 8                          # per-sequence state traffic
+        return "hbm", float(steps) * (W + B * S)
+    return None, 0.0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import i2l_import
+    pkg = i2l_import.load()
+    N = pkg._native
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from hmer_img2latex_b200.dist import gather_tokens
+
+    torch.manual_seed(0)
+    model = pkg.Seq2SeqModel("cnn_lstm", CFG["vocab_size"],
+                             dict(img_height=64, img_width=320, channels=3, embedding_dim=256),
+                             dict(hidden_dim=256, lstm_layers=1, attention=True), precision=args.precision)
+    model = model.to(dev).eval()
+    B = args.batch
+    g = torch.Generator().manual_seed(100 + rank)
+    x_host = torch.randn(B, 3, 64, 320, generator=g).pin_memory()
+    x = x_host.to(dev)
+    lib = N.lib()
+
+    def step(inp):
+        enc = model.encoder(inp)
+        tokens, lengths, steps = model.decoder.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_ALL_END_SAME_STEP)
+        if world > 1:
+            tokens, lengths, steps = gather_tokens(tokens, lengths, steps, B * world)
+        return tokens, lengths, steps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step(x)
+        barrier()
+        # ---- device-resident timed region ------------------------------------------------
+        sampler = ClockSampler(local); sampler.start()
+        lib.i2l_prof_reset(); lib.i2l_prof_enable(1)
+        l0 = lib.i2l_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out = step(x)
+        e1.record()
+        barrier()
+        launches = lib.i2l_launch_count() - l0
+        lib.i2l_prof_enable(0)
+        ms = e0.elapsed_time(e1)
+        sampler.stop_flag.set(); sampler.join()
+        prof = N.prof_results()
+        steps_run = int(out[2].item())
+        # ---- end-to-end through the public API with host buffers --------------------------
+        x_dev = torch.empty_like(x)
+        for _ in range(2):
+            x_dev.copy_(x_host, non_blocking=True); t = step(x_dev); t[0].cpu()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            x_dev.copy_(x_host, non_blocking=True)
+            tok, lens, st = step(x_dev)
+            tok_h, lens_h = tok.cpu(), lens.cpu()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    tms = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(tms[0]), float(tms[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * B * args.steps / (ms / 1e3)
+    pk = peaks()
+    # dominant kernel by measured time
+    roof = None
+    if prof:
+        name, (cnt, tot) = max(prof.items(), key=lambda kv: kv[1][1])
+        bound, work = kernel_work(name, B, steps_run)
+        if bound:
+            per_launch_s = tot / cnt / 1e3
+            if bound == "hbm":
+                ach, peak, unit = work / per_launch_s / 1e9, pk["hbm"], "GB/s"
+            else:
+                ach, peak, unit = work / per_launch_s / 1e12, pk["tf_sust"], "TFLOP/s"
+            roof = {"kernel": name, "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit,
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": pk["src"],
+                    "launch_ms": round(tot / cnt, 4), "share_of_step": round(tot / ms, 4)}
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: CNN-LSTM greedy decode, batch %d per GPU, 3x64x320 fp32 images, "
+                               "max_len 150, V=512, E=H=256, L=1, random init" % B,
+                   "global_batch": B * world, "parallelism": "dp%d (batch-sharded, token all-gather)" % world,
+                   "l2_policy": "inputs (%.0f MB of images per step) exceed the 126 MB L2" % (x.numel() * 4 / 1e6),
+                   "decode_steps_run": steps_run},
+        "us_per_decode_step": None,
+        "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items())},
+        "roofline": roof,
+        "e2e": {"value": round(world * B * args.steps / (e2e_ms / 1e3), 1), "unit": "images/s",
+                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": tok_h.numel() * 8 + lens_h.numel() * 4},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    dk = [v[1] for k, v in prof.items() if k.startswith("dec.")]
+    if dk and steps_run:
+        line["us_per_decode_step"] = round(sum(dk) / args.steps / steps_run * 1e3, 3)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(model, sample_batch=32, budget_s=20.0)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(model=None, sample_batch=32, budget_s=20.0, min_reps=1):
+    """The CPU oracle port of the reference path (oracle/port.py: the same ATen CPU kernels the
+    reference calls) timed on the host cores on a bounded sample: BASELINE configs[0]
+    (batch 32, 150 greedy steps), repeated until ~budget_s of CPU work."""
+    import torch
+    import oracle
+    torch.set_num_threads(os.cpu_count())
+    if model is not None:
+        p = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    else:
+        p = oracle.make_params(CFG, 0)
+    x = torch.randn(sample_batch, 3, 64, 320, generator=torch.Generator().manual_seed(7))
+    times = []
+    with torch.no_grad():
+        enc = oracle.encoder(p, x, CFG); oracle.greedy_search(p, enc, START, END, 10, 1.0, CFG)   # warm-up
+        t_all = time.perf_counter()
+        while True:
+            t0 = time.perf_counter()
+            enc = oracle.encoder(p, x, CFG)
+            oracle.greedy_search(p, enc, START, END, MAX_LEN, 1.0, CFG)
+            times.append(time.perf_counter() - t0)
+            if len(times) >= min_reps and time.perf_counter() - t_all > budget_s:
+                break
+    med = statistics.median(times)
+    return {"value": round(sample_batch / med, 2), "unit": "images/s", "cores": torch.get_num_threads(),
+            "kind": "port", "sample": "batch %d x %d greedy steps (BASELINE configs[0]), median of %d passes, fp32"
+                                      % (sample_batch, MAX_LEN, len(times))}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path = the oracle port
+    (the reference is pure Python on torch CPU ops and cannot travel to the GPU box; the port
+    calls the same ATen kernels).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    import oracle
+    torch.set_num_threads(os.cpu_count())
+    p = oracle.make_params(CFG, 0)
+    sb = 32
+    x = torch.randn(sb, 3, 64, 320, generator=torch.Generator().manual_seed(7))
+
+    def step():
+        enc = oracle.encoder(p, x, CFG)
+        oracle.greedy_search(p, enc, START, END, MAX_LEN, 1.0, CFG)
+
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+    v = round(sb * args.steps / dt, 2)
+    sample = "each step = batch %d slice of the workload, encoder + %d greedy steps, fp32, torch CPU" % (sb, MAX_LEN)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(dt / args.steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1] sampled: CNN-LSTM greedy decode, 3x64x320, max_len 150, V=512; " + sample},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,6 +87,11 @@ SIGNATURES = {
                                     _fp, _fp, C.c_size_t, _fp]),
     "i2l_decode_beam": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "i2l_launch_count": (C.c_longlong, []),
+    "i2l_prof_enable": (None, [C.c_int]),
+    "i2l_prof_reset": (None, []),
+    "i2l_prof_count": (C.c_int, []),
+    "i2l_prof_get": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
 }
 
 _lib = None
@@ -144,3 +149,16 @@ def ptr(t) -> C.c_void_p:
 def stream_ptr(device=None) -> C.c_void_p:
     import torch
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def prof_results() -> dict:
+    """{kernel name: (launches, total_ms)} from the library's CUDA-event kernel timers."""
+    l = lib()
+    out = {}
+    for i in range(l.i2l_prof_count()):
+        name = C.create_string_buffer(64)
+        cnt, ms = C.c_int(0), C.c_float(0.0)
+        check(l.i2l_prof_get(i, name, 64, C.byref(cnt), C.byref(ms)), "i2l_prof_get")
+        if cnt.value:
+            out[name.value.decode()] = (cnt.value, ms.value)
+    return out

@@ -10,6 +10,15 @@
 namespace i2l {
 
 void set_error(const char* fmt, ...);
+void count_launch();   // every kernel launch of the library is counted (bench.py "gpu_launches")
+
+// Optional per-kernel CUDA-event timing (bench.py roofline): enabled by i2l_prof_enable(1).
+// Usage: { KernelTimer t("conv2", stream); kernel<<<...>>>(...); }
+struct KernelTimer {
+  int slot; cudaStream_t s;
+  KernelTimer(const char* name, cudaStream_t stream);
+  ~KernelTimer();
+};
 
 #define I2L_CUDA_OK(expr)                                                                  \
   do {                                                                                     \
@@ -22,6 +31,7 @@ void set_error(const char* fmt, ...);
 
 #define I2L_LAUNCH_OK()                                                                    \
   do {                                                                                     \
+    i2l::count_launch();                                                                   \
     cudaError_t _e = cudaGetLastError();                                                   \
     if (_e != cudaSuccess) {                                                               \
       i2l::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

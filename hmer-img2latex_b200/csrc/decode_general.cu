@@ -754,6 +754,7 @@ static int run_loop(const i2l_dec_desc* d, const void* packed, const float* enc,
     I2L_CUDA_OK(cudaFuncSetAttribute(sample_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   const int do_sample = temperature > 0.f && (top_k > 0 || top_p > 0.0f);   // predictor.py:330
+  KernelTimer kt(sampling_path ? "dec.sample_loop_general" : "dec.greedy_loop_general", s);
   for (int step = 0; step < max_length; ++step) {
     I2L_TRY(step_rows(*d, pk, lay, w, w.h[0], w.c[0], batch, skip, s));
     if (sampling_path) {
@@ -835,6 +836,7 @@ extern "C" int i2l_decode_beam(const i2l_dec_desc* d, const void* packed, const 
     I2L_LAUNCH_OK();
   }
   int cur = 0;
+  KernelTimer kt("dec.beam_loop_general", s);
   for (int step = 0; step < max_length; ++step) {
     I2L_TRY(step_rows(*d, pk, lay, w, w.h[cur], w.c[cur], R, nullptr, s));
     beam_select_kernel<<<batch, 32 * K, 0, s>>>(w.logits, V, batch, K, step, end_id, w.bstate, w.score, w.tok_cur,

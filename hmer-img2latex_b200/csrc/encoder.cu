@@ -227,15 +227,17 @@ extern "C" int i2l_cnn_encoder_fwd(const i2l_cnn_desc* d, const void* packed, co
     c.x = cur; c.w = pk + L.conv_w[i]; c.bias = pk + L.conv_b[i]; c.y = w.a;
     c.B = batch; c.Ci = L.ci[i]; c.Hi = L.h[i]; c.Wi = L.w[i]; c.Co = d->filters[i];
     c.KH = c.KW = d->kernel_size; c.stride = 1; c.pad = d->kernel_size / 2; c.relu = 1;
-    I2L_TRY(conv2d_f32(c, s));
+    { char nm[32]; snprintf(nm, sizeof nm, "cnn.conv%d_f32", i + 1); KernelTimer kt(nm, s); I2L_TRY(conv2d_f32(c, s)); }
     // conv output -> w.a, pooled output -> w.b[i&1] (the next layer reads it while writing w.a)
-    I2L_TRY(maxpool2d_f32(w.a, w.b[i & 1], batch, d->filters[i], L.h[i], L.w[i], d->pool_size, d->pool_size, 0, s));
+    { char nm[32]; snprintf(nm, sizeof nm, "cnn.pool%d_f32", i + 1); KernelTimer kt(nm, s);
+      I2L_TRY(maxpool2d_f32(w.a, w.b[i & 1], batch, d->filters[i], L.h[i], L.w[i], d->pool_size, d->pool_size, 0, s)); }
     cur = w.b[i & 1];
   }
   GemmF32 g;
   g.M = batch; g.N = d->embedding_dim; g.C = out; g.ldc = d->embedding_dim;
   g.A1 = cur; g.lda1 = (int)L.flat; g.W1 = pk + L.fc_w; g.ldw1 = (int)L.flat; g.K1 = (int)L.flat;
   g.bias = pk + L.fc_b; g.relu = 1; g.splitk = w.splitk; g.splitk_ws = w.sk;
+  KernelTimer kt("cnn.fc_f32", s);
   return gemm_f32(g, s);
 }
 

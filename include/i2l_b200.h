@@ -195,6 +195,17 @@ int i2l_decode_beam(const i2l_dec_desc* d, const void* packed, const float* enc,
                     int32_t* trace_token, double* trace_score, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Measurement aids (bench.py): count of kernel launches issued by the library  */
+/* and optional CUDA-event timing of its named kernels on the launching stream. */
+/* ------------------------------------------------------------------------- */
+long long i2l_launch_count(void);
+void i2l_prof_enable(int on);
+void i2l_prof_reset(void);
+int i2l_prof_count(void);
+/* synchronises the recorded events; total_ms = sum over launches since the last reset */
+int i2l_prof_get(int idx, char* name, int name_len, int* launches, float* total_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,135 @@
+"""Generates the golden vectors under tests/golden/ by executing the LIVE reference
+(/root/reference, imported through oracle/ref_shim.py) on seeded inputs.  Run in the build
+container only:  python tests/golden/make_golden.py
+
+Inputs are not stored: they are regenerated from seeds by oracle.make_params /
+helpers.make_images (a checksum of both is stored to catch generator drift).  Outputs of
+the reference modules are stored as float32 / int64 arrays.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import helpers as H  # noqa: E402
+from helpers import oracle  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def checksum(params, x):
+    s = sum(float(v.double().abs().sum()) for v in params.values() if v.dtype.is_floating_point)
+    return np.array([s, float(x.double().abs().sum())])
+
+
+def save(name, **arrs):
+    np.savez_compressed(os.path.join(HERE, name), **{k: (v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v))
+                                                     for k, v in arrs.items()})
+    print("wrote", name, {k: np.asarray(v).shape for k, v in arrs.items()})
+
+
+def pad_rows(rows, fill=-1):
+    n = max(len(r) for r in rows)
+    return np.array([list(r) + [fill] * (n - len(r)) for r in rows], dtype=np.int64)
+
+
+@torch.no_grad()
+def seq2seq_case(name, cfg, seed, sharp, B, T, beam=0, end_boost=0.0):
+    p = oracle.make_params(cfg, seed, sharp=sharp)
+    if end_boost:
+        p["decoder.output_layer.bias"][H.END] += end_boost
+    m = ref_shim.build_reference_model(cfg, p)
+    x = H.make_images(cfg, B)
+    enc = m.encoder(x)
+    g = torch.Generator().manual_seed(5)
+    tok = torch.randint(0, cfg["vocab_size"], (B, 1), generator=g)
+    l1, (h1, c1) = m.decoder.decode_step(enc, tok, None)
+    tok2 = torch.randint(0, cfg["vocab_size"], (B, 1), generator=g)
+    l2, (h2, c2) = m.decoder.decode_step(enc, tok2, (h1, c1))
+    raw = m.inference(x, H.START, H.END, max_length=T)                       # B>1: raw lists
+    single = [m.inference(x[i:i + 1], H.START, H.END, max_length=T) for i in range(B)]   # B==1 post-processing
+    arrs = dict(checksum=checksum(p, x), enc=enc, tok=tok, tok2=tok2, logits1=l1, h1=h1, c1=c1, logits2=l2, h2=h2,
+                c2=c2, greedy_raw=pad_rows(raw), greedy_single=pad_rows(single), T=np.array(T),
+                seed=np.array(seed), sharp=np.array(int(sharp)), B=np.array(B), end_boost=np.array(end_boost))
+    if beam:
+        bs = [m.inference(x[i:i + 1], H.START, H.END, max_length=T, beam_size=beam) for i in range(B)]
+        arrs.update(beam=pad_rows(bs), beam_size=np.array(beam))
+    save(name, **arrs)
+
+
+@torch.no_grad()
+def resnet_case(name, cfg, widths, B=2):
+    p = oracle.make_params(cfg, 0)
+    m = ref_shim.build_reference_model(cfg, p)
+    arrs = {}
+    for w in widths:
+        x = H.make_images(cfg, B, width=w)
+        arrs[f"enc_w{w}"] = m.encoder(x)
+        arrs[f"checksum_w{w}"] = checksum(p, x)
+    save(name, widths=np.array(widths), **arrs)
+
+
+@torch.no_grad()
+def attention_case(name):
+    ref = ref_shim.load()
+    g = torch.Generator().manual_seed(3)
+    Hd, E, B, L = 48, 32, 6, 5
+    att = ref["Attention"](Hd, E)
+    w = oracle.port._uniform(g, (Hd, Hd + E), 0.2); b = oracle.port._uniform(g, (Hd,), 0.2)
+    v = oracle.port._uniform(g, (1, Hd), 0.3)
+    att.load_state_dict({"attn.weight": w, "attn.bias": b, "v.weight": v})
+    hid = torch.randn(B, 1, Hd, generator=g); enc = torch.randn(B, L, E, generator=g)
+    save(name, w=w, b=b, v=v, hid=hid, enc=enc, ctx=att(hid, enc))
+
+
+@torch.no_grad()
+def predict_batch_case(name, temperature, top_k, top_p, T=16, B=5):
+    """Runs the reference's Predictor.predict_batch (predictor.py:205-394) with
+    torch.multinomial replaced by the restated inverse-CDF draw on a fixed uniform stream,
+    recording the filtered distribution it is handed at every step."""
+    ref = ref_shim.load()
+    cfg = dict(model_type="cnn_lstm", vocab_size=46, embedding_dim=32, hidden_dim=48, lstm_layers=1, attention=True,
+               img_height=64, img_width=800, channels=1, conv_filters=[4, 8, 8])
+    p = oracle.make_params(cfg, 3, sharp=True)
+    m = ref_shim.build_reference_model(cfg, p)
+    tok = ref["LaTeXTokenizer"](); tok.default_init()
+    pred = ref["Predictor"](m, tok, device=torch.device("cpu"), model_type="cnn_lstm")
+    g = torch.Generator().manual_seed(11)
+    imgs = [torch.rand(1, 64, 800, generator=g) for _ in range(B)]             # in [0,1]: passes _preprocess_tensor untouched
+    u = torch.rand(T, B, generator=torch.Generator().manual_seed(9))
+    rec, step = [], [0]
+    real_multinomial = torch.multinomial
+
+    def fake_multinomial(probs, n):
+        rec.append(probs.clone())
+        out = oracle.inverse_cdf_draw(probs, u[step[0]]).unsqueeze(1)
+        step[0] += 1
+        return out
+
+    torch.multinomial = fake_multinomial
+    try:
+        strs = pred.predict_batch(imgs, max_length=T, temperature=temperature, top_k=top_k, top_p=top_p, batch_size=B)
+    finally:
+        torch.multinomial = real_multinomial
+    arrs = dict(strings=np.array(strs), u=u, temperature=np.array(temperature), top_k=np.array(top_k),
+                top_p=np.array(top_p), T=np.array(T), B=np.array(B))
+    if rec:
+        arrs["probs"] = torch.stack(rec)
+    save(name, **arrs)
+
+
+if __name__ == "__main__":
+    assert ref_shim.available(), "the live reference is needed to (re)generate golden vectors"
+    seq2seq_case("cnn_headline_sharp.npz", H.HEADLINE, seed=1, sharp=True, B=4, T=30)
+    seq2seq_case("cnn_headline_default.npz", H.HEADLINE, seed=0, sharp=False, B=3, T=12)
+    seq2seq_case("cnn_small_l2_beam.npz", H.SMALL, seed=2, sharp=True, B=6, T=20, beam=3, end_boost=0.0)
+    resnet_case("resnet18.npz", H.R18, [128, 160])
+    resnet_case("resnet50.npz", H.R50, [96])
+    attention_case("attention_L5.npz")
+    predict_batch_case("predict_batch_greedy.npz", 1.0, 0, 0.0)
+    predict_batch_case("predict_batch_topk_topp.npz", 0.8, 5, 0.9)
+    predict_batch_case("predict_batch_topp.npz", 1.2, 0, 0.7)

@@ -1,0 +1,71 @@
+"""GPU suite: the CUDA path (fp32 mode, through the C-ABI) against the golden vectors the
+LIVE reference produced (tests/golden/).  Tolerance 1e-3 relative for floats (north_star);
+token sequences identical (the golden cases contain no near ties)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from helpers import oracle
+from test_oracle_golden import PB_CFG, load, pb_inputs, unpad
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def cu(a):
+    return torch.as_tensor(np.asarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name,cfg", [("cnn_headline_sharp.npz", H.HEADLINE), ("cnn_headline_default.npz", H.HEADLINE),
+                                      ("cnn_small_l2_beam.npz", H.SMALL)])
+def test_seq2seq_vs_reference_golden(pkg, name, cfg):
+    d = load(name)
+    B, T = int(d["B"]), int(d["T"])
+    p = oracle.make_params(cfg, int(d["seed"]), sharp=bool(d["sharp"]))
+    m = H.build_model(pkg, cfg, p)
+    x = H.make_images(cfg, B).cuda()
+    enc = m.encoder(x)
+    assert H.rel_err(enc, torch.as_tensor(d["enc"])) < TOL
+    l1, (h1, c1) = m.decoder.decode_step(enc, cu(d["tok"]), None)
+    assert H.rel_err(l1, torch.as_tensor(d["logits1"])) < TOL and H.rel_err(c1, torch.as_tensor(d["c1"])) < TOL
+    l2, (h2, c2) = m.decoder.decode_step(enc, cu(d["tok2"]), (cu(d["h1"]), cu(d["c1"])))
+    assert H.rel_err(l2, torch.as_tensor(d["logits2"])) < TOL and H.rel_err(h2, torch.as_tensor(d["h2"])) < TOL
+    assert m.inference(x, H.START, H.END, max_length=T) == unpad(d["greedy_raw"])
+    assert [m.inference(x[i:i + 1], H.START, H.END, max_length=T) for i in range(B)] == unpad(d["greedy_single"])
+    if "beam" in d:
+        K = int(d["beam_size"])
+        assert [m.inference(x[i:i + 1], H.START, H.END, max_length=T, beam_size=K) for i in range(B)] == unpad(d["beam"])
+        assert m.beam_search_batch(enc, H.START, H.END, T, K) == unpad(d["beam"])
+
+
+@pytest.mark.parametrize("name,cfg", [("resnet18.npz", H.R18), ("resnet50.npz", H.R50)])
+def test_resnet_vs_reference_golden(pkg, name, cfg):
+    d = load(name)
+    p = oracle.make_params(cfg, 0)
+    m = H.build_model(pkg, cfg, p)
+    for w in d["widths"]:
+        x = H.make_images(cfg, 2, width=int(w)).cuda()
+        assert H.rel_err(m.encoder(x), torch.as_tensor(d[f"enc_w{w}"])) < TOL
+
+
+def test_attention_vs_reference_golden(pkg):
+    d = load("attention_L5.npz")
+    att = pkg.Attention(48, 32)
+    att.load_state_dict({"attn.weight": torch.as_tensor(d["w"]), "attn.bias": torch.as_tensor(d["b"]),
+                         "v.weight": torch.as_tensor(d["v"])})
+    out = att.cuda()(cu(d["hid"]), cu(d["enc"]))
+    assert H.rel_err(out, torch.as_tensor(d["ctx"])) < TOL
+
+
+@pytest.mark.parametrize("name", ["predict_batch_greedy.npz", "predict_batch_topk_topp.npz", "predict_batch_topp.npz"])
+def test_predict_batch_vs_reference_golden(pkg, name):
+    d = load(name)
+    p, x = pb_inputs(d)
+    m = H.build_model(pkg, PB_CFG, p)
+    tok = pkg.LaTeXTokenizer(); tok.default_init()
+    pred = pkg.Predictor(m, tok)
+    T = int(d["T"])
+    got = pred.predict_batch(list(x), max_length=T, temperature=float(d["temperature"]), top_k=int(d["top_k"]),
+                             top_p=float(d["top_p"]), batch_size=int(d["B"]), uniforms=torch.as_tensor(d["u"]))
+    assert got == [str(s) for s in d["strings"]]

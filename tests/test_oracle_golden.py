@@ -1,0 +1,132 @@
+"""CPU suite: pins the oracle (oracle/port.py) against the golden vectors produced by the
+LIVE reference (tests/golden/make_golden.py).  Tokens / strings must be identical; float
+tensors agree to 1e-6 (same ATen CPU kernels, possibly different summation grouping where
+the port writes out nn.LSTM by hand)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from helpers import oracle
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+torch.set_num_threads(min(8, os.cpu_count() or 1))
+
+
+def load(name):
+    return np.load(os.path.join(G, name), allow_pickle=False)
+
+
+def unpad(rows):
+    return [[int(t) for t in r if t >= 0] for r in rows]
+
+
+def close(a, b, tol=2e-6):
+    a, b = torch.as_tensor(np.asarray(a)).double(), torch.as_tensor(np.asarray(b)).double()
+    assert a.shape == b.shape
+    assert float((a - b).abs().max()) <= tol * max(1.0, float(b.abs().max()))
+
+
+def check_inputs(d, p, x, key="checksum"):
+    s = sum(float(v.double().abs().sum()) for v in p.values() if v.dtype.is_floating_point)
+    assert abs(s - d[key][0]) < 1e-6 * abs(d[key][0]) and abs(float(x.double().abs().sum()) - d[key][1]) < 1e-6 * d[key][1], \
+        "seeded inputs drifted from the ones the golden vectors were generated with"
+
+
+@pytest.mark.parametrize("name,cfg", [("cnn_headline_sharp.npz", H.HEADLINE), ("cnn_headline_default.npz", H.HEADLINE),
+                                      ("cnn_small_l2_beam.npz", H.SMALL)])
+def test_seq2seq_golden(name, cfg):
+    d = load(name)
+    B, T = int(d["B"]), int(d["T"])
+    p = oracle.make_params(cfg, int(d["seed"]), sharp=bool(d["sharp"]))
+    x = H.make_images(cfg, B)
+    check_inputs(d, p, x)
+    with torch.no_grad():
+        enc = oracle.encoder(p, x, cfg)
+        close(enc, d["enc"])
+        l1, (h1, c1) = oracle.decode_step(p, enc, torch.as_tensor(d["tok"]), None, cfg)
+        close(l1, d["logits1"]); close(h1, d["h1"]); close(c1, d["c1"])
+        l2, (h2, c2) = oracle.decode_step(p, enc, torch.as_tensor(d["tok2"]), (h1, c1), cfg)
+        close(l2, d["logits2"]); close(h2, d["h2"]); close(c2, d["c2"])
+        raw, _ = oracle.greedy_search(p, enc, H.START, H.END, T, 1.0, cfg)
+        assert raw == unpad(d["greedy_raw"])
+        single = [oracle.inference_postprocess(oracle.greedy_search(p, enc[i:i + 1], H.START, H.END, T, 1.0, cfg)[0],
+                                               H.START, H.END) for i in range(B)]
+        assert single == unpad(d["greedy_single"])
+        if "beam" in d:
+            got = oracle.beam_search_batched(p, enc, H.START, H.END, T, int(d["beam_size"]), cfg)
+            assert got == unpad(d["beam"])
+
+
+@pytest.mark.parametrize("name,cfg", [("resnet18.npz", H.R18), ("resnet50.npz", H.R50)])
+def test_resnet_golden(name, cfg):
+    d = load(name)
+    p = oracle.make_params(cfg, 0)
+    for w in d["widths"]:
+        x = H.make_images(cfg, 2, width=int(w))
+        check_inputs(d, p, x, f"checksum_w{w}")
+        with torch.no_grad():
+            close(oracle.resnet_encoder(p, x, cfg["model_name"]), d[f"enc_w{w}"], tol=1e-5)
+
+
+def test_attention_golden():
+    d = load("attention_L5.npz")
+    t = {k: torch.as_tensor(d[k]) for k in d.files}
+    close(oracle.attention(t["w"], t["b"], t["v"], t["hid"], t["enc"]), t["ctx"])
+    # src_len == 1 is the identity, bit for bit
+    one = oracle.attention(t["w"], t["b"], t["v"], t["hid"], t["enc"][:, :1])
+    assert torch.equal(one, t["enc"][:, :1])
+
+
+PB_CFG = dict(model_type="cnn_lstm", vocab_size=46, embedding_dim=32, hidden_dim=48, lstm_layers=1, attention=True,
+              img_height=64, img_width=800, channels=1, conv_filters=[4, 8, 8])
+
+
+def pb_inputs(d):
+    B = int(d["B"])
+    p = oracle.make_params(PB_CFG, 3, sharp=True)
+    g = torch.Generator().manual_seed(11)
+    x = torch.stack([torch.rand(1, 64, 800, generator=g) for _ in range(B)])
+    return p, x
+
+
+@pytest.mark.parametrize("name", ["predict_batch_greedy.npz", "predict_batch_topk_topp.npz", "predict_batch_topp.npz"])
+def test_predict_batch_golden(name, pkg):
+    d = load(name)
+    p, x = pb_inputs(d)
+    T = int(d["T"])
+    with torch.no_grad():
+        enc = oracle.encoder(p, x, PB_CFG)
+        seqs, trimmed, steps, ptrace = oracle.sample_loop(p, enc, H.START, H.END, T, float(d["temperature"]),
+                                                          int(d["top_k"]), float(d["top_p"]), PB_CFG,
+                                                          uniforms=torch.as_tensor(d["u"]), return_probs=True)
+    tok = pkg.LaTeXTokenizer(); tok.default_init()
+    strs = []
+    for s in trimmed:                                   # predictor.py:382-392
+        s = s[1:] if s and s[0] == H.START else s
+        s = s[:-1] if s and s[-1] == H.END else s
+        strs.append(tok.decode(s))
+    assert strs == [str(s) for s in d["strings"]]
+    if "probs" in d:
+        assert len(ptrace) == d["probs"].shape[0]
+        close(torch.stack(ptrace), d["probs"])
+
+
+def test_tokenizer_default_vocab(pkg):
+    tok = pkg.LaTeXTokenizer(); tok.default_init()
+    assert tok.vocab_size == 46 and (tok.pad_token_id, tok.start_token_id, tok.end_token_id, tok.unk_token_id) == (0, 1, 2, 3)
+    assert tok.decode([1, 13, 4, 99, 2]) == "\\frac + <UNK>"
+
+
+def test_filter_probs_edge_cases():
+    lg = torch.tensor([[0.0, 0.0, 0.0, 0.0], [5.0, 1.0, 1.0, -2.0]])
+    pr = oracle.filter_probs(lg, 1.0, 2, 0.0)           # ties at the k-th value are all kept (predictor.py:305)
+    assert torch.allclose(pr[0], torch.full((4,), 0.25)) and int((pr[1] > 0).sum()) == 3
+    pr = oracle.filter_probs(lg, 1.0, 0, 0.5)            # nucleus always keeps sorted index 0 (predictor.py:320)
+    assert int((pr[1] > 0).sum()) == 1 and abs(float(pr[1].sum()) - 1) < 1e-6
+    pr = oracle.filter_probs(lg, 1.0, 100, 0.0)          # top_k clamped to V (predictor.py:300)
+    assert torch.allclose(pr, torch.softmax(lg, -1))
+    u = torch.tensor([0.0, 0.999999])
+    assert oracle.inverse_cdf_draw(torch.tensor([[0.0, 0.5, 0.5, 0.0], [0.2, 0.8, 0.0, 0.0]]), u).tolist() == [1, 1]
