@@ -687,7 +687,7 @@ extern "C" int i2l_dec_pack(const i2l_dec_desc* d, const i2l_dec_params* p, void
   g.M = (int)V; g.N = 4 * (int)H; g.C = pk + lay.gtok; g.ldc = 4 * (int)H;
   g.A1 = pk + lay.emb; g.lda1 = (int)E; g.W1 = pk + lay.w_ih0; g.ldw1 = 2 * (int)E; g.K1 = (int)E;
   I2L_TRY(gemm_f32(g, s));
-  if (lay.bf16_section) I2L_TRY(persistent_pack(*d, *p, reinterpret_cast<char*>(packed) + lay.bf16_section, s));
+  if (lay.bf16_section) I2L_TRY(persistent_pack(*d, *p, pk + lay.gtok, reinterpret_cast<char*>(packed) + lay.bf16_section, s));
   return I2L_OK;
 }
 
@@ -893,3 +893,7 @@ extern "C" int i2l_attention_fwd(int32_t H, int32_t E, const float* attn_w, cons
   I2L_LAUNCH_OK();
   return I2L_OK;
 }
+
+// debug aid (tools/debug_persistent.py): dump intermediates of one step of the persistent kernel
+namespace i2l { int persistent_set_debug(float* buf); }
+extern "C" int i2l_debug_set_buffer(float* buf) { return i2l::persistent_set_debug(buf); }

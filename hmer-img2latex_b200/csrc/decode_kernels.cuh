@@ -30,7 +30,8 @@ int lstm_cell_f32(const float* gates, float* h, float* c, int rows, int H, const
 // shapes it does not cover so that the caller can take the general path.
 bool persistent_supported(const i2l_dec_desc& d);
 size_t persistent_packed_bytes(const i2l_dec_desc& d);
-int persistent_pack(const i2l_dec_desc& d, const i2l_dec_params& p, void* section, cudaStream_t s);
+int persistent_pack(const i2l_dec_desc& d, const i2l_dec_params& p, const float* gtok_f32, void* section,
+                    cudaStream_t s);
 size_t persistent_workspace_bytes(const i2l_dec_desc& d, int rows, int max_length);
 int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* packed_f32,
                       const PackedDec& lay, const float* enc, int batch, int start_id, int end_id,

@@ -1,9 +1,617 @@
+// Persistent greedy decode for the headline shape (E = H = 256, one LSTM layer, V <= 512, bf16):
+// ONE kernel runs all max_length steps.  A cluster of 4 CTAs owns a slice of 32 sequences
+// and keeps the whole decoder in shared memory for the lifetime of the kernel:
+//
+//   CTA rank r holds hidden units [64r, 64r+64): the 256 gate rows (i,f,g,o) of W_hh for
+//   those units (128 KB bf16, two M=128 tcgen05 tiles) and vocab rows [128r, 128r+128) of
+//   W_out (64 KB, one tile), both as K-major SWIZZLE_128B operand images that were
+//   pre-swizzled at pack time and arrive with plain bulk copies (cp.async.bulk).
+//
+//   The MMAs are "swapped": D[gate row, sequence] = W[gate row, :] . h[sequence, :], so the
+//   weights are the (resident) A operand with M = 128 and the 32 sequences are the N = 32
+//   B operand (h as bf16, 16 KB, double buffered).  Accumulators live in TMEM (3 x 32 cols).
+//
+//   per step:   MMA-G  gates  = W_hh h_s            (tcgen05, issued by one thread)
+//               Epi-G  + Gtok[tok_s] + Gctx, sigmoid/tanh (MUFU.TANH), c/h update in
+//                      registers; i/g and f/o of a unit sit in lanes l and l+16 of one warp
+//                      so sigma(i)tanh(g) moves by one shuffle; h_{s+1} slice (4 KB, one
+//                      K-block of the B operand) is written locally and pushed to the three
+//                      peers with cp.async.bulk shared::cta -> shared::cluster (DSMEM),
+//                      completing on the peer's mbarrier -- no cluster barrier per step
+//               MMA-L  logits = W_out h_{s+1}       (overlaps nothing: it is the critical path)
+//               MMA-G  for step s+1 is issued right behind it and overlaps Epi-L
+//               Epi-L  + bias, per-warp argmax with redux.sync.max.f32 + ballot, CTA
+//                      partials exchanged through DSMEM stores + remote mbarrier arrives
+//   Token append, EOS flags and both reference stop rules are handled on the device.
+//
+// Reference semantics: LSTMDecoder.decode_step (model/decoder.py:197-284) inside
+// Seq2SeqModel._greedy_search (model/seq2seq.py:192-232); attention with src_len == 1 is the
+// identity and W_ih [emb ; ctx] is hoisted into the Gtok table / Gctx (F4).
 #include "decode_kernels.cuh"
+
 namespace i2l {
-bool persistent_supported(const i2l_dec_desc&) { return false; }
-size_t persistent_packed_bytes(const i2l_dec_desc&) { return 0; }
-int persistent_pack(const i2l_dec_desc&, const i2l_dec_params&, void*, cudaStream_t) { return I2L_ERR_UNSUPPORTED; }
-size_t persistent_workspace_bytes(const i2l_dec_desc&, int, int) { return 0; }
-int persistent_greedy(const i2l_dec_desc&, const void*, const float*, const PackedDec&, const float*, int, int, int,
-                      int, float, int, int64_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t) { return I2L_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int H = 256, E = 256, VMAX = 512;
+constexpr int NB = 32;                // sequences per cluster
+constexpr int CL = 4;                 // CTAs per cluster
+constexpr int EPI_THREADS = 256;
+constexpr int THREADS = EPI_THREADS + 32;
+constexpr int WG_BYTES = 2 * 4 * 16384;   // 2 tiles x 4 K-blocks x (128 rows x 128 B)
+constexpr int WO_BYTES = 4 * 16384;
+constexpr int HB_BYTES = 4 * NB * 128;    // 4 K-blocks x (NB rows x 128 B) = 16 KB
+constexpr int HSLICE_BYTES = NB * 128;    // one K-block = one CTA's units
+// shared memory map (bytes)
+constexpr int OFF_WG = 0;
+constexpr int OFF_WO = OFF_WG + WG_BYTES;
+constexpr int OFF_H = OFF_WO + WO_BYTES;            // 2 buffers
+constexpr int OFF_PART = OFF_H + 2 * HB_BYTES;      // [8 warps][16 cols] (float,int)
+constexpr int OFF_XCHG = OFF_PART + 8 * 16 * 8;     // [4 ctas][32 cols] (float,int)
+constexpr int OFF_TOK = OFF_XCHG + CL * NB * 8;     // [32] int tokens of the current step
+constexpr int OFF_BAR = OFF_TOK + NB * 4;           // mbarriers
+constexpr int OFF_MISC = OFF_BAR + 8 * 8;           // tmem base, exit flag
+constexpr int SMEM_BYTES = OFF_MISC + 16;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+
+enum { BAR_W = 0, BAR_HFULL0 = 1, BAR_HFULL1 = 2, BAR_LDONE = 3, BAR_GDONE = 4, BAR_TOK = 5, BAR_FINAL = 6 };
+
+// ---- packed (bf16) section layout -------------------------------------------------------
+struct PSection {
+  size_t wimg;      // [4 ranks][WG_BYTES + WO_BYTES]
+  size_t gtok;      // fp32 [V][4][2][128]
+  size_t bias;      // fp32 [512]  (-inf beyond V)
+  size_t total;
+};
+PSection psection(int V) {
+  PSection s{};
+  size_t o = 0;
+  s.wimg = o; o += (size_t)CL * (WG_BYTES + WO_BYTES);
+  s.gtok = o; o += (size_t)V * 1024 * 4;
+  s.bias = o; o += VMAX * 4;
+  s.total = align_up(o, 1024);
+  return s;
 }
+
+// ---- PTX helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t a, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t a, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t a, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t cluster_addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(cluster_addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float redux_max(float v) {
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ float* g_dbg = nullptr;   // debug dump target (tools/debug_persistent.py), normally null
+
+struct Params {
+  const unsigned char* wimg;     // per-rank weight images
+  const float* gtok;             // [V][4][2][128]
+  const float* bias;             // [512]
+  const float* gctx;             // [B][1024] fp32 (PyTorch gate order)
+  int64_t* tokens;               // [B][T+1]
+  int* first_end;                // [B]
+  unsigned char* allend;         // [n_clusters][T]
+  int* cluster_steps;            // [n_clusters]
+  int B, T, start_id, end_id, stop_rule;
+  float temperature;
+};
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persistent_greedy_kernel(Params P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = (int)cluster_id_x();
+  const int row0 = cluster * NB;
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + OFF_MISC);
+  const uint32_t bar = sbase + OFF_BAR;
+  auto BAR = [&](int i) { return bar + 8u * i; };
+
+  if ((sbase & 1023u) != 0) __trap();
+
+  if (tid == 0) {
+    mbar_init(BAR(BAR_W), 1);
+    mbar_init(BAR(BAR_HFULL0), 1);
+    mbar_init(BAR(BAR_HFULL1), 1);
+    mbar_init(BAR(BAR_LDONE), 1);
+    mbar_init(BAR(BAR_GDONE), 1);
+    mbar_init(BAR(BAR_TOK), CL * NB);
+    mbar_init(BAR(BAR_FINAL), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    misc[1] = 0;
+  }
+  if (warp == 8) {   // TMEM: 128 columns (3 accumulators of NB columns)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(sbase + OFF_MISC) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // zero both h buffers (h_0 = 0, decoder.py:253-266)
+  for (int i = tid; i < 2 * HB_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem + OFF_H)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc[0];
+  if (tid == 0) {   // resident weights: one bulk copy per 16 KB
+    const unsigned char* src = P.wimg + (size_t)rank * (WG_BYTES + WO_BYTES);
+    mbar_arrive_expect_tx(BAR(BAR_W), WG_BYTES + WO_BYTES);
+    for (int o = 0; o < WG_BYTES + WO_BYTES; o += 16384) bulk_g2s(sbase + OFF_WG + o, src + o, 16384, BAR(BAR_W));
+  }
+  cluster_sync_all();   // every CTA's barriers are initialised before any remote traffic
+
+  const uint32_t TM_L = tmem, TM_G0 = tmem + NB, TM_G1 = tmem + 2 * NB;
+
+  if (warp == 8) {
+    // =========================== MMA issuer (one thread) ===========================
+    if (lane == 0) {
+      mbar_wait(BAR(BAR_W), 0);
+      auto issue_tile = [&](uint32_t d_tmem, uint32_t a_base, uint32_t h_base) {
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint64_t ad = make_desc(a_base + kb * 16384 + k * 32);
+            uint64_t bd = make_desc(h_base + kb * HSLICE_BYTES + k * 32);
+            tc_mma(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+          }
+        }
+      };
+      tc_fence_after();
+      // gates of step 0 from h_0 = 0 (buffer 0)
+      issue_tile(TM_G0, sbase + OFF_WG, sbase + OFF_H);
+      issue_tile(TM_G1, sbase + OFF_WG + 65536, sbase + OFF_H);
+      tc_commit(BAR(BAR_GDONE));
+      for (int s = 0; s < P.T; ++s) {
+        const int nb = (s + 1) & 1;                       // buffer holding h_{s+1}
+        mbar_wait(BAR(BAR_HFULL0 + nb), (uint32_t)((s >> 1) & 1));     // h_j (j = s+1) is use (j-1)/2 of its buffer
+        if (*reinterpret_cast<volatile uint32_t*>(&misc[1])) break;
+        tc_fence_after();
+        const uint32_t hb = sbase + OFF_H + nb * HB_BYTES;
+        issue_tile(TM_L, sbase + OFF_WO, hb);             // logits_s = W_out h_{s+1}
+        tc_commit(BAR(BAR_LDONE));
+        if (s + 1 < P.T) {
+          issue_tile(TM_G0, sbase + OFF_WG, hb);          // gates of step s+1
+          issue_tile(TM_G1, sbase + OFF_WG + 65536, hb);
+          tc_commit(BAR(BAR_GDONE));
+        }
+      }
+      tc_commit(BAR(BAR_FINAL));       // every MMA issued above has completed before TMEM is released
+      mbar_wait(BAR(BAR_FINAL), 0);
+    }
+    __syncwarp();
+  } else {
+    // =========================== epilogue warps (256 threads) ===========================
+    const int q = warp & 3, cg = warp >> 2;               // TMEM lane quadrant, column group
+    const int p = 32 * q + lane;                          // accumulator row (TMEM lane)
+    const int u = 16 * q + (lane & 15);                   // CTA-local hidden unit
+    const bool hi = lane >= 16;                           // lanes 16-31 hold f / o and the cell state
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const int col0 = 16 * cg;
+    float gctx0[16], gctx1[16], c[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      int row = row0 + col0 + j;
+      c[j] = 0.f;
+      if (row < P.B) {
+        const float* g = P.gctx + (size_t)row * 1024 + 64 * rank + u;
+        gctx0[j] = g[(hi ? 1 : 0) * 256];
+        gctx1[j] = g[(hi ? 3 : 2) * 256];
+      } else {
+        gctx0[j] = 0.f; gctx1[j] = 0.f;
+      }
+    }
+    const float bias = P.bias[128 * rank + p];
+    const float s1 = hi ? 0.5f : 1.0f, m1 = hi ? 0.5f : 1.0f, b1 = hi ? 0.5f : 0.0f;
+    int tok[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) tok[j] = P.start_id;
+    int fe = -1;                                          // first END position (threads tid < 32 of rank 0)
+    bool finished = false;
+    float* part = reinterpret_cast<float*>(smem + OFF_PART);
+    int* tok_s = reinterpret_cast<int*>(smem + OFF_TOK);
+    const float* gt_base = P.gtok + (size_t)rank * 256 + p;
+    int s = 0;
+    for (; s < P.T; ++s) {
+      // ---------------- Epi-G(s): gates -> c_{s+1}, h_{s+1} ----------------
+      float gt0[16], gt1[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {                      // token -> gate table rows (L2 resident)
+        const float* g = gt_base + (size_t)tok[j] * 1024;
+        gt0[j] = __ldg(g);
+        gt1[j] = __ldg(g + 128);
+      }
+      mbar_wait(BAR(BAR_GDONE), s & 1);
+      tc_fence_after();
+      float a0[16], a1[16];
+      tc_ld16(TM_G0 + lane_addr + col0, a0);
+      tc_ld16(TM_G1 + lane_addr + col0, a1);
+      const int nb = (s + 1) & 1;
+      unsigned char* hdst = smem + OFF_H + nb * HB_BYTES + rank * HSLICE_BYTES;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x0 = a0[j] + gt0[j] + gctx0[j];
+        float x1 = a1[j] + gt1[j] + gctx1[j];
+        if (g_dbg != nullptr && s == (int)g_dbg[0]) {
+          float* da = g_dbg + 16 + (size_t)((cluster * 4 + rank) * 2) * 4096;
+          da[p * 32 + col0 + j] = x0; da[4096 + p * 32 + col0 + j] = x1;
+          float* dm = g_dbg + 16 + 200000 + (size_t)((cluster * 4 + rank) * 2) * 4096;
+          dm[p * 32 + col0 + j] = a0[j]; dm[4096 + p * 32 + col0 + j] = a1[j];
+        }
+        float y0 = fmaf(tanh_approx(0.5f * x0), 0.5f, 0.5f);       // sigmoid(i) | sigmoid(f)
+        float y1 = fmaf(tanh_approx(s1 * x1), m1, b1);             // tanh(g)    | sigmoid(o)
+        float pig = __shfl_xor_sync(0xffffffffu, y0 * y1, 16);     // sigma(i) tanh(g): lanes 0..15 -> 16..31
+        float cn = fmaf(y0, c[j], pig);
+        float hn = y1 * tanh_approx(cn);
+        if (hi) {
+          c[j] = cn;
+          const int n = col0 + j;                                  // B-operand row (sequence)
+          const int chunk = (u >> 3) ^ (n & 7);                    // SWIZZLE_128B
+          *reinterpret_cast<__nv_bfloat16*>(hdst + n * 128 + chunk * 16 + (u & 7) * 2) = __float2bfloat16(hn);
+          if (g_dbg != nullptr && s == (int)g_dbg[0]) g_dbg[16 + 65536 + (cluster * 32 + n) * 256 + 64 * rank + u] = hn;
+        }
+      }
+      fence_proxy_async();           // generic-proxy h writes -> visible to tcgen05.mma and bulk copies
+      tc_fence_before();
+      epi_bar_sync();
+      if (tid == 0) {
+        const uint32_t src = sbase + OFF_H + nb * HB_BYTES + rank * HSLICE_BYTES;
+        mbar_arrive_expect_tx(BAR(BAR_HFULL0 + nb), (CL - 1) * HSLICE_BYTES);
+#pragma unroll
+        for (uint32_t d = 1; d < CL; ++d) {
+          uint32_t peer = (rank + d) & (CL - 1);
+          bulk_s2peer(mapa(src, peer), src, HSLICE_BYTES, mapa(BAR(BAR_HFULL0 + nb), peer));
+        }
+      }
+      // ---------------- Epi-L(s): logits -> tok_{s+1} ----------------
+      mbar_wait(BAR(BAR_LDONE), s & 1);
+      tc_fence_after();
+      float lg[16];
+      tc_ld16(TM_L + lane_addr + col0, lg);
+      tc_fence_before();
+      float myv = -INFINITY; int myi = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float v = lg[j] + bias;
+        if (g_dbg != nullptr && s == (int)g_dbg[0]) g_dbg[16 + 131072 + ((cluster * 4 + rank) * 128 + p) * 32 + col0 + j] = v;
+        if (P.temperature != 1.0f) v = v / P.temperature;           // seq2seq.py:213-214
+        float m = redux_max(v);
+        unsigned bal = __ballot_sync(0xffffffffu, v == m);
+        int src = bal ? (__ffs(bal) - 1) : 0;                       // first index wins (torch.argmax)
+        if (lane == j) { myv = m; myi = 128 * (int)rank + 32 * q + src; }
+      }
+      if (lane < 16) { part[(warp * 16 + lane) * 2] = myv; reinterpret_cast<int*>(part)[(warp * 16 + lane) * 2 + 1] = myi; }
+      epi_bar_sync();
+      if (tid < NB) {
+        const int cgrp = tid >> 4, j = tid & 15;
+        float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          int w = cgrp * 4 + qq;
+          float v = part[(w * 16 + j) * 2]; int i = reinterpret_cast<int*>(part)[(w * 16 + j) * 2 + 1];
+          if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+        const uint32_t slot = sbase + OFF_XCHG + (rank * NB + tid) * 8;
+#pragma unroll
+        for (uint32_t d = 0; d < CL; ++d) {
+          st_cluster_v2(mapa(slot, d), __float_as_uint(bv), (uint32_t)bi);
+          mbar_arrive_remote(mapa(BAR(BAR_TOK), d));
+        }
+        mbar_wait_cluster(BAR(BAR_TOK), s & 1);
+        const float* xf = reinterpret_cast<const float*>(smem + OFF_XCHG);
+        const int* xi = reinterpret_cast<const int*>(smem + OFF_XCHG);
+        bv = -INFINITY; bi = 0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < CL; ++r) {
+          float v = xf[(r * NB + tid) * 2]; int i = xi[(r * NB + tid) * 2 + 1];
+          if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+        if (bi == 0x7fffffff) bi = 0;
+        tok_s[tid] = bi;
+        // token append + EOS bookkeeping (seq2seq.py:216-221 / predictor.py:338-347)
+        const int row = row0 + tid;
+        const bool valid = row < P.B;
+        const bool is_end = bi == P.end_id;
+        if (valid && is_end && fe < 0) fe = s + 1;
+        finished = finished || is_end;
+        if (rank == 0 && valid) P.tokens[(size_t)row * (P.T + 1) + s + 1] = bi;
+        const bool all_end = __all_sync(0xffffffffu, !valid || is_end);
+        const bool all_fin = __all_sync(0xffffffffu, !valid || finished);
+        if (tid == 0) {
+          if (rank == 0) P.allend[(size_t)cluster * P.T + s] = all_end ? 1 : 0;
+          if (P.stop_rule == I2L_STOP_ALL_FINISHED_STICKY && all_fin) misc[1] = 1;   // this cluster is done
+        }
+      }
+      epi_bar_sync();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tok[j] = tok_s[col0 + j];
+      if (*reinterpret_cast<volatile uint32_t*>(&misc[1])) { ++s; break; }
+    }
+    if (rank == 0 && tid < NB) {
+      const int row = row0 + tid;
+      if (row < P.B) P.first_end[row] = fe;
+      if (tid == 0) P.cluster_steps[cluster] = s;
+    }
+    if (*reinterpret_cast<volatile uint32_t*>(&misc[1]) && tid == 0) {
+      // early exit: release the MMA thread that is waiting for an h buffer that will never fill
+      mbar_arrive(BAR(BAR_HFULL0 + ((s + 1) & 1)));
+    }
+  }
+  // ---- teardown: peers may still be reading / writing our shared memory ----
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ---- packing ---------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w_hh, const float* __restrict__ out_w, int V,
+                                    unsigned char* __restrict__ wimg) {
+  // one thread per (rank, tile(0..2), row p, k): tiles 0,1 = gates, tile 2 = vocab rows
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)CL * 3 * 128 * H) return;
+  int k = (int)(i % H);
+  int p = (int)((i / H) % 128);
+  int t = (int)((i / (H * 128)) % 3);
+  int r = (int)(i / ((size_t)H * 128 * 3));
+  float v;
+  if (t < 2) {
+    int qd = p >> 5, l = p & 31;
+    int unit = 64 * r + 16 * qd + (l & 15);
+    int gate = 2 * t + (l >= 16 ? 1 : 0);               // PyTorch gate order i,f,g,o
+    v = w_hh[(size_t)(gate * H + unit) * H + k];
+  } else {
+    int vr = 128 * r + p;
+    v = vr < V ? out_w[(size_t)vr * H + k] : 0.f;
+  }
+  int kb = k >> 6, kk = k & 63;
+  size_t off = (size_t)r * (WG_BYTES + WO_BYTES) + (t < 2 ? (size_t)t * 65536 : (size_t)WG_BYTES) + (size_t)kb * 16384 +
+               (size_t)p * 128 + (size_t)(((kk >> 3) ^ (p & 7)) * 16) + (size_t)(kk & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(wimg + off) = __float2bfloat16(v);
+}
+
+__global__ void pack_gtok_kernel(const float* __restrict__ gtok, int V, float* __restrict__ out) {
+  // out[v][r][t][p] = gtok[v][gate(t,p)*256 + 64 r + unit(p)]
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)V * 1024) return;
+  int p = (int)(i & 127), t = (int)((i >> 7) & 1), r = (int)((i >> 8) & 3), v = (int)(i >> 10);
+  int qd = p >> 5, l = p & 31;
+  int unit = 64 * r + 16 * qd + (l & 15);
+  int gate = 2 * t + (l >= 16 ? 1 : 0);
+  out[i] = gtok[(size_t)v * 1024 + gate * 256 + unit];
+}
+
+__global__ void pack_bias_kernel(const float* __restrict__ out_b, int V, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < VMAX) out[i] = i < V ? out_b[i] : -INFINITY;
+}
+
+__global__ void persistent_init_kernel(int64_t* tokens, int T1, int B, int start_id) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)B * T1) tokens[i] = (i % T1 == 0) ? start_id : -1;
+}
+
+__global__ void persistent_finalize_kernel(const int* first_end, const unsigned char* allend, const int* cluster_steps,
+                                           int n_clusters, int B, int T, int stop_rule, int32_t* lengths,
+                                           int32_t* steps_out) {
+  __shared__ int steps_sh;
+  if (threadIdx.x == 0) {
+    int steps = T;
+    if (stop_rule == I2L_STOP_ALL_END_SAME_STEP) {
+      for (int s = 0; s < T; ++s) {
+        bool all = true;
+        for (int cidx = 0; cidx < n_clusters && all; ++cidx) all = allend[(size_t)cidx * T + s] != 0;
+        if (all) { steps = s + 1; break; }
+      }
+    } else if (stop_rule == I2L_STOP_ALL_FINISHED_STICKY) {
+      steps = 0;
+      for (int cidx = 0; cidx < n_clusters; ++cidx) steps = max(steps, cluster_steps[cidx]);
+    }
+    steps_sh = steps;
+    if (steps_out) *steps_out = steps;
+  }
+  __syncthreads();
+  const int steps = steps_sh;
+  if (lengths)
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+      int fe = first_end[i];
+      lengths[i] = (fe >= 0 && fe <= steps) ? fe : steps + 1;
+    }
+}
+
+struct PWs { float* gctx; int* first_end; unsigned char* allend; int* cluster_steps; size_t bytes; };
+PWs pcarve(int rows, int T, void* ws) {
+  Arena a(ws, (size_t)-1);
+  PWs w{};
+  int ncl = cdiv(rows, NB);
+  w.gctx = a.take<float>((size_t)rows * 1024);
+  w.first_end = a.take<int>(rows);
+  w.allend = a.take<unsigned char>((size_t)ncl * (T > 0 ? T : 1));
+  w.cluster_steps = a.take<int>(ncl);
+  w.bytes = align_up(a.off, 256);
+  return w;
+}
+
+}  // namespace
+
+int persistent_set_debug(float* buf) {
+  I2L_CUDA_OK(cudaMemcpyToSymbol(g_dbg, &buf, sizeof(buf)));
+  return I2L_OK;
+}
+
+bool persistent_supported(const i2l_dec_desc& d) {
+  return d.hidden_dim == H && d.embedding_dim == E && d.lstm_layers == 1 && d.vocab_size <= VMAX && d.vocab_size >= 1;
+}
+size_t persistent_packed_bytes(const i2l_dec_desc& d) { return psection(d.vocab_size).total; }
+
+int persistent_pack(const i2l_dec_desc& d, const i2l_dec_params& p, const float* gtok_f32, void* section,
+                    cudaStream_t s) {
+  // gtok_f32: the fp32 token->gate table (V,4H) already produced on this stream by i2l_dec_pack
+  PSection ps = psection(d.vocab_size);
+  {
+    size_t n = (size_t)d.vocab_size * 1024;
+    pack_gtok_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+        gtok_f32, d.vocab_size, reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(section) + ps.gtok));
+    I2L_LAUNCH_OK();
+  }
+  unsigned char* sec = reinterpret_cast<unsigned char*>(section);
+  size_t n = (size_t)CL * 3 * 128 * H;
+  pack_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p.w_hh[0], p.out_w, d.vocab_size, sec + ps.wimg);
+  I2L_LAUNCH_OK();
+  pack_bias_kernel<<<2, 256, 0, s>>>(p.out_b, d.vocab_size, reinterpret_cast<float*>(sec + ps.bias));
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
+
+size_t persistent_workspace_bytes(const i2l_dec_desc&, int rows, int max_length) { return pcarve(rows, max_length, nullptr).bytes; }
+
+int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* packed_f32, const PackedDec& lay,
+                      const float* enc, int batch, int start_id, int end_id, int max_length, float temperature,
+                      int stop_rule, int64_t* tokens, int32_t* lengths, int32_t* steps_run, void* ws, size_t ws_bytes,
+                      cudaStream_t s) {
+  I2L_REQUIRE(start_id >= 0 && start_id < d.vocab_size, "decode_greedy: start token out of range");
+  PWs w = pcarve(batch, max_length, ws);
+  if (ws_bytes < w.bytes) { set_error("persistent_greedy: workspace too small"); return I2L_ERR_WORKSPACE; }
+  PSection ps = psection(d.vocab_size);
+  const unsigned char* sec = reinterpret_cast<const unsigned char*>(section);
+  const int T1 = max_length + 1;
+  {
+    size_t tot = (size_t)batch * T1;
+    persistent_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(tokens, T1, batch, start_id);
+    I2L_LAUNCH_OK();
+  }
+  // per-sequence constant gates: enc W_ih[:, E:2E]^T + b_ih + b_hh  (fp32 GEMM)
+  {
+    GemmF32 g;
+    g.M = batch; g.N = 4 * H; g.C = w.gctx; g.ldc = 4 * H;
+    g.A1 = enc; g.lda1 = E; g.W1 = packed_f32 + lay.w_ih0 + E; g.ldw1 = 2 * E; g.K1 = E; g.bias = packed_f32 + lay.bsum[0];
+    KernelTimer kt("dec.gctx_gemm", s);
+    I2L_TRY(gemm_f32(g, s));
+  }
+  const int ncl = cdiv(batch, NB);
+  if (max_length > 0) {
+    Params P{};
+    P.wimg = sec + ps.wimg; P.gtok = reinterpret_cast<const float*>(sec + ps.gtok);
+    P.bias = reinterpret_cast<const float*>(sec + ps.bias);
+    P.gctx = w.gctx; P.tokens = tokens; P.first_end = w.first_end; P.allend = w.allend; P.cluster_steps = w.cluster_steps;
+    P.B = batch; P.T = max_length; P.start_id = start_id; P.end_id = end_id; P.stop_rule = stop_rule;
+    P.temperature = temperature;
+    I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    KernelTimer kt("dec.greedy_persistent", s);
+    persistent_greedy_kernel<<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
+    I2L_LAUNCH_OK();
+  } else {
+    I2L_CUDA_OK(cudaMemsetAsync(w.first_end, 0xff, (size_t)batch * 4, s));
+    I2L_CUDA_OK(cudaMemsetAsync(w.cluster_steps, 0, (size_t)ncl * 4, s));
+  }
+  persistent_finalize_kernel<<<1, 256, 0, s>>>(w.first_end, w.allend, w.cluster_steps, ncl, batch, max_length, stop_rule,
+                                               lengths, steps_run);
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
+
+}  // namespace i2l
