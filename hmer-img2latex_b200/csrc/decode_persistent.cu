@@ -3,9 +3,11 @@
 // and keeps the whole decoder in shared memory for the lifetime of the kernel:
 //
 //   CTA rank r holds hidden units [64r, 64r+64): the 256 gate rows (i,f,g,o) of W_hh for
-//   those units (128 KB bf16, two M=128 tcgen05 tiles) and vocab rows [128r, 128r+128) of
-//   W_out (64 KB, one tile), both as K-major SWIZZLE_128B operand images that were
-//   pre-swizzled at pack time and arrive with plain bulk copies (cp.async.bulk).
+//   those units (two M=128 tcgen05 tiles) and vocab rows [128r, 128r+128) of W_out (one
+//   tile).  All 192 KB of bf16 weights live in TENSOR MEMORY for the whole kernel (3 x 128
+//   columns, written once with tcgen05.st) and feed the MMAs as the TMEM A operand, so a
+//   step re-reads only the 1 KB/MMA B operand from shared memory instead of 4 KB/MMA of
+//   weights (with N = 32 the SMEM operand fetch, not the tensor pipe, was the MMA bound).
 //
 //   The MMAs are "swapped": D[gate row, sequence] = W[gate row, :] . h[sequence, :], so the
 //   weights are the (resident) A operand with M = 128 and the 32 sequences are the N = 32
@@ -38,14 +40,14 @@ constexpr int NB = 32;                // sequences per cluster
 constexpr int CL = 4;                 // CTAs per cluster
 constexpr int EPI_THREADS = 256;
 constexpr int THREADS = EPI_THREADS + 32;
-constexpr int WG_BYTES = 2 * 4 * 16384;   // 2 tiles x 4 K-blocks x (128 rows x 128 B)
-constexpr int WO_BYTES = 4 * 16384;
+constexpr int WROW_BYTES = 3 * 128 * H * 2;    // per-rank weight rows: 3 tiles x 128 rows x 256 bf16 (row-major)
 constexpr int HB_BYTES = 4 * NB * 128;    // 4 K-blocks x (NB rows x 128 B) = 16 KB
 constexpr int HSLICE_BYTES = NB * 128;    // one K-block = one CTA's units
+// tensor-memory column map (512 columns allocated)
+constexpr int TC_L = 0, TC_G0 = NB, TC_G1 = 2 * NB;           // fp32 accumulators
+constexpr int TC_WO = 128, TC_WG0 = 256, TC_WG1 = 384;        // bf16 weight tiles, 128 columns each (2 K-elements / column)
 // shared memory map (bytes)
-constexpr int OFF_WG = 0;
-constexpr int OFF_WO = OFF_WG + WG_BYTES;
-constexpr int OFF_H = OFF_WO + WO_BYTES;            // 2 buffers
+constexpr int OFF_H = 0;                            // 2 h buffers (B operand, K-major SWIZZLE_128B)
 constexpr int OFF_PART = OFF_H + 2 * HB_BYTES;      // [8 warps][16 cols] (float,int)
 constexpr int OFF_XCHG = OFF_PART + 8 * 16 * 8;     // [4 ctas][32 cols] (float,int)
 constexpr int OFF_TOK = OFF_XCHG + CL * NB * 8;     // [32] int tokens of the current step
@@ -58,7 +60,7 @@ enum { BAR_W = 0, BAR_HFULL0 = 1, BAR_HFULL1 = 2, BAR_LDONE = 3, BAR_GDONE = 4, 
 
 // ---- packed (bf16) section layout -------------------------------------------------------
 struct PSection {
-  size_t wimg;      // [4 ranks][WG_BYTES + WO_BYTES]
+  size_t wimg;      // [4 ranks][3 tiles][128 rows][256] bf16
   size_t gtok;      // fp32 [V][4][2][128]
   size_t bias;      // fp32 [512]  (-inf beyond V)
   size_t total;
@@ -66,7 +68,7 @@ struct PSection {
 PSection psection(int V) {
   PSection s{};
   size_t o = 0;
-  s.wimg = o; o += (size_t)CL * (WG_BYTES + WO_BYTES);
+  s.wimg = o; o += (size_t)CL * WROW_BYTES;
   s.gtok = o; o += (size_t)V * 1024 * 4;
   s.bias = o; o += VMAX * 4;
   s.total = align_up(o, 1024);
@@ -113,6 +115,11 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 __device__ __forceinline__ void st_cluster_v2(uint32_t cluster_addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(cluster_addr), "r"(a), "r"(b) : "memory");
 }
+__device__ __forceinline__ void st_async_v2(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr),
+               "r"(a), "r"(b), "r"(cluster_bar)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -139,6 +146,11 @@ __device__ __forceinline__ uint32_t cluster_id_x() {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -149,6 +161,20 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
@@ -163,6 +189,15 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -184,9 +219,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
   return d;
 }
+constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ float* g_dbg = nullptr;   // debug dump target (tools/debug_persistent.py), normally null
+// debug build of the kernel only (tools/debug_persistent.py): per-phase clock64() stamps of one
+// step of cluster 0 / rank 0, and optional dumps of gates / h / logits of that step
+#define I2L_TS(slot)                                                                       \
+  do {                                                                                     \
+    if (DBG && dbg_ts) reinterpret_cast<long long*>(P.dbg + 16 + 300000)[slot] = clock64(); \
+  } while (0)
 
 struct Params {
   const unsigned char* wimg;     // per-rank weight images
@@ -199,8 +240,11 @@ struct Params {
   int* cluster_steps;            // [n_clusters]
   int B, T, start_id, end_id, stop_rule;
   float temperature;
+  float* dbg;                    // debug kernel only
+  int dbg_step, dbg_dump;
 };
 
+template <int DBG>   // 0 = production, 1 = clock stamps, 2 = stamps + value dumps
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persistent_greedy_kernel(Params P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -215,18 +259,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
   if ((sbase & 1023u) != 0) __trap();
 
   if (tid == 0) {
-    mbar_init(BAR(BAR_W), 1);
     mbar_init(BAR(BAR_HFULL0), 1);
     mbar_init(BAR(BAR_HFULL1), 1);
     mbar_init(BAR(BAR_LDONE), 1);
     mbar_init(BAR(BAR_GDONE), 1);
-    mbar_init(BAR(BAR_TOK), CL * NB);
+    mbar_init(BAR(BAR_TOK), 1);
     mbar_init(BAR(BAR_FINAL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     misc[1] = 0;
   }
-  if (warp == 8) {   // TMEM: 128 columns (3 accumulators of NB columns)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(sbase + OFF_MISC) : "memory");
+  if (warp == 8) {   // all 512 TMEM columns: 3 accumulators + 3 resident weight tiles
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + OFF_MISC) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // zero both h buffers (h_0 = 0, decoder.py:253-266)
@@ -236,53 +279,81 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = misc[0];
-  if (tid == 0) {   // resident weights: one bulk copy per 16 KB
-    const unsigned char* src = P.wimg + (size_t)rank * (WG_BYTES + WO_BYTES);
-    mbar_arrive_expect_tx(BAR(BAR_W), WG_BYTES + WO_BYTES);
-    for (int o = 0; o < WG_BYTES + WO_BYTES; o += 16384) bulk_g2s(sbase + OFF_WG + o, src + o, 16384, BAR(BAR_W));
+  if (warp < 8) {
+    // resident weights -> tensor memory: thread (quadrant q, lane) owns row p = 32q + lane of each
+    // tile; warps 0-3 write K columns [0,64), warps 4-7 columns [64,128) (two bf16 per column)
+    const int p = 32 * (warp & 3) + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    const int half = warp >> 2;
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+      const uint4* src = reinterpret_cast<const uint4*>(P.wimg + (size_t)rank * WROW_BYTES + ((size_t)t * 128 + p) * (H * 2)) + half * 16;
+      const uint32_t tcol = t == 0 ? TC_WG0 : (t == 1 ? TC_WG1 : TC_WO);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 v = __ldg(src + c * 4 + i);
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        tc_st16(tmem + lane_addr + tcol + half * 64 + c * 16, r);
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
   }
+  __syncthreads();
+  tc_fence_after();
   cluster_sync_all();   // every CTA's barriers are initialised before any remote traffic
 
-  const uint32_t TM_L = tmem, TM_G0 = tmem + NB, TM_G1 = tmem + 2 * NB;
+  const uint32_t TM_L = tmem + TC_L, TM_G0 = tmem + TC_G0, TM_G1 = tmem + TC_G1;
 
   if (warp == 8) {
-    // =========================== MMA issuer (one thread) ===========================
-    if (lane == 0) {
-      mbar_wait(BAR(BAR_W), 0);
-      auto issue_tile = [&](uint32_t d_tmem, uint32_t a_base, uint32_t h_base) {
+    // =========================== MMA issuer warp ===========================
+    // the whole warp stays converged (waits are executed by all lanes); one elected lane issues
+    const uint64_t dbase = DESC_HI | (uint64_t)(((sbase >> 4) & 0x3FFFu) | (1u << 16));
+    auto issue_tile = [&](uint32_t d_tmem, uint32_t a_col, uint32_t h_off) {
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
+      for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint64_t ad = make_desc(a_base + kb * 16384 + k * 32);
-            uint64_t bd = make_desc(h_base + kb * HSLICE_BYTES + k * 32);
-            tc_mma(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
-          }
+        for (int k = 0; k < 4; ++k) {
+          uint64_t bd = dbase + (uint64_t)((h_off + kb * HSLICE_BYTES + k * 32) >> 4);
+          tc_mma_ts(d_tmem, tmem + a_col + (kb * 4 + k) * 8, bd, IDESC, (kb | k) ? 1u : 0u);   // 16 K-elements = 8 columns
         }
-      };
-      tc_fence_after();
-      // gates of step 0 from h_0 = 0 (buffer 0)
-      issue_tile(TM_G0, sbase + OFF_WG, sbase + OFF_H);
-      issue_tile(TM_G1, sbase + OFF_WG + 65536, sbase + OFF_H);
+      }
+    };
+    tc_fence_after();
+    if (elect_one()) {   // gates of step 0 from h_0 = 0 (buffer 0)
+      issue_tile(TM_G0, TC_WG0, OFF_H);
+      issue_tile(TM_G1, TC_WG1, OFF_H);
       tc_commit(BAR(BAR_GDONE));
-      for (int s = 0; s < P.T; ++s) {
-        const int nb = (s + 1) & 1;                       // buffer holding h_{s+1}
-        mbar_wait(BAR(BAR_HFULL0 + nb), (uint32_t)((s >> 1) & 1));     // h_j (j = s+1) is use (j-1)/2 of its buffer
-        if (*reinterpret_cast<volatile uint32_t*>(&misc[1])) break;
-        tc_fence_after();
-        const uint32_t hb = sbase + OFF_H + nb * HB_BYTES;
-        issue_tile(TM_L, sbase + OFF_WO, hb);             // logits_s = W_out h_{s+1}
+    }
+    __syncwarp();
+    for (int s = 0; s < P.T; ++s) {
+      const bool dbg_ts = DBG && cluster == 0 && rank == 0 && s == P.dbg_step && lane == 0;
+      const int nb = (s + 1) & 1;                       // buffer holding h_{s+1}
+      I2L_TS(16);
+      mbar_wait(BAR(BAR_HFULL0 + nb), (uint32_t)((s >> 1) & 1));     // h_j (j = s+1) is use (j-1)/2 of its buffer
+      I2L_TS(17);
+      if (*reinterpret_cast<volatile uint32_t*>(&misc[1])) break;
+      tc_fence_after();
+      const uint32_t hb = OFF_H + nb * HB_BYTES;
+      if (elect_one()) {
+        issue_tile(TM_L, TC_WO, hb);                    // logits_s = W_out h_{s+1}
         tc_commit(BAR(BAR_LDONE));
         if (s + 1 < P.T) {
-          issue_tile(TM_G0, sbase + OFF_WG, hb);          // gates of step s+1
-          issue_tile(TM_G1, sbase + OFF_WG + 65536, hb);
+          issue_tile(TM_G0, TC_WG0, hb);                // gates of step s+1
+          issue_tile(TM_G1, TC_WG1, hb);
           tc_commit(BAR(BAR_GDONE));
         }
       }
-      tc_commit(BAR(BAR_FINAL));       // every MMA issued above has completed before TMEM is released
-      mbar_wait(BAR(BAR_FINAL), 0);
+      __syncwarp();
+      I2L_TS(18);
     }
+    if (elect_one()) tc_commit(BAR(BAR_FINAL));         // every MMA issued above has completed before TMEM is released
     __syncwarp();
+    mbar_wait(BAR(BAR_FINAL), 0);
   } else {
     // =========================== epilogue warps (256 threads) ===========================
     const int q = warp & 3, cg = warp >> 2;               // TMEM lane quadrant, column group
@@ -316,7 +387,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
     const float* gt_base = P.gtok + (size_t)rank * 256 + p;
     int s = 0;
     for (; s < P.T; ++s) {
+      const bool dbg_ts = DBG && cluster == 0 && rank == 0 && s == P.dbg_step;
+      const bool dbg_dump = DBG == 2 && s == P.dbg_step;
       // ---------------- Epi-G(s): gates -> c_{s+1}, h_{s+1} ----------------
+      if (tid == 0) I2L_TS(0);
       float gt0[16], gt1[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {                      // token -> gate table rows (L2 resident)
@@ -324,36 +398,54 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
         gt0[j] = __ldg(g);
         gt1[j] = __ldg(g + 128);
       }
+      if (tid == 0) I2L_TS(1);
       mbar_wait(BAR(BAR_GDONE), s & 1);
       tc_fence_after();
-      float a0[16], a1[16];
-      tc_ld16(TM_G0 + lane_addr + col0, a0);
-      tc_ld16(TM_G1 + lane_addr + col0, a1);
+      if (tid == 0) I2L_TS(2);
+      uint32_t r0[16], r1[16];
+      tc_ld16_nowait(TM_G0 + lane_addr + col0, r0);
+      tc_ld16_nowait(TM_G1 + lane_addr + col0, r1);
+      tc_wait_ld();
+      if (tid == 0) I2L_TS(3);
       const int nb = (s + 1) & 1;
       unsigned char* hdst = smem + OFF_H + nb * HB_BYTES + rank * HSLICE_BYTES;
+      // phase 1: gate activations for all 16 sequences (32 independent MUFU.TANH)
+      float y0[16], y1[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float x0 = a0[j] + gt0[j] + gctx0[j];
-        float x1 = a1[j] + gt1[j] + gctx1[j];
-        if (g_dbg != nullptr && s == (int)g_dbg[0]) {
-          float* da = g_dbg + 16 + (size_t)((cluster * 4 + rank) * 2) * 4096;
+        float x0 = __uint_as_float(r0[j]) + gt0[j] + gctx0[j];
+        float x1 = __uint_as_float(r1[j]) + gt1[j] + gctx1[j];
+        if (DBG == 2 && dbg_dump) {
+          float* da = P.dbg + 16 + (size_t)((cluster * 4 + rank) * 2) * 4096;
           da[p * 32 + col0 + j] = x0; da[4096 + p * 32 + col0 + j] = x1;
-          float* dm = g_dbg + 16 + 200000 + (size_t)((cluster * 4 + rank) * 2) * 4096;
-          dm[p * 32 + col0 + j] = a0[j]; dm[4096 + p * 32 + col0 + j] = a1[j];
+          float* dm = P.dbg + 16 + 200000 + (size_t)((cluster * 4 + rank) * 2) * 4096;
+          dm[p * 32 + col0 + j] = __uint_as_float(r0[j]); dm[4096 + p * 32 + col0 + j] = __uint_as_float(r1[j]);
         }
-        float y0 = fmaf(tanh_approx(0.5f * x0), 0.5f, 0.5f);       // sigmoid(i) | sigmoid(f)
-        float y1 = fmaf(tanh_approx(s1 * x1), m1, b1);             // tanh(g)    | sigmoid(o)
-        float pig = __shfl_xor_sync(0xffffffffu, y0 * y1, 16);     // sigma(i) tanh(g): lanes 0..15 -> 16..31
-        float cn = fmaf(y0, c[j], pig);
-        float hn = y1 * tanh_approx(cn);
-        if (hi) {
-          c[j] = cn;
+        y0[j] = fmaf(tanh_approx(0.5f * x0), 0.5f, 0.5f);          // sigmoid(i) | sigmoid(f)
+        y1[j] = fmaf(tanh_approx(s1 * x1), m1, b1);                // tanh(g)    | sigmoid(o)
+      }
+      // phase 2: sigma(i) tanh(g) moves from lanes 0..15 to the lanes 16..31 that own c
+      float pg[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pg[j] = __shfl_xor_sync(0xffffffffu, y0[j] * y1[j], 16);
+      // phase 3: cell / hidden update (lanes 16..31 are the owners; 0..15 compute don't-cares)
+      float hn[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float cn = fmaf(y0[j], c[j], pg[j]);
+        c[j] = cn;
+        hn[j] = y1[j] * tanh_approx(cn);
+      }
+      if (hi) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
           const int n = col0 + j;                                  // B-operand row (sequence)
           const int chunk = (u >> 3) ^ (n & 7);                    // SWIZZLE_128B
-          *reinterpret_cast<__nv_bfloat16*>(hdst + n * 128 + chunk * 16 + (u & 7) * 2) = __float2bfloat16(hn);
-          if (g_dbg != nullptr && s == (int)g_dbg[0]) g_dbg[16 + 65536 + (cluster * 32 + n) * 256 + 64 * rank + u] = hn;
+          *reinterpret_cast<__nv_bfloat16*>(hdst + n * 128 + chunk * 16 + (u & 7) * 2) = __float2bfloat16(hn[j]);
+          if (DBG == 2 && dbg_dump) P.dbg[16 + 65536 + (cluster * 32 + n) * 256 + 64 * rank + u] = hn[j];
         }
       }
+      if (tid == 0) I2L_TS(4);
       fence_proxy_async();           // generic-proxy h writes -> visible to tcgen05.mma and bulk copies
       tc_fence_before();
       epi_bar_sync();
@@ -367,24 +459,53 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
         }
       }
       // ---------------- Epi-L(s): logits -> tok_{s+1} ----------------
+      if (tid == 0) I2L_TS(5);
       mbar_wait(BAR(BAR_LDONE), s & 1);
       tc_fence_after();
+      if (tid == 0) I2L_TS(6);
       float lg[16];
       tc_ld16(TM_L + lane_addr + col0, lg);
       tc_fence_before();
-      float myv = -INFINITY; int myi = 0;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float v = lg[j] + bias;
-        if (g_dbg != nullptr && s == (int)g_dbg[0]) g_dbg[16 + 131072 + ((cluster * 4 + rank) * 128 + p) * 32 + col0 + j] = v;
-        if (P.temperature != 1.0f) v = v / P.temperature;           // seq2seq.py:213-214
-        float m = redux_max(v);
-        unsigned bal = __ballot_sync(0xffffffffu, v == m);
-        int src = bal ? (__ffs(bal) - 1) : 0;                       // first index wins (torch.argmax)
-        if (lane == j) { myv = m; myi = 128 * (int)rank + 32 * q + src; }
+        lg[j] += bias;
+        if (DBG == 2 && dbg_dump) P.dbg[16 + 131072 + ((cluster * 4 + rank) * 128 + p) * 32 + col0 + j] = lg[j];
+        if (P.temperature != 1.0f) lg[j] = lg[j] / P.temperature;   // seq2seq.py:213-214
       }
-      if (lane < 16) { part[(warp * 16 + lane) * 2] = myv; reinterpret_cast<int*>(part)[(warp * 16 + lane) * 2 + 1] = myi; }
+      // per-column argmax over the warp's 32 vocab rows: transposing butterfly, 16 + 16 shuffles.
+      // After the xor-16/8/4/2 steps lane l holds column (l >> 1) & 15 reduced over 16 rows; the
+      // xor-1 step finishes it.  Ties keep the lower row (torch.argmax: first index wins).
+      float myv; int myi;
+      {
+        int ix[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ix[j] = lane;
+#pragma unroll
+        for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+          const bool up = (lane & bit) != 0;
+#pragma unroll
+          for (int j = 0; j < w; ++j) {
+            float keep_v = up ? lg[j + w] : lg[j];
+            int keep_i = up ? ix[j + w] : ix[j];
+            float send_v = up ? lg[j] : lg[j + w];
+            int send_i = up ? ix[j] : ix[j + w];
+            float ov = __shfl_xor_sync(0xffffffffu, send_v, bit);
+            int oi = __shfl_xor_sync(0xffffffffu, send_i, bit);
+            const bool take = ov > keep_v || (ov == keep_v && oi < keep_i);
+            lg[j] = take ? ov : keep_v;
+            ix[j] = take ? oi : keep_i;
+          }
+        }
+        float ov = __shfl_xor_sync(0xffffffffu, lg[0], 1);
+        int oi = __shfl_xor_sync(0xffffffffu, ix[0], 1);
+        const bool take = ov > lg[0] || (ov == lg[0] && oi < ix[0]);
+        myv = take ? ov : lg[0];
+        myi = 128 * (int)rank + 32 * q + (take ? oi : ix[0]);
+      }
+      if (tid == 0) I2L_TS(7);
+      if ((lane & 1) == 0) { const int cj = lane >> 1; part[(warp * 16 + cj) * 2] = myv; reinterpret_cast<int*>(part)[(warp * 16 + cj) * 2 + 1] = myi; }
       epi_bar_sync();
+      if (tid == 0) I2L_TS(8);
       if (tid < NB) {
         const int cgrp = tid >> 4, j = tid & 15;
         float bv = -INFINITY; int bi = 0x7fffffff;
@@ -394,13 +515,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
           float v = part[(w * 16 + j) * 2]; int i = reinterpret_cast<int*>(part)[(w * 16 + j) * 2 + 1];
           if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
         }
+        // CTA partial -> slot [rank][column] of every CTA of the cluster; the store itself
+        // signals the destination's mbarrier (st.async + complete_tx), no fence / arrive round trip
         const uint32_t slot = sbase + OFF_XCHG + (rank * NB + tid) * 8;
+        if (tid == 0) mbar_arrive_expect_tx(BAR(BAR_TOK), CL * NB * 8);
 #pragma unroll
-        for (uint32_t d = 0; d < CL; ++d) {
-          st_cluster_v2(mapa(slot, d), __float_as_uint(bv), (uint32_t)bi);
-          mbar_arrive_remote(mapa(BAR(BAR_TOK), d));
-        }
+        for (uint32_t d = 0; d < CL; ++d) st_async_v2(mapa(slot, d), __float_as_uint(bv), (uint32_t)bi, mapa(BAR(BAR_TOK), d));
+        if (tid == 0) I2L_TS(9);
         mbar_wait_cluster(BAR(BAR_TOK), s & 1);
+        if (tid == 0) I2L_TS(10);
         const float* xf = reinterpret_cast<const float*>(smem + OFF_XCHG);
         const int* xi = reinterpret_cast<const int*>(smem + OFF_XCHG);
         bv = -INFINITY; bi = 0x7fffffff;
@@ -425,7 +548,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
           if (P.stop_rule == I2L_STOP_ALL_FINISHED_STICKY && all_fin) misc[1] = 1;   // this cluster is done
         }
       }
+      if (tid == 0) I2L_TS(11);
       epi_bar_sync();
+      if (tid == 0) I2L_TS(12);
 #pragma unroll
       for (int j = 0; j < 16; ++j) tok[j] = tok_s[col0 + j];
       if (*reinterpret_cast<volatile uint32_t*>(&misc[1])) { ++s; break; }
@@ -444,7 +569,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
   tc_fence_before();
   cluster_sync_all();
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
 }
 
@@ -468,9 +593,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_hh, const float*
     int vr = 128 * r + p;
     v = vr < V ? out_w[(size_t)vr * H + k] : 0.f;
   }
-  int kb = k >> 6, kk = k & 63;
-  size_t off = (size_t)r * (WG_BYTES + WO_BYTES) + (t < 2 ? (size_t)t * 65536 : (size_t)WG_BYTES) + (size_t)kb * 16384 +
-               (size_t)p * 128 + (size_t)(((kk >> 3) ^ (p & 7)) * 16) + (size_t)(kk & 7) * 2;
+  size_t off = (size_t)r * WROW_BYTES + (((size_t)t * 128 + p) * H + k) * 2;
   *reinterpret_cast<__nv_bfloat16*>(wimg + off) = __float2bfloat16(v);
 }
 
@@ -538,8 +661,9 @@ PWs pcarve(int rows, int T, void* ws) {
 
 }  // namespace
 
+static float* g_dbg_buf = nullptr;   // host-side: when set, the DBG instantiation of the kernel is launched
 int persistent_set_debug(float* buf) {
-  I2L_CUDA_OK(cudaMemcpyToSymbol(g_dbg, &buf, sizeof(buf)));
+  g_dbg_buf = buf;
   return I2L_OK;
 }
 
@@ -600,9 +724,23 @@ int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* p
     P.gctx = w.gctx; P.tokens = tokens; P.first_end = w.first_end; P.allend = w.allend; P.cluster_steps = w.cluster_steps;
     P.B = batch; P.T = max_length; P.start_id = start_id; P.end_id = end_id; P.stop_rule = stop_rule;
     P.temperature = temperature;
-    I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     KernelTimer kt("dec.greedy_persistent", s);
-    persistent_greedy_kernel<<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
+    if (g_dbg_buf != nullptr) {
+      float hdr[2];
+      I2L_CUDA_OK(cudaMemcpyAsync(hdr, g_dbg_buf, sizeof(hdr), cudaMemcpyDeviceToHost, s));
+      I2L_CUDA_OK(cudaStreamSynchronize(s));
+      P.dbg = g_dbg_buf; P.dbg_step = (int)hdr[0]; P.dbg_dump = (int)hdr[1];
+      if (P.dbg_dump) {
+        I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        persistent_greedy_kernel<2><<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
+      } else {
+        I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        persistent_greedy_kernel<1><<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
+      }
+    } else {
+      I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      persistent_greedy_kernel<0><<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
+    }
     I2L_LAUNCH_OK();
   } else {
     I2L_CUDA_OK(cudaMemsetAsync(w.first_end, 0xff, (size_t)batch * 4, s));

@@ -56,7 +56,8 @@ def test_persistent_greedy_vs_oracle(pkg, B, T, seed, sharp):
 
 def test_persistent_sticky_stop_and_lengths(pkg):
     cfg = H.HEADLINE
-    p = oracle.make_params(cfg, 2, sharp=True)        # seed 2: every row ends within ~10 steps
+    p = oracle.make_params(cfg, 2, sharp=True)
+    p["decoder.output_layer.bias"][H.END] += 2.0      # every row emits END early: the sticky rule fires
     m16 = H.build_model(pkg, cfg, p, precision="bf16")
     m32 = H.build_model(pkg, cfg, p, precision="fp32")
     B, T = 70, 60

@@ -16,18 +16,27 @@ pkg = i2l_import.load()
 step = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 cfg = H.HEADLINE
 p = oracle.make_params(cfg, 1, sharp=True)
-B, T = 32, step + 2
+B = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+T = step + 2
 m32 = H.build_model(pkg, cfg, p, "fp32"); m16 = H.build_model(pkg, cfg, p, "bf16")
 x = H.make_images(cfg, B)
 enc_ref = oracle.encoder(p, x, cfg)
 lib = pkg._native.lib()
-dbg = torch.zeros(16 + 400000 + 200000, device="cuda"); dbg[0] = step
+dump = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+dbg = torch.zeros(16 + 400000 + 200000, device="cuda"); dbg[0] = step; dbg[1] = dump
 lib.i2l_debug_set_buffer.argtypes = [C.c_void_p]; lib.i2l_debug_set_buffer.restype = C.c_int
 assert lib.i2l_debug_set_buffer(C.c_void_p(dbg.data_ptr())) == 0
 enc = m32.encoder(x.cuda())
 tokens, lengths, steps = m16.decoder.greedy(enc, H.START, H.END, T)
 torch.cuda.synchronize()
 d = dbg.cpu()[16:]
+NAMES = {0: 'epiG start', 1: 'gtok loads issued', 2: 'GDONE waited', 3: 'tmem ld done', 4: 'pointwise+h st done', 5: 'bar+bulk issued', 6: 'LDONE waited', 7: 'argmax partial', 8: 'bar', 9: 'xchg sent', 10: 'TOK waited', 11: 'tok final', 12: 'bar (end step)', 16: 'mma: before HFULL wait', 17: 'mma: HFULL ok', 18: 'mma: L issued', 19: 'mma: G issued'}
+if not dump:
+    ts = dbg.cpu()[16 + 300000: 16 + 300000 + 64].view(torch.int64)
+    t0 = int(ts[0])
+    for k in sorted(NAMES):
+        print(f'  ts[{k:2d}] {NAMES[k]:28s} {int(ts[k]) - t0:8d} cyc')
+    sys.exit(0)
 # oracle up to `step`
 tok = torch.full((B, 1), H.START, dtype=torch.long); hid = None
 for s in range(step):
