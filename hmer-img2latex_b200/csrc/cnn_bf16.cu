@@ -1,8 +1,597 @@
+// bf16 CNN encoder for the headline shape (3x64x320 -> conv 32/64/128 -> FC 40960->256),
+// CNNEncoder.forward (model/encoder.py:111-129), as tcgen05 implicit-GEMM kernels:
+//
+//   conv1  fp32 NCHW input -> bf16.  K = 27 (padded to 32): the im2col rows are built in shared
+//          memory by the CTA (K-major SWIZZLE_64B UMMA operand), 4 accumulators = the 4 pixels
+//          of each 2x2 pooling window, so bias + ReLU + max-pool are a per-thread epilogue.
+//   conv2/3  activations live in HBM as bf16 "parity planes" [ph%2,pw%2][H/2][B][W/2][C] written
+//          by the previous layer's epilogue.  With that layout every (pool-quadrant, filter-tap)
+//          operand tile is a DENSE 5-D TMA box (zero fill outside the image = conv padding), and
+//          a +1 row shift is a 16-row offset of the shared-memory descriptor, so one tile needs
+//          8 TMA loads for its 36 (quadrant, tap) MMA groups.  Filter taps stay resident in
+//          shared memory; accumulators (4 x Cout columns) in TMEM; epilogue = max over the 4
+//          accumulators + bias + ReLU, written straight in the next layer's layout.
+//   fc     TMA + tcgen05 split-K GEMM (A = conv3 output viewed as [B][40960], weight columns
+//          permuted to NHWC order at pack time), fp32 partials + bias/ReLU reduction.
 #include "encoder_bf16.cuh"
+#include "tc_common.cuh"
+
 namespace i2l {
-bool cnn_bf16_supported(const i2l_cnn_desc&) { return false; }
-size_t cnn_bf16_packed_bytes(const i2l_cnn_desc&) { return 0; }
-int cnn_bf16_pack(const i2l_cnn_desc&, const i2l_cnn_params&, void*, cudaStream_t) { return I2L_ERR_UNSUPPORTED; }
-size_t cnn_bf16_workspace_bytes(const i2l_cnn_desc&, int) { return 0; }
-int cnn_bf16_fwd(const i2l_cnn_desc&, const void*, const float*, int, float*, void*, size_t, cudaStream_t) { return I2L_ERR_UNSUPPORTED; }
+namespace {
+
+using namespace tc;
+
+constexpr int IMG_H = 64, IMG_W = 320, C0 = 3, C1 = 32, C2 = 64, C3 = 128, EMB = 256;
+constexpr int FLAT = C3 * 8 * 40;   // 40960
+
+// ------------------------------------------------------------------ packed section layout
+struct Sec {
+  size_t w1, b1, w2, b2, w3, b3, wfc, bfc, total;
+};
+Sec sec_layout() {
+  Sec s{};
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o = align_up(o + n, 1024); return r; };
+  s.w1 = take(32 * 64);                 // [32 co][32 k] bf16, SW64 image
+  s.b1 = take(C1 * 4);
+  s.w2 = take(9 * C2 * C1 * 2);         // 9 taps x [64][32] SW64
+  s.b2 = take(C2 * 4);
+  s.w3 = take(9 * C3 * C2 * 2);         // 9 taps x [128][64] SW128
+  s.b3 = take(C3 * 4);
+  s.wfc = take((size_t)EMB * FLAT * 2); // [256][40960] bf16, NHWC column order
+  s.bfc = take(EMB * 4);
+  s.total = o;
+  return s;
 }
+
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, int co_n, int ci_n, int layer, unsigned char* __restrict__ dst) {
+  // layer 1: dst [co][k = ci*9+kh*3+kw (27 -> 32)], 64 B rows; layers 2,3: dst [tap][co][ci]
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (layer == 1) {
+    if (i >= 32 * 32) return;
+    int co = i / 32, k = i % 32;
+    float v = k < 27 ? w[co * 27 + k] : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(dst + swz_off(co, k / 8, 64) + (k % 8) * 2) = __float2bfloat16(v);
+  } else {
+    if (i >= 9 * co_n * ci_n) return;
+    int ci = i % ci_n, co = (i / ci_n) % co_n, tap = i / (ci_n * co_n);
+    float v = w[((size_t)co * ci_n + ci) * 9 + tap];
+    uint32_t rb = ci_n * 2;
+    *reinterpret_cast<__nv_bfloat16*>(dst + (size_t)tap * co_n * rb + swz_off(co, ci / 8, rb) + (ci % 8) * 2) = __float2bfloat16(v);
+  }
+}
+
+__global__ void pack_fc_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst) {
+  // dst[e][(h*40+w)*128 + c] = w[e][c*320 + h*40 + w]    (nn.Flatten on NCHW, encoder.py:125)
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)EMB * FLAT) return;
+  int kk = (int)(i % FLAT), e = (int)(i / FLAT);
+  int c = kk % C3, hw = kk / C3;
+  dst[i] = __float2bfloat16(w[(size_t)e * FLAT + (size_t)c * 320 + hw]);
+}
+
+// ------------------------------------------------------------------ conv1
+// pooled tile 8 x 16 of one image = 16 x 32 conv pixels; input patch 18 x 34 x 3 (fp32, zero padded)
+constexpr int C1_THREADS = 256;
+constexpr int PATCH_W = 36;   // padded row pitch (floats)
+constexpr int C1_OFF_A = 0;                       // 4 quadrant tiles [128][32] bf16 SW64 = 4 x 8 KB
+constexpr int C1_OFF_W = 4 * 8192;                // 2 KB
+constexpr int C1_OFF_PATCH = C1_OFF_W + 2048;     // 3 x 18 x 36 floats
+constexpr int C1_OFF_BAR = C1_OFF_PATCH + 3 * 18 * PATCH_W * 4;
+constexpr int C1_SMEM = C1_OFF_BAR + 32;
+
+__global__ void __launch_bounds__(C1_THREADS, 4)
+conv1_kernel(const float* __restrict__ x, const unsigned char* __restrict__ w1img, const float* __restrict__ bias1,
+             __nv_bfloat16* __restrict__ act1, int B, int n_tiles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* patch = reinterpret_cast<float*>(smem + C1_OFF_PATCH);
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + C1_OFF_BAR + 16);
+  const uint32_t bar = sbase + C1_OFF_BAR;
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc<128>(sbase + C1_OFF_BAR + 16);
+  for (int i = tid; i < 2048 / 16; i += C1_THREADS) reinterpret_cast<uint4*>(smem + C1_OFF_W)[i] = reinterpret_cast<const uint4*>(w1img)[i];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc[0];
+  const uint64_t dA = desc_base(sbase + C1_OFF_A, 64), dW = desc_base(sbase + C1_OFF_W, 64);
+  constexpr uint32_t IDESC = idesc_bf16(128, 32);
+  const int q = warp & 3, chalf = warp >> 2;
+  const float4* b4 = reinterpret_cast<const float4*>(bias1 + chalf * 16);
+  float bias[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float4 v = b4[i]; bias[4 * i] = v.x; bias[4 * i + 1] = v.y; bias[4 * i + 2] = v.z; bias[4 * i + 3] = v.w; }
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tw = tile % 10, th = (tile / 10) % 4, b = tile / 40;
+    const int ph0 = th * 8, pw0 = tw * 16;
+    // ---- input patch -> smem (rows 2*ph0-1 .. +17, cols 2*pw0-1 .. +33), zero outside the image
+    const float* xb = x + (size_t)b * C0 * IMG_H * IMG_W;
+    for (int i = tid; i < 3 * 18 * 34; i += C1_THREADS) {
+      int j = i % 34, r = (i / 34) % 18, ci = i / (34 * 18);
+      int gy = 2 * ph0 - 1 + r, gx = 2 * pw0 - 1 + j;
+      float v = 0.f;
+      if (gy >= 0 && gy < IMG_H && gx >= 0 && gx < IMG_W) v = __ldg(xb + ((size_t)ci * IMG_H + gy) * IMG_W + gx);
+      patch[(ci * 18 + r) * PATCH_W + j] = v;
+    }
+    __syncthreads();
+    // ---- im2col: 4 quadrants x 128 pooled pixels, K = (ci,kh,kw) -> 32 bf16 per row
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = tid + rr * C1_THREADS;        // 0..511 = quadrant*128 + m
+      const int qd = row >> 7, m = row & 127;
+      const int qh = qd >> 1, qw = qd & 1;
+      const int pl = m >> 4, pwl = m & 15;
+      const float* p0 = patch + (2 * pl + qh) * PATCH_W + 2 * pwl + qw;
+      uint32_t pk[16];
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = 2 * k2 + e;
+          if (k < 27) {
+            const int ci = k / 9, kh = (k % 9) / 3, kw = k % 3;
+            v[e] = p0[(ci * 18 + kh) * PATCH_W + kw];
+          } else {
+            v[e] = 0.f;
+          }
+        }
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
+        pk[k2] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      unsigned char* dst = smem + C1_OFF_A + qd * 8192;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(dst + swz_off(m, ch, 64)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    // ---- 4 x (128 x 32 x 32) MMAs
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            tc_mma_ss(tmem + qd * 32, dA + (uint64_t)((qd * 8192 + ks * 32) >> 4), dW + (uint64_t)((ks * 32) >> 4), IDESC, ks);
+        tc_commit(bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: max over the 2x2 window, + bias, ReLU, bf16, parity-plane store
+    {
+      uint32_t r0[16], r1[16], r2[16], r3[16];
+      const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + chalf * 16;
+      tc_ld16_nowait(ta, r0); tc_ld16_nowait(ta + 32, r1); tc_ld16_nowait(ta + 64, r2); tc_ld16_nowait(ta + 96, r3);
+      tc_wait_ld();
+      const int m = 32 * q + lane;
+      const int ph = ph0 + (m >> 4), pw = pw0 + (m & 15);
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = fmaxf(fmaxf(__uint_as_float(r0[2 * i]), __uint_as_float(r1[2 * i])),
+                        fmaxf(__uint_as_float(r2[2 * i]), __uint_as_float(r3[2 * i])));
+        float c = fmaxf(fmaxf(__uint_as_float(r0[2 * i + 1]), __uint_as_float(r1[2 * i + 1])),
+                        fmaxf(__uint_as_float(r2[2 * i + 1]), __uint_as_float(r3[2 * i + 1])));
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(a + bias[2 * i], 0.f), fmaxf(c + bias[2 * i + 1], 0.f));
+        o[i] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      // act1 layout [plane = (ph&1)*2 + (pw&1)][16][B][80][32]
+      size_t pix = ((((size_t)((ph & 1) * 2 + (pw & 1)) * 16 + (ph >> 1)) * B + b) * 80 + (pw >> 1));
+      uint4* dst = reinterpret_cast<uint4*>(act1 + pix * C1 + chalf * 16);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
+// ------------------------------------------------------------------ conv2 / conv3
+template <int CIN, int COUT, int WW, int NIMG, int STAGES, int NACC>
+struct ConvCfg {
+  static constexpr int HH = 8;
+  static constexpr int ROWB = CIN * 2;                               // bytes per operand row = swizzle span
+  static constexpr int A_ROWS = (HH + 1) * NIMG * WW;                // 144
+  static constexpr int STAGE_BYTES = A_ROWS * ROWB;
+  static constexpr int SHIFT_BYTES = NIMG * WW * ROWB;               // one pooled row down
+  static constexpr int W_TAP_BYTES = COUT * ROWB;
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_A = 9 * W_TAP_BYTES;
+  static constexpr int OFF_BAR = OFF_A + STAGES * STAGE_BYTES;
+  static constexpr int SMEM = OFF_BAR + 256;
+  static constexpr int KSTEPS = CIN / 16;
+  static constexpr int TMEM_COLS = 4 * COUT * NACC;
+  static_assert(NIMG * WW == 16 && HH * NIMG * WW == 128, "tile must be 128 pooled pixels with 16-row h shifts");
+  static_assert(STAGE_BYTES % 1024 == 0 && SHIFT_BYTES % 1024 == 0, "alignment");
+  static_assert(TMEM_COLS <= 512 && SMEM <= 232448, "budget");
+};
+
+// OUT_PARITY: write [plane][PH/2][B][PW/2][COUT] (next conv's input) else plain [B][PH][PW][COUT]
+template <class Cfg, int CIN, int COUT, int WW, int NIMG, int STAGES, int NACC, bool OUT_PARITY>
+__global__ void __launch_bounds__(192, 1)
+conv_pool_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ wimg,
+                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B, int PH, int PW, int n_tiles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar = sbase + Cfg::OFF_BAR;
+  auto FULL = [&](int s) { return bar + 8u * s; };
+  auto EMPTY = [&](int s) { return bar + 8u * (STAGES + s); };
+  auto TFULL = [&](int a) { return bar + 8u * (2 * STAGES + a); };
+  auto TEMPTY = [&](int a) { return bar + 8u * (2 * STAGES + NACC + a); };
+  const uint32_t WBAR = bar + 8u * (2 * STAGES + 2 * NACC);
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 8 * (2 * STAGES + 2 * NACC + 1));
+  if ((sbase & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(TFULL(a), 1); mbar_init(TEMPTY(a), 128); }
+    mbar_init(WBAR, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap);
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(misc));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc[0];
+  const int tiles_w = PW / WW, tiles_h = PH / Cfg::HH;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(WBAR, 9 * Cfg::W_TAP_BYTES);
+      for (int o = 0; o < 9 * Cfg::W_TAP_BYTES; o += 4096) bulk_g2s(sbase + Cfg::OFF_W + o, wimg + o, 4096, WBAR);
+      int stage = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tn = tile / (tiles_w * tiles_h);
+        const int ph0 = th * Cfg::HH, pw0 = tw * WW, n0 = tn * NIMG;
+#pragma unroll 1
+        for (int l = 0; l < 8; ++l) {
+          const int rp = l < 4 ? 1 : 0, c = l & 3;              // plane_h; column case
+          const int plane = rp * 2 + ((c - 1) & 1);
+          // source pixel y = 2*ph + r - 1 lives in plane (y & 1) at row ph + floor((r-1)/2); same for x
+          const int w2 = pw0 + (c == 0 ? -1 : (c == 3 ? 1 : 0));
+          const int h2 = ph0 + (rp ? -1 : 0);
+          mbar_wait(EMPTY(stage), ph ^ 1);
+          mbar_arrive_expect_tx(FULL(stage), Cfg::STAGE_BYTES);
+          tma_load_5d(sbase + Cfg::OFF_A + stage * Cfg::STAGE_BYTES, &tmap, 0, w2, n0, h2, plane, FULL(stage));
+          if (++stage == STAGES) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    mbar_wait(WBAR, 0);
+    tc_fence_after();
+    const uint64_t dA0 = desc_base(sbase + Cfg::OFF_A, Cfg::ROWB), dW0 = desc_base(sbase + Cfg::OFF_W, Cfg::ROWB);
+    constexpr uint32_t IDESC = idesc_bf16(128, COUT);
+    int stage = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      mbar_wait(TEMPTY(acc), aph ^ 1);
+      tc_fence_after();
+      uint32_t started = 0;      // accumulators already written in this tile (warp-uniform)
+#pragma unroll 1
+      for (int l = 0; l < 8; ++l) {
+        const int rp = l < 4 ? 1 : 0, c = l & 3;
+        mbar_wait(FULL(stage), ph);
+        tc_fence_after();
+        uint32_t touched = 0;
+        if (elect_one()) {
+          uint32_t st = started;
+#pragma unroll
+          for (int off = 0; off < 2; ++off) {
+            const int r = rp ? (off ? 2 : 0) : (off ? 3 : 1);
+#pragma unroll
+            for (int qh = 0; qh < 2; ++qh) {
+              const int kh = r - qh;
+              if (kh < 0 || kh > 2) continue;
+#pragma unroll
+              for (int qw = 0; qw < 2; ++qw) {
+                const int kw = c - qw;
+                if (kw < 0 || kw > 2) continue;
+                const int qd = qh * 2 + qw, tap = kh * 3 + kw;
+                const uint32_t d = tmem + (uint32_t)(acc * 4 * COUT + qd * COUT);
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+                  uint64_t ad = dA0 + (uint64_t)((stage * Cfg::STAGE_BYTES + off * Cfg::SHIFT_BYTES + ks * 32) >> 4);
+                  uint64_t bd = dW0 + (uint64_t)((tap * Cfg::W_TAP_BYTES + ks * 32) >> 4);
+                  tc_mma_ss(d, ad, bd, IDESC, (ks > 0 || ((st >> qd) & 1)) ? 1u : 0u);
+                }
+                st |= 1u << qd;
+              }
+            }
+          }
+          tc_commit(EMPTY(stage));
+          if (l == 7) tc_commit(TFULL(acc));
+        }
+        __syncwarp();
+        // same bookkeeping on every lane (whichever lane is elected next sees the right mask)
+        for (int off = 0; off < 2; ++off) {
+          const int r = rp ? (off ? 2 : 0) : (off ? 3 : 1);
+          for (int qh = 0; qh < 2; ++qh) {
+            const int kh = r - qh;
+            if (kh < 0 || kh > 2) continue;
+            for (int qw = 0; qw < 2; ++qw) {
+              const int kw = c - qw;
+              if (kw < 0 || kw > 2) continue;
+              touched |= 1u << (qh * 2 + qw);
+            }
+          }
+        }
+        started |= touched;
+        if (++stage == STAGES) { stage = 0; ph ^= 1; }
+      }
+      if (++acc == NACC) { acc = 0; aph ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps 2..5 =====================
+    const int q = warp & 3;
+    const int m = 32 * q + lane;
+    const int w = m % WW, n = (m / WW) % NIMG, h = m / (WW * NIMG);
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tn = tile / (tiles_w * tiles_h);
+      const int ph = th * Cfg::HH + h, pw = tw * WW + w, img = tn * NIMG + n;
+      size_t pix;
+      if (OUT_PARITY) pix = ((((size_t)((ph & 1) * 2 + (pw & 1)) * (PH >> 1) + (ph >> 1)) * B + img) * (PW >> 1) + (pw >> 1));
+      else pix = ((size_t)img * PH + ph) * PW + pw;
+      __nv_bfloat16* dst = out + pix * COUT;
+      mbar_wait(TFULL(acc), aph);
+      tc_fence_after();
+      const uint32_t ta = tmem + lane_addr + (uint32_t)(acc * 4 * COUT);
+#pragma unroll 1
+      for (int cc = 0; cc < COUT / 16; ++cc) {
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        tc_ld16_nowait(ta + cc * 16, r0); tc_ld16_nowait(ta + COUT + cc * 16, r1);
+        tc_ld16_nowait(ta + 2 * COUT + cc * 16, r2); tc_ld16_nowait(ta + 3 * COUT + cc * 16, r3);
+        tc_wait_ld();
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = fmaxf(fmaxf(__uint_as_float(r0[2 * i]), __uint_as_float(r1[2 * i])),
+                          fmaxf(__uint_as_float(r2[2 * i]), __uint_as_float(r3[2 * i])));
+          float c = fmaxf(fmaxf(__uint_as_float(r0[2 * i + 1]), __uint_as_float(r1[2 * i + 1])),
+                          fmaxf(__uint_as_float(r2[2 * i + 1]), __uint_as_float(r3[2 * i + 1])));
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(a + __ldg(bias + cc * 16 + 2 * i), 0.f),
+                                                    fmaxf(c + __ldg(bias + cc * 16 + 2 * i + 1), 0.f));
+          o[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        if (img < B) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + cc * 16);
+          d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(TEMPTY(acc));
+      if (++acc == NACC) { acc = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ------------------------------------------------------------------ FC (split-K GEMM)
+constexpr int FC_BM = 128, FC_BN = 256, FC_BK = 64, FC_STAGES = 4;
+constexpr int FC_A_BYTES = FC_BM * FC_BK * 2, FC_B_BYTES = FC_BN * FC_BK * 2;
+constexpr int FC_STAGE = FC_A_BYTES + FC_B_BYTES;
+constexpr int FC_OFF_BAR = FC_STAGES * FC_STAGE;
+constexpr int FC_SMEM = FC_OFF_BAR + 128;
+
+__global__ void __launch_bounds__(192, 1)
+fc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, float* __restrict__ partial,
+                 int M, int kblocks_per_split) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar = sbase + FC_OFF_BAR;
+  auto FULL = [&](int s) { return bar + 8u * s; };
+  auto EMPTY = [&](int s) { return bar + 8u * (FC_STAGES + s); };
+  const uint32_t TFULL = bar + 8u * (2 * FC_STAGES);
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + FC_OFF_BAR + 8 * (2 * FC_STAGES + 1));
+  if (tid == 0) {
+    for (int s = 0; s < FC_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    mbar_init(TFULL, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) tmem_alloc<256>(smem_u32(misc));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc[0];
+  const int m0 = blockIdx.x * FC_BM, split = blockIdx.y;
+  const int kb0 = split * kblocks_per_split;
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < kblocks_per_split; ++kb) {
+        mbar_wait(EMPTY(stage), ph ^ 1);
+        mbar_arrive_expect_tx(FULL(stage), FC_STAGE);
+        const uint32_t a = sbase + stage * FC_STAGE;
+        tma_load_2d(a, &tmA, (kb0 + kb) * FC_BK, m0, FULL(stage));
+        tma_load_2d(a + FC_A_BYTES, &tmW, (kb0 + kb) * FC_BK, 0, FULL(stage));
+        if (++stage == FC_STAGES) { stage = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t IDESC = idesc_bf16(128, 256);
+    const uint64_t d0 = desc_base(sbase, 128);
+    int stage = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < kblocks_per_split; ++kb) {
+      mbar_wait(FULL(stage), ph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint64_t ad = d0 + (uint64_t)((stage * FC_STAGE + ks * 32) >> 4);
+          uint64_t bd = d0 + (uint64_t)((stage * FC_STAGE + FC_A_BYTES + ks * 32) >> 4);
+          tc_mma_ss(tmem, ad, bd, IDESC, (kb | ks) ? 1u : 0u);
+        }
+        tc_commit(EMPTY(stage));
+        if (kb == kblocks_per_split - 1) tc_commit(TFULL);
+      }
+      __syncwarp();
+      if (++stage == FC_STAGES) { stage = 0; ph ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + 32 * q + lane;
+    mbar_wait(TFULL, 0);
+    tc_fence_after();
+    float* dst = partial + ((size_t)split * M + m) * FC_BN;
+#pragma unroll 1
+    for (int cc = 0; cc < FC_BN / 16; ++cc) {
+      uint32_t r[16];
+      tc_ld16_nowait(tmem + ((uint32_t)(32 * q) << 16) + cc * 16, r);
+      tc_wait_ld();
+      if (m < M) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst + cc * 16)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+__global__ void fc_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias, float* __restrict__ out,
+                                 int M, int splits) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * EMB) return;
+  float v = bias[i % EMB];
+  for (int s = 0; s < splits; ++s) v += partial[(size_t)s * M * EMB + i];
+  out[i] = fmaxf(v, 0.f);   // encoder.py:126-127
+}
+
+// ------------------------------------------------------------------ workspace
+struct Ws { __nv_bfloat16 *act1, *act2, *act3; float* partial; size_t bytes; int splits; };
+constexpr int FC_SPLITS = 16;
+Ws carve(int B, void* ws) {
+  Arena a(ws, (size_t)-1);
+  Ws w{};
+  int Bp = (B + 1) & ~1;   // conv3 tiles cover image pairs
+  w.act1 = a.take<__nv_bfloat16>((size_t)Bp * 32 * 160 * C1);
+  w.act2 = a.take<__nv_bfloat16>((size_t)Bp * 16 * 80 * C2);
+  w.act3 = a.take<__nv_bfloat16>((size_t)Bp * 8 * 40 * C3);
+  w.splits = FC_SPLITS;
+  w.partial = a.take<float>((size_t)w.splits * B * EMB);
+  w.bytes = align_up(a.off, 256);
+  return w;
+}
+
+using Cfg2 = ConvCfg<C1, C2, 16, 1, 8, 2>;
+using Cfg3 = ConvCfg<C2, C3, 8, 2, 4, 1>;
+
+}  // namespace
+
+bool cnn_bf16_supported(const i2l_cnn_desc& d) {
+  return d.img_height == IMG_H && d.img_width == IMG_W && d.channels == C0 && d.n_conv == 3 && d.filters[0] == C1 &&
+         d.filters[1] == C2 && d.filters[2] == C3 && d.kernel_size == 3 && d.pool_size == 2 && d.embedding_dim == EMB;
+}
+size_t cnn_bf16_packed_bytes(const i2l_cnn_desc&) { return sec_layout().total; }
+
+int cnn_bf16_pack(const i2l_cnn_desc&, const i2l_cnn_params& p, void* section, cudaStream_t s) {
+  Sec L = sec_layout();
+  unsigned char* sec = reinterpret_cast<unsigned char*>(section);
+  pack_conv_w_kernel<<<4, 256, 0, s>>>(p.conv_w[0], C1, C0, 1, sec + L.w1);
+  I2L_LAUNCH_OK();
+  pack_conv_w_kernel<<<cdiv(9 * C2 * C1, 256), 256, 0, s>>>(p.conv_w[1], C2, C1, 2, sec + L.w2);
+  I2L_LAUNCH_OK();
+  pack_conv_w_kernel<<<cdiv(9 * C3 * C2, 256), 256, 0, s>>>(p.conv_w[2], C3, C2, 3, sec + L.w3);
+  I2L_LAUNCH_OK();
+  I2L_CUDA_OK(cudaMemcpyAsync(sec + L.b1, p.conv_b[0], C1 * 4, cudaMemcpyDeviceToDevice, s));
+  I2L_CUDA_OK(cudaMemcpyAsync(sec + L.b2, p.conv_b[1], C2 * 4, cudaMemcpyDeviceToDevice, s));
+  I2L_CUDA_OK(cudaMemcpyAsync(sec + L.b3, p.conv_b[2], C3 * 4, cudaMemcpyDeviceToDevice, s));
+  I2L_CUDA_OK(cudaMemcpyAsync(sec + L.bfc, p.fc_b, EMB * 4, cudaMemcpyDeviceToDevice, s));
+  size_t n = (size_t)EMB * FLAT;
+  pack_fc_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p.fc_w, reinterpret_cast<__nv_bfloat16*>(sec + L.wfc));
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
+
+size_t cnn_bf16_workspace_bytes(const i2l_cnn_desc&, int batch) { return carve(batch, nullptr).bytes; }
+
+int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const float* x, int B, float* out, void* ws, size_t ws_bytes,
+                 cudaStream_t s) {
+  Ws w = carve(B, ws);
+  if (ws_bytes < w.bytes) { set_error("cnn_bf16_fwd: workspace too small (%zu < %zu)", ws_bytes, w.bytes); return I2L_ERR_WORKSPACE; }
+  Sec L = sec_layout();
+  const unsigned char* sec = reinterpret_cast<const unsigned char*>(section);
+  const int sms = num_sms();
+  const int Bp = (B + 1) & ~1;
+  if (Bp != B) {   // the odd tail image of conv3's pair tiles reads zeros
+    I2L_CUDA_OK(cudaMemsetAsync(w.act2, 0, (size_t)Bp * 16 * 80 * C2 * 2, s));
+  }
+  // ---- conv1
+  {
+    I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
+    const int n_tiles = B * 40;
+    KernelTimer kt("cnn.conv1_bf16", s);
+    conv1_kernel<<<min(n_tiles, sms * 4), C1_THREADS, C1_SMEM, s>>>(x, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1),
+                                                                  w.act1, Bp, n_tiles);
+    I2L_LAUNCH_OK();
+  }
+  // ---- conv2: input planes [4][16][Bp][80][32]
+  {
+    CUtensorMap tm;
+    uint64_t dims[5] = {C1, 80, (uint64_t)Bp, 16, 4};
+    uint64_t str[4] = {C1 * 2, 80ull * C1 * 2, (uint64_t)Bp * 80 * C1 * 2, 16ull * Bp * 80 * C1 * 2};
+    uint32_t box[5] = {C1, 16, 1, 9, 1};
+    I2L_TRY(make_tensor_map_bf16(&tm, w.act1, 5, dims, str, box, 64));
+    auto kern = conv_pool_kernel<Cfg2, C1, C2, 16, 1, 8, 2, true>;
+    I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM));
+    const int n_tiles = B * 2 * 5;
+    KernelTimer kt("cnn.conv2_bf16", s);
+    kern<<<min(n_tiles, sms), 192, Cfg2::SMEM, s>>>(tm, sec + L.w2, reinterpret_cast<const float*>(sec + L.b2), w.act2, Bp, 16, 80, n_tiles);
+    I2L_LAUNCH_OK();
+  }
+  // ---- conv3: input planes [4][8][Bp][40][64]
+  {
+    CUtensorMap tm;
+    uint64_t dims[5] = {C2, 40, (uint64_t)Bp, 8, 4};
+    uint64_t str[4] = {C2 * 2, 40ull * C2 * 2, (uint64_t)Bp * 40 * C2 * 2, 8ull * Bp * 40 * C2 * 2};
+    uint32_t box[5] = {C2, 8, 2, 9, 1};
+    I2L_TRY(make_tensor_map_bf16(&tm, w.act2, 5, dims, str, box, 128));
+    auto kern = conv_pool_kernel<Cfg3, C2, C3, 8, 2, 4, 1, false>;
+    I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM));
+    const int n_tiles = (Bp / 2) * 1 * 5;
+    KernelTimer kt("cnn.conv3_bf16", s);
+    kern<<<min(n_tiles, sms), 192, Cfg3::SMEM, s>>>(tm, sec + L.w3, reinterpret_cast<const float*>(sec + L.b3), w.act3, B, 8, 40, n_tiles);
+    I2L_LAUNCH_OK();
+  }
+  // ---- fc
+  {
+    CUtensorMap tmA, tmW;
+    uint64_t dA[2] = {FLAT, (uint64_t)B}; uint64_t sA[1] = {FLAT * 2ull}; uint32_t bA[2] = {FC_BK, FC_BM};
+    uint64_t dW[2] = {FLAT, EMB}; uint32_t bW[2] = {FC_BK, FC_BN};
+    I2L_TRY(make_tensor_map_bf16(&tmA, w.act3, 2, dA, sA, bA, 128));
+    I2L_TRY(make_tensor_map_bf16(&tmW, sec + L.wfc, 2, dW, sA, bW, 128));
+    I2L_CUDA_OK(cudaFuncSetAttribute(fc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
+    const int kbs = FLAT / FC_BK / w.splits;
+    KernelTimer kt("cnn.fc_bf16", s);
+    fc_splitk_kernel<<<dim3(cdiv(B, FC_BM), w.splits), 192, FC_SMEM, s>>>(tmA, tmW, w.partial, B, kbs);
+    I2L_LAUNCH_OK();
+    size_t n = (size_t)B * EMB;
+    fc_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w.partial, reinterpret_cast<const float*>(sec + L.bfc), out, B, w.splits);
+    I2L_LAUNCH_OK();
+  }
+  return I2L_OK;
+}
+
+}  // namespace i2l

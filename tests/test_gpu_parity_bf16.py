@@ -74,3 +74,18 @@ def test_persistent_sticky_stop_and_lengths(pkg):
     assert agree >= 0.8 * B
     if agree == B:
         assert int(s16) == int(s32)
+
+
+@pytest.mark.parametrize("B,sharp", [(2, False), (1, True), (5, True), (16, True), (33, False)])
+def test_cnn_encoder_bf16(pkg, B, sharp):
+    """tcgen05 implicit-GEMM conv stack + split-K FC vs the fp32 oracle: within 3e-2 of max|out|."""
+    cfg = H.HEADLINE
+    p = oracle.make_params(cfg, 1, sharp=sharp)
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    x = H.make_images(cfg, B)
+    ref = oracle.cnn_encoder(p, x)
+    out = m16.encoder(x.cuda())
+    torch.cuda.synchronize()
+    err = H.rel_err(out, ref)
+    print(f"bf16 encoder B={B}: rel err {err:.3e}")
+    assert out.shape == ref.shape and err < 3e-2
