@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libi2l_b200.so")
+LIB_PATH = os.environ.get("I2L_LIB", os.path.join(CSRC, "libi2l_b200.so"))
 
 MAX_CONV = 8
 MAX_LSTM = 8

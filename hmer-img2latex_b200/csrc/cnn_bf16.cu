@@ -15,6 +15,7 @@
 //          permuted to NHWC order at pack time), fp32 partials + bias/ReLU reduction.
 #include "encoder_bf16.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace i2l {
 namespace {
@@ -71,129 +72,190 @@ __global__ void pack_fc_w_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------ conv1
-// pooled tile 8 x 16 of one image = 16 x 32 conv pixels; input patch 18 x 34 x 3 (fp32, zero padded)
-constexpr int C1_THREADS = 256;
-constexpr int PATCH_W = 36;   // padded row pitch (floats)
-constexpr int C1_OFF_A = 0;                       // 4 quadrant tiles [128][32] bf16 SW64 = 4 x 8 KB
-constexpr int C1_OFF_W = 4 * 8192;                // 2 KB
-constexpr int C1_OFF_PATCH = C1_OFF_W + 2048;     // 3 x 18 x 36 floats
-constexpr int C1_OFF_BAR = C1_OFF_PATCH + 3 * 18 * PATCH_W * 4;
-constexpr int C1_SMEM = C1_OFF_BAR + 32;
+// Persistent, warp-specialised: pooled tile 8 x 16 of one image = 16 x 32 conv pixels.
+//   warp 0      TMA producer: the zero-padded fp32 input patch (3 x 18 x 36) of the tile is one
+//               4-D box load straight from the NCHW image (out-of-image = conv padding = OOB fill)
+//   warps 6-13  im2col builders: thread (pooled pixel, qh) reads 3 ci x 3 rows x 4 floats as
+//               LDS.64 and emits the two K=(ci,kh,kw) rows (qw = 0,1) as packed bf16 straight into
+//               TENSOR MEMORY (tcgen05.st): the im2col matrix is the TMEM A operand of the MMA, so
+//               there is no shared-memory round trip and no generic->async proxy fence per tile
+//   warp 1      MMA issuer: 4 quadrants x 2 k-steps of 128x32x16 (A from TMEM, W from smem)
+//   warps 2-5   epilogue: max over the 2x2 window, + bias, ReLU, bf16, parity-plane store
+constexpr int C1_THREADS = 448;
+constexpr int C1_PS = 8;                               // patch ring depth
+// TMA needs a 16-byte aligned start in the innermost (W) dimension: the box starts at x = 32*tw - 4
+// (3 columns left of the first needed one, 2*pw0 - 1) and is 40 floats wide
+constexpr int PATCH_W = 40, PATCH_H = 18, PATCH_X0 = 3;
+constexpr int C1_PATCH_BYTES = 3 * PATCH_H * PATCH_W * 4;   // 7776
+constexpr int C1_PATCH_STRIDE = (C1_PATCH_BYTES + 1023) / 1024 * 1024;
+constexpr int C1_OFF_W = 0;                            // [32 co][32 k] bf16 SW64, 2 KB
+constexpr int C1_TC_ACC = 0, C1_TC_A = 256;            // TMEM columns: 2 x (4 x 32) accumulators, 2 x (4 x 16) im2col A tiles
+constexpr int C1_OFF_PATCH = C1_OFF_W + 2048;
+constexpr int C1_OFF_BAR = C1_OFF_PATCH + C1_PS * C1_PATCH_STRIDE;
+constexpr int C1_SMEM = C1_OFF_BAR + 256;
 
-__global__ void __launch_bounds__(C1_THREADS, 4)
-conv1_kernel(const float* __restrict__ x, const unsigned char* __restrict__ w1img, const float* __restrict__ bias1,
-             __nv_bfloat16* __restrict__ act1, int B, int n_tiles) {
+__global__ void __launch_bounds__(C1_THREADS, 1)
+conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __restrict__ w1img,
+             const float* __restrict__ bias1, __nv_bfloat16* __restrict__ act1, int B, int n_tiles, int dbg) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* patch = reinterpret_cast<float*>(smem + C1_OFF_PATCH);
-  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + C1_OFF_BAR + 16);
   const uint32_t bar = sbase + C1_OFF_BAR;
-  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-  if (warp == 0) tmem_alloc<128>(sbase + C1_OFF_BAR + 16);
+  auto PFULL = [&](int s) { return bar + 8u * s; };
+  auto PEMPTY = [&](int s) { return bar + 8u * (C1_PS + s); };
+  auto AFULL = [&](int g) { return bar + 8u * (2 * C1_PS + g); };
+  auto AEMPTY = [&](int g) { return bar + 8u * (2 * C1_PS + 2 + g); };
+  auto TFULL = [&](int g) { return bar + 8u * (2 * C1_PS + 4 + g); };
+  auto TEMPTY = [&](int g) { return bar + 8u * (2 * C1_PS + 6 + g); };
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + C1_OFF_BAR + 8 * (2 * C1_PS + 8));
+  if ((sbase & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int i = 0; i < C1_PS; ++i) { mbar_init(PFULL(i), 1); mbar_init(PEMPTY(i), 8); }
+    for (int g = 0; g < 2; ++g) { mbar_init(AFULL(g), 8); mbar_init(AEMPTY(g), 1); mbar_init(TFULL(g), 1); mbar_init(TEMPTY(g), 4); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmx);
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(misc));
   for (int i = tid; i < 2048 / 16; i += C1_THREADS) reinterpret_cast<uint4*>(smem + C1_OFF_W)[i] = reinterpret_cast<const uint4*>(w1img)[i];
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = misc[0];
-  const uint64_t dA = desc_base(sbase + C1_OFF_A, 64), dW = desc_base(sbase + C1_OFF_W, 64);
-  constexpr uint32_t IDESC = idesc_bf16(128, 32);
-  const int q = warp & 3, chalf = warp >> 2;
-  const float4* b4 = reinterpret_cast<const float4*>(bias1 + chalf * 16);
-  float bias[16];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { float4 v = b4[i]; bias[4 * i] = v.x; bias[4 * i + 1] = v.y; bias[4 * i + 2] = v.z; bias[4 * i + 3] = v.w; }
-  uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int tw = tile % 10, th = (tile / 10) % 4, b = tile / 40;
-    const int ph0 = th * 8, pw0 = tw * 16;
-    // ---- input patch -> smem (rows 2*ph0-1 .. +17, cols 2*pw0-1 .. +33), zero outside the image
-    const float* xb = x + (size_t)b * C0 * IMG_H * IMG_W;
-    for (int i = tid; i < 3 * 18 * 34; i += C1_THREADS) {
-      int j = i % 34, r = (i / 34) % 18, ci = i / (34 * 18);
-      int gy = 2 * ph0 - 1 + r, gx = 2 * pw0 - 1 + j;
-      float v = 0.f;
-      if (gy >= 0 && gy < IMG_H && gx >= 0 && gx < IMG_W) v = __ldg(xb + ((size_t)ci * IMG_H + gy) * IMG_W + gx);
-      patch[(ci * 18 + r) * PATCH_W + j] = v;
-    }
-    __syncthreads();
-    // ---- im2col: 4 quadrants x 128 pooled pixels, K = (ci,kh,kw) -> 32 bf16 per row
-#pragma unroll 1
-    for (int rr = 0; rr < 2; ++rr) {
-      const int row = tid + rr * C1_THREADS;        // 0..511 = quadrant*128 + m
-      const int qd = row >> 7, m = row & 127;
-      const int qh = qd >> 1, qw = qd & 1;
-      const int pl = m >> 4, pwl = m & 15;
-      const float* p0 = patch + (2 * pl + qh) * PATCH_W + 2 * pwl + qw;
-      uint32_t pk[16];
-#pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2) {
-        float v[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int k = 2 * k2 + e;
-          if (k < 27) {
-            const int ci = k / 9, kh = (k % 9) / 3, kw = k % 3;
-            v[e] = p0[(ci * 18 + kh) * PATCH_W + kw];
-          } else {
-            v[e] = 0.f;
-          }
-        }
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
-        pk[k2] = *reinterpret_cast<uint32_t*>(&h2);
+  // contiguous tile range per CTA: neighbouring tiles share halo rows and DRAM pages
+  const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile_beg = blockIdx.x * per, tile_end = min(n_tiles, tile_beg + per);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+        const int tw = tile % 10, th = (tile / 10) % 4, b = tile / 40;
+        const int s = it % C1_PS;
+        mbar_wait(PEMPTY(s), ((it / C1_PS) & 1) ^ 1);
+        if (dbg & 1) { mbar_arrive(PFULL(s)); continue; }
+        mbar_arrive_expect_tx(PFULL(s), C1_PATCH_BYTES);
+        tma_load_4d(sbase + C1_OFF_PATCH + s * C1_PATCH_STRIDE, &tmx, 32 * tw - 1 - PATCH_X0, 16 * th - 1, 0, b, PFULL(s));
       }
-      unsigned char* dst = smem + C1_OFF_A + qd * 8192;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
-        *reinterpret_cast<uint4*>(dst + swz_off(m, ch, 64)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
     }
-    fence_proxy_async();
-    __syncthreads();
-    // ---- 4 x (128 x 32 x 32) MMAs
-    if (warp == 0) {
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint64_t dW = desc_base(sbase + C1_OFF_W, 64);
+    constexpr uint32_t IDESC = idesc_bf16(128, 32);
+    int it = 0;
+    for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+      const int g = it & 1; const uint32_t par = (it >> 1) & 1;
+      mbar_wait(TEMPTY(g), par ^ 1);
+      mbar_wait(AFULL(g), par);
       tc_fence_after();
       if (elect_one()) {
+        if (!(dbg & 2))
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd)
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks)
-            tc_mma_ss(tmem + qd * 32, dA + (uint64_t)((qd * 8192 + ks * 32) >> 4), dW + (uint64_t)((ks * 32) >> 4), IDESC, ks);
-        tc_commit(bar);
+            tc_mma_ts(tmem + C1_TC_ACC + g * 128 + qd * 32, tmem + C1_TC_A + g * 64 + qd * 16 + ks * 8,
+                      dW + (uint64_t)((ks * 32) >> 4), IDESC, ks);
+        tc_commit(AEMPTY(g));
+        tc_commit(TFULL(g));
       }
       __syncwarp();
     }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ---- epilogue: max over the 2x2 window, + bias, ReLU, bf16, parity-plane store
-    {
-      uint32_t r0[16], r1[16], r2[16], r3[16];
-      const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + chalf * 16;
-      tc_ld16_nowait(ta, r0); tc_ld16_nowait(ta + 32, r1); tc_ld16_nowait(ta + 64, r2); tc_ld16_nowait(ta + 96, r3);
-      tc_wait_ld();
-      const int m = 32 * q + lane;
-      const int ph = ph0 + (m >> 4), pw = pw0 + (m & 15);
-      uint32_t o[8];
+  } else if (warp < 6) {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int m = 32 * q + lane;
+    float bias[32];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float a = fmaxf(fmaxf(__uint_as_float(r0[2 * i]), __uint_as_float(r1[2 * i])),
-                        fmaxf(__uint_as_float(r2[2 * i]), __uint_as_float(r3[2 * i])));
-        float c = fmaxf(fmaxf(__uint_as_float(r0[2 * i + 1]), __uint_as_float(r1[2 * i + 1])),
-                        fmaxf(__uint_as_float(r2[2 * i + 1]), __uint_as_float(r3[2 * i + 1])));
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(a + bias[2 * i], 0.f), fmaxf(c + bias[2 * i + 1], 0.f));
-        o[i] = *reinterpret_cast<uint32_t*>(&h2);
-      }
+    for (int i = 0; i < 8; ++i) { float4 v = reinterpret_cast<const float4*>(bias1)[i]; bias[4 * i] = v.x; bias[4 * i + 1] = v.y; bias[4 * i + 2] = v.z; bias[4 * i + 3] = v.w; }
+    int it = 0;
+    for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+      const int tw = tile % 10, th = (tile / 10) % 4, b = tile / 40;
+      const int g = it & 1; const uint32_t par = (it >> 1) & 1;
+      const int ph = th * 8 + (m >> 4), pw = tw * 16 + (m & 15);
       // act1 layout [plane = (ph&1)*2 + (pw&1)][16][B][80][32]
-      size_t pix = ((((size_t)((ph & 1) * 2 + (pw & 1)) * 16 + (ph >> 1)) * B + b) * 80 + (pw >> 1));
-      uint4* dst = reinterpret_cast<uint4*>(act1 + pix * C1 + chalf * 16);
-      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      const size_t pix = ((((size_t)((ph & 1) * 2 + (pw & 1)) * 16 + (ph >> 1)) * B + b) * 80 + (pw >> 1));
+      uint4* dst = reinterpret_cast<uint4*>(act1 + pix * C1);
+      mbar_wait(TFULL(g), par);
+      tc_fence_after();
+      const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + g * 128;
+      if (!(dbg & 4))
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        tc_ld16_nowait(ta + half * 16, r0); tc_ld16_nowait(ta + 32 + half * 16, r1);
+        tc_ld16_nowait(ta + 64 + half * 16, r2); tc_ld16_nowait(ta + 96 + half * 16, r3);
+        tc_wait_ld();
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = fmaxf(fmaxf(__uint_as_float(r0[2 * i]), __uint_as_float(r1[2 * i])),
+                          fmaxf(__uint_as_float(r2[2 * i]), __uint_as_float(r3[2 * i])));
+          float c = fmaxf(fmaxf(__uint_as_float(r0[2 * i + 1]), __uint_as_float(r1[2 * i + 1])),
+                          fmaxf(__uint_as_float(r2[2 * i + 1]), __uint_as_float(r3[2 * i + 1])));
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(a + bias[half * 16 + 2 * i], 0.f), fmaxf(c + bias[half * 16 + 2 * i + 1], 0.f));
+          o[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        dst[half * 2] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[half * 2 + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(TEMPTY(g));
     }
-    tc_fence_before();
-    __syncthreads();
+  } else {
+    // ===================== im2col builders (warps 6..13) =====================
+    // TMEM lanes are owned per warp quadrant: warp w writes rows 32*(w%4) .. +31; warps 6-9 build qh = 0, 10-13 qh = 1
+    const int q = warp & 3, qh = (warp - 6) >> 2;
+    const int m = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const int pl = m >> 4, pwl = m & 15;
+    int it = 0;
+    for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+      const int s = it % C1_PS;
+      const int g = it & 1; const uint32_t par = (it >> 1) & 1;
+      mbar_wait(PFULL(s), (it / C1_PS) & 1);
+      const float* p0 = reinterpret_cast<const float*>(smem + C1_OFF_PATCH + s * C1_PATCH_STRIDE) + (2 * pl + qh) * PATCH_W + 2 * pwl;
+      float f[3][3][4];
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          // needed columns 2*pwl + 3 .. + 6 of the patch row: three aligned LDS.64 (cols 2*pwl + 2 .. + 7)
+          const float2* pp = reinterpret_cast<const float2*>(p0 + (ci * PATCH_H + kh) * PATCH_W + 2);
+          float2 a = pp[0], c = pp[1], e = pp[2];
+          f[ci][kh][0] = a.y; f[ci][kh][1] = c.x; f[ci][kh][2] = c.y; f[ci][kh][3] = e.x;
+        }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(PEMPTY(s));       // patch values are in registers
+      mbar_wait(AEMPTY(g), par ^ 1);
+#pragma unroll
+      for (int qw = 0; qw < 2; ++qw) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+          float v[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k = 2 * k2 + e;
+            v[e] = k < 27 ? f[k / 9][(k % 9) / 3][qw + k % 3] : 0.f;
+          }
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
+          pk[k2] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        tc_st16(tmem + lane_addr + C1_TC_A + g * 64 + (qh * 2 + qw) * 16, pk);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(AFULL(g));
+    }
   }
-  if (warp == 0) tmem_dealloc<128>(tmem);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------ conv2 / conv3
@@ -527,6 +589,15 @@ int cnn_bf16_pack(const i2l_cnn_desc&, const i2l_cnn_params& p, void* section, c
 
 size_t cnn_bf16_workspace_bytes(const i2l_cnn_desc&, int batch) { return carve(batch, nullptr).bytes; }
 
+// I2L_DEBUG_SYNC=1: synchronise after every encoder kernel so that a device fault is attributed
+static int dbg_sync(const char* what, cudaStream_t s) {
+  static const bool on = getenv("I2L_DEBUG_SYNC") != nullptr;
+  if (!on) return I2L_OK;
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return I2L_ERR_CUDA; }
+  return I2L_OK;
+}
+
 int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const float* x, int B, float* out, void* ws, size_t ws_bytes,
                  cudaStream_t s) {
   Ws w = carve(B, ws);
@@ -538,22 +609,28 @@ int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const float* x, int B
   if (Bp != B) {   // the odd tail image of conv3's pair tiles reads zeros
     I2L_CUDA_OK(cudaMemsetAsync(w.act2, 0, (size_t)Bp * 16 * 80 * C2 * 2, s));
   }
-  // ---- conv1
+  // ---- conv1: input x (B,3,64,320) fp32 NCHW read through a 4-D tensor map
   {
+    CUtensorMap tm;
+    uint64_t dims[4] = {IMG_W, IMG_H, C0, (uint64_t)B};
+    uint64_t str[3] = {IMG_W * 4ull, (uint64_t)IMG_W * IMG_H * 4, (uint64_t)IMG_W * IMG_H * C0 * 4};
+    uint32_t box[4] = {PATCH_W, PATCH_H, C0, 1};
+    I2L_TRY(make_tensor_map(&tm, x, 4, dims, str, box, 0, 4));
     I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
     const int n_tiles = B * 40;
     KernelTimer kt("cnn.conv1_bf16", s);
-    conv1_kernel<<<min(n_tiles, sms * 4), C1_THREADS, C1_SMEM, s>>>(x, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1),
-                                                                  w.act1, Bp, n_tiles);
+    conv1_kernel<<<min(n_tiles, sms), C1_THREADS, C1_SMEM, s>>>(tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1),
+                                                              w.act1, Bp, n_tiles, getenv("I2L_CONV1_DBG") ? atoi(getenv("I2L_CONV1_DBG")) : 0);
     I2L_LAUNCH_OK();
   }
+  I2L_TRY(dbg_sync("conv1", s));
   // ---- conv2: input planes [4][16][Bp][80][32]
   {
     CUtensorMap tm;
     uint64_t dims[5] = {C1, 80, (uint64_t)Bp, 16, 4};
     uint64_t str[4] = {C1 * 2, 80ull * C1 * 2, (uint64_t)Bp * 80 * C1 * 2, 16ull * Bp * 80 * C1 * 2};
     uint32_t box[5] = {C1, 16, 1, 9, 1};
-    I2L_TRY(make_tensor_map_bf16(&tm, w.act1, 5, dims, str, box, 64));
+    I2L_TRY(make_tensor_map(&tm, w.act1, 5, dims, str, box, 64, 2));
     auto kern = conv_pool_kernel<Cfg2, C1, C2, 16, 1, 8, 2, true>;
     I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM));
     const int n_tiles = B * 2 * 5;
@@ -561,13 +638,14 @@ int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const float* x, int B
     kern<<<min(n_tiles, sms), 192, Cfg2::SMEM, s>>>(tm, sec + L.w2, reinterpret_cast<const float*>(sec + L.b2), w.act2, Bp, 16, 80, n_tiles);
     I2L_LAUNCH_OK();
   }
+  I2L_TRY(dbg_sync("conv2", s));
   // ---- conv3: input planes [4][8][Bp][40][64]
   {
     CUtensorMap tm;
     uint64_t dims[5] = {C2, 40, (uint64_t)Bp, 8, 4};
     uint64_t str[4] = {C2 * 2, 40ull * C2 * 2, (uint64_t)Bp * 40 * C2 * 2, 8ull * Bp * 40 * C2 * 2};
     uint32_t box[5] = {C2, 8, 2, 9, 1};
-    I2L_TRY(make_tensor_map_bf16(&tm, w.act2, 5, dims, str, box, 128));
+    I2L_TRY(make_tensor_map(&tm, w.act2, 5, dims, str, box, 128, 2));
     auto kern = conv_pool_kernel<Cfg3, C2, C3, 8, 2, 4, 1, false>;
     I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM));
     const int n_tiles = (Bp / 2) * 1 * 5;
@@ -575,13 +653,14 @@ int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const float* x, int B
     kern<<<min(n_tiles, sms), 192, Cfg3::SMEM, s>>>(tm, sec + L.w3, reinterpret_cast<const float*>(sec + L.b3), w.act3, B, 8, 40, n_tiles);
     I2L_LAUNCH_OK();
   }
+  I2L_TRY(dbg_sync("conv3", s));
   // ---- fc
   {
     CUtensorMap tmA, tmW;
     uint64_t dA[2] = {FLAT, (uint64_t)B}; uint64_t sA[1] = {FLAT * 2ull}; uint32_t bA[2] = {FC_BK, FC_BM};
     uint64_t dW[2] = {FLAT, EMB}; uint32_t bW[2] = {FC_BK, FC_BN};
-    I2L_TRY(make_tensor_map_bf16(&tmA, w.act3, 2, dA, sA, bA, 128));
-    I2L_TRY(make_tensor_map_bf16(&tmW, sec + L.wfc, 2, dW, sA, bW, 128));
+    I2L_TRY(make_tensor_map(&tmA, w.act3, 2, dA, sA, bA, 128, 2));
+    I2L_TRY(make_tensor_map(&tmW, sec + L.wfc, 2, dW, sA, bW, 128, 2));
     I2L_CUDA_OK(cudaFuncSetAttribute(fc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
     const int kbs = FLAT / FC_BK / w.splits;
     KernelTimer kt("cnn.fc_bf16", s);
