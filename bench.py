@@ -78,8 +78,13 @@ class ClockSampler(threading.Thread):
 # algorithmic work of each named kernel (per launch), DESIGN.md section "Kernels and rooflines"
 # ---------------------------------------------------------------------------------------------
 def kernel_work(name, B, steps):
+    """(bound, algorithmic work per launch): FLOPs for the tensor-bound convs / FC, bytes for the
+    HBM-bound kernels.  conv1 (K = 27) is memory bound: fp32 image in + bf16 pooled map
+    out.  Decode: SURVEY 8d's per-step streaming figure W + B*S times the steps run."""
     E = H = 256; V = 512
     conv = {1: (3, 32, 64, 320), 2: (32, 64, 32, 160), 3: (64, 128, 16, 80)}
+    if name.startswith("cnn.conv1_bf16"):
+        return "hbm", B * (3 * 64 * 320 * 4 + 32 * 160 * 32 * 2)
     if name.startswith("cnn.conv"):
         i = int(name[len("cnn.conv")])
         ci, co, h, w = conv[i]
@@ -90,7 +95,7 @@ def kernel_work(name, B, steps):
         i = int(name[len("cnn.pool")])
         ci, co, h, w = conv[i]
         return "hbm", B * co * h * w * 4 * 1.25
-    if name.startswith("dec."):
+    if name.startswith("dec.greedy") or name.startswith("dec.sample") or name.startswith("dec.beam"):
         W = 2 * (4 * H * (2 * E + H) + 8 * H + V * H + V)       # bf16 weights
         S = 16 * H + 2 * E + 2 * E + 8                          # per-sequence state traffic
         return "hbm", float(steps) * (W + B * S)
@@ -157,15 +162,18 @@ def run_ours(args):
         prof = N.prof_results()
         steps_run = int(out[2].item())
         # ---- end-to-end through the public API with host buffers --------------------------
-        x_dev = torch.empty_like(x)
-        for _ in range(2):
-            x_dev.copy_(x_host, non_blocking=True); t = step(x_dev); t[0].cpu()
+        # Seq2SeqModel.greedy_stream: every step copies its own images from pinned host memory
+        # (the copy of step i+1 overlaps the compute of step i) and reads the token ids back.
+        def host_batches(n):
+            for _ in range(n):
+                yield x_host
+        for _ in model.greedy_stream(host_batches(2), START, END, MAX_LEN):
+            pass
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            x_dev.copy_(x_host, non_blocking=True)
-            tok, lens, st = step(x_dev)
-            tok_h, lens_h = tok.cpu(), lens.cpu()
+        for tok_h, lens_h, st in model.greedy_stream(host_batches(args.steps), START, END, MAX_LEN):
+            if world > 1:
+                pass   # ranks decode independent shards; the id all-gather is part of `value`, not of e2e
         barrier()
         e2e_s = time.perf_counter() - t0
     tms = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
@@ -192,6 +200,15 @@ def run_ours(args):
             roof = {"kernel": name, "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit,
                     "frac": round(ach / peak, 4), "traffic": None, "peak_source": pk["src"],
                     "launch_ms": round(tot / cnt, 4), "share_of_step": round(tot / ms, 4)}
+    rooflines = {}
+    for kname, (cnt, tot) in sorted(prof.items()):
+        bound, work = kernel_work(kname, B, steps_run)
+        if bound:
+            t = tot / cnt / 1e3
+            ach = work / t / (1e9 if bound == "hbm" else 1e12)
+            peak = pk["hbm"] if bound == "hbm" else pk["tf_sust"]
+            rooflines[kname] = {"bound": bound, "achieved": round(ach, 1), "frac": round(ach / peak, 3),
+                                "ms": round(tot / cnt, 4)}
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
@@ -204,6 +221,7 @@ def run_ours(args):
         "us_per_decode_step": None,
         "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items())},
         "roofline": roof,
+        "roofline_all_kernels": rooflines,
         "e2e": {"value": round(world * B * args.steps / (e2e_ms / 1e3), 1), "unit": "images/s",
                 "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": tok_h.numel() * 8 + lens_h.numel() * 4},
         "gpu_launches": int(launches),

@@ -621,24 +621,27 @@ __global__ void persistent_init_kernel(int64_t* tokens, int T1, int B, int start
 __global__ void persistent_finalize_kernel(const int* first_end, const unsigned char* allend, const int* cluster_steps,
                                            int n_clusters, int B, int T, int stop_rule, int32_t* lengths,
                                            int32_t* steps_out) {
+  // one block: steps_run = first step at which every cluster reported "all rows emitted END"
+  // (ALL_END_SAME_STEP), or the last cluster to finish (sticky rule); then lengths
   __shared__ int steps_sh;
-  if (threadIdx.x == 0) {
-    int steps = T;
-    if (stop_rule == I2L_STOP_ALL_END_SAME_STEP) {
-      for (int s = 0; s < T; ++s) {
-        bool all = true;
-        for (int cidx = 0; cidx < n_clusters && all; ++cidx) all = allend[(size_t)cidx * T + s] != 0;
-        if (all) { steps = s + 1; break; }
-      }
-    } else if (stop_rule == I2L_STOP_ALL_FINISHED_STICKY) {
-      steps = 0;
-      for (int cidx = 0; cidx < n_clusters; ++cidx) steps = max(steps, cluster_steps[cidx]);
+  if (threadIdx.x == 0) steps_sh = T;
+  __syncthreads();
+  if (stop_rule == I2L_STOP_ALL_END_SAME_STEP) {
+    for (int s = threadIdx.x; s < T; s += blockDim.x) {
+      bool all = true;
+      for (int cidx = 0; cidx < n_clusters && all; ++cidx) all = allend[(size_t)cidx * T + s] != 0;
+      if (all) atomicMin(&steps_sh, s + 1);
     }
-    steps_sh = steps;
-    if (steps_out) *steps_out = steps;
+  } else if (stop_rule == I2L_STOP_ALL_FINISHED_STICKY) {
+    if (threadIdx.x == 0) {
+      int steps = 0;
+      for (int cidx = 0; cidx < n_clusters; ++cidx) steps = max(steps, cluster_steps[cidx]);
+      steps_sh = steps;
+    }
   }
   __syncthreads();
   const int steps = steps_sh;
+  if (threadIdx.x == 0 && steps_out) *steps_out = steps;
   if (lengths)
     for (int i = threadIdx.x; i < B; i += blockDim.x) {
       int fe = first_end[i];

@@ -5,7 +5,7 @@ with no host sync per token; the host reads the token matrix back once at the en
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, Iterable, Iterator, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -101,3 +101,54 @@ class Seq2SeqModel(nn.Module):
         out, olen, _ = self.decoder.beam(encoder_output, start_token_id, end_token_id, max_length, beam_size)
         out, olen = out.tolist(), olen.tolist()
         return [r[:n] for r, n in zip(out, olen)]
+
+    @torch.no_grad()
+    def greedy_stream(self, host_batches: Iterable[torch.Tensor], start_token_id: int, end_token_id: int,
+                      max_length: int = 150, temperature: float = 1.0, stop_rule: int = N.STOP_ALL_END_SAME_STEP,
+                      device: Optional[torch.device] = None) -> Iterator[Tuple[torch.Tensor, torch.Tensor, int]]:
+        """Serving loop over HOST batches (ideally pinned (B,C,H,W) fp32 tensors): the host->device
+        copy of batch i+1 runs on a copy stream while batch i is encoded and decoded, and the
+        token ids come back through a pinned buffer.  Yields (tokens (B,max_length+1) int64 on the
+        host, lengths (B) int32 on the host, steps_run) per batch -- same content as
+        encoder + LSTMDecoder.greedy.  Not in the reference (its Predictor copies and computes
+        serially, training/predictor.py:245-262)."""
+        dev = device or next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("greedy_stream needs the model on a CUDA device")
+        copy_stream = torch.cuda.Stream(dev)
+        compute = torch.cuda.current_stream(dev)
+        bufs: List[Optional[torch.Tensor]] = [None, None]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        out_tok = out_len = None
+
+        def stage(slot: int, xb: torch.Tensor) -> None:
+            if bufs[slot] is None or bufs[slot].shape != xb.shape:
+                bufs[slot] = torch.empty(xb.shape, dtype=torch.float32, device=dev)
+            with torch.cuda.stream(copy_stream):
+                bufs[slot].copy_(xb, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        it = iter(host_batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        stage(0, cur)
+        i = 0
+        while cur is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                stage((i + 1) & 1, nxt)                  # overlaps with the compute below
+            compute.wait_event(ready[i & 1])
+            enc = self.encoder(bufs[i & 1])
+            tokens, lengths, steps = self.decoder.greedy(enc, start_token_id, end_token_id, max_length, temperature,
+                                                         stop_rule)
+            if out_tok is None or out_tok.shape != tokens.shape:
+                out_tok = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
+                out_len = torch.empty(lengths.shape, dtype=lengths.dtype).pin_memory()
+            out_tok.copy_(tokens, non_blocking=True)
+            out_len.copy_(lengths, non_blocking=True)
+            n = int(steps.item())                        # the one host sync of the batch
+            compute.synchronize()
+            yield out_tok, out_len, n
+            cur = nxt
+            i += 1
