@@ -83,6 +83,8 @@ def kernel_work(name, B, steps):
     out.  Decode: SURVEY 8d's per-step streaming figure W + B*S times the steps run."""
     E = H = 256; V = 512
     conv = {1: (3, 32, 64, 320), 2: (32, 64, 32, 160), 3: (64, 128, 16, 80)}
+    if name.startswith("cnn.conv1_bf16in"):
+        return "hbm", B * (3 * 64 * 320 * 2 + 32 * 160 * 32 * 2)
     if name.startswith("cnn.conv1_bf16"):
         return "hbm", B * (3 * 64 * 320 * 4 + 32 * 160 * 32 * 2)
     if name.startswith("cnn.conv"):
@@ -125,8 +127,11 @@ def run_ours(args):
     model = model.to(dev).eval()
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
-    x_host = torch.randn(B, 3, 64, 320, generator=g).pin_memory()
-    x = x_host.to(dev)
+    in_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[args.input_dtype]
+    # two different batches, used alternately: 2 x B x 3x64x320 exceeds the 126 MB L2 in either dtype
+    x_master = [torch.randn(B, 3, 64, 320, generator=g) for _ in range(2)]
+    x_host = [xm.to(in_dtype).pin_memory() for xm in x_master]
+    x_dev = [xh.to(dev) for xh in x_host]
     lib = N.lib()
 
     def step(inp):
@@ -141,9 +146,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def e2e_run(hosts, n):
+        """n batches through Seq2SeqModel.greedy_stream from pinned HOST buffers; returns seconds."""
+        def host_batches(k):
+            for i in range(k):
+                yield hosts[i & 1]
+        for _ in model.greedy_stream(host_batches(2), START, END, MAX_LEN):
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        last = None
+        for last in model.greedy_stream(host_batches(n), START, END, MAX_LEN):
+            pass   # ranks decode independent shards; the id all-gather is part of `value`, not of e2e
+        barrier()
+        return time.perf_counter() - t0, last
+
     with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
-            step(x)
+        for i in range(max(args.warmup, 3)):
+            step(x_dev[i & 1])
         barrier()
         # ---- device-resident timed region ------------------------------------------------
         sampler = ClockSampler(local); sampler.start()
@@ -151,35 +171,58 @@ def run_ours(args):
         l0 = lib.i2l_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
-            out = step(x)
+        for i in range(args.steps):
+            out = step(x_dev[i & 1])
         e1.record()
         barrier()
         launches = lib.i2l_launch_count() - l0
         lib.i2l_prof_enable(0)
         ms = e0.elapsed_time(e1)
-        sampler.stop_flag.set(); sampler.join()
         prof = N.prof_results()
         steps_run = int(out[2].item())
         # ---- end-to-end through the public API with host buffers --------------------------
         # Seq2SeqModel.greedy_stream: every step copies its own images from pinned host memory
         # (the copy of step i+1 overlaps the compute of step i) and reads the token ids back.
-        def host_batches(n):
-            for _ in range(n):
-                yield x_host
-        for _ in model.greedy_stream(host_batches(2), START, END, MAX_LEN):
-            pass
-        barrier()
-        t0 = time.perf_counter()
-        for tok_h, lens_h, st in model.greedy_stream(host_batches(args.steps), START, END, MAX_LEN):
-            if world > 1:
-                pass   # ranks decode independent shards; the id all-gather is part of `value`, not of e2e
-        barrier()
-        e2e_s = time.perf_counter() - t0
-    tms = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+        e2e_s, (tok_h, lens_h, _) = e2e_run(x_host, args.steps)
+        sampler.stop_flag.set(); sampler.join()
+        # the same call with the other host element types (reported next to the headline e2e)
+        e2e_other = {}
+        if world == 1 and not args.no_extras:
+            for nm, mk in (("fp32", lambda xm: xm.float()), ("bf16", lambda xm: xm.bfloat16()),
+                           ("uint8", lambda xm: ((xm.clamp(-1, 1) + 1) * 127.5).round().to(torch.uint8))):
+                if nm == args.input_dtype:
+                    continue
+                hosts = [mk(xm).pin_memory() for xm in x_master]
+                sec, _ = e2e_run(hosts, args.steps)
+                e2e_other[nm] = {"value": round(B * args.steps / sec, 1), "unit": "images/s",
+                                 "h2d_bytes_per_step": hosts[0].numel() * hosts[0].element_size()}
+                del hosts
+        # ---- BASELINE configs[2]: beam search, beam 5, batch 512 per GPU --------------------
+        beam = None
+        if not args.no_extras:
+            Bb, K = args.beam_batch, 5
+            encb = model.encoder(x_dev[0][:Bb])
+            for _ in range(2):
+                model.decoder.beam(encb, START, END, MAX_LEN, K)
+            barrier()
+            lib.i2l_prof_reset(); lib.i2l_prof_enable(1)
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nb = max(2, min(args.steps, 5))
+            b0.record()
+            for i in range(nb):
+                encb = model.encoder(x_dev[i & 1][:Bb])
+                model.decoder.beam(encb, START, END, MAX_LEN, K)
+            b1.record()
+            barrier()
+            lib.i2l_prof_enable(0)
+            bms = b0.elapsed_time(b1) / nb
+            bprof = N.prof_results()
+            bdec = sum(v[1] for k, v in bprof.items() if k.startswith("dec.")) / nb
+            beam = [bms, bdec, Bb, K, {k: round(v[1] / nb, 4) for k, v in sorted(bprof.items())}]
+    tms = torch.tensor([ms, e2e_s * 1e3, beam[0] if beam else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(tms[0]), float(tms[1])
+    ms, e2e_ms, beam_ms = float(tms[0]), float(tms[1]), float(tms[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -213,20 +256,37 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: CNN-LSTM greedy decode, batch %d per GPU, 3x64x320 fp32 images, "
-                               "max_len 150, V=512, E=H=256, L=1, random init" % B,
+        "config": {"workload": "BASELINE configs[1]: CNN-LSTM greedy decode, batch %d per GPU, 3x64x320 %s images, "
+                               "max_len 150, V=512, E=H=256, L=1, random init" % (B, args.input_dtype),
                    "global_batch": B * world, "parallelism": "dp%d (batch-sharded, token all-gather)" % world,
-                   "l2_policy": "inputs (%.0f MB of images per step) exceed the 126 MB L2" % (x.numel() * 4 / 1e6),
-                   "decode_steps_run": steps_run},
+                   "l2_policy": "two input batches used alternately (2 x %.0f MB of images) exceed the 126 MB L2; "
+                                "the bf16 activations written per step (587 MB) flush it as well"
+                                % (x_dev[0].numel() * x_dev[0].element_size() / 1e6),
+                   "decode_steps_run": steps_run, "host_input_dtype": args.input_dtype},
         "us_per_decode_step": None,
         "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items())},
         "roofline": roof,
         "roofline_all_kernels": rooflines,
         "e2e": {"value": round(world * B * args.steps / (e2e_ms / 1e3), 1), "unit": "images/s",
-                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": tok_h.numel() * 8 + lens_h.numel() * 4},
+                "h2d_bytes_per_step": x_host[0].numel() * x_host[0].element_size(),
+                "d2h_bytes_per_step": tok_h.numel() * 8 + lens_h.numel() * 4, "host_dtype": args.input_dtype},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
+    if e2e_other:
+        line["e2e_other_host_dtypes"] = e2e_other
+    if beam:
+        _, bdec, Bb, K, bk = beam
+        W = 2 * (4 * 256 * 768 + 8 * 256 + 512 * 256 + 512)
+        S = 16 * 256 + 2 * 256 + 2 * 256 + 8 + 16 * 256      # + the K-way h/c gather
+        bbytes = MAX_LEN * (W + Bb * K * S)
+        line["beam5"] = {"value": round(world * Bb / (beam_ms / 1e3), 1), "unit": "images/s", "batch_per_gpu": Bb,
+                         "beam": K, "ms_per_step": round(beam_ms, 3),
+                         "us_per_decode_step": round(bdec / MAX_LEN * 1e3, 3), "kernels_ms_per_step": bk,
+                         "roofline": {"bound": "hbm", "achieved": round(bbytes / (bdec / 1e3) / 1e9, 1),
+                                      "peak": pk["hbm"], "unit": "GB/s",
+                                      "frac": round(bbytes / (bdec / 1e3) / 1e9 / pk["hbm"], 4)},
+                         "workload": "BASELINE configs[2]: CNN-LSTM beam search, beam 5, batch %d per GPU, max_len 150" % Bb}
     dk = [v[1] for k, v in prof.items() if k.startswith("dec.")]
     if dk and steps_run:
         line["us_per_decode_step"] = round(sum(dk) / args.steps / steps_run * 1e3, 3)
@@ -311,6 +371,10 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--input-dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="element type of the image tensors (HBM-resident for `value`, pinned host for `e2e`)")
+    ap.add_argument("--beam-batch", type=int, default=512, help="images per GPU for the beam-5 line")
+    ap.add_argument("--no-extras", action="store_true", help="skip the beam-5 and other-host-dtype measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

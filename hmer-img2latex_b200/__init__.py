@@ -3,10 +3,10 @@ path of Jeremy-Cleland/hmer-img2latex behind the reference's own model / decoder
 Hand-written CUDA kernels behind a C-ABI (include/i2l_b200.h); PyTorch only provides
 device memory, streams and torch.distributed.  CUDA only: no CPU fallback."""
 from . import _native
-from .model import Attention, CNNEncoder, LSTMDecoder, ResNetEncoder, Seq2SeqModel
+from .model import Attention, CNNEncoder, LSTMDecoder, ResNetEncoder, Seq2SeqModel, normalize_u8
 from .predictor import Predictor
 from .tokenizer import LaTeXTokenizer
 
 __all__ = ["Attention", "CNNEncoder", "LSTMDecoder", "ResNetEncoder", "Seq2SeqModel", "Predictor",
-           "LaTeXTokenizer", "_native"]
+           "LaTeXTokenizer", "normalize_u8", "_native"]
 __version__ = "0.1.0"

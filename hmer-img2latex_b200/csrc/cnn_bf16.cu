@@ -83,20 +83,28 @@ __global__ void pack_fc_w_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 //   warps 2-5   epilogue: max over the 2x2 window, + bias, ReLU, bf16, parity-plane store
 constexpr int C1_THREADS = 448;
 constexpr int C1_PS = 8;                               // patch ring depth
-// TMA needs a 16-byte aligned start in the innermost (W) dimension: the box starts at x = 32*tw - 4
-// (3 columns left of the first needed one, 2*pw0 - 1) and is 40 floats wide
-constexpr int PATCH_W = 40, PATCH_H = 18, PATCH_X0 = 3;
-constexpr int C1_PATCH_BYTES = 3 * PATCH_H * PATCH_W * 4;   // 7776
-constexpr int C1_PATCH_STRIDE = (C1_PATCH_BYTES + 1023) / 1024 * 1024;
+constexpr int PATCH_H = 18;
+// Input element type of conv1: fp32 (the reference's tensor dtype) or bf16 (half the H2D / HBM
+// bytes; the im2col operand is bf16 either way, so the two give bit-identical results whenever the
+// fp32 values are bf16-representable).  The TMA box starts on a 16-byte boundary of the image row:
+// X0 columns left of the first needed one (2*pw0 - 1).
+template <typename T> struct C1In;
+template <> struct C1In<float> { static constexpr int PATCH_W = 40, X0 = 3, ELT = 4; };
+template <> struct C1In<__nv_bfloat16> { static constexpr int PATCH_W = 48, X0 = 7, ELT = 2; };
+constexpr int C1_PATCH_STRIDE = 9216;                  // ring slot (fp32 patch = 8640 B, bf16 patch = 5184 B)
 constexpr int C1_OFF_W = 0;                            // [32 co][32 k] bf16 SW64, 2 KB
 constexpr int C1_TC_ACC = 0, C1_TC_A = 256;            // TMEM columns: 2 x (4 x 32) accumulators, 2 x (4 x 16) im2col A tiles
 constexpr int C1_OFF_PATCH = C1_OFF_W + 2048;
 constexpr int C1_OFF_BAR = C1_OFF_PATCH + C1_PS * C1_PATCH_STRIDE;
 constexpr int C1_SMEM = C1_OFF_BAR + 256;
 
+template <typename InT>
 __global__ void __launch_bounds__(C1_THREADS, 1)
 conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __restrict__ w1img,
              const float* __restrict__ bias1, __nv_bfloat16* __restrict__ act1, int B, int n_tiles, int dbg) {
+  constexpr int PATCH_W = C1In<InT>::PATCH_W, PATCH_X0 = C1In<InT>::X0;
+  constexpr int C1_PATCH_BYTES = 3 * PATCH_H * PATCH_W * C1In<InT>::ELT;
+  static_assert(C1_PATCH_BYTES <= C1_PATCH_STRIDE, "patch ring slot too small");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -217,17 +225,34 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
       const int s = it % C1_PS;
       const int g = it & 1; const uint32_t par = (it >> 1) & 1;
       mbar_wait(PFULL(s), (it / C1_PS) & 1);
-      const float* p0 = reinterpret_cast<const float*>(smem + C1_OFF_PATCH + s * C1_PATCH_STRIDE) + (2 * pl + qh) * PATCH_W + 2 * pwl;
-      float f[3][3][4];
+      const unsigned char* patch = smem + C1_OFF_PATCH + s * C1_PATCH_STRIDE;
+      // raw[ci][kh][j]: 32-bit words holding the 4 needed columns (qw + kw = 0..3) of patch row
+      // (ci, 2*pl + qh + kh); fp32: one value per word, bf16: column e of the pair in half (e & 1)
+      uint32_t raw[3][3][4];
+      if constexpr (sizeof(InT) == 4) {
+        const float* p0 = reinterpret_cast<const float*>(patch) + (2 * pl + qh) * PATCH_W + 2 * pwl;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci)
+        for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          // needed columns 2*pwl + 3 .. + 6 of the patch row: three aligned LDS.64 (cols 2*pwl + 2 .. + 7)
-          const float2* pp = reinterpret_cast<const float2*>(p0 + (ci * PATCH_H + kh) * PATCH_W + 2);
-          float2 a = pp[0], c = pp[1], e = pp[2];
-          f[ci][kh][0] = a.y; f[ci][kh][1] = c.x; f[ci][kh][2] = c.y; f[ci][kh][3] = e.x;
-        }
+          for (int kh = 0; kh < 3; ++kh) {
+            // needed columns 2*pwl + 3 .. + 6 of the patch row: three aligned LDS.64 (cols 2*pwl + 2 .. + 7)
+            const float2* pp = reinterpret_cast<const float2*>(p0 + (ci * PATCH_H + kh) * PATCH_W + 2);
+            float2 a = pp[0], c = pp[1], e = pp[2];
+            raw[ci][kh][0] = __float_as_uint(a.y); raw[ci][kh][1] = __float_as_uint(c.x);
+            raw[ci][kh][2] = __float_as_uint(c.y); raw[ci][kh][3] = __float_as_uint(e.x);
+          }
+      } else {
+        // needed columns 2*pwl + 7 .. + 10: words pwl + 3 (hi), pwl + 4 (lo, hi), pwl + 5 (lo)
+        const uint32_t* p0 = reinterpret_cast<const uint32_t*>(patch) + (2 * pl + qh) * (PATCH_W / 2) + pwl + 3;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t* pp = p0 + (ci * PATCH_H + kh) * (PATCH_W / 2);
+            uint32_t a = pp[0], c = pp[1], e = pp[2];
+            raw[ci][kh][0] = a; raw[ci][kh][1] = c; raw[ci][kh][2] = c; raw[ci][kh][3] = e;
+          }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(PEMPTY(s));       // patch values are in registers
       mbar_wait(AEMPTY(g), par ^ 1);
@@ -236,14 +261,20 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
         uint32_t pk[16];
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) {
-          float v[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int k = 2 * k2 + e;
-            v[e] = k < 27 ? f[k / 9][(k % 9) / 3][qw + k % 3] : 0.f;
+          const int ka = 2 * k2, kb = 2 * k2 + 1;
+          const int ja = qw + ka % 3, jb = qw + kb % 3;       // column index 0..3 within raw[][][]
+          if constexpr (sizeof(InT) == 4) {
+            float va = ka < 27 ? __uint_as_float(raw[ka / 9 % 3][(ka % 9) / 3][ja]) : 0.f;
+            float vb = kb < 27 ? __uint_as_float(raw[kb / 9 % 3][(kb % 9) / 3][jb]) : 0.f;
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
+            pk[k2] = *reinterpret_cast<uint32_t*>(&h2);
+          } else {
+            // columns j = 0, 2 sit in the high half of their word, j = 1, 3 in the low half
+            const uint32_t wa = ka < 27 ? raw[ka / 9 % 3][(ka % 9) / 3][ja] : 0u;
+            const uint32_t wb = kb < 27 ? raw[kb / 9 % 3][(kb % 9) / 3][jb] : 0u;
+            const uint32_t sel = ((ja & 1) ? 0x10u : 0x32u) | (((jb & 1) ? 0x54u : 0x76u) << 8);
+            pk[k2] = __byte_perm(wa, wb, sel);
           }
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
-          pk[k2] = *reinterpret_cast<uint32_t*>(&h2);
         }
         tc_st16(tmem + lane_addr + C1_TC_A + g * 64 + (qh * 2 + qw) * 16, pk);
       }
@@ -598,8 +629,8 @@ static int dbg_sync(const char* what, cudaStream_t s) {
   return I2L_OK;
 }
 
-int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const float* x, int B, float* out, void* ws, size_t ws_bytes,
-                 cudaStream_t s) {
+int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const void* x, int in_dtype, int B, float* out, void* ws,
+                 size_t ws_bytes, cudaStream_t s) {
   Ws w = carve(B, ws);
   if (ws_bytes < w.bytes) { set_error("cnn_bf16_fwd: workspace too small (%zu < %zu)", ws_bytes, w.bytes); return I2L_ERR_WORKSPACE; }
   Sec L = sec_layout();
@@ -609,18 +640,27 @@ int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const float* x, int B
   if (Bp != B) {   // the odd tail image of conv3's pair tiles reads zeros
     I2L_CUDA_OK(cudaMemsetAsync(w.act2, 0, (size_t)Bp * 16 * 80 * C2 * 2, s));
   }
-  // ---- conv1: input x (B,3,64,320) fp32 NCHW read through a 4-D tensor map
+  // ---- conv1: input x (B,3,64,320) fp32 / bf16 NCHW read through a 4-D tensor map
   {
+    const bool in_bf16 = in_dtype == I2L_IN_BF16;
+    const uint64_t el = in_bf16 ? 2 : 4;
     CUtensorMap tm;
     uint64_t dims[4] = {IMG_W, IMG_H, C0, (uint64_t)B};
-    uint64_t str[3] = {IMG_W * 4ull, (uint64_t)IMG_W * IMG_H * 4, (uint64_t)IMG_W * IMG_H * C0 * 4};
-    uint32_t box[4] = {PATCH_W, PATCH_H, C0, 1};
-    I2L_TRY(make_tensor_map(&tm, x, 4, dims, str, box, 0, 4));
-    I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
+    uint64_t str[3] = {IMG_W * el, (uint64_t)IMG_W * IMG_H * el, (uint64_t)IMG_W * IMG_H * C0 * el};
+    uint32_t box[4] = {(uint32_t)(in_bf16 ? C1In<__nv_bfloat16>::PATCH_W : C1In<float>::PATCH_W), PATCH_H, C0, 1};
+    I2L_TRY(make_tensor_map(&tm, x, 4, dims, str, box, 0, (int)el));
     const int n_tiles = B * 40;
-    KernelTimer kt("cnn.conv1_bf16", s);
-    conv1_kernel<<<min(n_tiles, sms), C1_THREADS, C1_SMEM, s>>>(tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1),
-                                                              w.act1, Bp, n_tiles, getenv("I2L_CONV1_DBG") ? atoi(getenv("I2L_CONV1_DBG")) : 0);
+    const int dbg = getenv("I2L_CONV1_DBG") ? atoi(getenv("I2L_CONV1_DBG")) : 0;
+    KernelTimer kt(in_bf16 ? "cnn.conv1_bf16in" : "cnn.conv1_bf16", s);
+    if (in_bf16) {
+      I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
+      conv1_kernel<__nv_bfloat16><<<min(n_tiles, sms), C1_THREADS, C1_SMEM, s>>>(
+          tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1), w.act1, Bp, n_tiles, dbg);
+    } else {
+      I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
+      conv1_kernel<float><<<min(n_tiles, sms), C1_THREADS, C1_SMEM, s>>>(
+          tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1), w.act1, Bp, n_tiles, dbg);
+    }
     I2L_LAUNCH_OK();
   }
   I2L_TRY(dbg_sync("conv1", s));

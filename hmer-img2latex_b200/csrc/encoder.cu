@@ -208,16 +208,108 @@ extern "C" size_t i2l_cnn_workspace_bytes(const i2l_cnn_desc* d, int32_t batch) 
 
 extern "C" int i2l_cnn_encoder_fwd(const i2l_cnn_desc* d, const void* packed, const float* x, int32_t batch,
                                    float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return i2l_cnn_encoder_fwd_in(d, packed, x, I2L_IN_F32, batch, out, workspace, workspace_bytes, stream);
+}
+
+namespace i2l {
+namespace {
+struct NormArgs { float mean[4], stdv[4]; int mode; };
+
+template <typename OutT>
+__device__ __forceinline__ OutT norm_px(unsigned v, int c, const NormArgs& a) {
+  float t = (float)v / 255.0f;                                        // data/utils.py:68, predictor.py:444
+  float y = a.mode == I2L_NORM_PM1 ? t * 2.0f - 1.0f                  // utils.py:74 / predictor.py:446
+                                   : (t - a.mean[c]) / a.stdv[c];     // utils.py:77-79
+  if constexpr (sizeof(OutT) == 4) return y; else return __float2bfloat16(y);
+}
+
+// NCHW -> NCHW, 16 pixels per thread (requires H*W % 16 == 0)
+template <typename OutT>
+__global__ void normalize_u8_vec_kernel(const uint4* __restrict__ src, OutT* __restrict__ dst, size_t n16, int hw16,
+                                        int C, NormArgs a) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n16) return;
+  const int c = (int)((i / hw16) % C);
+  uint4 v = __ldg(src + i);
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  OutT o[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) o[k] = norm_px<OutT>((w[k >> 2] >> (8 * (k & 3))) & 0xffu, c, a);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + i * 16);
+  const uint4* o4 = reinterpret_cast<const uint4*>(o);
+#pragma unroll
+  for (int k = 0; k < (int)(16 * sizeof(OutT) / 16); ++k) d4[k] = o4[k];
+}
+
+template <typename OutT>
+__global__ void normalize_u8_kernel(const uint8_t* __restrict__ src, OutT* __restrict__ dst, size_t n, int C, int HW,
+                                    int nhwc, NormArgs a) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into dst (B,C,H,W)
+  if (i >= n) return;
+  const int c = (int)((i / HW) % C);
+  size_t si = i;
+  if (nhwc) { size_t b = i / ((size_t)C * HW); size_t p = i % HW; si = (b * HW + p) * C + c; }
+  dst[i] = norm_px<OutT>(src[si], c, a);
+}
+}  // namespace
+}  // namespace i2l
+
+extern "C" int i2l_normalize_u8(const uint8_t* src, int32_t src_layout, int32_t batch, int32_t channels,
+                                int32_t height, int32_t width, int32_t mode, const float* mean, const float* stdv,
+                                void* dst, int32_t dst_dtype, void* stream) {
+  I2L_TRY(device_check());
+  I2L_REQUIRE(batch >= 0 && channels >= 1 && channels <= 4 && height > 0 && width > 0, "i2l_normalize_u8: invalid shape");
+  I2L_REQUIRE(src_layout == 0 || src_layout == 1, "i2l_normalize_u8: src_layout must be 0 (NCHW) or 1 (NHWC)");
+  I2L_REQUIRE(mode == I2L_NORM_PM1 || mode == I2L_NORM_MEANSTD, "i2l_normalize_u8: invalid mode");
+  I2L_REQUIRE(dst_dtype == I2L_IN_F32 || dst_dtype == I2L_IN_BF16, "i2l_normalize_u8: invalid dst dtype");
+  I2L_REQUIRE(mode == I2L_NORM_PM1 || (mean && stdv), "i2l_normalize_u8: mean/std required");
+  if (batch == 0) return I2L_OK;
+  I2L_REQUIRE(src && dst, "i2l_normalize_u8: null buffer");
+  NormArgs a{};
+  a.mode = mode;
+  for (int c = 0; c < channels; ++c) { a.mean[c] = mean ? mean[c] : 0.f; a.stdv[c] = stdv ? stdv[c] : 1.f; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int HW = height * width;
+  const size_t n = (size_t)batch * channels * HW;
+  const bool vec = src_layout == 0 && HW % 16 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+  KernelTimer kt("pre.normalize_u8", s);
+  if (vec) {
+    const size_t n16 = n / 16;
+    const unsigned grid = (unsigned)((n16 + 255) / 256);
+    if (dst_dtype == I2L_IN_F32)
+      normalize_u8_vec_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<float*>(dst), n16, HW / 16, channels, a);
+    else
+      normalize_u8_vec_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<__nv_bfloat16*>(dst), n16, HW / 16, channels, a);
+  } else {
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (dst_dtype == I2L_IN_F32)
+      normalize_u8_kernel<float><<<grid, 256, 0, s>>>(src, reinterpret_cast<float*>(dst), n, channels, HW, src_layout, a);
+    else
+      normalize_u8_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n, channels, HW, src_layout, a);
+  }
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
+
+extern "C" int i2l_cnn_encoder_fwd_in(const i2l_cnn_desc* d, const void* packed, const void* xin, int32_t x_dtype,
+                                      int32_t batch, float* out, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
   I2L_TRY(device_check());
   I2L_TRY(cnn_check(d));
   I2L_REQUIRE(packed && batch >= 0, "i2l_cnn_encoder_fwd: invalid argument");
+  I2L_REQUIRE(x_dtype == I2L_IN_F32 || x_dtype == I2L_IN_BF16, "i2l_cnn_encoder_fwd: invalid input dtype");
   if (batch == 0) return I2L_OK;
-  I2L_REQUIRE(x && out && workspace, "i2l_cnn_encoder_fwd: null buffer");
+  I2L_REQUIRE(xin && out && workspace, "i2l_cnn_encoder_fwd: null buffer");
   cudaStream_t s = (cudaStream_t)stream;
   CnnLayout L = cnn_layout(*d);
   if (L.bf16_section)
-    return cnn_bf16_fwd(*d, reinterpret_cast<const char*>(packed) + L.bf16_section, x, batch, out, workspace,
+    return cnn_bf16_fwd(*d, reinterpret_cast<const char*>(packed) + L.bf16_section, xin, x_dtype, batch, out, workspace,
                         workspace_bytes, s);
+  if (x_dtype != I2L_IN_F32) {
+    set_error("i2l_cnn_encoder_fwd: bf16 input needs precision == I2L_BF16 and the tcgen05 shape (3x64x320, 32/64/128, E=256)");
+    return I2L_ERR_UNSUPPORTED;
+  }
+  const float* x = reinterpret_cast<const float*>(xin);
   CnnWs w = cnn_carve(*d, L, batch, workspace);
   if (workspace_bytes < w.bytes) { set_error("i2l_cnn_encoder_fwd: workspace too small (%zu < %zu)", workspace_bytes, w.bytes); return I2L_ERR_WORKSPACE; }
   const float* pk = reinterpret_cast<const float*>(packed);

@@ -18,6 +18,41 @@ from ._common import Workspace, default_precision, f32c, params_key, require_cud
 _RESNET_DEPTH = {"resnet18": 18, "resnet34": 34, "resnet50": 50, "resnet101": 101, "resnet152": 152}
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)          # data/utils.py:77-78
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def normalize_u8(pixels: torch.Tensor, mode: str = "pm1", mean=IMAGENET_MEAN, std=IMAGENET_STD,
+                 channels_last: bool = False, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """uint8 pixels on the device -> normalised (B,C,H,W) image tensor (fp32 or bf16), the
+    arithmetic of the reference's ``load_image`` / ``_prepare_image`` (data/utils.py:68-80,
+    training/predictor.py:441-446) as one kernel (``i2l_normalize_u8``): ``mode="pm1"`` is
+    x/255*2-1, ``mode="meanstd"`` is (x/255-mean)/std per channel."""
+    require_cuda(pixels, "normalize_u8")
+    if pixels.dtype != torch.uint8 or pixels.dim() != 4:
+        raise RuntimeError("normalize_u8 expects a 4-D uint8 tensor")
+    if mode not in ("pm1", "meanstd"):
+        raise ValueError("mode must be 'pm1' or 'meanstd'")
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("out_dtype must be torch.float32 or torch.bfloat16")
+    pixels = pixels.contiguous()
+    if channels_last:
+        B, H, W, Cc = pixels.shape
+    else:
+        B, Cc, H, W = pixels.shape
+    if Cc > 4 or (mode == "meanstd" and (len(mean) < Cc or len(std) < Cc)):
+        raise ValueError("normalize_u8 supports up to 4 channels with one mean/std per channel")
+    out = torch.empty(B, Cc, H, W, dtype=out_dtype, device=pixels.device)
+    m = (C.c_float * 4)(*([float(v) for v in mean[:Cc]] + [0.0] * (4 - Cc)))
+    sd = (C.c_float * 4)(*([float(v) for v in std[:Cc]] + [1.0] * (4 - Cc)))
+    with torch.cuda.device(pixels.device):
+        N.check(N.lib().i2l_normalize_u8(N.ptr(pixels), 1 if channels_last else 0, B, Cc, H, W,
+                                         N.NORM_PM1 if mode == "pm1" else N.NORM_MEANSTD, m, sd, N.ptr(out),
+                                         N.IN_BF16 if out_dtype == torch.bfloat16 else N.IN_F32,
+                                         N.stream_ptr(pixels.device)), "i2l_normalize_u8")
+    return out
+
+
 class CNNEncoder(nn.Module):
     """reference: img2latex/model/encoder.py:16-129."""
 
@@ -105,16 +140,25 @@ class CNNEncoder(nn.Module):
             self._ensure_packed(x.device)
             lib = N.lib()
             d = self._desc()
-            x = f32c(x)
+            # bf16 images are consumed as they are by the tcgen05 conv1 (precision "bf16", headline
+            # shape); every other dtype goes through fp32 like the reference's tensors
+            if x.dtype == torch.bfloat16 and self.precision == "bf16" and self._bf16_shape():
+                x, in_dtype = x.detach().contiguous(), N.IN_BF16
+            else:
+                x, in_dtype = f32c(x), N.IN_F32
             B = x.shape[0]
             out = torch.empty(B, self.embedding_dim, dtype=torch.float32, device=x.device)
             if B == 0:
                 return out
             wsb = lib.i2l_cnn_workspace_bytes(C.byref(d), B)
             ws = self._ws.get(wsb, x.device)
-            N.check(lib.i2l_cnn_encoder_fwd(C.byref(d), N.ptr(self._packed), N.ptr(x), B, N.ptr(out), N.ptr(ws),
-                                            ws.numel(), N.stream_ptr(x.device)), "i2l_cnn_encoder_fwd")
+            N.check(lib.i2l_cnn_encoder_fwd_in(C.byref(d), N.ptr(self._packed), N.ptr(x), in_dtype, B, N.ptr(out),
+                                               N.ptr(ws), ws.numel(), N.stream_ptr(x.device)), "i2l_cnn_encoder_fwd")
         return out
+
+    def _bf16_shape(self) -> bool:
+        return ((self.channels, self.img_height, self.img_width) == (3, 64, 320) and self.conv_filters == [32, 64, 128]
+                and self.kernel_size == 3 and self.pool_size == 2 and self.embedding_dim == 256)
 
 
 class ResNetEncoder(nn.Module):

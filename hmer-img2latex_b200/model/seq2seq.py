@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from .. import _native as N
 from .decoder import LSTMDecoder
-from .encoder import CNNEncoder, ResNetEncoder
+from .encoder import CNNEncoder, ResNetEncoder, normalize_u8
 
 
 class Seq2SeqModel(nn.Module):
@@ -105,8 +105,11 @@ class Seq2SeqModel(nn.Module):
     @torch.no_grad()
     def greedy_stream(self, host_batches: Iterable[torch.Tensor], start_token_id: int, end_token_id: int,
                       max_length: int = 150, temperature: float = 1.0, stop_rule: int = N.STOP_ALL_END_SAME_STEP,
-                      device: Optional[torch.device] = None) -> Iterator[Tuple[torch.Tensor, torch.Tensor, int]]:
-        """Serving loop over HOST batches (ideally pinned (B,C,H,W) fp32 tensors): the host->device
+                      device: Optional[torch.device] = None, normalize: str = "pm1",
+                      ) -> Iterator[Tuple[torch.Tensor, torch.Tensor, int]]:
+        """Serving loop over HOST batches (ideally pinned (B,C,H,W) tensors: fp32 like the
+        reference's, bf16, or raw uint8 pixels that are normalised on the device with
+        ``normalize`` = "pm1" | "meanstd", see ``normalize_u8``): the host->device
         copy of batch i+1 runs on a copy stream while batch i is encoded and decoded, and the
         token ids come back through a pinned buffer.  Yields (tokens (B,max_length+1) int64 on the
         host, lengths (B) int32 on the host, steps_run) per batch -- same content as
@@ -122,8 +125,8 @@ class Seq2SeqModel(nn.Module):
         out_tok = out_len = None
 
         def stage(slot: int, xb: torch.Tensor) -> None:
-            if bufs[slot] is None or bufs[slot].shape != xb.shape:
-                bufs[slot] = torch.empty(xb.shape, dtype=torch.float32, device=dev)
+            if bufs[slot] is None or bufs[slot].shape != xb.shape or bufs[slot].dtype != xb.dtype:
+                bufs[slot] = torch.empty(xb.shape, dtype=xb.dtype, device=dev)
             with torch.cuda.stream(copy_stream):
                 bufs[slot].copy_(xb, non_blocking=True)
                 ready[slot].record(copy_stream)
@@ -139,7 +142,11 @@ class Seq2SeqModel(nn.Module):
             if nxt is not None:
                 stage((i + 1) & 1, nxt)                  # overlaps with the compute below
             compute.wait_event(ready[i & 1])
-            enc = self.encoder(bufs[i & 1])
+            xin = bufs[i & 1]
+            if xin.dtype == torch.uint8:
+                xin = normalize_u8(xin, normalize, out_dtype=torch.bfloat16 if self.encoder.precision == "bf16"
+                                   else torch.float32)
+            enc = self.encoder(xin)
             tokens, lengths, steps = self.decoder.greedy(enc, start_token_id, end_token_id, max_length, temperature,
                                                          stop_rule)
             if out_tok is None or out_tok.shape != tokens.shape:

@@ -88,6 +88,26 @@ size_t i2l_cnn_workspace_bytes(const i2l_cnn_desc* d, int32_t batch);
 int i2l_cnn_encoder_fwd(const i2l_cnn_desc* d, const void* packed, const float* x, int32_t batch,
                         float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same call with the input element type stated: I2L_IN_F32 (the reference's tensor dtype)
+ * or I2L_IN_BF16 (precision == I2L_BF16 only: halves the host->device and HBM bytes of the
+ * image; the conv1 operand is bf16 either way).  SURVEY 8d: "fp32 master -> bf16 for the bf16 runs". */
+typedef enum { I2L_IN_F32 = 0, I2L_IN_BF16 = 1 } i2l_input_dtype;
+int i2l_cnn_encoder_fwd_in(const i2l_cnn_desc* d, const void* packed, const void* x, int32_t x_dtype,
+                           int32_t batch, float* out, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* Device-side pixel normalisation -- replaces the arithmetic of Predictor._prepare_image /
+ * load_image (training/predictor.py:441-446: x/255*2-1; data/utils.py:68-80: x/255 then
+ * *2-1 (1 channel) or (x-mean)/std (RGB)), so that raw uint8 pixels cross PCIe instead of
+ * fp32 tensors.  src: uint8, layout NCHW (0) or NHWC (1); dst: (B,C,H,W) fp32 or bf16
+ * (i2l_input_dtype).  mode I2L_NORM_PM1: y = x/255*2-1; I2L_NORM_MEANSTD: y = (x/255-mean[c])/std[c]
+ * (mean/std: HOST pointers to `channels` floats).  fp32 results are bit-identical to the
+ * reference's float32 arithmetic. */
+typedef enum { I2L_NORM_PM1 = 0, I2L_NORM_MEANSTD = 1 } i2l_norm_mode;
+int i2l_normalize_u8(const uint8_t* src, int32_t src_layout, int32_t batch, int32_t channels,
+                     int32_t height, int32_t width, int32_t mode, const float* mean, const float* stdev,
+                     void* dst, int32_t dst_dtype, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* ResNet encoder -- replaces ResNetEncoder.forward, model/encoder.py:231-249   */
 /* (torchvision trunk minus fc, model/encoder.py:184-199; eval-mode BN folded). */

@@ -25,7 +25,7 @@ __all__ = [
     "make_params", "cnn_encoder", "resnet_encoder", "encoder", "attention",
     "lstm_step", "decode_step", "greedy_search", "inference_postprocess",
     "filter_probs", "sample_loop", "beam_search", "beam_search_batched",
-    "RESNET_LAYERS", "trim_at_end", "inverse_cdf_draw",
+    "RESNET_LAYERS", "trim_at_end", "inverse_cdf_draw", "normalize_u8",
 ]
 
 RESNET_LAYERS = {
@@ -35,6 +35,24 @@ RESNET_LAYERS = {
     "resnet101": ("bottleneck", (3, 4, 23, 3)),
     "resnet152": ("bottleneck", (3, 8, 36, 3)),
 }
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def normalize_u8(pixels: torch.Tensor, mode: str = "pm1") -> torch.Tensor:
+    """Pixel arithmetic of `load_image` (data/utils.py:53-80) and the PIL branch of
+    `Predictor._prepare_image` (training/predictor.py:441-446): uint8 (.., C, H, W) ->
+    float32 / 255.0, then `* 2.0 - 1.0` ("pm1": grayscale utils.py:72-74, PIL predictor.py:446)
+    or ImageNet `(x - mean) / std` ("meanstd": RGB, utils.py:76-79)."""
+    t = pixels.float() / 255.0
+    if mode == "pm1":
+        return t * 2.0 - 1.0
+    C = pixels.shape[-3]
+    mean = torch.tensor(IMAGENET_MEAN[:C]).view(-1, 1, 1)
+    std = torch.tensor(IMAGENET_STD[:C]).view(-1, 1, 1)
+    return (t - mean) / std
 
 
 # --------------------------------------------------------------------------

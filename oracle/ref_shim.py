@@ -61,6 +61,13 @@ def load():
                 LaTeXTokenizer=LaTeXTokenizer)
 
 
+def reference_module(name: str):
+    """Import a module of the live reference by dotted name (after the shims of `load`)."""
+    load()
+    import importlib
+    return importlib.import_module(name)
+
+
 def build_reference_model(cfg: dict, params: dict):
     """Instantiate the reference Seq2SeqModel for ``cfg`` and load ``params``
     (keys = reference state_dict keys) into it; eval mode."""

@@ -122,6 +122,23 @@ def predict_batch_case(name, temperature, top_k, top_p, T=16, B=5):
     save(name, **arrs)
 
 
+def load_image_case(name):
+    """Reference `load_image` (data/utils.py:18-90) on PNG files whose size already equals the
+    target size (ResizeWithAspectRatio is then the identity, transforms.py:38-43)."""
+    import tempfile
+    from PIL import Image
+    load_image = ref_shim.reference_module("img2latex.data.utils").load_image
+    g = np.random.default_rng(4)
+    rgb = g.integers(0, 256, size=(16, 48, 3), dtype=np.uint8)
+    gray = g.integers(0, 256, size=(16, 48), dtype=np.uint8)
+    with tempfile.TemporaryDirectory() as td:
+        Image.fromarray(rgb, "RGB").save(os.path.join(td, "rgb.png"))
+        Image.fromarray(gray, "L").save(os.path.join(td, "gray.png"))
+        out_rgb = load_image(os.path.join(td, "rgb.png"), (16, 48), 3)
+        out_gray = load_image(os.path.join(td, "gray.png"), (16, 48), 1)
+    save(name, rgb=rgb, gray=gray, out_rgb=out_rgb, out_gray=out_gray)
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "the live reference is needed to (re)generate golden vectors"
     seq2seq_case("cnn_headline_sharp.npz", H.HEADLINE, seed=1, sharp=True, B=4, T=30)
@@ -130,6 +147,7 @@ if __name__ == "__main__":
     resnet_case("resnet18.npz", H.R18, [128, 160])
     resnet_case("resnet50.npz", H.R50, [96])
     attention_case("attention_L5.npz")
+    load_image_case("load_image.npz")
     predict_batch_case("predict_batch_greedy.npz", 1.0, 0, 0.0)
     predict_batch_case("predict_batch_topk_topp.npz", 0.8, 5, 0.9)
     predict_batch_case("predict_batch_topp.npz", 1.2, 0, 0.7)

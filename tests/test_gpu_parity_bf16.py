@@ -89,3 +89,53 @@ def test_cnn_encoder_bf16(pkg, B, sharp):
     err = H.rel_err(out, ref)
     print(f"bf16 encoder B={B}: rel err {err:.3e}")
     assert out.shape == ref.shape and err < 3e-2
+
+
+@pytest.mark.parametrize("B", [1, 6, 33])
+def test_cnn_encoder_bf16_input_matches_fp32_input(pkg, B):
+    """bf16 image tensors (half the H2D / HBM bytes) feed conv1 directly; since the conv1
+    operand is bf16 either way the result must be BIT-identical to feeding the same values
+    as fp32, and within the bf16 tolerance of the fp32 oracle on the unrounded images."""
+    cfg = H.HEADLINE
+    p = oracle.make_params(cfg, 1, sharp=True)
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    x = H.make_images(cfg, B)
+    xb = x.bfloat16()
+    out_b = m16.encoder(xb.cuda())
+    out_f = m16.encoder(xb.float().cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(out_b, out_f)
+    assert H.rel_err(out_b, oracle.cnn_encoder(p, x)) < 3e-2
+
+
+@pytest.mark.parametrize("shape,mode,nhwc", [((3, 3, 64, 320), "pm1", False), ((2, 3, 64, 320), "meanstd", False),
+                                             ((2, 1, 17, 23), "pm1", False), ((3, 3, 9, 31), "meanstd", True),
+                                             ((2, 3, 64, 320), "meanstd", True)])
+def test_normalize_u8(pkg, shape, mode, nhwc):
+    """i2l_normalize_u8 vs the reference's load_image arithmetic (oracle.normalize_u8, pinned by
+    tests/golden/load_image.npz): fp32 output bit-exact, bf16 output = RN(fp32 result)."""
+    g = torch.Generator().manual_seed(3)
+    px = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g)
+    ref = oracle.normalize_u8(px, mode)
+    src = px.permute(0, 2, 3, 1).contiguous() if nhwc else px
+    out32 = pkg.normalize_u8(src.cuda(), mode, channels_last=nhwc)
+    out16 = pkg.normalize_u8(src.cuda(), mode, channels_last=nhwc, out_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    assert torch.equal(out32.cpu(), ref)
+    assert torch.equal(out16.cpu(), ref.bfloat16())
+
+
+def test_greedy_stream_uint8_and_bf16_hosts(pkg):
+    """Seq2SeqModel.greedy_stream with raw uint8 pixels / bf16 tensors on the host gives the same
+    tokens as the fp32-tensor call on the normalised images."""
+    cfg = H.HEADLINE
+    p = oracle.make_params(cfg, 1, sharp=True)
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    g = torch.Generator().manual_seed(8)
+    px = torch.randint(0, 256, (9, 3, 64, 320), dtype=torch.uint8, generator=g)
+    xn = oracle.normalize_u8(px, "pm1").bfloat16()
+    enc = m16.encoder(xn.float().cuda())
+    t_ref, l_ref, s_ref = m16.decoder.greedy(enc, H.START, H.END, 20)
+    for host in (px.pin_memory(), xn.pin_memory()):
+        (tok, lens, steps), = list(m16.greedy_stream([host], H.START, H.END, 20))
+        assert torch.equal(tok, t_ref.cpu()) and torch.equal(lens, l_ref.cpu()) and steps == int(s_ref)

@@ -130,3 +130,12 @@ def test_filter_probs_edge_cases():
     assert torch.allclose(pr, torch.softmax(lg, -1))
     u = torch.tensor([0.0, 0.999999])
     assert oracle.inverse_cdf_draw(torch.tensor([[0.0, 0.5, 0.5, 0.0], [0.2, 0.8, 0.0, 0.0]]), u).tolist() == [1, 1]
+
+
+def test_load_image_golden():
+    """oracle.normalize_u8 == the pixel arithmetic of the live reference's load_image."""
+    d = load("load_image.npz")
+    rgb = torch.as_tensor(d["rgb"]).permute(2, 0, 1)          # HWC -> CHW (data/utils.py:63-65)
+    gray = torch.as_tensor(d["gray"]).unsqueeze(0)
+    assert torch.equal(oracle.normalize_u8(rgb, "meanstd"), torch.as_tensor(d["out_rgb"]))
+    assert torch.equal(oracle.normalize_u8(gray, "pm1"), torch.as_tensor(d["out_gray"]))
