@@ -349,16 +349,6 @@ __global__ void sample_select_kernel(const float* __restrict__ logits, int V, in
 }
 
 // ------------------------------------------------------------------ beam (seq2seq.py:234-298)
-struct BeamState {              // per image
-  int alive;                    // loop still running for this image
-  int nbeams;                   // len(beams)
-  int has_completed;
-  int best_step, best_slot;     // best entry of `completed` (first-wins max)
-  double best_score;
-  int last_step;                // last executed iteration
-};
-
-#define I2L_MAX_BEAM 16
 
 __global__ void beam_init_kernel(BeamState* bs, double* score, int64_t* tok_cur, int* live, int B, int K,
                                  int start_id) {
@@ -821,6 +811,17 @@ extern "C" int i2l_decode_beam(const i2l_dec_desc* d, const void* packed, const 
   int* trp = trace_parent ? trace_parent : w.tr_parent;
   int* trt = trace_token ? trace_token : w.tr_token;
   double* trs = trace_score ? trace_score : w.tr_score;
+  if (d->precision == I2L_BF16 && persistent_beam_supported(*d, K) && end_id >= 0 && end_id < V && start_id >= 0 &&
+      start_id < V) {
+    // headline shape in bf16: the whole search runs inside one persistent cluster kernel
+    I2L_TRY(make_gctx(*d, pk, lay, enc, batch, w.gates, s));
+    I2L_TRY(persistent_beam(*d, reinterpret_cast<const char*>(packed) + lay.bf16_section, w.gates, batch, K, start_id,
+                            end_id, max_length, w.bstate, w.score, trp, trt, trace_score, s));
+    beam_finalize_kernel<<<cdiv(batch, 128), 128, 0, s>>>(w.bstate, w.score, trp, trt, batch, K, max_length, end_id,
+                                                          out_tokens, out_len, out_score);
+    I2L_LAUNCH_OK();
+    return I2L_OK;
+  }
   beam_init_kernel<<<cdiv(R, 256), 256, 0, s>>>(w.bstate, w.score, w.tok_cur, w.live, batch, K, start_id);
   I2L_LAUNCH_OK();
   size_t n = (size_t)d->lstm_layers * R * H * sizeof(float);
@@ -897,3 +898,9 @@ extern "C" int i2l_attention_fwd(int32_t H, int32_t E, const float* attn_w, cons
 // debug aid (tools/debug_persistent.py): dump intermediates of one step of the persistent kernel
 namespace i2l { int persistent_set_debug(float* buf); }
 extern "C" int i2l_debug_set_buffer(float* buf) { return i2l::persistent_set_debug(buf); }
+// test aid: (T,B,K,K) device buffers that receive every live beam's top-K (token, log-prob) of the
+// next persistent beam calls (NULL, NULL switches the dump off)
+namespace i2l { int persistent_beam_set_debug(int* cand_tok, float* cand_logp); }
+extern "C" int i2l_debug_set_beam_trace(int32_t* cand_tok, float* cand_logp) {
+  return i2l::persistent_beam_set_debug(cand_tok, cand_logp);
+}

@@ -15,6 +15,18 @@ struct LoopState {
   int end_count;       // ALL_END_SAME_STEP rule: rows emitting END in the current step
 };
 
+// Per-image state of the beam search (seq2seq.py:234-298), shared by the general and the
+// persistent beam kernels and read by the finalize kernel.
+struct BeamState {
+  int alive;                    // loop still running for this image
+  int nbeams;                   // len(beams)
+  int has_completed;
+  int best_step, best_slot;     // best entry of `completed` (first-wins max)
+  double best_score;
+  int last_step;                // last executed iteration
+};
+#define I2L_MAX_BEAM 16
+
 struct PackedDec {     // offsets (in floats) into the packed decoder buffer, fp32 section
   size_t emb, gtok, w_ih0, bsum[I2L_MAX_LSTM_LAYERS], w_hh[I2L_MAX_LSTM_LAYERS],
       w_ih[I2L_MAX_LSTM_LAYERS], out_w, out_b, end_f32;
@@ -37,5 +49,12 @@ int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* p
                       const PackedDec& lay, const float* enc, int batch, int start_id, int end_id,
                       int max_length, float temperature, int stop_rule, int64_t* tokens, int32_t* lengths,
                       int32_t* steps_run, void* ws, size_t ws_bytes, cudaStream_t s);
+
+// persistent bf16 beam search (decode_persistent_beam.cu): same resident-weight cluster kernel with
+// log-softmax + top-K, per-image candidate merge, back-pointers and state reorder on the device.
+bool persistent_beam_supported(const i2l_dec_desc& d, int beam_size);
+int persistent_beam(const i2l_dec_desc& d, const void* section, const float* gctx_img, int batch, int beam_size,
+                    int start_id, int end_id, int max_length, BeamState* bstate, double* score, int* tr_parent,
+                    int* tr_token, double* tr_score, cudaStream_t s);
 
 }  // namespace i2l

@@ -1,0 +1,162 @@
+"""Persistent bf16 beam-search kernel (decode_persistent_beam.cu) -- BASELINE configs[2].
+
+Three layers of checks, all through the C-ABI (`i2l_decode_beam`, precision bf16):
+ 1. bookkeeping is BIT-EXACT given the scores: the kernel dumps every live beam's top-K
+    (token, fp32 log-prob); replaying the reference's loop (seq2seq.py:254-290, restated in
+    `replay_reference_beam`) on those candidates must reproduce the kernel's parents, tokens,
+    fp64 scores, final sequences and final scores exactly.
+ 2. against the fp32 CPU oracle under the bf16 tolerance: per-step parents / tokens must match the
+    oracle while its neighbouring candidate scores are further apart than BF16_GAP; an image is
+    dropped from the comparison at its first near tie.
+ 3. beam 1 == the persistent greedy kernel (same MMAs, same logits) cut at the first END.
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+import helpers as H
+from helpers import oracle
+
+pytestmark = pytest.mark.gpu
+
+BF16_GAP = 0.08       # oracle candidate-score gap (nats) below which bf16 rounding may reorder
+
+
+def replay_reference_beam(ctok, clogp, start, end, T, K):
+    """seq2seq.py:254-290 for one image driven by dumped candidates ctok/clogp[t][slot][rank]."""
+    beams = [dict(tokens=[start], score=0.0, slot=0)]
+    completed, trace = [], []
+    for t in range(T):
+        cands = []
+        for bi, beam in enumerate(beams):
+            if beam["tokens"][-1] == end:                                    # :258-260
+                completed.append(beam)
+                continue
+            for r in range(K):                                               # :268-275
+                cands.append(dict(tokens=beam["tokens"] + [int(ctok[t][bi][r])],
+                                  score=beam["score"] + float(clogp[t][bi][r]), parent=bi))
+        if not cands:                                                        # :276-277
+            break
+        cands = sorted(cands, key=lambda b: b["score"], reverse=True)        # :279
+        beams = cands[:K]                                                    # :280
+        trace.append([(b["parent"], b["tokens"][-1], b["score"]) for b in beams])
+        if all(b["tokens"][-1] == end for b in beams):                       # :282-284
+            completed.extend(beams)
+            break
+    best = max(completed, key=lambda b: b["score"]) if completed else beams[0]   # :286-290
+    seq = best["tokens"][1:]
+    if end in seq:
+        seq = seq[: seq.index(end)]
+    return seq, best["score"], trace
+
+
+def run_beam_with_dump(pkg, m, enc, T, K):
+    B = enc.shape[0]
+    lib = pkg._native.lib()
+    lib.i2l_debug_set_beam_trace.restype = C.c_int
+    lib.i2l_debug_set_beam_trace.argtypes = [C.c_void_p, C.c_void_p]
+    ctok = torch.full((T, B, K, K), -1, dtype=torch.int32, device="cuda")
+    clogp = torch.full((T, B, K, K), float("nan"), dtype=torch.float32, device="cuda")
+    lib.i2l_debug_set_beam_trace(ctok.data_ptr(), clogp.data_ptr())
+    try:
+        out, olen, score, (trp, trt, trs) = m.decoder.beam(enc, H.START, H.END, T, K, return_trace=True)
+        torch.cuda.synchronize()
+    finally:
+        lib.i2l_debug_set_beam_trace(None, None)
+    return [t.cpu() for t in (out, olen, score, trp, trt, trs, ctok, clogp)]
+
+
+@pytest.mark.parametrize("B,K,T,seed,end_boost", [(7, 5, 30, 2, 1.0), (40, 5, 25, 1, 0.5), (13, 3, 40, 2, 2.0),
+                                                  (9, 8, 16, 3, 1.0), (5, 1, 30, 1, 1.0), (6, 2, 20, 2, 0.0),
+                                                  (11, 4, 20, 1, 1.5), (3, 7, 12, 2, 1.0), (4, 6, 12, 3, 3.0)])
+def test_beam_bookkeeping_bit_exact_given_scores(pkg, B, K, T, seed, end_boost):
+    cfg = H.HEADLINE
+    p = oracle.make_params(cfg, seed, sharp=True)
+    p["decoder.output_layer.bias"][H.END] += end_boost
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    enc = torch.relu(torch.randn(B, 256, generator=torch.Generator().manual_seed(seed))).cuda()
+    out, olen, score, trp, trt, trs, ctok, clogp = run_beam_with_dump(pkg, m16, enc, T, K)
+    n_completed_early = 0
+    for b in range(B):
+        seq, sc, trace = replay_reference_beam(ctok[:, b].tolist(), clogp[:, b].tolist(), H.START, H.END, T, K)
+        for t, beams in enumerate(trace):
+            nb = len(beams)
+            assert trp[t, b, :nb].tolist() == [x[0] for x in beams], (b, t)
+            assert trt[t, b, :nb].tolist() == [x[1] for x in beams], (b, t)
+            assert trs[t, b, :nb].tolist() == [x[2] for x in beams], (b, t)          # fp64, bit for bit
+            assert trp[t, b, nb:].tolist() == [-1] * (K - nb)
+        for t in range(len(trace), T):                                             # image no longer alive
+            assert trp[t, b].tolist() == [-1] * K and trt[t, b].tolist() == [-1] * K
+        assert out[b, : int(olen[b])].tolist() == seq, b
+        assert out[b, int(olen[b]):].tolist() == [-1] * (T - int(olen[b]))
+        assert float(score[b]) == sc
+        n_completed_early += len(trace) < T
+    print(f"beam K={K} B={B}: {n_completed_early}/{B} images finished before max_length")
+
+
+@pytest.mark.parametrize("B,K,T", [(12, 5, 20), (6, 3, 25)])
+def test_beam_bf16_vs_fp32_oracle(pkg, B, K, T):
+    cfg = H.HEADLINE
+    p = oracle.make_params(cfg, 2, sharp=True)
+    p["decoder.output_layer.bias"][H.END] += 1.0
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    m32 = H.build_model(pkg, cfg, p, precision="fp32")
+    x = H.make_images(cfg, B)
+    enc_ref = oracle.encoder(p, x, cfg)
+    enc = m32.encoder(x.cuda())                              # isolate the decoder
+    out, olen, score, (trp, trt, trs) = m16.decoder.beam(enc, H.START, H.END, T, K, return_trace=True)
+    out, olen, score, trp, trt, trs = (t.cpu() for t in (out, olen, score, trp, trt, trs))
+    full, steps_cmp = 0, 0
+    for b in range(B):
+        seq, sc, trace = oracle.beam_search(p, enc_ref[b:b + 1], H.START, H.END, T, K, cfg, return_trace=True)
+        ok = True
+        for t, beams in enumerate(trace):
+            ref_sc = torch.tensor([s for _, _, s in beams], dtype=torch.float64)
+            gaps = (ref_sc[:-1] - ref_sc[1:]).abs()
+            if len(gaps) and float(gaps.min()) < BF16_GAP:
+                ok = False
+                break
+            nb = len(beams)
+            if trp[t, b, :nb].tolist() != [pb for pb, _, _ in beams] or trt[t, b, :nb].tolist() != [tk for _, tk, _ in beams]:
+                # a candidate just outside the kept K may have been within BF16_GAP of the K-th: not pinned
+                ok = False
+                break
+            assert torch.allclose(trs[t, b, :nb], ref_sc, rtol=0, atol=0.02 * (t + 1)), (b, t)
+            steps_cmp += 1
+        if ok:
+            full += 1
+            assert out[b, : int(olen[b])].tolist() == seq, b
+            assert abs(float(score[b]) - sc) < 0.02 * (len(trace) + 1)
+    print(f"bf16 beam vs fp32 oracle: {full}/{B} images identical end to end, {steps_cmp} steps compared")
+    assert steps_cmp >= 3 * B, "too few comparable steps: tolerance or kernel is off"
+
+
+def test_beam1_equals_persistent_greedy(pkg):
+    cfg = H.HEADLINE
+    p = oracle.make_params(cfg, 1, sharp=True)
+    p["decoder.output_layer.bias"][H.END] += 1.0
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    B, T = 37, 40
+    enc = torch.relu(torch.randn(B, 256, generator=torch.Generator().manual_seed(4))).cuda()
+    tokens, lengths, _ = m16.decoder.greedy(enc, H.START, H.END, T, 1.0, pkg._native.STOP_NONE)
+    out, olen, _ = m16.decoder.beam(enc, H.START, H.END, T, 1)
+    tokens, lengths, out, olen = tokens.cpu(), lengths.cpu(), out.cpu(), olen.cpu()
+    for b in range(B):
+        g = tokens[b, 1:].tolist()
+        g = g[: g.index(H.END)] if H.END in g else g
+        assert out[b, : int(olen[b])].tolist() == g, b
+
+
+def test_beam_bf16_model_api_and_general_fallback(pkg):
+    """Seq2SeqModel.inference(beam_size=K) on the bf16 model, and shapes the persistent kernel does
+    not cover (K > 8) still run through the general path."""
+    cfg = H.HEADLINE
+    p = oracle.make_params(cfg, 2, sharp=True)
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    x = H.make_images(cfg, 2)
+    one = m16.inference(x[:1].cuda(), H.START, H.END, max_length=12, beam_size=5)
+    batch = m16.beam_search_batch(m16.encoder(x.cuda()), H.START, H.END, 12, 5)
+    assert one == batch[0]
+    big = m16.beam_search_batch(m16.encoder(x.cuda()), H.START, H.END, 6, 10)
+    assert len(big) == 2 and all(len(r) <= 6 for r in big)
