@@ -39,25 +39,35 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+class ClockSampler:
+    """Samples SM clocks / throttle reasons while the timed region runs: ONE long-running
+    `nvidia-smi -lms` child (no fork per sample, nothing competing with the launch thread)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+        self.index, self.proc, self.rows = index, None, []
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            out = ""
+        for ln in out.splitlines():
+            cols = [c.strip() for c in ln.split(",")]
+            if len(cols) >= 6:
+                self.rows.append(cols)
 
     def summary(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -184,7 +194,7 @@ def run_ours(args):
         # Seq2SeqModel.greedy_stream: every step copies its own images from pinned host memory
         # (the copy of step i+1 overlaps the compute of step i) and reads the token ids back.
         e2e_s, (tok_h, lens_h, _) = e2e_run(x_host, args.steps)
-        sampler.stop_flag.set(); sampler.join()
+        sampler.stop()
         # the same call with the other host element types (reported next to the headline e2e)
         e2e_other = {}
         if world == 1 and not args.no_extras:
@@ -365,7 +375,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")

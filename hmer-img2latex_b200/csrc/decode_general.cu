@@ -900,7 +900,8 @@ namespace i2l { int persistent_set_debug(float* buf); }
 extern "C" int i2l_debug_set_buffer(float* buf) { return i2l::persistent_set_debug(buf); }
 // test aid: (T,B,K,K) device buffers that receive every live beam's top-K (token, log-prob) of the
 // next persistent beam calls (NULL, NULL switches the dump off)
-namespace i2l { int persistent_beam_set_debug(int* cand_tok, float* cand_logp); }
+namespace i2l { int persistent_beam_set_debug(int* cand_tok, float* cand_logp); int persistent_beam_set_ts(long long* ts, int step); }
+extern "C" int i2l_debug_set_beam_ts(long long* ts, int32_t step) { return i2l::persistent_beam_set_ts(ts, step); }
 extern "C" int i2l_debug_set_beam_trace(int32_t* cand_tok, float* cand_logp) {
   return i2l::persistent_beam_set_debug(cand_tok, cand_logp);
 }

@@ -46,6 +46,11 @@ struct Geo {
   static_assert(K >= 1 && K <= 16 && SMEM <= 232448, "beam geometry");
 };
 
+// 8 warps, no dedicated MMA warp: a 9th warp would put 3 warps on one SM sub-partition and cap the
+// kernel at 168 registers (16384 / (3 x 32)); warp 0 issues the MMAs at the point where it would
+// otherwise just wait for them.
+constexpr int BT = EPI_THREADS;
+
 enum { BAR_HFULL0 = 1, BAR_HFULL1 = 2, BAR_LDONE = 3, BAR_GDONE = 4, BAR_TOK = 5, BAR_FINAL = 6 };
 
 __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
@@ -62,6 +67,30 @@ __device__ __forceinline__ uint32_t tc_ld1_nowait(uint32_t taddr) {
 // (value, index) total order of torch.topk / argmax: larger value first, lower index among equals
 __device__ __forceinline__ bool before(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
 
+// float -> int with the same ordering under signed compare (-0.0 < +0.0, NaNs at the extremes)
+__device__ __forceinline__ int ordered_int(float f) {
+  const int b = __float_as_int(f);
+  return b ^ ((b >> 31) & 0x7fffffff);
+}
+// fp64 score <-> int64 key with the same ordering (signed compare); the map is an involution
+__device__ __forceinline__ long long score_key(double d) {
+  const long long b = __double_as_longlong(d);
+  return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double key_score(long long k) { return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL)); }
+
+// exact float -> double widening with integer ops only (the FP64 pipe of sm_100 has a ~100-cycle
+// latency: F2F.F64 / DSETP stay off the critical path, DADD is the one FP64 instruction left).
+// Denormal inputs flush to zero (a log-prob is 0, < -1e-7 or -inf, never denormal).
+__device__ __forceinline__ double widen_f32(float f) {
+  const uint32_t b = __float_as_uint(f);
+  const uint32_t e = (b >> 23) & 0xffu, m = b & 0x7fffffu;
+  const uint32_t ex = e == 0xffu ? 0x7ffu : e + 896u;      // inf / nan keep the all-ones exponent
+  const uint32_t hi = (b & 0x80000000u) | (e == 0u ? 0u : ((ex << 20) | (m >> 3)));
+  const uint32_t lo = e == 0u ? 0u : (m << 29);
+  return __hiloint2double((int)hi, (int)lo);
+}
+
 struct BeamParams {
   const unsigned char* wimg;
   const float* gtok;
@@ -72,10 +101,18 @@ struct BeamParams {
   double* score;                 // [B*K] final beam scores
   int B, T, start_id, end_id;
   int* dbg_ctok; float* dbg_clogp;   // optional (T,B,K,K) dump of every live beam's top-K (token, log-prob)
+  long long* dbg_ts; int dbg_step;   // optional clock64() stamps of one step of cluster 0 / rank 0 / thread 0
 };
 
+#define BEAM_TS(slot)                                              \
+  do {                                                             \
+    asm volatile("" ::: "memory");                                 \
+    if (ts_on && tid == 0) P.dbg_ts[slot] = clock64();             \
+    asm volatile("" ::: "memory");                                 \
+  } while (0)
+
 template <int K>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persistent_beam_kernel(BeamParams P) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_beam_kernel(BeamParams P) {
   using G = Geo<K>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -97,17 +134,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     misc[1] = 0;
   }
-  if (warp == 8) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + G::OFF_MISC) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < 2 * HB_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem + G::OFF_H)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * HB_BYTES / 16; i += BT) reinterpret_cast<uint4*>(smem + G::OFF_H)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = misc[0];
-  if (warp < 8) {   // resident weights -> tensor memory (same image as the greedy kernel)
+  {   // resident weights -> tensor memory (same image as the greedy kernel)
     const int p = 32 * (warp & 3) + lane;
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     const int half = warp >> 2;
@@ -135,19 +172,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
 
   const uint32_t TM_L = tmem + TC_L, TM_G0 = tmem + TC_G0, TM_G1 = tmem + TC_G1;
 
-  if (warp == 8) {
-    // =========================== MMA issuer warp (identical to the greedy kernel) ===========================
-    const uint64_t dbase = DESC_HI | (uint64_t)(((sbase >> 4) & 0x3FFFu) | (1u << 16));
-    auto issue_tile = [&](uint32_t d_tmem, uint32_t a_col, uint32_t h_off) {
+  // MMA issue (warp 0, one elected lane): D[gate/vocab row, beam row] = W (TMEM A operand) x h^T (smem B operand)
+  const uint64_t dbase = DESC_HI | (uint64_t)(((sbase >> 4) & 0x3FFFu) | (1u << 16));
+  auto issue_tile = [&](uint32_t d_tmem, uint32_t a_col, uint32_t h_off) {
 #pragma unroll
-      for (int kb = 0; kb < 4; ++kb) {
+    for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t bd = dbase + (uint64_t)((h_off + kb * HSLICE_BYTES + k * 32) >> 4);
-          tc_mma_ts(d_tmem, tmem + a_col + (kb * 4 + k) * 8, bd, IDESC, (kb | k) ? 1u : 0u);
-        }
+      for (int k = 0; k < 4; ++k) {
+        uint64_t bd = dbase + (uint64_t)((h_off + kb * HSLICE_BYTES + k * 32) >> 4);
+        tc_mma_ts(d_tmem, tmem + a_col + (kb * 4 + k) * 8, bd, IDESC, (kb | k) ? 1u : 0u);
       }
-    };
+    }
+  };
+  if (warp == 0) {   // gates of step 0 from h_0 = 0 (buffer 0)
     tc_fence_after();
     if (elect_one()) {
       issue_tile(TM_G0, TC_WG0, G::OFF_H);
@@ -155,27 +192,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       tc_commit(BAR(BAR_GDONE));
     }
     __syncwarp();
-    for (int s = 0; s < P.T; ++s) {
-      const int nb = (s + 1) & 1;
-      mbar_wait(BAR(BAR_HFULL0 + nb), (uint32_t)((s >> 1) & 1));
-      if (*reinterpret_cast<volatile uint32_t*>(&misc[1])) break;
-      tc_fence_after();
-      const uint32_t hb = G::OFF_H + nb * HB_BYTES;
-      if (elect_one()) {
-        issue_tile(TM_L, TC_WO, hb);
-        tc_commit(BAR(BAR_LDONE));
-        if (s + 1 < P.T) {
-          issue_tile(TM_G0, TC_WG0, hb);
-          issue_tile(TM_G1, TC_WG1, hb);
-          tc_commit(BAR(BAR_GDONE));
-        }
-      }
-      __syncwarp();
-    }
-    if (elect_one()) tc_commit(BAR(BAR_FINAL));
-    __syncwarp();
-    mbar_wait(BAR(BAR_FINAL), 0);
-  } else {
+  }
+  {
     // =========================== epilogue warps (256 threads) ===========================
     const int q = warp & 3, cg = warp >> 2;
     const int p = 32 * q + lane;                          // accumulator row (TMEM lane) = CTA-local gate row / vocab row
@@ -210,14 +228,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
     const int n_leader = n - n_slot;                      // lane of beam slot 0 of the image
     const bool is_leader = n_valid && n_slot == 0;
     double base = 0.0;                                    // score of the beam in this row
+    long long basekey = 0;                                // score_key(base)
     int curtok = P.start_id;
     // image state (leader lanes)
     int st_alive = n_valid ? 1 : 0, st_nbeams = 1, st_has = 0, st_best_step = -1, st_best_slot = -1, st_last = -1;
-    double st_best = 0.0;
+    long long st_best = 0;                                // best completed score as an order-preserving key
 
+    if (warp == 0) {   // row record of step 0: only slot 0 (the START beam) is live
+      reinterpret_cast<double*>(smem + G::OFF_ROW)[n * 2] = 0.0;
+      reinterpret_cast<int*>(smem + G::OFF_ROW)[n * 4 + 2] = (n_valid && n_slot == 0) ? 1 : 0;
+    }
     int s = 0;
     for (; s < P.T; ++s) {
       // ---------------- Epi-G(s): gates (read from the parent's column) -> c_{s+1}, h_{s+1} ----------------
+      const bool ts_on = P.dbg_ts != nullptr && cluster == 0 && rank == 0 && s == P.dbg_step;
+      BEAM_TS(0);
       float gt0[16], gt1[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -225,8 +250,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
         gt0[j] = __ldg(g);
         gt1[j] = __ldg(g + 128);
       }
+      BEAM_TS(1);
       mbar_wait(BAR(BAR_GDONE), s & 1);
       tc_fence_after();
+      BEAM_TS(2);
       uint32_t r0[16], r1[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -234,6 +261,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
         r1[j] = tc_ld1_nowait(TM_G1 + lane_addr + col0 + par[j]);
       }
       tc_wait_ld();
+      BEAM_TS(3);
       {   // c follows the parent beam: K-way select inside each image's K columns
         float cn[16];
 #pragma unroll
@@ -279,6 +307,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
           *reinterpret_cast<__nv_bfloat16*>(hdst + nn * 128 + chunk * 16 + (u & 7) * 2) = __float2bfloat16(hn[j]);
         }
       }
+      BEAM_TS(4);
       fence_proxy_async();
       tc_fence_before();
       epi_bar_sync();
@@ -291,9 +320,26 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
           bulk_s2peer(mapa(src, peer), src, HSLICE_BYTES, mapa(BAR(BAR_HFULL0 + nb), peer));
         }
       }
+      if (warp == 0) {   // MMA-L(s) and MMA-G(s+1) as soon as the four h slices are in place
+        mbar_wait(BAR(BAR_HFULL0 + nb), (uint32_t)((s >> 1) & 1));
+        tc_fence_after();
+        const uint32_t hb = G::OFF_H + nb * HB_BYTES;
+        if (elect_one()) {
+          issue_tile(TM_L, TC_WO, hb);                      // logits_s = W_out h_{s+1}
+          tc_commit(BAR(BAR_LDONE));
+          if (s + 1 < P.T) {
+            issue_tile(TM_G0, TC_WG0, hb);                  // gates of step s+1
+            issue_tile(TM_G1, TC_WG1, hb);
+            tc_commit(BAR(BAR_GDONE));
+          }
+        }
+        __syncwarp();
+      }
       // ---------------- Epi-L(s): logits -> per-row top-K + log-sum-exp partials ----------------
+      BEAM_TS(5);
       mbar_wait(BAR(BAR_LDONE), s & 1);
       tc_fence_after();
+      BEAM_TS(6);
       {
         float lg[16];
         tc_ld16(TM_L + lane_addr + col0, lg);
@@ -301,7 +347,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
 #pragma unroll
         for (int j = 0; j < 16; ++j) LT[(col0 + j) * 128 + p] = lg[j] + bias;   // lanes -> consecutive words
       }
+      BEAM_TS(7);
       epi_bar_sync();
+      BEAM_TS(8);
       {
         const int row = tid >> 3, part = tid & 7;           // 8 threads per beam row, 16 vocabulary entries each
         float v[16];
@@ -324,167 +372,233 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
             x = tv; ix = ti;
           }
         }
-#pragma unroll
-        for (int m = 1; m < 8; m <<= 1) {                   // merge with the partner's list (both end up identical)
-          // bitonic half-cleaner against the reversed partner list (staged copy: entries k and K-1-k cross)
-          float av[K]; int ai[K];
-#pragma unroll
-          for (int k = 0; k < K; ++k) { av[k] = lv[k]; ai[k] = li[k]; }
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            const float ov = __shfl_xor_sync(0xffffffffu, av[K - 1 - k], m);
-            const int oi = __shfl_xor_sync(0xffffffffu, ai[K - 1 - k], m);
-            const bool take = before(ov, oi, av[k], ai[k]);
-            lv[k] = take ? ov : av[k]; li[k] = take ? oi : ai[k];
-          }
-          // odd-even transposition sort of the K survivors (descending, index-ascending among equals)
-#pragma unroll
-          for (int r = 0; r < K; ++r) {
-#pragma unroll
-            for (int k = r & 1; k + 1 < K; k += 2) {
-              const bool sw = before(lv[k + 1], li[k + 1], lv[k], li[k]);
-              const float tv = lv[k]; const int ti = li[k];
-              lv[k] = sw ? lv[k + 1] : lv[k]; li[k] = sw ? li[k + 1] : li[k];
-              lv[k + 1] = sw ? tv : lv[k + 1]; li[k + 1] = sw ? ti : li[k + 1];
-            }
-          }
-        }
-        const float mref = lv[0] == -INFINITY ? 0.f : lv[0];
+        BEAM_TS(9);
+        // sum of exp against the thread's own maximum: independent of the merge below, so the MUFU work
+        // overlaps the shuffle chain; rescaled to the row maximum afterwards
+        const float mloc = lv[0] == -INFINITY ? 0.f : lv[0];
         float se = 0.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) se += __expf(v[e] - mref);
+        for (int e = 0; e < 16; ++e) se += __expf(v[e] - mloc);
+        // merge of the 8 sorted lists of the row: K rounds of "best head over the 8 lanes" (xor butterfly on
+        // (value, index)); the lane that owns the winner pops its list.  Every lane ends with the row's top-K.
+        {
+          float wv[K]; int wi[K];
+#pragma unroll
+          for (int r = 0; r < K; ++r) {
+            float mv = lv[0]; int mi = li[0];
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, mv, m);
+              const int oi = __shfl_xor_sync(0xffffffffu, mi, m);
+              const bool take = before(ov, oi, mv, mi);
+              mv = take ? ov : mv; mi = take ? oi : mi;
+            }
+            wv[r] = mv; wi[r] = mi;
+            const bool won = mi == li[0];                   // indices are unique within the row (sentinels pop sentinels)
+#pragma unroll
+            for (int k = 0; k + 1 < K; ++k) { lv[k] = won ? lv[k + 1] : lv[k]; li[k] = won ? li[k + 1] : li[k]; }
+            lv[K - 1] = won ? -INFINITY : lv[K - 1]; li[K - 1] = won ? 0x7fffffff : li[K - 1];
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) { lv[k] = wv[k]; li[k] = wi[k]; }
+        }
+        BEAM_TS(10);
+        const float mref = lv[0] == -INFINITY ? 0.f : lv[0];
+        se *= __expf(mloc - mref);
         se += __shfl_xor_sync(0xffffffffu, se, 1);
         se += __shfl_xor_sync(0xffffffffu, se, 2);
         se += __shfl_xor_sync(0xffffffffu, se, 4);
-        if (part == 0) {
+        if (part == 0) {                                    // record -> own slot of the local exchange buffer
           uint32_t w[G::XW];
 #pragma unroll
           for (int i = 0; i < G::XW; ++i) w[i] = 0;
 #pragma unroll
           for (int k = 0; k < K; ++k) { w[2 * k] = __float_as_uint(lv[k]); w[2 * k + 1] = (uint32_t)(li[k] == 0x7fffffff ? 0x7fffffff : li[k] + 128 * (int)rank); }
           w[2 * K] = __float_as_uint(mref); w[2 * K + 1] = __float_as_uint(se);
-          const uint32_t slot = sbase + G::OFF_XCHG + (rank * NB + row) * (G::XW * 4);
+          uint4* dst = reinterpret_cast<uint4*>(smem + G::OFF_XCHG + (rank * NB + row) * (G::XW * 4));
 #pragma unroll
-          for (uint32_t d = 0; d < CL; ++d) {
-            const uint32_t dst = mapa(slot, d), dbar = mapa(BAR(BAR_TOK), d);
+          for (int i = 0; i < G::XW / 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          fence_proxy_async();
+        }
+      }
+      if (warp == 0) {                                      // slots of the new beams start empty
+        double* new_sc = reinterpret_cast<double*>(smem + G::OFF_NEW);
+        int* new_i = reinterpret_cast<int*>(smem + G::OFF_NEW);
+        new_sc[n * 2] = 0.0; new_i[n * 4 + 2] = -1; new_i[n * 4 + 3] = -1;
+      }
+      BEAM_TS(11);
+      epi_bar_sync();
+      BEAM_TS(23);
+      if (tid == 0) {                                       // the CTA's 32 records -> the three peers (one bulk copy each)
+        const uint32_t src = sbase + G::OFF_XCHG + rank * NB * (G::XW * 4);
+        mbar_arrive_expect_tx(BAR(BAR_TOK), (CL - 1) * NB * G::XW * 4);
 #pragma unroll
-            for (int i = 0; i < G::XW / 4; ++i) st_async_v4(dst + 16 * i, w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3], dbar);
+        for (uint32_t d = 1; d < CL; ++d) {
+          const uint32_t peer = (rank + d) & (CL - 1);
+          bulk_s2peer(mapa(src, peer), src, NB * G::XW * 4, mapa(BAR(BAR_TOK), peer));
+        }
+      }
+      BEAM_TS(24);
+      if (warp == 0 && s > 0) {
+        // finished beams retire to `completed` when next visited (258-260): depends on the previous step
+        // only, so it runs while the records are in flight.  First-wins max in slot order.
+        const int alive_i = __shfl_sync(0xffffffffu, st_alive, n_leader);
+        const int nbeams_i = __shfl_sync(0xffffffffu, st_nbeams, n_leader);
+        const bool ret = n_valid && alive_i && n_slot < nbeams_i && curtok == P.end_id;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int src = (n_leader + k) & 31;
+          const int rk = __shfl_sync(0xffffffffu, ret ? 1 : 0, src);
+          const long long sk = __shfl_sync(0xffffffffu, basekey, src);
+          if (rk && (!st_has || sk > st_best)) { st_has = 1; st_best = sk; st_best_step = s - 1; st_best_slot = k; }
+        }
+      }
+      BEAM_TS(12);
+      mbar_wait_cluster(BAR(BAR_TOK), s & 1);
+      BEAM_TS(18);
+      if (warp < 4) {
+        // ---- torch.topk(log_softmax(logits), K) per row (seq2seq.py:266-267) on warps 0-3: 4 lanes per row take
+        // one CTA record each; 4-way merge = K rounds of best-head butterfly (lower rank = lower vocabulary
+        // index wins ties); log-sum-exp combined over the 4 partials
+        const int row = tid >> 2, part = tid & 3;
+        const float* X = reinterpret_cast<const float*>(smem + G::OFF_XCHG) + (part * NB + row) * G::XW;
+        float lv[K]; int li[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float2 e = reinterpret_cast<const float2*>(X)[k];
+          lv[k] = e.x; li[k] = __float_as_int(e.y);
+        }
+        const float2 ms = reinterpret_cast<const float2*>(X)[K];
+        float M = ms.x;
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 1));
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 2));
+        float S = ms.y * __expf(ms.x - M);
+        S += __shfl_xor_sync(0xffffffffu, S, 1);
+        S += __shfl_xor_sync(0xffffffffu, S, 2);
+        const float lse = logf(S);
+        const double* row_sc = reinterpret_cast<const double*>(smem + G::OFF_ROW);
+        const int* row_i = reinterpret_cast<const int*>(smem + G::OFF_ROW);
+        const double rbase = row_sc[row * 2];
+        const bool rlive = row_i[row * 4 + 2] != 0;
+        long long* cand_key = reinterpret_cast<long long*>(smem + G::OFF_CAND);
+        int* cand_tk = reinterpret_cast<int*>(smem + G::OFF_CAND);
+        // rank of every own entry among the 4 x K entries of the row by counting (no dependent rounds): the
+        // own list is sorted, an entry of CTA record `q` precedes an equal value iff q < part (lower index)
+        // (values as order-preserving ints: one compare + one add per pair, the tie rule is folded into the threshold)
+        int rk[K], vi[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { rk[k] = k; vi[k] = ordered_int(lv[k] + 0.0f); }   // + 0.0f: -0.0 and +0.0 compare equal
+#pragma unroll
+        for (int d = 1; d < 4; ++d) {
+          const int lower = ((part ^ d) < part) ? 1 : 0;    // o precedes v  <=>  o > v, or o == v and lower  <=>  o > v - lower
+          int thr[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) thr[k] = vi[k] - lower;
+#pragma unroll
+          for (int k2 = 0; k2 < K; ++k2) {
+            const int o = __shfl_xor_sync(0xffffffffu, vi[k2], d);
+#pragma unroll
+            for (int k = 0; k < K; ++k) rk[k] += o > thr[k] ? 1 : 0;
+          }
+        }
+        BEAM_TS(25);
+        // candidates of the row (268-275), written at their rank: fp64 score as an order-preserving int64
+        // key; dead rows sort last
+        {
+          long long ck[K]; float clp[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) {                     // K independent DADDs (the FP64 pipe is slow: keep them in flight together)
+            clp[k] = (lv[k] - M) - lse;                     // log-prob of the rk-th best token
+            ck[k] = score_key(rlive ? rbase + widen_f32(clp[k]) : -INFINITY);
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            if (rk[k] < K) {
+              cand_key[(row * K + rk[k]) * 2] = ck[k];
+              cand_tk[(row * K + rk[k]) * 4 + 2] = li[k];
+            }
+          }
+          if (P.dbg_ctok != nullptr && rank == 0 && rlive) {
+            const int w16 = row & 15, img = cluster * G::IPC + (row >> 4) * G::IPG + w16 / K;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              if (rk[k] < K) {
+                const size_t o = ((((size_t)s * P.B + img) * K + w16 % K) * K) + rk[k];
+                P.dbg_ctok[o] = li[k]; P.dbg_clogp[o] = clp[k];
+              }
+            }
+          }
+        }
+        BEAM_TS(13);
+      }
+      BEAM_TS(14);
+      epi_bar_sync();
+      BEAM_TS(19);
+      {
+        // stable descending order of the image's K x K candidates (sorted(..., reverse=True)[:K], 279-280) by
+        // rank counting: thread (row, r) counts the candidates that precede candidate r of beam `row`
+        // (higher score, or equal score and earlier in (beam, rank) order); ranks < K are the new beams
+        const int row = tid >> 3, r = tid & 7;
+        const int w = row & 15, slot = w % K, row0i = row - slot;
+        const long long* cand_key = reinterpret_cast<const long long*>(smem + G::OFF_CAND);
+        const int* cand_tk = reinterpret_cast<const int*>(smem + G::OFF_CAND);
+        const int* row_i = reinterpret_cast<const int*>(smem + G::OFF_ROW);
+        if (r < K && w < G::USED && row_i[row * 4 + 2]) {
+          const long long key = cand_key[(row * K + r) * 2];
+          int rk = r;                                        // the beam's own list is sorted: r earlier entries
+#pragma unroll
+          for (int k2 = 0; k2 < K; ++k2) {
+            // o precedes key  <=>  o > key, or o == key and k2 < slot  <=>  o > key - (k2 < slot)
+            const long long thr = key - (k2 < slot ? 1 : 0);
+            const bool other = k2 != slot;
+#pragma unroll
+            for (int r2 = 0; r2 < K; ++r2) {
+              const long long o = cand_key[((row0i + k2) * K + r2) * 2];
+              rk += (other && o > thr) ? 1 : 0;
+            }
+          }
+          if (rk < K) {
+            long long* new_key = reinterpret_cast<long long*>(smem + G::OFF_NEW);
+            int* new_i = reinterpret_cast<int*>(smem + G::OFF_NEW);
+            new_key[(row0i + rk) * 2] = key; new_i[(row0i + rk) * 4 + 2] = slot; new_i[(row0i + rk) * 4 + 3] = cand_tk[(row * K + r) * 4 + 2];
           }
         }
       }
-      // ---------------- merge (warp 0): topk(log_softmax) per row, beam update per image ----------------
+      BEAM_TS(20);
+      epi_bar_sync();
+      BEAM_TS(15);
       if (warp == 0) {
-        if (lane == 0) mbar_arrive_expect_tx(BAR(BAR_TOK), CL * NB * G::XW * 4);
-        mbar_wait_cluster(BAR(BAR_TOK), s & 1);
-        const float* X = reinterpret_cast<const float*>(smem + G::OFF_XCHG);
-        const int* Xi = reinterpret_cast<const int*>(smem + G::OFF_XCHG);
-        // log-sum-exp over the 4 CTA partials (torch.log_softmax, seq2seq.py:266)
-        float M = -INFINITY;
-#pragma unroll
-        for (int r = 0; r < CL; ++r) M = fmaxf(M, X[(r * NB + n) * G::XW + 2 * K]);
-        float S = 0.f;
-#pragma unroll
-        for (int r = 0; r < CL; ++r) S += X[(r * NB + n) * G::XW + 2 * K + 1] * expf(X[(r * NB + n) * G::XW + 2 * K] - M);
-        const float lse = logf(S);
-        // 4-way merge of the sorted CTA lists (lower rank = lower vocabulary index wins ties)
-        int pos0 = 0, pos1 = 0, pos2 = 0, pos3 = 0;
-        float tv[K]; int ti[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          float bv = -INFINITY; int bi = 0x7fffffff, br = 0;
-#pragma unroll
-          for (int r = 0; r < CL; ++r) {
-            const int ps = r == 0 ? pos0 : (r == 1 ? pos1 : (r == 2 ? pos2 : pos3));
-            if (ps < K) {
-              const float hv = X[(r * NB + n) * G::XW + 2 * ps];
-              const int hidx = Xi[(r * NB + n) * G::XW + 2 * ps + 1];
-              if (r == 0 || before(hv, hidx, bv, bi)) { bv = hv; bi = hidx; br = r; }
-            }
-          }
-          pos0 += br == 0; pos1 += br == 1; pos2 += br == 2; pos3 += br == 3;
-          tv[k] = (bv - M) - lse;                          // log-prob of the k-th best token
-          ti[k] = bi;
-        }
-        // ---- beam bookkeeping (seq2seq.py:254-284) ----
+        const long long* new_key = reinterpret_cast<const long long*>(smem + G::OFF_NEW);
+        const int* new_i = reinterpret_cast<const int*>(smem + G::OFF_NEW);
         const int alive_i = __shfl_sync(0xffffffffu, st_alive, n_leader);
-        const int nbeams_i = __shfl_sync(0xffffffffu, st_nbeams, n_leader);
-        const bool live = n_valid && alive_i && n_slot < nbeams_i && curtok != P.end_id;   // 258-260
-        double* cand_sc = reinterpret_cast<double*>(smem + G::OFF_CAND);
-        int* cand_tk = reinterpret_cast<int*>(smem + G::OFF_CAND);
-        double* row_sc = reinterpret_cast<double*>(smem + G::OFF_ROW);
-        int* row_i = reinterpret_cast<int*>(smem + G::OFF_ROW);
-        double* new_sc = reinterpret_cast<double*>(smem + G::OFF_NEW);
-        int* new_i = reinterpret_cast<int*>(smem + G::OFF_NEW);
-        row_sc[n * 2] = base; row_i[n * 4 + 2] = live ? 1 : 0;
-        if (P.dbg_ctok != nullptr && rank == 0 && live) {
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            const size_t o = ((((size_t)s * P.B + n_img) * K + n_slot) * K) + k;
-            P.dbg_ctok[o] = ti[k]; P.dbg_clogp[o] = tv[k];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          cand_sc[(n * K + k) * 2] = base + (double)tv[k];                                   // 268-275
-          cand_tk[(n * K + k) * 4 + 2] = ti[k];
-        }
-        __syncwarp();
+        const int ps = new_i[n * 4 + 2], tk = new_i[n * 4 + 3];
+        const long long nkey = new_key[n * 2];
+        const double nsc = key_score(nkey);
+        const uint32_t img_mask = ((1u << K) - 1u) << n_leader;
+        const uint32_t kept = __ballot_sync(0xffffffffu, n_valid && ps >= 0) & img_mask;
+        const uint32_t notend = __ballot_sync(0xffffffffu, n_valid && ps >= 0 && tk != P.end_id) & img_mask;
         if (is_leader && st_alive) {
-          for (int k = 0; k < st_nbeams; ++k) {             // finished beams retire to `completed` (258-260)
-            if (!row_i[(n + k) * 4 + 2]) {
-              const double sc = row_sc[(n + k) * 2];
-              if (!st_has || sc > st_best) { st_has = 1; st_best = sc; st_best_step = s - 1; st_best_slot = k; }
-            }
-          }
-          // stable descending merge of the live beams' sorted candidate lists (sorted(..., reverse=True), 279-280)
-          int hp[K];
-#pragma unroll
-          for (int k = 0; k < K; ++k) hp[k] = 0;
-          int nkeep = 0;
-          bool all_end = true;
-#pragma unroll 1
-          for (int r = 0; r < K; ++r) {
-            int best = -1; double bsc = 0.0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-              if (k < st_nbeams && row_i[(n + k) * 4 + 2] && hp[k] < K) {
-                const double sc = cand_sc[((n + k) * K + hp[k]) * 2];
-                if (best < 0 || sc > bsc) { best = k; bsc = sc; }
-              }
-            }
-            if (best < 0) break;
-            int bh = 0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) { if (k == best) { bh = hp[k]; hp[k] += 1; } }
-            const int tk = cand_tk[((n + best) * K + bh) * 4 + 2];
-            new_sc[(n + r) * 2] = bsc; new_i[(n + r) * 4 + 2] = best; new_i[(n + r) * 4 + 3] = tk;
-            all_end = all_end && tk == P.end_id;
-            ++nkeep;
-          }
-          for (int k = nkeep; k < K; ++k) { new_sc[(n + k) * 2] = 0.0; new_i[(n + k) * 4 + 2] = -1; new_i[(n + k) * 4 + 3] = -1; }
+          const int nkeep = __popc(kept);
           if (nkeep == 0) {                                 // `if not candidates: break` (276-277)
             st_alive = 0;
           } else {
             st_nbeams = nkeep; st_last = s;
-            if (all_end) {                                  // 282-284
-              for (int k = 0; k < nkeep; ++k) {
-                const double sc = new_sc[(n + k) * 2];
-                if (!st_has || sc > st_best) { st_has = 1; st_best = sc; st_best_step = s; st_best_slot = k; }
-              }
+            if (notend == 0) {                              // all new beams end with END (282-284): completed.extend
+              // the new beams are sorted by score, max() keeps the first maximum: only slot 0 can displace
+              if (!st_has || nkey > st_best) { st_has = 1; st_best = nkey; st_best_step = s; st_best_slot = 0; }
               st_alive = 0;
             }
           }
         }
-        __syncwarp();
         int* pub = reinterpret_cast<int*>(smem + G::OFF_PUB);
         if (n_valid && alive_i) {
-          const int ps = new_i[n * 4 + 2], tk = new_i[n * 4 + 3];
           const size_t tro = ((size_t)s * P.B + n_img) * K + n_slot;
           if (rank == 0) {
             P.tr_parent[tro] = ps; P.tr_token[tro] = tk;
-            if (P.tr_score) P.tr_score[tro] = ps >= 0 ? new_sc[n * 2] : nan("");
+            if (P.tr_score) P.tr_score[tro] = ps >= 0 ? nsc : nan("");
           }
-          base = ps >= 0 ? new_sc[n * 2] : 0.0;
+          base = ps >= 0 ? nsc : 0.0;
+          basekey = score_key(base);
           curtok = ps >= 0 ? tk : P.end_id;
           pub[n * 2] = ps >= 0 ? (n_w - n_slot + ps) : n_w;
           pub[n * 2 + 1] = curtok;
@@ -493,10 +607,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
           pub[n * 2 + 1] = n_valid ? curtok : P.start_id;
         }
         const int alive_now = __shfl_sync(0xffffffffu, st_alive, n_leader);
+        const int nbeams_now = __shfl_sync(0xffffffffu, st_nbeams, n_leader);
+        // row record of the next step: (score, live) -- a beam whose last token is END is not expanded (258-260)
+        double* row_sc = reinterpret_cast<double*>(smem + G::OFF_ROW);
+        int* row_i = reinterpret_cast<int*>(smem + G::OFF_ROW);
+        row_sc[n * 2] = base;
+        row_i[n * 4 + 2] = (n_valid && alive_now && n_slot < nbeams_now && curtok != P.end_id) ? 1 : 0;
         const bool cluster_done = __all_sync(0xffffffffu, !n_valid || !alive_now);
         if (lane == 0 && cluster_done) misc[1] = 1;
+        BEAM_TS(16);
       }
       epi_bar_sync();
+      BEAM_TS(17);
       {
         const int* pub = reinterpret_cast<const int*>(smem + G::OFF_PUB);
 #pragma unroll
@@ -509,17 +631,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       if (is_leader) {
         BeamState st;
         st.alive = st_alive; st.nbeams = st_nbeams; st.has_completed = st_has; st.best_step = st_best_step;
-        st.best_slot = st_best_slot; st.best_score = st_best; st.last_step = st_last;
+        st.best_slot = st_best_slot; st.best_score = key_score(st_best); st.last_step = st_last;
         P.bstate[n_img] = st;
       }
     }
-    if (*reinterpret_cast<volatile uint32_t*>(&misc[1]) && tid == 0) {
-      mbar_arrive(BAR(BAR_HFULL0 + ((s + 1) & 1)));       // release the MMA warp (early exit)
+    if (warp == 0) {   // every MMA issued above has completed before tensor memory is released
+      if (elect_one()) tc_commit(BAR(BAR_FINAL));
+      __syncwarp();
+      mbar_wait(BAR(BAR_FINAL), 0);
     }
   }
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 8) {
+  if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
 }
@@ -529,7 +653,7 @@ int launch_beam(const BeamParams& P, int batch, cudaStream_t s) {
   using G = Geo<K>;
   const int ncl = cdiv(batch, G::IPC);
   I2L_CUDA_OK(cudaFuncSetAttribute(persistent_beam_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
-  persistent_beam_kernel<K><<<ncl * CL, THREADS, G::SMEM, s>>>(P);
+  persistent_beam_kernel<K><<<ncl * CL, BT, G::SMEM, s>>>(P);
   I2L_LAUNCH_OK();
   return I2L_OK;
 }
@@ -538,6 +662,9 @@ int launch_beam(const BeamParams& P, int batch, cudaStream_t s) {
 
 static int* g_dbg_ctok = nullptr;     // tests only: see i2l_debug_set_beam_trace
 static float* g_dbg_clogp = nullptr;
+static long long* g_dbg_ts = nullptr;
+static int g_dbg_step = 0;
+int persistent_beam_set_ts(long long* ts, int step) { g_dbg_ts = ts; g_dbg_step = step; return I2L_OK; }
 int persistent_beam_set_debug(int* cand_tok, float* cand_logp) {
   g_dbg_ctok = cand_tok; g_dbg_clogp = cand_logp;
   return I2L_OK;
@@ -560,7 +687,7 @@ int persistent_beam(const i2l_dec_desc& d, const void* section, const float* gct
   P.gctx = gctx_img; P.tr_parent = tr_parent; P.tr_token = tr_token; P.tr_score = tr_score;
   P.bstate = bstate; P.score = score;
   P.B = batch; P.T = max_length; P.start_id = start_id; P.end_id = end_id;
-  P.dbg_ctok = g_dbg_ctok; P.dbg_clogp = g_dbg_clogp;
+  P.dbg_ctok = g_dbg_ctok; P.dbg_clogp = g_dbg_clogp; P.dbg_ts = g_dbg_ts; P.dbg_step = g_dbg_step;
   // traces default to "empty slot" (-1 / NaN): the kernel writes only the steps an image is alive in
   const size_t n = (size_t)max_length * batch * beam_size;
   I2L_CUDA_OK(cudaMemsetAsync(tr_parent, 0xff, n * sizeof(int), s));

@@ -429,7 +429,7 @@ def sample_loop(p: Params, encoder_output: torch.Tensor, start: int, end: int, m
 
 
 def beam_search(p: Params, encoder_output: torch.Tensor, start: int, end: int, max_length: int,
-                beam_size: int, cfg: dict, return_trace: bool = False):
+                beam_size: int, cfg: dict, return_trace: bool = False, return_cands: bool = False):
     """`Seq2SeqModel._beam_search` (seq2seq.py:234-298) for ONE image
     (encoder_output (1,E)).  Scores accumulate as Python floats (double) from
     fp32 log-probs; finished beams retire to `completed` when next visited;
@@ -438,6 +438,7 @@ def beam_search(p: Params, encoder_output: torch.Tensor, start: int, end: int, m
     beams = [{"tokens": [start], "hidden": None, "score": 0.0}]
     completed = []
     trace = []
+    all_cands = []
     for _ in range(max_length):
         cands = []
         for bi, beam in enumerate(beams):
@@ -455,8 +456,9 @@ def beam_search(p: Params, encoder_output: torch.Tensor, start: int, end: int, m
         if not cands:                                                          # :276-277
             break
         cands = sorted(cands, key=lambda b: b["score"], reverse=True)          # :279
+        all_cands.append([(b["parent"], b["tokens"][-1], b["score"]) for b in cands])
         beams = cands[:beam_size]                                              # :280
-        if return_trace:
+        if return_trace or return_cands:
             trace.append([(b["parent"], b["tokens"][-1], b["score"]) for b in beams])
         if all(b["tokens"][-1] == end for b in beams):                         # :282-284
             completed.extend(beams)
@@ -467,6 +469,8 @@ def beam_search(p: Params, encoder_output: torch.Tensor, start: int, end: int, m
         seq = seq[1:]
     if end in seq:
         seq = seq[: seq.index(end)]
+    if return_cands:
+        return seq, best["score"], trace, all_cands
     if return_trace:
         return seq, best["score"], trace
     return seq

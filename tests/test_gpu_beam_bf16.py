@@ -5,9 +5,9 @@ Three layers of checks, all through the C-ABI (`i2l_decode_beam`, precision bf16
     (token, fp32 log-prob); replaying the reference's loop (seq2seq.py:254-290, restated in
     `replay_reference_beam`) on those candidates must reproduce the kernel's parents, tokens,
     fp64 scores, final sequences and final scores exactly.
- 2. against the fp32 CPU oracle under the bf16 tolerance: per-step parents / tokens must match the
-    oracle while its neighbouring candidate scores are further apart than BF16_GAP; an image is
-    dropped from the comparison at its first near tie.
+ 2. against the fp32 CPU oracle under the bf16 tolerance: per-step parents / tokens / scores must
+    match the oracle up to the first step where they differ, and that step must be a near tie
+    (oracle scores of the two candidates within BF16_GAP).
  3. beam 1 == the persistent greedy kernel (same MMAs, same logits) cut at the first END.
 """
 import ctypes as C
@@ -20,7 +20,7 @@ from helpers import oracle
 
 pytestmark = pytest.mark.gpu
 
-BF16_GAP = 0.08       # oracle candidate-score gap (nats) below which bf16 rounding may reorder
+BF16_GAP = 0.02       # oracle candidate-score gap (nats) below which bf16 rounding may reorder (observed <= 0.003)
 
 
 def replay_reference_beam(ctok, clogp, start, end, T, K):
@@ -97,6 +97,11 @@ def test_beam_bookkeeping_bit_exact_given_scores(pkg, B, K, T, seed, end_boost):
 
 @pytest.mark.parametrize("B,K,T", [(12, 5, 20), (6, 3, 25)])
 def test_beam_bf16_vs_fp32_oracle(pkg, B, K, T):
+    """Walk every image step by step against the fp32 oracle.  While the kept beams (parents and
+    tokens, in order) are identical the fp64 scores must agree within the accumulated bf16 error;
+    the first step where they differ must be a near tie -- the oracle's own score of the candidate
+    the kernel kept is within BF16_GAP of the candidate the oracle kept at that rank -- after which
+    the image is no longer comparable (the beam states differ)."""
     cfg = H.HEADLINE
     p = oracle.make_params(cfg, 2, sharp=True)
     p["decoder.output_layer.bias"][H.END] += 1.0
@@ -107,29 +112,36 @@ def test_beam_bf16_vs_fp32_oracle(pkg, B, K, T):
     enc = m32.encoder(x.cuda())                              # isolate the decoder
     out, olen, score, (trp, trt, trs) = m16.decoder.beam(enc, H.START, H.END, T, K, return_trace=True)
     out, olen, score, trp, trt, trs = (t.cpu() for t in (out, olen, score, trp, trt, trs))
-    full, steps_cmp = 0, 0
+    full, steps_cmp, near, bad = 0, 0, [], []
     for b in range(B):
-        seq, sc, trace = oracle.beam_search(p, enc_ref[b:b + 1], H.START, H.END, T, K, cfg, return_trace=True)
-        ok = True
+        seq, sc, trace, cands = oracle.beam_search(p, enc_ref[b:b + 1], H.START, H.END, T, K, cfg, return_cands=True)
+        same = True
         for t, beams in enumerate(trace):
-            ref_sc = torch.tensor([s for _, _, s in beams], dtype=torch.float64)
-            gaps = (ref_sc[:-1] - ref_sc[1:]).abs()
-            if len(gaps) and float(gaps.min()) < BF16_GAP:
-                ok = False
-                break
             nb = len(beams)
-            if trp[t, b, :nb].tolist() != [pb for pb, _, _ in beams] or trt[t, b, :nb].tolist() != [tk for _, tk, _ in beams]:
-                # a candidate just outside the kept K may have been within BF16_GAP of the K-th: not pinned
-                ok = False
-                break
-            assert torch.allclose(trs[t, b, :nb], ref_sc, rtol=0, atol=0.02 * (t + 1)), (b, t)
-            steps_cmp += 1
-        if ok:
+            got = list(zip(trp[t, b, :nb].tolist(), trt[t, b, :nb].tolist()))
+            ref = [(pb, tk) for pb, tk, _ in beams]
+            if got == ref:
+                ref_sc = torch.tensor([s for _, _, s in beams], dtype=torch.float64)
+                assert torch.allclose(trs[t, b, :nb], ref_sc, rtol=0, atol=0.03 * (t + 1)), (b, t)
+                steps_cmp += 1
+                continue
+            same = False
+            r = next(i for i in range(nb) if got[i] != ref[i])
+            table = {(pb, tk): s for pb, tk, s in cands[t]}
+            # the oracle's score of the kernel's choice; a token from outside the oracle's per-beam top-K
+            # (near tie at rank K / K+1 inside one beam) has no oracle score: use the kernel's own
+            s_dev = table.get(got[r], float(trs[t, b, r]))
+            gap = abs(s_dev - beams[r][2])
+            (near if gap < BF16_GAP else bad).append((b, t, r, round(gap, 4)))
+            break
+        if same:
             full += 1
             assert out[b, : int(olen[b])].tolist() == seq, b
-            assert abs(float(score[b]) - sc) < 0.02 * (len(trace) + 1)
-    print(f"bf16 beam vs fp32 oracle: {full}/{B} images identical end to end, {steps_cmp} steps compared")
-    assert steps_cmp >= 3 * B, "too few comparable steps: tolerance or kernel is off"
+            assert abs(float(score[b]) - sc) < 0.03 * (len(trace) + 1)
+    print(f"bf16 beam vs fp32 oracle: {full}/{B} images identical end to end, {steps_cmp} steps compared, "
+          f"near-tie divergences {near}")
+    assert not bad, f"divergence away from a near tie: {bad}"
+    assert steps_cmp >= 2 * B, "too few comparable steps: tolerance or kernel is off"
 
 
 def test_beam1_equals_persistent_greedy(pkg):
