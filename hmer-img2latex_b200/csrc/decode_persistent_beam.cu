@@ -219,6 +219,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
     const float s1 = hi ? 0.5f : 1.0f, m1 = hi ? 0.5f : 1.0f, b1 = hi ? 0.5f : 0.0f;
     const float* gt_base = P.gtok + (size_t)rank * 256 + p;
     float* LT = reinterpret_cast<float*>(smem + G::OFF_LT);
+    // word of vocabulary row p inside a row of the transposed logits tile: 16-byte chunk c = p / 4 is stored at
+    // c ^ ((c >> 3) & 3), so that the top-K threads (8 per row, 16 CONTIGUOUS vocabulary entries each = chunks
+    // 4*part .. 4*part+3) read conflict-free float4s
+    const int pw = 32 * q + ((((lane >> 2) ^ q) << 2) | (lane & 3));
 
     // ---- row / image state of the merge warp (warp 0: lane n <-> beam row n of the cluster) ----
     const int n = lane;                                   // meaningful in warp 0 only
@@ -345,25 +349,25 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
         tc_ld16(TM_L + lane_addr + col0, lg);
         tc_fence_before();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) LT[(col0 + j) * 128 + p] = lg[j] + bias;   // lanes -> consecutive words
+        for (int j = 0; j < 16; ++j) LT[(col0 + j) * 128 + pw] = lg[j] + bias;  // lanes -> distinct banks
       }
       BEAM_TS(7);
       epi_bar_sync();
       BEAM_TS(8);
       {
-        const int row = tid >> 3, part = tid & 7;           // 8 threads per beam row, 16 vocabulary entries each
+        const int row = tid >> 3, part = tid & 7;           // 8 threads per beam row, vocabulary entries [16 part, 16 part + 16)
         float v[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float4 t4 = reinterpret_cast<const float4*>(LT)[row * 32 + i * 8 + part];
+          float4 t4 = reinterpret_cast<const float4*>(LT)[row * 32 + 4 * part + (i ^ (part >> 1))];
           v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
         }
-        float lv[K]; int li[K];
+        float lv[K]; int li[K];                             // sorted top-K of the 16 entries: (value, entry 0..15)
 #pragma unroll
-        for (int k = 0; k < K; ++k) { lv[k] = -INFINITY; li[k] = 0x7fffffff; }
+        for (int k = 0; k < K; ++k) { lv[k] = -INFINITY; li[k] = 0; }
 #pragma unroll
         for (int e = 0; e < 16; ++e) {                      // ascending index: strict > keeps the lower index first
-          float x = v[e]; int ix = 4 * ((e >> 2) * 8 + part) + (e & 3);
+          float x = v[e]; int ix = e;
 #pragma unroll
           for (int k = 0; k < K; ++k) {
             const bool gt = x > lv[k];
@@ -379,25 +383,26 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
         float se = 0.f;
 #pragma unroll
         for (int e = 0; e < 16; ++e) se += __expf(v[e] - mloc);
-        // merge of the 8 sorted lists of the row: K rounds of "best head over the 8 lanes" (xor butterfly on
-        // (value, index)); the lane that owns the winner pops its list.  Every lane ends with the row's top-K.
+        // merge of the 8 sorted lists of the row: K rounds of "best head over the 8 lanes".  The vocabulary index
+        // grows with the lane, so among equal heads the lowest lane wins (ballot + ffs) and only values travel
+        // through the max butterfly; the winner pops its list.  Every lane ends with the row's top-K.
         {
           float wv[K]; int wi[K];
+          const int gsh = lane & 24;                        // first lane of the row's 8-lane group
 #pragma unroll
           for (int r = 0; r < K; ++r) {
-            float mv = lv[0]; int mi = li[0];
-#pragma unroll
-            for (int m = 1; m < 8; m <<= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, mv, m);
-              const int oi = __shfl_xor_sync(0xffffffffu, mi, m);
-              const bool take = before(ov, oi, mv, mi);
-              mv = take ? ov : mv; mi = take ? oi : mi;
-            }
-            wv[r] = mv; wi[r] = mi;
-            const bool won = mi == li[0];                   // indices are unique within the row (sentinels pop sentinels)
+            float m = lv[0];
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            const uint32_t grp = (__ballot_sync(0xffffffffu, lv[0] == m) >> gsh) & 0xffu;
+            const int wl = (__ffs(grp) - 1) & 7;
+            const int we = __shfl_sync(0xffffffffu, li[0], gsh + wl);
+            wv[r] = m; wi[r] = 16 * wl + we;
+            const bool won = part == wl;
 #pragma unroll
             for (int k = 0; k + 1 < K; ++k) { lv[k] = won ? lv[k + 1] : lv[k]; li[k] = won ? li[k + 1] : li[k]; }
-            lv[K - 1] = won ? -INFINITY : lv[K - 1]; li[K - 1] = won ? 0x7fffffff : li[K - 1];
+            lv[K - 1] = won ? -INFINITY : lv[K - 1];
           }
 #pragma unroll
           for (int k = 0; k < K; ++k) { lv[k] = wv[k]; li[k] = wi[k]; }
@@ -413,7 +418,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
 #pragma unroll
           for (int i = 0; i < G::XW; ++i) w[i] = 0;
 #pragma unroll
-          for (int k = 0; k < K; ++k) { w[2 * k] = __float_as_uint(lv[k]); w[2 * k + 1] = (uint32_t)(li[k] == 0x7fffffff ? 0x7fffffff : li[k] + 128 * (int)rank); }
+          for (int k = 0; k < K; ++k) { w[2 * k] = __float_as_uint(lv[k]); w[2 * k + 1] = (uint32_t)(li[k] + 128 * (int)rank); }
           w[2 * K] = __float_as_uint(mref); w[2 * K + 1] = __float_as_uint(se);
           uint4* dst = reinterpret_cast<uint4*>(smem + G::OFF_XCHG + (rank * NB + row) * (G::XW * 4));
 #pragma unroll
