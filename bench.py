@@ -127,7 +127,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL may print its version banner to stdout at communicator creation (NCCL_DEBUG=VERSION on
+        # some boxes): keep stdout to the one JSON line by pointing fd 1 at stderr until the first collective ran
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from hmer_img2latex_b200.dist import gather_tokens
 
     torch.manual_seed(0)
