@@ -46,7 +46,7 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 namespace {
-constexpr int kMaxProf = 32, kMaxEv = 4096;
+constexpr int kMaxProf = 96, kMaxEv = 4096;
 struct ProfEntry {
   char name[48];
   std::vector<cudaEvent_t> ev;   // start/stop pairs

@@ -3,6 +3,8 @@
 // convs on CUDA cores; the bf16 CNN path (tcgen05 implicit GEMM, NHWC) is in cnn_bf16.cu.
 #include "common.cuh"
 #include "encoder_bf16.cuh"
+#include "resnet_net.cuh"
+#include "resnet_bf16.cuh"
 #include <vector>
 
 namespace i2l {
@@ -81,60 +83,7 @@ CnnWs cnn_carve(const i2l_cnn_desc& d, const CnnLayout& L, int B, void* ws) {
   return w;
 }
 
-// ---------------------------------------------------------------- ResNet
-struct RConv { int ci, co, k, stride, pad; size_t w_off, b_off; };
-struct RBlock { int c1, c2, c3, ds; };
-struct RNet { std::vector<RConv> convs; std::vector<RBlock> blocks; int feat; bool ok; };
-
-RNet build_resnet(int depth) {
-  RNet n; n.ok = true; n.feat = 0;
-  bool bottleneck; int layers[4];
-  switch (depth) {
-    case 18: bottleneck = false; layers[0] = 2; layers[1] = 2; layers[2] = 2; layers[3] = 2; break;
-    case 34: bottleneck = false; layers[0] = 3; layers[1] = 4; layers[2] = 6; layers[3] = 3; break;
-    case 50: bottleneck = true; layers[0] = 3; layers[1] = 4; layers[2] = 6; layers[3] = 3; break;
-    case 101: bottleneck = true; layers[0] = 3; layers[1] = 4; layers[2] = 23; layers[3] = 3; break;
-    case 152: bottleneck = true; layers[0] = 3; layers[1] = 8; layers[2] = 36; layers[3] = 3; break;
-    default: n.ok = false; return n;
-  }
-  auto add = [&](int ci, int co, int k, int s, int p) { n.convs.push_back(RConv{ci, co, k, s, p, 0, 0}); return (int)n.convs.size() - 1; };
-  add(3, 64, 7, 2, 3);
-  int inpl = 64, exp = bottleneck ? 4 : 1;
-  for (int li = 0; li < 4; ++li) {
-    int planes = 64 << li;
-    for (int b = 0; b < layers[li]; ++b) {
-      int stride = (li > 0 && b == 0) ? 2 : 1;
-      RBlock blk{-1, -1, -1, -1};
-      if (!bottleneck) {
-        blk.c1 = add(inpl, planes, 3, stride, 1);
-        blk.c2 = add(planes, planes, 3, 1, 1);
-      } else {
-        blk.c1 = add(inpl, planes, 1, 1, 0);
-        blk.c2 = add(planes, planes, 3, stride, 1);
-        blk.c3 = add(planes, planes * 4, 1, 1, 0);
-      }
-      if (stride != 1 || inpl != planes * exp) blk.ds = add(inpl, planes * exp, 1, stride, 0);
-      inpl = planes * exp;
-      n.blocks.push_back(blk);
-    }
-  }
-  n.feat = inpl;
-  size_t o = 0;
-  auto take = [&](size_t c) { size_t r = o; o += (c + 63) / 64 * 64; return r; };
-  for (auto& c : n.convs) { c.w_off = take((size_t)c.co * c.ci * c.k * c.k); c.b_off = take(c.co); }
-  return n;
-}
-
-struct RLayout { size_t fc_w, fc_b, end_f32; };
-RLayout resnet_layout(const RNet& n, int E) {
-  size_t o = n.convs.back().b_off + (n.convs.back().co + 63) / 64 * 64;
-  RLayout L{};
-  L.fc_w = o; o += ((size_t)E * n.feat + 63) / 64 * 64;
-  L.fc_b = o; o += (E + 63) / 64 * 64;
-  L.end_f32 = o;
-  return L;
-}
-
+// ---------------------------------------------------------------- ResNet (topology: resnet_net.cuh)
 __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ b,
                                const float* __restrict__ m, const float* __restrict__ v, float* __restrict__ wo,
                                float* __restrict__ bo, int co, int per) {
@@ -144,25 +93,6 @@ __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restr
   float sc = g[c] / sqrtf(v[c] + 1e-5f);
   wo[i] = w[i] * sc;
   if (i % per == 0) bo[c] = b[c] - m[c] * sc;
-}
-
-size_t resnet_max_act(const RNet& n, int H, int W) {
-  // per-image float count of the largest activation
-  auto o = [](int x, int k, int s, int p) { return (x + 2 * p - k) / s + 1; };
-  int h = o(H, 7, 2, 3), w = o(W, 7, 2, 3);
-  size_t mx = (size_t)64 * h * w;
-  h = o(h, 3, 2, 1); w = o(w, 3, 2, 1);
-  for (auto& b : n.blocks) {
-    const RConv& c1 = n.convs[b.c1];
-    const RConv& c2 = n.convs[b.c2];
-    int h1 = o(h, c1.k, c1.stride, c1.pad), w1 = o(w, c1.k, c1.stride, c1.pad);
-    mx = std::max(mx, (size_t)c1.co * h1 * w1);
-    int h2 = o(h1, c2.k, c2.stride, c2.pad), w2 = o(w1, c2.k, c2.stride, c2.pad);
-    mx = std::max(mx, (size_t)c2.co * h2 * w2);
-    if (b.c3 >= 0) mx = std::max(mx, (size_t)n.convs[b.c3].co * h2 * w2);
-    h = h2; w = w2;
-  }
-  return mx;
 }
 
 }  // namespace
@@ -343,7 +273,9 @@ extern "C" size_t i2l_resnet_packed_bytes(const i2l_resnet_desc* d) {
   if (!d) return 0;
   RNet n = build_resnet(d->depth);
   if (!n.ok || d->embedding_dim <= 0) return 0;
-  return resnet_layout(n, d->embedding_dim).end_f32 * 4;
+  size_t bytes = resnet_layout(n, d->embedding_dim).end_f32 * 4;
+  if (d->precision == I2L_BF16) bytes = align_up(bytes, 1024) + resnet_bf16_packed_bytes(n);
+  return bytes;
 }
 
 extern "C" int i2l_resnet_pack(const i2l_resnet_desc* d, const i2l_resnet_params* p, void* packed,
@@ -354,7 +286,7 @@ extern "C" int i2l_resnet_pack(const i2l_resnet_desc* d, const i2l_resnet_params
   I2L_REQUIRE(n.ok, "Invalid ResNet model name: resnet%d", d->depth);      // encoder.py:195-196
   I2L_REQUIRE(p->n_convs == (int)n.convs.size(), "i2l_resnet_pack: expected %d convs, got %d", (int)n.convs.size(), p->n_convs);
   RLayout L = resnet_layout(n, d->embedding_dim);
-  if (packed_bytes < L.end_f32 * 4) { set_error("i2l_resnet_pack: packed buffer too small"); return I2L_ERR_WORKSPACE; }
+  if (packed_bytes < i2l_resnet_packed_bytes(d)) { set_error("i2l_resnet_pack: packed buffer too small"); return I2L_ERR_WORKSPACE; }
   cudaStream_t s = (cudaStream_t)stream;
   float* pk = reinterpret_cast<float*>(packed);
   for (size_t i = 0; i < n.convs.size(); ++i) {
@@ -371,6 +303,8 @@ extern "C" int i2l_resnet_pack(const i2l_resnet_desc* d, const i2l_resnet_params
   I2L_REQUIRE(p->fc_w && p->fc_b, "i2l_resnet_pack: missing embedding layer");
   I2L_CUDA_OK(cudaMemcpyAsync(pk + L.fc_w, p->fc_w, (size_t)d->embedding_dim * n.feat * 4, cudaMemcpyDeviceToDevice, s));
   I2L_CUDA_OK(cudaMemcpyAsync(pk + L.fc_b, p->fc_b, (size_t)d->embedding_dim * 4, cudaMemcpyDeviceToDevice, s));
+  if (d->precision == I2L_BF16)
+    I2L_TRY(resnet_bf16_pack(n, pk, reinterpret_cast<char*>(packed) + align_up(L.end_f32 * 4, 1024), s));
   return I2L_OK;
 }
 
@@ -378,6 +312,7 @@ extern "C" size_t i2l_resnet_workspace_bytes(const i2l_resnet_desc* d, int32_t b
   if (!d || batch <= 0 || img_width <= 0) return 0;
   RNet n = build_resnet(d->depth);
   if (!n.ok) return 0;
+  if (resnet_bf16_supported(*d, img_width)) return resnet_bf16_workspace_bytes(n, batch, d->img_height, img_width);
   size_t act = align_up(resnet_max_act(n, d->img_height, img_width) * (size_t)batch * 4, 256);
   return 5 * act + align_up((size_t)batch * n.feat * 4, 256);
 }
@@ -396,6 +331,9 @@ extern "C" int i2l_resnet_encoder_fwd(const i2l_resnet_desc* d, const void* pack
   cudaStream_t s = (cudaStream_t)stream;
   RLayout L = resnet_layout(n, d->embedding_dim);
   const float* pk = reinterpret_cast<const float*>(packed);
+  if (resnet_bf16_supported(*d, img_width))
+    return resnet_bf16_fwd(n, *d, pk, reinterpret_cast<const char*>(packed) + align_up(L.end_f32 * 4, 1024), pk + L.fc_w, pk + L.fc_b,
+                           x, batch, img_width, out, workspace, workspace_bytes, s);
   size_t act = align_up(resnet_max_act(n, d->img_height, img_width) * (size_t)batch * 4, 256);
   char* base = reinterpret_cast<char*>(workspace);
   float* buf[5];

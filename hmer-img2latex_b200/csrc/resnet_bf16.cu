@@ -1,0 +1,454 @@
+// bf16 ResNet trunk (ResNetEncoder.forward, model/encoder.py:231-249; torchvision resnet18/34/50/101/152
+// minus fc, eval-mode BatchNorm folded into the convs) as tcgen05 implicit-GEMM kernels.
+//
+//   activations  bf16 NHWC [B][H][W][C] in HBM
+//   conv         one persistent warp-specialised kernel for every 1x1 / 3x3, stride 1 / 2 conv:
+//                M tile = 128 consecutive output pixels (linear over n, ho, wo), N tile = 64 / 128
+//                output channels, K loop over (kh, kw, 64-channel block).  The A operand tile of a
+//                (tap, channel block) is ONE im2col-mode TMA load (cp.async.bulk.tensor...im2col):
+//                the TMA unit walks the 128 output positions across row / image boundaries, applies
+//                the conv stride and zero-fills the padding, and writes a K-major SWIZZLE_128B tile.
+//                Weights are pre-packed as shared-memory images (BN folded, bf16, swizzled), one
+//                bulk copy per K block.  Accumulators are double buffered in TMEM; the epilogue adds
+//                bias (+ residual), applies ReLU and stores bf16 NHWC.
+//   stem         7x7 stride-2 conv on 3 channels: the image is re-laid-out as NHWC4 bf16 and viewed as
+//                pixel PAIRS [B][H][W/2][8]; in pair space the conv is 7 (kh) x 4 (pair taps), stride
+//                (2, 1), K = 224 (147 useful).  Same kernel, no-swizzle operand tiles (16-byte rows).
+//   maxpool 3x3/2, global average pool: bandwidth kernels; embedding Linear + ReLU: fp32 GEMM.
+#include "resnet_bf16.cuh"
+#include "tc_common.cuh"
+
+namespace i2l {
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128;                       // output pixels per tile
+constexpr int A_BYTES = BM * 128;             // generic A stage: 128 pixels x 64 channels bf16
+constexpr int STEM_A_BYTES = 4 * BM * 16;     // stem A stage: 4 pair taps x (128 pixels x 8 elements)
+constexpr int STEM_B_BYTES = 4 * 64 * 16;     // stem B stage: 4 pair taps x (64 co x 8 elements)
+
+__host__ __device__ constexpr int conv_bn(int co) { return co == 64 ? 64 : 128; }
+
+// ------------------------------------------------------------------ packing
+// generic conv: image [n_nt][n_kb][BN rows][64 k] bf16, rows 128 B, SWIZZLE_128B; k block kb = tap * (Ci/64) + cb
+__global__ void pack_conv_kernel(const float* __restrict__ w /*(Co,Ci,KH,KW) folded*/, int Co, int Ci, int KH, int KW, int BN,
+                                 unsigned char* __restrict__ dst) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t tot = (size_t)Co * Ci * KH * KW;
+  if (i >= tot) return;
+  const int c = (int)(i % Ci);
+  const int tap = (int)((i / Ci) % (KH * KW));
+  const int co = (int)(i / ((size_t)Ci * KH * KW));
+  const int nkb = KH * KW * (Ci / 64);
+  const int kb = tap * (Ci / 64) + c / 64, kc = c % 64;
+  const int nt = co / BN, r = co % BN;
+  const float v = w[((size_t)co * Ci + c) * KH * KW + tap];
+  const size_t off = ((size_t)nt * nkb + kb) * BN * 128 + swz_off(r, kc / 8, 128) + (kc % 8) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16(v);
+}
+
+// stem: image [7 kh][4 pair taps j][64 co][8 e], e = (pixel of the pair p, channel c of 4); input column
+// w = 2 (wo - 2 + j) + p  ->  kw = 2 j + p - 1
+__global__ void pack_stem_kernel(const float* __restrict__ w /*(64,3,7,7) folded*/, unsigned char* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 7 * 4 * 64 * 8) return;
+  const int e = i & 7, co = (i >> 3) & 63, j = (i >> 9) & 3, kh = i >> 11;
+  const int p = e >> 2, c = e & 3, kw = 2 * j + p - 1;
+  float v = 0.f;
+  if (c < 3 && kw >= 0 && kw < 7) v = w[((co * 3 + c) * 7 + kh) * 7 + kw];
+  reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16(v);
+}
+
+// ------------------------------------------------------------------ the conv kernel
+struct ConvArgs {
+  const unsigned char* wimg;
+  const float* bias;            // [Co] folded BN shift
+  const __nv_bfloat16* res;     // residual (same shape as out) or null
+  __nv_bfloat16* out;           // [P][Co]
+  int P, HoWo, Wo, Co;
+  int KH, KW, cblocks;          // taps and 64-channel blocks (stem: KW = 4 pair taps, cblocks = 1)
+  int stride_w, stride_h, pad_w, pad_h;
+  int relu, n_mt, n_nt;
+};
+
+template <int BN, bool STEM>
+struct IgCfg {
+  static constexpr int A_ST = STEM ? STEM_A_BYTES : A_BYTES;
+  static constexpr int B_ST = STEM ? STEM_B_BYTES : BN * 128;
+  static constexpr int STAGE = A_ST + B_ST;
+  static constexpr int STAGES = STEM ? 8 : (BN == 128 ? 6 : 8);
+  static constexpr int OFF_BAR = STAGES * STAGE;
+  static constexpr int SMEM = OFF_BAR + 256;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static_assert(STAGE % 1024 == 0, "stage alignment");
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+// no-swizzle K-major descriptor: 8x16-byte core matrices, LBO = K-direction chunk stride, SBO = 8-row group stride
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+         ((uint64_t)1 << 46);
+}
+
+template <int BN, bool STEM>
+__global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const ConvArgs a) {
+  using Cfg = IgCfg<BN, STEM>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar = sbase + Cfg::OFF_BAR;
+  auto FULL = [&](int s) { return bar + 8u * s; };
+  auto EMPTY = [&](int s) { return bar + 8u * (STAGES + s); };
+  auto TFULL = [&](int i) { return bar + 8u * (2 * STAGES + i); };
+  auto TEMPTY = [&](int i) { return bar + 8u * (2 * STAGES + 2 + i); };
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 8 * (2 * STAGES + 4));
+  if ((sbase & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), 1); mbar_init(TEMPTY(i), 128); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(misc));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc[0];
+  const int n_tiles = a.n_mt * a.n_nt;
+  const int nkb = a.KH * a.KW * a.cblocks;              // K blocks per tile (stem: stages = KH)
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int mt = tile / a.n_nt, nt = tile % a.n_nt;
+        const int p0 = mt * BM;
+        const int n0 = p0 / a.HoWo, rem = p0 % a.HoWo;
+        const int w0 = (rem % a.Wo) * a.stride_w - a.pad_w, h0 = (rem / a.Wo) * a.stride_h - a.pad_h;
+        if constexpr (STEM) {
+          for (int kh = 0; kh < a.KH; ++kh) {
+            mbar_wait(EMPTY(stage), ph ^ 1);
+            mbar_arrive_expect_tx(FULL(stage), Cfg::STAGE);
+            const uint32_t dst = sbase + stage * Cfg::STAGE;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_im2col(dst + j * (BM * 16), &tmA, 0, w0, h0, n0, j, kh, FULL(stage));
+            bulk_g2s(dst + Cfg::A_ST, a.wimg + (size_t)kh * STEM_B_BYTES, STEM_B_BYTES, FULL(stage));
+            if (++stage == STAGES) { stage = 0; ph ^= 1; }
+          }
+        } else {
+          const unsigned char* wt = a.wimg + (size_t)nt * nkb * (BN * 128);
+          int kb = 0;
+          for (int kh = 0; kh < a.KH; ++kh)
+            for (int kw = 0; kw < a.KW; ++kw)
+              for (int cb = 0; cb < a.cblocks; ++cb, ++kb) {
+                mbar_wait(EMPTY(stage), ph ^ 1);
+                mbar_arrive_expect_tx(FULL(stage), Cfg::STAGE);
+                const uint32_t dst = sbase + stage * Cfg::STAGE;
+                tma_load_im2col(dst, &tmA, cb * 64, w0, h0, n0, kw, kh, FULL(stage));
+                bulk_g2s(dst + Cfg::A_ST, wt + (size_t)kb * (BN * 128), BN * 128, FULL(stage));
+                if (++stage == STAGES) { stage = 0; ph ^= 1; }
+              }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t IDESC = idesc_bf16(128, BN);
+    const int nstages = STEM ? a.KH : nkb;
+    int stage = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      mbar_wait(TEMPTY(acc), aph ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < nstages; ++kb) {
+        mbar_wait(FULL(stage), ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_ST;
+          if constexpr (STEM) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              tc_mma_ss(d, desc_nosw(sa + ks * 2 * (BM * 16), BM * 16, 128), desc_nosw(sb + ks * 2 * (64 * 16), 64 * 16, 128), IDESC,
+                        (kb | ks) ? 1u : 0u);
+          } else {
+            const uint64_t ad = desc_base(sa, 128), bd = desc_base(sb, 128);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) tc_mma_ss(d, ad + (uint64_t)((ks * 32) >> 4), bd + (uint64_t)((ks * 32) >> 4), IDESC, (kb | ks) ? 1u : 0u);
+          }
+          tc_commit(EMPTY(stage));
+          if (kb == nstages - 1) tc_commit(TFULL(acc));
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; ph ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps 2..5 =====================
+    const int q = warp & 3;
+    const int m = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int mt = tile / a.n_nt, nt = tile % a.n_nt;
+      const int p = mt * BM + m;
+      const bool valid = p < a.P;
+      const size_t o = (size_t)p * a.Co + (size_t)nt * BN;
+      const float* bias = a.bias + nt * BN;
+      mbar_wait(TFULL(acc), aph);
+      tc_fence_after();
+      const uint32_t ta = tmem + lane_addr + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t r[32];
+        tc_ld16_nowait(ta + cc * 32, r);
+        tc_ld16_nowait(ta + cc * 32 + 16, r + 16);
+        uint4 rs[4] = {};
+        if (a.res != nullptr && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.res + o + cc * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rs[i] = __ldg(rp + i);
+        }
+        tc_wait_ld();
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(rs);
+        uint32_t ov[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float v0 = __uint_as_float(r[2 * i]) + __ldg(bias + cc * 32 + 2 * i);
+          float v1 = __uint_as_float(r[2 * i + 1]) + __ldg(bias + cc * 32 + 2 * i + 1);
+          if (a.res != nullptr) {
+            __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162*>(&rw[i]);
+            v0 += __low2float(rr); v1 += __high2float(rr);
+          }
+          if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+          ov[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        if (valid) {
+          uint4* d4 = reinterpret_cast<uint4*>(a.out + o + cc * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d4[i] = make_uint4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(TEMPTY(acc));
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+}
+
+// ------------------------------------------------------------------ bandwidth kernels
+// (B,3,H,W) fp32 NCHW -> [B][H][W][4] bf16 (channel 3 = 0)
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, uint2* __restrict__ y, int HW, size_t total /*B*HW*/) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t b = i / HW, p = i % HW;
+  const float* s = x + b * 3 * (size_t)HW + p;
+  __nv_bfloat162 lo = __floats2bfloat162_rn(__ldg(s), __ldg(s + HW));
+  __nv_bfloat162 hi = __floats2bfloat162_rn(__ldg(s + 2 * (size_t)HW), 0.f);
+  y[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
+// MaxPool2d(3, stride 2, padding 1) on NHWC bf16; one thread = one output pixel x 8 channels
+__global__ void maxpool3s2_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int Hi, int Wi, int Ho,
+                                       int Wo, int C, size_t total /*B*Ho*Wo*C/8*/) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = C / 8;
+  const int cg = (int)(i % c8);
+  size_t pix = i / c8;
+  const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho);
+  const size_t b = pix / ((size_t)Wo * Ho);
+  float m[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+  for (int dh = 0; dh < 3; ++dh) {
+    const int h = 2 * ho - 1 + dh;
+    if (h < 0 || h >= Hi) continue;
+#pragma unroll
+    for (int dw = 0; dw < 3; ++dw) {
+      const int w = 2 * wo - 1 + dw;
+      if (w < 0 || w >= Wi) continue;
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((b * Hi + h) * Wi + w) * C) + cg);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { m[2 * k] = fmaxf(m[2 * k], __low2float(h2[k])); m[2 * k + 1] = fmaxf(m[2 * k + 1], __high2float(h2[k])); }
+    }
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { __nv_bfloat162 h2 = __floats2bfloat162_rn(m[2 * k], m[2 * k + 1]); o[k] = *reinterpret_cast<uint32_t*>(&h2); }
+  reinterpret_cast<uint4*>(y + pix * C)[cg] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// AdaptiveAvgPool2d(1) on NHWC bf16 -> fp32 [B][C]
+__global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int HW, int C) {
+  const int b = blockIdx.x;
+  for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(x + (size_t)b * HW * C) + c2;
+    for (int i = 0; i < HW; ++i) { __nv_bfloat162 v = p[(size_t)i * (C / 2)]; s0 += __low2float(v); s1 += __high2float(v); }
+    y[(size_t)b * C + 2 * c2] = s0 / (float)HW;
+    y[(size_t)b * C + 2 * c2 + 1] = s1 / (float)HW;
+  }
+}
+
+// ------------------------------------------------------------------ layout of the bf16 section
+size_t conv_img_bytes(const RConv& c) { return (size_t)c.co * c.ci * c.k * c.k * 2; }   // generic convs: no padding elements
+constexpr size_t STEM_IMG_BYTES = 7 * STEM_B_BYTES;
+
+struct Sec { std::vector<size_t> off; size_t total; };
+Sec sec_layout(const RNet& n) {
+  Sec s; size_t o = 0;
+  for (size_t i = 0; i < n.convs.size(); ++i) {
+    s.off.push_back(o);
+    o = align_up(o + (i == 0 ? STEM_IMG_BYTES : conv_img_bytes(n.convs[i])), 1024);
+  }
+  s.total = o;
+  return s;
+}
+
+int out_dim(int v, int k, int st, int p) { return (v + 2 * p - k) / st + 1; }
+
+struct Ws { __nv_bfloat16* x4; __nv_bfloat16* buf[5]; float* pooled; size_t bytes; };
+Ws carve(const RNet& n, int B, int H, int W, void* ws) {
+  Arena a(ws, (size_t)-1);
+  Ws w{};
+  w.x4 = a.take<__nv_bfloat16>((size_t)B * H * W * 4);
+  const size_t act = resnet_max_act(n, H, W) * (size_t)B;
+  for (int i = 0; i < 5; ++i) w.buf[i] = a.take<__nv_bfloat16>(act);
+  w.pooled = a.take<float>((size_t)B * n.feat);
+  w.bytes = align_up(a.off, 256);
+  return w;
+}
+
+template <int BN, bool STEM>
+int launch_conv(const CUtensorMap& tm, const ConvArgs& a, cudaStream_t s) {
+  using Cfg = IgCfg<BN, STEM>;
+  auto kern = conv_igemm_kernel<BN, STEM>;
+  I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  const int n_tiles = a.n_mt * a.n_nt;
+  kern<<<std::min(n_tiles, num_sms()), 192, Cfg::SMEM, s>>>(tm, a);
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
+
+}  // namespace
+
+bool resnet_bf16_supported(const i2l_resnet_desc& d, int img_width) {
+  return d.precision == I2L_BF16 && d.img_height >= 2 && img_width >= 2 && (img_width % 2) == 0;
+}
+
+size_t resnet_bf16_packed_bytes(const RNet& n) { return sec_layout(n).total; }
+
+int resnet_bf16_pack(const RNet& n, const float* folded /* fp32 packed region */, void* section, cudaStream_t s) {
+  Sec L = sec_layout(n);
+  unsigned char* sec = reinterpret_cast<unsigned char*>(section);
+  pack_stem_kernel<<<cdiv(7 * 4 * 64 * 8, 256), 256, 0, s>>>(folded + n.convs[0].w_off, sec + L.off[0]);
+  I2L_LAUNCH_OK();
+  for (size_t i = 1; i < n.convs.size(); ++i) {
+    const RConv& c = n.convs[i];
+    I2L_REQUIRE(c.ci % 64 == 0 && c.co % 64 == 0, "resnet_bf16_pack: channel counts must be multiples of 64");
+    const size_t tot = (size_t)c.co * c.ci * c.k * c.k;
+    pack_conv_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(folded + c.w_off, c.co, c.ci, c.k, c.k, conv_bn(c.co), sec + L.off[i]);
+    I2L_LAUNCH_OK();
+  }
+  return I2L_OK;
+}
+
+size_t resnet_bf16_workspace_bytes(const RNet& n, int batch, int H, int W) { return carve(n, batch, H, W, nullptr).bytes; }
+
+int resnet_bf16_fwd(const RNet& n, const i2l_resnet_desc& d, const float* folded, const void* section, const float* fc_w,
+                    const float* fc_b, const float* x, int B, int W, float* out, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const int H = d.img_height;
+  Ws w = carve(n, B, H, W, ws);
+  if (ws_bytes < w.bytes) { set_error("resnet_bf16_fwd: workspace too small (%zu < %zu)", ws_bytes, w.bytes); return I2L_ERR_WORKSPACE; }
+  Sec L = sec_layout(n);
+  const unsigned char* sec = reinterpret_cast<const unsigned char*>(section);
+  char tag[40];
+  snprintf(tag, sizeof tag, "resnet%d", d.depth);
+  // ---- input re-layout
+  {
+    const size_t tot = (size_t)B * H * W;
+    KernelTimer kt("rn.nchw_to_nhwc4", s);
+    nchw_to_nhwc4_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(x, reinterpret_cast<uint2*>(w.x4), H * W, tot);
+    I2L_LAUNCH_OK();
+  }
+  // ---- stem: conv 7x7/2 + bn + relu in pixel-pair space
+  int h = out_dim(H, 7, 2, 3), wd = out_dim(W, 7, 2, 3);    // = H/2 (ceil), W/2
+  {
+    CUtensorMap tm;
+    I2L_TRY(make_im2col_map(&tm, w.x4, 8, W / 2, H, B, -2, -3, -2, -3, 8, BM, 1, 2, 0));
+    ConvArgs a{};
+    a.wimg = sec + L.off[0]; a.bias = folded + n.convs[0].b_off; a.res = nullptr; a.out = w.buf[1];
+    a.P = B * h * wd; a.HoWo = h * wd; a.Wo = wd; a.Co = 64; a.KH = 7; a.KW = 4; a.cblocks = 1;
+    a.stride_w = 1; a.stride_h = 2; a.pad_w = 2; a.pad_h = 3; a.relu = 1; a.n_mt = cdiv(a.P, BM); a.n_nt = 1;
+    KernelTimer kt("rn.stem_conv7x7", s);
+    I2L_TRY((launch_conv<64, true>(tm, a, s)));
+  }
+  // ---- maxpool 3x3/2
+  {
+    const int ho = out_dim(h, 3, 2, 1), wo = out_dim(wd, 3, 2, 1);
+    const size_t tot = (size_t)B * ho * wo * (64 / 8);
+    KernelTimer kt("rn.maxpool", s);
+    maxpool3s2_nhwc_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(w.buf[1], w.buf[0], h, wd, ho, wo, 64, tot);
+    I2L_LAUNCH_OK();
+    h = ho; wd = wo;
+  }
+  auto run = [&](int idx, const __nv_bfloat16* in, __nv_bfloat16* o, int hi, int wi, const __nv_bfloat16* res, int relu) -> int {
+    const RConv& c = n.convs[idx];
+    const int ho = out_dim(hi, c.k, c.stride, c.pad), wo = out_dim(wi, c.k, c.stride, c.pad);
+    CUtensorMap tm;
+    I2L_TRY(make_im2col_map(&tm, in, c.ci, wi, hi, B, -c.pad, -c.pad, c.pad - (c.k - 1), c.pad - (c.k - 1), 64, BM, c.stride, c.stride, 128));
+    ConvArgs a{};
+    a.wimg = sec + L.off[idx]; a.bias = folded + c.b_off; a.res = res; a.out = o;
+    a.P = B * ho * wo; a.HoWo = ho * wo; a.Wo = wo; a.Co = c.co; a.KH = c.k; a.KW = c.k; a.cblocks = c.ci / 64;
+    a.stride_w = a.stride_h = c.stride; a.pad_w = a.pad_h = c.pad; a.relu = relu; a.n_mt = cdiv(a.P, BM);
+    const int bn = conv_bn(c.co);
+    a.n_nt = c.co / bn;
+    char nm[48];
+    snprintf(nm, sizeof nm, "rn.conv%dx%d_c%d", c.k, c.k, c.co);
+    KernelTimer kt(nm, s);
+    if (bn == 64) return launch_conv<64, false>(tm, a, s);
+    return launch_conv<128, false>(tm, a, s);
+  };
+  __nv_bfloat16 *cur = w.buf[0], *nxt = w.buf[1], *t1 = w.buf[2], *t2 = w.buf[3], *idt = w.buf[4];
+  for (const RBlock& b : n.blocks) {
+    const RConv& c1 = n.convs[b.c1];
+    const RConv& c2 = n.convs[b.c2];
+    const int h1 = out_dim(h, c1.k, c1.stride, c1.pad), w1 = out_dim(wd, c1.k, c1.stride, c1.pad);
+    const int h2 = out_dim(h1, c2.k, c2.stride, c2.pad), w2 = out_dim(w1, c2.k, c2.stride, c2.pad);
+    const __nv_bfloat16* res = cur;
+    if (b.ds >= 0) { I2L_TRY(run(b.ds, cur, idt, h, wd, nullptr, 0)); res = idt; }
+    I2L_TRY(run(b.c1, cur, t1, h, wd, nullptr, 1));
+    if (b.c3 < 0) {
+      I2L_TRY(run(b.c2, t1, nxt, h1, w1, res, 1));
+    } else {
+      I2L_TRY(run(b.c2, t1, t2, h1, w1, nullptr, 1));
+      I2L_TRY(run(b.c3, t2, nxt, h2, w2, res, 1));
+    }
+    std::swap(cur, nxt);
+    h = h2; wd = w2;
+  }
+  {
+    KernelTimer kt("rn.avgpool", s);
+    avgpool_nhwc_kernel<<<B, 256, 0, s>>>(cur, w.pooled, h * wd, n.feat);
+    I2L_LAUNCH_OK();
+  }
+  GemmF32 g;
+  g.M = B; g.N = d.embedding_dim; g.C = out; g.ldc = d.embedding_dim;
+  g.A1 = w.pooled; g.lda1 = n.feat; g.W1 = fc_w; g.ldw1 = n.feat; g.K1 = n.feat;
+  g.bias = fc_b; g.relu = 1;
+  KernelTimer kt("rn.fc_f32", s);
+  return gemm_f32(g, s);
+}
+
+}  // namespace i2l

@@ -61,6 +61,15 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
       "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
       : "memory");
 }
+// im2col-mode load of an NHWC tensor (tensor map from make_im2col_map): `pixels` consecutive output
+// positions starting at base input pixel (w, h, n), filter tap offsets (off_w, off_h), channels from c
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* tm, int c, int w, int h, int n,
+                                                uint32_t off_w, uint32_t off_h, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6], {%7, %8};" ::"r"(dst),
+      "l"(tm), "r"(c), "r"(w), "r"(h), "r"(n), "r"(bar), "h"((unsigned short)off_w), "h"((unsigned short)off_h)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -141,5 +150,12 @@ __host__ __device__ inline uint32_t swz_off(uint32_t row, uint32_t chunk, uint32
 // elem_bytes: 2 = bf16, 4 = fp32.  swizzle_bytes 0 = no swizzle.
 int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, int swizzle_bytes, int elem_bytes);
+
+// im2col-mode map of an NHWC bf16 tensor (dims C,W,H,N): base pixels run over the bounding box
+// [lower, extent-1+upper] per spatial dim with traversal stride (stride_w, stride_h); one load
+// fetches `pixels` consecutive base pixels x `channels` channels.  Semantics probed on sm_100a:
+// tools/probes/im2col_probe.cu.
+int make_im2col_map(CUtensorMap* out, const void* base, int C, int W, int H, int N, int lower_w, int lower_h,
+                    int upper_w, int upper_h, int channels, int pixels, int stride_w, int stride_h, int swizzle_bytes);
 
 }  // namespace i2l

@@ -139,3 +139,49 @@ def test_greedy_stream_uint8_and_bf16_hosts(pkg):
     for host in (px.pin_memory(), xn.pin_memory()):
         (tok, lens, steps), = list(m16.greedy_stream([host], H.START, H.END, 20))
         assert torch.equal(tok, t_ref.cpu()) and torch.equal(lens, l_ref.cpu()) and steps == int(s_ref)
+
+
+# ---- bf16 tcgen05 ResNet trunk (resnet_bf16.cu): im2col-TMA implicit GEMM, NHWC bf16 activations.
+# Stated tolerance: encoder output within 3e-2 of max|out| of the fp32 oracle (measured 3e-3 for
+# resnet18, 6e-3 for resnet50: every activation is rounded to bf16 once per layer).
+RESNET_BF16_TOL = 3e-2
+
+
+@pytest.mark.parametrize("cfg,B,width", [(H.R18, 3, 128), (H.R18, 5, 224), (H.R18, 2, 320), (H.R18, 37, 160),
+                                         (H.R50, 2, 96), (H.R50, 9, 192)])
+def test_resnet_bf16_encoder(pkg, cfg, B, width):
+    p = oracle.make_params(cfg, 0)
+    m = H.build_model(pkg, cfg, p, precision="bf16")
+    x = H.make_images(cfg, B, width=width)
+    ref = oracle.resnet_encoder(p, x, cfg["model_name"])
+    lib = pkg._native.lib()
+    l0 = lib.i2l_launch_count()
+    out = m.encoder(x.cuda())
+    torch.cuda.synchronize()
+    err = H.rel_err(out, ref)
+    print(f"{cfg['model_name']} bf16 B={B} W={width}: rel err {err:.3e}, launches {lib.i2l_launch_count() - l0}")
+    assert out.shape == ref.shape
+    assert err < RESNET_BF16_TOL
+
+
+def test_resnet_bf16_rows_are_batch_independent(pkg):
+    """An image's encoding must not depend on its batch neighbours (im2col tiles run across image
+    boundaries): bit-identical rows for the same image at different batch positions / sizes."""
+    cfg = H.R18
+    p = oracle.make_params(cfg, 1)
+    m = H.build_model(pkg, cfg, p, precision="bf16")
+    x = H.make_images(cfg, 6, width=192).cuda()
+    full = m.encoder(x)
+    part = m.encoder(x[2:5].contiguous())
+    assert torch.equal(full[2:5], part)
+    assert torch.equal(m.encoder(x[5:6].contiguous()), full[5:6])
+
+
+def test_resnet_bf16_odd_width_uses_fp32_path(pkg):
+    """The pixel-pair stem needs an even width; other widths run on the fp32 kernels (still CUDA)."""
+    cfg = H.R18
+    p = oracle.make_params(cfg, 0)
+    m = H.build_model(pkg, cfg, p, precision="bf16")
+    x = H.make_images(cfg, 2, width=131)
+    ref = oracle.resnet_encoder(p, x, cfg["model_name"])
+    assert H.rel_err(m.encoder(x.cuda()), ref) < 1e-3
