@@ -11,9 +11,11 @@
 //                Weights are pre-packed as shared-memory images (BN folded, bf16, swizzled), one
 //                bulk copy per K block.  Accumulators are double buffered in TMEM; the epilogue adds
 //                bias (+ residual), applies ReLU and stores bf16 NHWC.
-//   stem         7x7 stride-2 conv on 3 channels: the image is re-laid-out as NHWC4 bf16 and viewed as
-//                pixel PAIRS [B][H][W/2][8]; in pair space the conv is 7 (kh) x 4 (pair taps), stride
-//                (2, 1), K = 224 (147 useful).  Same kernel, no-swizzle operand tiles (16-byte rows).
+//   stem         7x7 stride-2 conv on 3 channels: the image is re-laid-out as NHWC4 bf16 with zero columns
+//                physically padded left / right and viewed as pixel PAIRS (8 elements, 16 B).  Output
+//                column wo reads the 4 consecutive pairs wo-2..wo+1 = 64 contiguous bytes, so the tensor
+//                map describes OVERLAPPING 32-"channel" pixels (W stride 16 B): one im2col load per kh
+//                fetches a K = 32 operand block (7 x 32 = 224, 147 useful), SWIZZLE_64B.  Same kernel.
 //   maxpool 3x3/2, global average pool: bandwidth kernels; embedding Linear + ReLU: fp32 GEMM.
 #include "resnet_bf16.cuh"
 #include "tc_common.cuh"
@@ -24,9 +26,7 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128;                       // output pixels per tile
-constexpr int A_BYTES = BM * 128;             // generic A stage: 128 pixels x 64 channels bf16
-constexpr int STEM_A_BYTES = 4 * BM * 16;     // stem A stage: 4 pair taps x (128 pixels x 8 elements)
-constexpr int STEM_B_BYTES = 4 * 64 * 16;     // stem B stage: 4 pair taps x (64 co x 8 elements)
+constexpr int STEM_PADL = 2, STEM_PADR = 2;   // zero pixel pairs stored left / right of every image row
 
 __host__ __device__ constexpr int conv_bn(int co) { return co == 64 ? 64 : 128; }
 
@@ -48,16 +48,16 @@ __global__ void pack_conv_kernel(const float* __restrict__ w /*(Co,Ci,KH,KW) fol
   *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16(v);
 }
 
-// stem: image [7 kh][4 pair taps j][64 co][8 e], e = (pixel of the pair p, channel c of 4); input column
-// w = 2 (wo - 2 + j) + p  ->  kw = 2 j + p - 1
+// stem: image [7 kh][64 co][32 k] bf16, rows 64 B, SWIZZLE_64B; k = 8 j + 4 p + c with j = pair tap, p = pixel of
+// the pair, c = channel of 4; input column w = 2 (wo - 2 + j) + p  ->  kw = 2 j + p - 1
 __global__ void pack_stem_kernel(const float* __restrict__ w /*(64,3,7,7) folded*/, unsigned char* __restrict__ dst) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 7 * 4 * 64 * 8) return;
-  const int e = i & 7, co = (i >> 3) & 63, j = (i >> 9) & 3, kh = i >> 11;
-  const int p = e >> 2, c = e & 3, kw = 2 * j + p - 1;
+  if (i >= 7 * 64 * 32) return;
+  const int k = i & 31, co = (i >> 5) & 63, kh = i >> 11;
+  const int j = k >> 3, p = (k >> 2) & 1, c = k & 3, kw = 2 * j + p - 1;
   float v = 0.f;
   if (c < 3 && kw >= 0 && kw < 7) v = w[((co * 3 + c) * 7 + kh) * 7 + kw];
-  reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16(v);
+  *reinterpret_cast<__nv_bfloat16*>(dst + (size_t)kh * (64 * 64) + swz_off(co, k / 8, 64) + (k % 8) * 2) = __float2bfloat16(v);
 }
 
 // ------------------------------------------------------------------ the conv kernel
@@ -67,17 +67,18 @@ struct ConvArgs {
   const __nv_bfloat16* res;     // residual (same shape as out) or null
   __nv_bfloat16* out;           // [P][Co]
   int P, HoWo, Wo, Co;
-  int KH, KW, cblocks;          // taps and 64-channel blocks (stem: KW = 4 pair taps, cblocks = 1)
+  int KH, KW, cblocks;          // taps and KB-channel blocks (stem: KW = 1, cblocks = 1, KB = 32)
   int stride_w, stride_h, pad_w, pad_h;
   int relu, n_mt, n_nt;
 };
 
-template <int BN, bool STEM>
+template <int BN, int KB>     // KB = K elements per pipeline stage: 64 (generic, SWIZZLE_128B rows) or 32 (stem, SWIZZLE_64B)
 struct IgCfg {
-  static constexpr int A_ST = STEM ? STEM_A_BYTES : A_BYTES;
-  static constexpr int B_ST = STEM ? STEM_B_BYTES : BN * 128;
+  static constexpr int ROWB = KB * 2;
+  static constexpr int A_ST = BM * ROWB;
+  static constexpr int B_ST = BN * ROWB;
   static constexpr int STAGE = A_ST + B_ST;
-  static constexpr int STAGES = STEM ? 8 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = KB == 32 ? 12 : (BN == 128 ? 6 : 8);
   static constexpr int OFF_BAR = STAGES * STAGE;
   static constexpr int SMEM = OFF_BAR + 256;
   static constexpr int TMEM_COLS = 2 * BN;
@@ -85,15 +86,9 @@ struct IgCfg {
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-// no-swizzle K-major descriptor: 8x16-byte core matrices, LBO = K-direction chunk stride, SBO = 8-row group stride
-__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
-         ((uint64_t)1 << 46);
-}
-
-template <int BN, bool STEM>
+template <int BN, int KB>
 __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const ConvArgs a) {
-  using Cfg = IgCfg<BN, STEM>;
+  using Cfg = IgCfg<BN, KB>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -117,7 +112,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem = misc[0];
   const int n_tiles = a.n_mt * a.n_nt;
-  const int nkb = a.KH * a.KW * a.cblocks;              // K blocks per tile (stem: stages = KH)
+  const int nkb = a.KH * a.KW * a.cblocks;              // K blocks (= pipeline stages) per tile
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -128,18 +123,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         const int p0 = mt * BM;
         const int n0 = p0 / a.HoWo, rem = p0 % a.HoWo;
         const int w0 = (rem % a.Wo) * a.stride_w - a.pad_w, h0 = (rem / a.Wo) * a.stride_h - a.pad_h;
-        if constexpr (STEM) {
-          for (int kh = 0; kh < a.KH; ++kh) {
-            mbar_wait(EMPTY(stage), ph ^ 1);
-            mbar_arrive_expect_tx(FULL(stage), Cfg::STAGE);
-            const uint32_t dst = sbase + stage * Cfg::STAGE;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_im2col(dst + j * (BM * 16), &tmA, 0, w0, h0, n0, j, kh, FULL(stage));
-            bulk_g2s(dst + Cfg::A_ST, a.wimg + (size_t)kh * STEM_B_BYTES, STEM_B_BYTES, FULL(stage));
-            if (++stage == STAGES) { stage = 0; ph ^= 1; }
-          }
-        } else {
-          const unsigned char* wt = a.wimg + (size_t)nt * nkb * (BN * 128);
+        {
+          const unsigned char* wt = a.wimg + (size_t)nt * nkb * Cfg::B_ST;
           int kb = 0;
           for (int kh = 0; kh < a.KH; ++kh)
             for (int kw = 0; kw < a.KW; ++kw)
@@ -147,8 +132,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
                 mbar_wait(EMPTY(stage), ph ^ 1);
                 mbar_arrive_expect_tx(FULL(stage), Cfg::STAGE);
                 const uint32_t dst = sbase + stage * Cfg::STAGE;
-                tma_load_im2col(dst, &tmA, cb * 64, w0, h0, n0, kw, kh, FULL(stage));
-                bulk_g2s(dst + Cfg::A_ST, wt + (size_t)kb * (BN * 128), BN * 128, FULL(stage));
+                tma_load_im2col(dst, &tmA, cb * KB, w0, h0, n0, kw, kh, FULL(stage));
+                bulk_g2s(dst + Cfg::A_ST, wt + (size_t)kb * Cfg::B_ST, Cfg::B_ST, FULL(stage));
                 if (++stage == STAGES) { stage = 0; ph ^= 1; }
               }
         }
@@ -158,7 +143,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t IDESC = idesc_bf16(128, BN);
-    const int nstages = STEM ? a.KH : nkb;
+    const int nstages = nkb;
     int stage = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(TEMPTY(acc), aph ^ 1);
@@ -169,15 +154,10 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_ST;
-          if constexpr (STEM) {
+          {
+            const uint64_t ad = desc_base(sa, Cfg::ROWB), bd = desc_base(sb, Cfg::ROWB);
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-              tc_mma_ss(d, desc_nosw(sa + ks * 2 * (BM * 16), BM * 16, 128), desc_nosw(sb + ks * 2 * (64 * 16), 64 * 16, 128), IDESC,
-                        (kb | ks) ? 1u : 0u);
-          } else {
-            const uint64_t ad = desc_base(sa, 128), bd = desc_base(sb, 128);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) tc_mma_ss(d, ad + (uint64_t)((ks * 32) >> 4), bd + (uint64_t)((ks * 32) >> 4), IDESC, (kb | ks) ? 1u : 0u);
+            for (int ks = 0; ks < KB / 16; ++ks) tc_mma_ss(d, ad + (uint64_t)((ks * 32) >> 4), bd + (uint64_t)((ks * 32) >> 4), IDESC, (kb | ks) ? 1u : 0u);
           }
           tc_commit(EMPTY(stage));
           if (kb == nstages - 1) tc_commit(TFULL(acc));
@@ -245,15 +225,21 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------ bandwidth kernels
-// (B,3,H,W) fp32 NCHW -> [B][H][W][4] bf16 (channel 3 = 0)
-__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, uint2* __restrict__ y, int HW, size_t total /*B*HW*/) {
+// (B,3,H,W) fp32 NCHW -> [B][H][Wp][4] bf16, Wp = W + 2 (PADL + PADR) pixels per row (zero columns), channel 3 = 0
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, uint2* __restrict__ y, int H, int W, int Wp, size_t total /*B*H*Wp*/) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const size_t b = i / HW, p = i % HW;
-  const float* s = x + b * 3 * (size_t)HW + p;
-  __nv_bfloat162 lo = __floats2bfloat162_rn(__ldg(s), __ldg(s + HW));
-  __nv_bfloat162 hi = __floats2bfloat162_rn(__ldg(s + 2 * (size_t)HW), 0.f);
-  y[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  const int wp = (int)(i % Wp), w = wp - 2 * STEM_PADL;
+  const size_t bh = i / Wp, b = bh / H, h = bh % H;
+  uint2 o = make_uint2(0u, 0u);
+  if (w >= 0 && w < W) {
+    const size_t HW = (size_t)H * W;
+    const float* s = x + b * 3 * HW + h * W + w;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(__ldg(s), __ldg(s + HW));
+    __nv_bfloat162 hi = __floats2bfloat162_rn(__ldg(s + 2 * HW), 0.f);
+    o = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+  y[i] = o;
 }
 
 // MaxPool2d(3, stride 2, padding 1) on NHWC bf16; one thread = one output pixel x 8 channels
@@ -303,7 +289,7 @@ __global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, float* 
 
 // ------------------------------------------------------------------ layout of the bf16 section
 size_t conv_img_bytes(const RConv& c) { return (size_t)c.co * c.ci * c.k * c.k * 2; }   // generic convs: no padding elements
-constexpr size_t STEM_IMG_BYTES = 7 * STEM_B_BYTES;
+constexpr size_t STEM_IMG_BYTES = 7 * 64 * 64;
 
 struct Sec { std::vector<size_t> off; size_t total; };
 Sec sec_layout(const RNet& n) {
@@ -322,7 +308,7 @@ struct Ws { __nv_bfloat16* x4; __nv_bfloat16* buf[5]; float* pooled; size_t byte
 Ws carve(const RNet& n, int B, int H, int W, void* ws) {
   Arena a(ws, (size_t)-1);
   Ws w{};
-  w.x4 = a.take<__nv_bfloat16>((size_t)B * H * W * 4);
+  w.x4 = a.take<__nv_bfloat16>((size_t)B * H * (W + 2 * (STEM_PADL + STEM_PADR)) * 4);
   const size_t act = resnet_max_act(n, H, W) * (size_t)B;
   for (int i = 0; i < 5; ++i) w.buf[i] = a.take<__nv_bfloat16>(act);
   w.pooled = a.take<float>((size_t)B * n.feat);
@@ -330,10 +316,10 @@ Ws carve(const RNet& n, int B, int H, int W, void* ws) {
   return w;
 }
 
-template <int BN, bool STEM>
+template <int BN, int KB>
 int launch_conv(const CUtensorMap& tm, const ConvArgs& a, cudaStream_t s) {
-  using Cfg = IgCfg<BN, STEM>;
-  auto kern = conv_igemm_kernel<BN, STEM>;
+  using Cfg = IgCfg<BN, KB>;
+  auto kern = conv_igemm_kernel<BN, KB>;
   I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   const int n_tiles = a.n_mt * a.n_nt;
   kern<<<std::min(n_tiles, num_sms()), 192, Cfg::SMEM, s>>>(tm, a);
@@ -352,7 +338,7 @@ size_t resnet_bf16_packed_bytes(const RNet& n) { return sec_layout(n).total; }
 int resnet_bf16_pack(const RNet& n, const float* folded /* fp32 packed region */, void* section, cudaStream_t s) {
   Sec L = sec_layout(n);
   unsigned char* sec = reinterpret_cast<unsigned char*>(section);
-  pack_stem_kernel<<<cdiv(7 * 4 * 64 * 8, 256), 256, 0, s>>>(folded + n.convs[0].w_off, sec + L.off[0]);
+  pack_stem_kernel<<<cdiv(7 * 64 * 32, 256), 256, 0, s>>>(folded + n.convs[0].w_off, sec + L.off[0]);
   I2L_LAUNCH_OK();
   for (size_t i = 1; i < n.convs.size(); ++i) {
     const RConv& c = n.convs[i];
@@ -377,22 +363,25 @@ int resnet_bf16_fwd(const RNet& n, const i2l_resnet_desc& d, const float* folded
   snprintf(tag, sizeof tag, "resnet%d", d.depth);
   // ---- input re-layout
   {
-    const size_t tot = (size_t)B * H * W;
+    const int Wp = W + 2 * (STEM_PADL + STEM_PADR);
+    const size_t tot = (size_t)B * H * Wp;
     KernelTimer kt("rn.nchw_to_nhwc4", s);
-    nchw_to_nhwc4_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(x, reinterpret_cast<uint2*>(w.x4), H * W, tot);
+    nchw_to_nhwc4_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(x, reinterpret_cast<uint2*>(w.x4), H, W, Wp, tot);
     I2L_LAUNCH_OK();
   }
   // ---- stem: conv 7x7/2 + bn + relu in pixel-pair space
   int h = out_dim(H, 7, 2, 3), wd = out_dim(W, 7, 2, 3);    // = H/2 (ceil), W/2
   {
     CUtensorMap tm;
-    I2L_TRY(make_im2col_map(&tm, w.x4, 8, W / 2, H, B, -2, -3, -2, -3, 8, BM, 1, 2, 0));
+    // overlapping view: "pixel" wo = the 32 elements (4 pairs) starting at stored pair wo = logical pair wo - PADL
+    const int Wpp = W / 2 + STEM_PADL + STEM_PADR;      // stored pairs per row
+    I2L_TRY(make_im2col_map_strided(&tm, w.x4, 32, W / 2, H, B, 16, (uint64_t)Wpp * 16, (uint64_t)H * Wpp * 16, 0, -3, 0, -3, 32, BM, 1, 2, 64));
     ConvArgs a{};
     a.wimg = sec + L.off[0]; a.bias = folded + n.convs[0].b_off; a.res = nullptr; a.out = w.buf[1];
-    a.P = B * h * wd; a.HoWo = h * wd; a.Wo = wd; a.Co = 64; a.KH = 7; a.KW = 4; a.cblocks = 1;
-    a.stride_w = 1; a.stride_h = 2; a.pad_w = 2; a.pad_h = 3; a.relu = 1; a.n_mt = cdiv(a.P, BM); a.n_nt = 1;
+    a.P = B * h * wd; a.HoWo = h * wd; a.Wo = wd; a.Co = 64; a.KH = 7; a.KW = 1; a.cblocks = 1;
+    a.stride_w = 1; a.stride_h = 2; a.pad_w = 0; a.pad_h = 3; a.relu = 1; a.n_mt = cdiv(a.P, BM); a.n_nt = 1;
     KernelTimer kt("rn.stem_conv7x7", s);
-    I2L_TRY((launch_conv<64, true>(tm, a, s)));
+    I2L_TRY((launch_conv<64, 32>(tm, a, s)));
   }
   // ---- maxpool 3x3/2
   {
@@ -417,8 +406,8 @@ int resnet_bf16_fwd(const RNet& n, const i2l_resnet_desc& d, const float* folded
     char nm[48];
     snprintf(nm, sizeof nm, "rn.conv%dx%d_c%d", c.k, c.k, c.co);
     KernelTimer kt(nm, s);
-    if (bn == 64) return launch_conv<64, false>(tm, a, s);
-    return launch_conv<128, false>(tm, a, s);
+    if (bn == 64) return launch_conv<64, 64>(tm, a, s);
+    return launch_conv<128, 64>(tm, a, s);
   };
   __nv_bfloat16 *cur = w.buf[0], *nxt = w.buf[1], *t1 = w.buf[2], *t2 = w.buf[3], *idt = w.buf[4];
   for (const RBlock& b : n.blocks) {

@@ -157,5 +157,9 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t
 // tools/probes/im2col_probe.cu.
 int make_im2col_map(CUtensorMap* out, const void* base, int C, int W, int H, int N, int lower_w, int lower_h,
                     int upper_w, int upper_h, int channels, int pixels, int stride_w, int stride_h, int swizzle_bytes);
+// same with explicit byte strides of the W / H / N dims (padded rows, overlapping pixels)
+int make_im2col_map_strided(CUtensorMap* out, const void* base, int C, int W, int H, int N, uint64_t w_bytes, uint64_t h_bytes,
+                            uint64_t n_bytes, int lower_w, int lower_h, int upper_w, int upper_h, int channels, int pixels,
+                            int stride_w, int stride_h, int swizzle_bytes);
 
 }  // namespace i2l

@@ -64,10 +64,17 @@ static EncodeIm2colFn get_encode_im2col() {
 
 int make_im2col_map(CUtensorMap* out, const void* base, int C, int W, int H, int N, int lower_w, int lower_h,
                     int upper_w, int upper_h, int channels, int pixels, int stride_w, int stride_h, int swizzle_bytes) {
+  return make_im2col_map_strided(out, base, C, W, H, N, (uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, lower_w, lower_h,
+                                 upper_w, upper_h, channels, pixels, stride_w, stride_h, swizzle_bytes);
+}
+
+int make_im2col_map_strided(CUtensorMap* out, const void* base, int C, int W, int H, int N, uint64_t w_bytes, uint64_t h_bytes,
+                            uint64_t n_bytes, int lower_w, int lower_h, int upper_w, int upper_h, int channels, int pixels,
+                            int stride_w, int stride_h, int swizzle_bytes) {
   EncodeIm2colFn fn = get_encode_im2col();
   if (!fn) { set_error("cuTensorMapEncodeIm2col is not available from the driver"); return I2L_ERR_CUDA; }
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t gstr[3] = {w_bytes, h_bytes, n_bytes};
   int lo[2] = {lower_w, lower_h}, hi[2] = {upper_w, upper_h};      // corner order is {W, H}
   cuuint32_t es[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
