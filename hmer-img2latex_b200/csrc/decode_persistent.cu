@@ -30,6 +30,14 @@
 // Seq2SeqModel._greedy_search (model/seq2seq.py:192-232); attention with src_len == 1 is the
 // identity and W_ih [emb ; ctx] is hoisted into the Gtok table / Gctx (F4).
 #include "decode_persistent_common.cuh"
+#include <limits.h>
+
+// Timing ablations (tools/ablate_greedy.sh builds one library per mask; results are WRONG by design):
+//  1 gtok gather from a fixed row   2 no MUFU in the cell update   4 no cluster token exchange
+//  8 no cluster h exchange          16 no argmax                   32 no logits MMA wait (use stale accumulator)
+#ifndef I2L_ABL
+#define I2L_ABL 0
+#endif
 
 namespace i2l {
 
@@ -54,9 +62,15 @@ enum { BAR_W = 0, BAR_HFULL0 = 1, BAR_HFULL1 = 2, BAR_LDONE = 3, BAR_GDONE = 4, 
     if (DBG && dbg_ts) reinterpret_cast<long long*>(P.dbg + 16 + 300000)[slot] = clock64(); \
   } while (0)
 
+#if I2L_ABL & 2
+#define TANH(x) ((x) * 0.25f)
+#else
+#define TANH(x) tanh_approx(x)
+#endif
+
 struct Params {
   const unsigned char* wimg;     // per-rank weight images
-  const float* gtok;             // [V][4][2][128]
+  const float* gtok;             // [V][4][128][2]
   const float* bias;             // [512]
   const float* gctx;             // [B][1024] fp32 (PyTorch gate order)
   int64_t* tokens;               // [B][T+1]
@@ -205,11 +219,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
     int tok[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) tok[j] = P.start_id;
-    int fe = -1;                                          // first END position (threads tid < 32 of rank 0)
+    constexpr int XW = 1;                                 // epilogue warp that runs the token exchange (not warp 0:
+    const int xt = tid - 32 * XW;                         //  thread 0 issues the h bulk copies, warp 8 shares its scheduler)
+    int fe = -1;                                          // first END position (exchange warp of rank 0)
     bool finished = false;
     float* part = reinterpret_cast<float*>(smem + OFF_PART);
     int* tok_s = reinterpret_cast<int*>(smem + OFF_TOK);
-    const float* gt_base = P.gtok + (size_t)rank * 256 + p;
+    const float2* gt_base = reinterpret_cast<const float2*>(P.gtok + (size_t)rank * 256) + p;   // [V][rank][128 rows][tile 0,1]
     int s = 0;
     for (; s < P.T; ++s) {
       const bool dbg_ts = DBG && cluster == 0 && rank == 0 && s == P.dbg_step;
@@ -219,9 +235,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       float gt0[16], gt1[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {                      // token -> gate table rows (L2 resident)
-        const float* g = gt_base + (size_t)tok[j] * 1024;
-        gt0[j] = __ldg(g);
-        gt1[j] = __ldg(g + 128);
+        const float2 g = __ldg(gt_base + (size_t)((I2L_ABL & 1) ? 1 : tok[j]) * 512);
+        gt0[j] = g.x;
+        gt1[j] = g.y;
       }
       if (tid == 0) I2L_TS(1);
       mbar_wait(BAR(BAR_GDONE), s & 1);
@@ -246,8 +262,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
           float* dm = P.dbg + 16 + 200000 + (size_t)((cluster * 4 + rank) * 2) * 4096;
           dm[p * 32 + col0 + j] = __uint_as_float(r0[j]); dm[4096 + p * 32 + col0 + j] = __uint_as_float(r1[j]);
         }
-        y0[j] = fmaf(tanh_approx(0.5f * x0), 0.5f, 0.5f);          // sigmoid(i) | sigmoid(f)
-        y1[j] = fmaf(tanh_approx(s1 * x1), m1, b1);                // tanh(g)    | sigmoid(o)
+        y0[j] = fmaf(TANH(0.5f * x0), 0.5f, 0.5f);                 // sigmoid(i) | sigmoid(f)
+        y1[j] = fmaf(TANH(s1 * x1), m1, b1);                       // tanh(g)    | sigmoid(o)
       }
       // phase 2: sigma(i) tanh(g) moves from lanes 0..15 to the lanes 16..31 that own c
       float pg[16];
@@ -259,7 +275,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       for (int j = 0; j < 16; ++j) {
         float cn = fmaf(y0[j], c[j], pg[j]);
         c[j] = cn;
-        hn[j] = y1[j] * tanh_approx(cn);
+        hn[j] = y1[j] * TANH(cn);
       }
       if (hi) {
 #pragma unroll
@@ -276,16 +292,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       epi_bar_sync();
       if (tid == 0) {
         const uint32_t src = sbase + OFF_H + nb * HB_BYTES + rank * HSLICE_BYTES;
-        mbar_arrive_expect_tx(BAR(BAR_HFULL0 + nb), (CL - 1) * HSLICE_BYTES);
+        mbar_arrive_expect_tx(BAR(BAR_HFULL0 + nb), (I2L_ABL & 8) ? 0 : (CL - 1) * HSLICE_BYTES);
 #pragma unroll
-        for (uint32_t d = 1; d < CL; ++d) {
+        for (uint32_t d = 1; d < ((I2L_ABL & 8) ? 1 : CL); ++d) {
           uint32_t peer = (rank + d) & (CL - 1);
           bulk_s2peer(mapa(src, peer), src, HSLICE_BYTES, mapa(BAR(BAR_HFULL0 + nb), peer));
         }
       }
       // ---------------- Epi-L(s): logits -> tok_{s+1} ----------------
       if (tid == 0) I2L_TS(5);
-      mbar_wait(BAR(BAR_LDONE), s & 1);
+      if (!(I2L_ABL & 32)) mbar_wait(BAR(BAR_LDONE), s & 1);
       tc_fence_after();
       if (tid == 0) I2L_TS(6);
       float lg[16];
@@ -297,70 +313,61 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
         if (DBG == 2 && dbg_dump) P.dbg[16 + 131072 + ((cluster * 4 + rank) * 128 + p) * 32 + col0 + j] = lg[j];
         if (P.temperature != 1.0f) lg[j] = lg[j] / P.temperature;   // seq2seq.py:213-214
       }
-      // per-column argmax over the warp's 32 vocab rows: transposing butterfly, 16 + 16 shuffles.
-      // After the xor-16/8/4/2 steps lane l holds column (l >> 1) & 15 reduced over 16 rows; the
-      // xor-1 step finishes it.  Ties keep the lower row (torch.argmax: first index wins).
-      float myv; int myi;
+      // per-column argmax over the warp's 32 vocab rows: order-preserving integer keys, one
+      // redux.sync.max.s32 + one ballot per column (uniform results, ~6 instructions per column).
+      // The ballot keeps every row holding the maximum; the lowest one wins later (torch.argmax:
+      // first index).  Lane 0 publishes the 16 (key, ballot) pairs of the warp.
       {
-        int ix[16];
+        int kmax[16]; unsigned bal[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) ix[j] = lane;
-#pragma unroll
-        for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
-          const bool up = (lane & bit) != 0;
-#pragma unroll
-          for (int j = 0; j < w; ++j) {
-            float keep_v = up ? lg[j + w] : lg[j];
-            int keep_i = up ? ix[j + w] : ix[j];
-            float send_v = up ? lg[j] : lg[j + w];
-            int send_i = up ? ix[j] : ix[j + w];
-            float ov = __shfl_xor_sync(0xffffffffu, send_v, bit);
-            int oi = __shfl_xor_sync(0xffffffffu, send_i, bit);
-            const bool take = ov > keep_v || (ov == keep_v && oi < keep_i);
-            lg[j] = take ? ov : keep_v;
-            ix[j] = take ? oi : keep_i;
-          }
+        for (int j = 0; j < 16; ++j) {
+          int key = __float_as_int(lg[j] + 0.0f);                    // -0 -> +0 (equal under torch's compare)
+          key ^= (key >> 31) & 0x7fffffff;                           // monotone: float order == signed int order
+          kmax[j] = (I2L_ABL & 16) ? key : redux_max_s32(key);
+          bal[j] = (I2L_ABL & 16) ? 1u : __ballot_sync(0xffffffffu, key == kmax[j]);
         }
-        float ov = __shfl_xor_sync(0xffffffffu, lg[0], 1);
-        int oi = __shfl_xor_sync(0xffffffffu, ix[0], 1);
-        const bool take = ov > lg[0] || (ov == lg[0] && oi < ix[0]);
-        myv = take ? ov : lg[0];
-        myi = 128 * (int)rank + 32 * q + (take ? oi : ix[0]);
+        if (tid == 0) I2L_TS(7);
+        if (lane == 0) {
+          uint4* dst = reinterpret_cast<uint4*>(part) + warp * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_uint4((uint32_t)kmax[2 * j], bal[2 * j], (uint32_t)kmax[2 * j + 1], bal[2 * j + 1]);
+        }
       }
-      if (tid == 0) I2L_TS(7);
-      if ((lane & 1) == 0) { const int cj = lane >> 1; part[(warp * 16 + cj) * 2] = myv; reinterpret_cast<int*>(part)[(warp * 16 + cj) * 2 + 1] = myi; }
       epi_bar_sync();
       if (tid == 0) I2L_TS(8);
-      if (tid < NB) {
-        const int cgrp = tid >> 4, j = tid & 15;
-        float bv = -INFINITY; int bi = 0x7fffffff;
+      if (xt >= 0 && xt < NB) {
+        const int cgrp = xt >> 4, j = xt & 15;
+        const int2* pp = reinterpret_cast<const int2*>(part);
+        int bk = INT_MIN, bi = 0;
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          int w = cgrp * 4 + qq;
-          float v = part[(w * 16 + j) * 2]; int i = reinterpret_cast<int*>(part)[(w * 16 + j) * 2 + 1];
-          if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        for (int qq = 0; qq < 4; ++qq) {                             // ascending row order: strict > keeps the first maximum
+          const int2 e = pp[(cgrp * 4 + qq) * 16 + j];
+          if (qq == 0 || e.x > bk) { bk = e.x; bi = 128 * (int)rank + 32 * qq + __ffs(e.y) - 1; }
         }
         // CTA partial -> slot [rank][column] of every CTA of the cluster; the store itself
         // signals the destination's mbarrier (st.async + complete_tx), no fence / arrive round trip
-        const uint32_t slot = sbase + OFF_XCHG + (rank * NB + tid) * 8;
-        if (tid == 0) mbar_arrive_expect_tx(BAR(BAR_TOK), CL * NB * 8);
+        const uint32_t slot = sbase + OFF_XCHG + (rank * NB + xt) * 8;
+        if (xt == 0) I2L_TS(13);
+        if (xt == 0) mbar_arrive_expect_tx(BAR(BAR_TOK), ((I2L_ABL & 4) ? 1 : CL) * NB * 8);
+        if (xt == 0) I2L_TS(14);
 #pragma unroll
-        for (uint32_t d = 0; d < CL; ++d) st_async_v2(mapa(slot, d), __float_as_uint(bv), (uint32_t)bi, mapa(BAR(BAR_TOK), d));
-        if (tid == 0) I2L_TS(9);
-        mbar_wait_cluster(BAR(BAR_TOK), s & 1);
-        if (tid == 0) I2L_TS(10);
-        const float* xf = reinterpret_cast<const float*>(smem + OFF_XCHG);
-        const int* xi = reinterpret_cast<const int*>(smem + OFF_XCHG);
-        bv = -INFINITY; bi = 0x7fffffff;
-#pragma unroll
-        for (int r = 0; r < CL; ++r) {
-          float v = xf[(r * NB + tid) * 2]; int i = xi[(r * NB + tid) * 2 + 1];
-          if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        for (uint32_t d = 0; d < CL; ++d) {
+          if ((I2L_ABL & 4) && d != rank) continue;
+          st_async_v2(mapa(slot, d), (uint32_t)bk, (uint32_t)bi, mapa(BAR(BAR_TOK), d));
+          if (d == 0 && xt == 0) I2L_TS(15);
         }
-        if (bi == 0x7fffffff) bi = 0;
-        tok_s[tid] = bi;
+        if (xt == 0) I2L_TS(9);
+        mbar_wait_cluster(BAR(BAR_TOK), s & 1);
+        if (xt == 0) I2L_TS(10);
+        const int2* xe = reinterpret_cast<const int2*>(smem + OFF_XCHG);
+#pragma unroll
+        for (int r = 0; r < CL; ++r) {                               // ascending rank = ascending vocab index
+          const int2 e = xe[r * NB + xt];
+          if (r == 0 || e.x > bk) { bk = e.x; bi = e.y; }
+        }
+        tok_s[xt] = bi;
         // token append + EOS bookkeeping (seq2seq.py:216-221 / predictor.py:338-347)
-        const int row = row0 + tid;
+        const int row = row0 + xt;
         const bool valid = row < P.B;
         const bool is_end = bi == P.end_id;
         if (valid && is_end && fe < 0) fe = s + 1;
@@ -368,7 +375,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
         if (rank == 0 && valid) P.tokens[(size_t)row * (P.T + 1) + s + 1] = bi;
         const bool all_end = __all_sync(0xffffffffu, !valid || is_end);
         const bool all_fin = __all_sync(0xffffffffu, !valid || finished);
-        if (tid == 0) {
+        if (xt == 0) {
           if (rank == 0) P.allend[(size_t)cluster * P.T + s] = all_end ? 1 : 0;
           if (P.stop_rule == I2L_STOP_ALL_FINISHED_STICKY && all_fin) misc[1] = 1;   // this cluster is done
         }
@@ -380,10 +387,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       for (int j = 0; j < 16; ++j) tok[j] = tok_s[col0 + j];
       if (*reinterpret_cast<volatile uint32_t*>(&misc[1])) { ++s; break; }
     }
-    if (rank == 0 && tid < NB) {
-      const int row = row0 + tid;
+    if (rank == 0 && xt >= 0 && xt < NB) {
+      const int row = row0 + xt;
       if (row < P.B) P.first_end[row] = fe;
-      if (tid == 0) P.cluster_steps[cluster] = s;
+      if (xt == 0) P.cluster_steps[cluster] = s;
     }
     if (*reinterpret_cast<volatile uint32_t*>(&misc[1]) && tid == 0) {
       // early exit: release the MMA thread that is waiting for an h buffer that will never fill
@@ -423,14 +430,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_hh, const float*
 }
 
 __global__ void pack_gtok_kernel(const float* __restrict__ gtok, int V, float* __restrict__ out) {
-  // out[v][r][t][p] = gtok[v][gate(t,p)*256 + 64 r + unit(p)]
+  // out[v][r][p][t] = gtok[v][gate(t,p)*256 + 64 r + unit(p)]   (both tiles of a row in one 8-byte load)
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)V * 1024) return;
   int p = (int)(i & 127), t = (int)((i >> 7) & 1), r = (int)((i >> 8) & 3), v = (int)(i >> 10);
   int qd = p >> 5, l = p & 31;
   int unit = 64 * r + 16 * qd + (l & 15);
   int gate = 2 * t + (l >= 16 ? 1 : 0);
-  out[i] = gtok[(size_t)v * 1024 + gate * 256 + unit];
+  out[(size_t)v * 1024 + r * 256 + p * 2 + t] = gtok[(size_t)v * 1024 + gate * 256 + unit];
 }
 
 __global__ void pack_bias_kernel(const float* __restrict__ out_b, int V, float* __restrict__ out) {

@@ -217,7 +217,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
     }
     const float bias = P.bias[128 * rank + p];
     const float s1 = hi ? 0.5f : 1.0f, m1 = hi ? 0.5f : 1.0f, b1 = hi ? 0.5f : 0.0f;
-    const float* gt_base = P.gtok + (size_t)rank * 256 + p;
+    const float2* gt_base = reinterpret_cast<const float2*>(P.gtok + (size_t)rank * 256) + p;   // [V][rank][128 rows][tile 0,1]
     float* LT = reinterpret_cast<float*>(smem + G::OFF_LT);
     // word of vocabulary row p inside a row of the transposed logits tile: 16-byte chunk c = p / 4 is stored at
     // c ^ ((c >> 3) & 3), so that the top-K threads (8 per row, 16 CONTIGUOUS vocabulary entries each = chunks
@@ -250,9 +250,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
       float gt0[16], gt1[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float* g = gt_base + (size_t)tok[j] * 1024;
-        gt0[j] = __ldg(g);
-        gt1[j] = __ldg(g + 128);
+        const float2 g = __ldg(gt_base + (size_t)tok[j] * 512);
+        gt0[j] = g.x;
+        gt1[j] = g.y;
       }
       BEAM_TS(1);
       mbar_wait(BAR(BAR_GDONE), s & 1);

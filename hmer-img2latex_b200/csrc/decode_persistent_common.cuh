@@ -21,7 +21,7 @@ constexpr int TC_WO = 128, TC_WG0 = 256, TC_WG1 = 384;        // bf16 weight til
 // ---- packed (bf16) section layout -------------------------------------------------------
 struct PSection {
   size_t wimg;      // [4 ranks][3 tiles][128 rows][256] bf16
-  size_t gtok;      // fp32 [V][4][2][128]
+  size_t gtok;      // fp32 [V][4 ranks][128 rows][2 tiles]
   size_t bias;      // fp32 [512]  (-inf beyond V)
   size_t total;
 };
@@ -166,6 +166,12 @@ __device__ __forceinline__ float tanh_approx(float x) {
 __device__ __forceinline__ float redux_max(float v) {
   float m;
   asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
+}
+
+__device__ __forceinline__ int redux_max_s32(int v) {
+  int m;
+  asm volatile("redux.sync.max.s32 %0, %1, 0xffffffff;" : "=r"(m) : "r"(v));
   return m;
 }
 

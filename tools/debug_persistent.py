@@ -30,11 +30,11 @@ enc = m32.encoder(x.cuda())
 tokens, lengths, steps = m16.decoder.greedy(enc, H.START, H.END, T)
 torch.cuda.synchronize()
 d = dbg.cpu()[16:]
-NAMES = {0: 'epiG start', 1: 'gtok loads issued', 2: 'GDONE waited', 3: 'tmem ld done', 4: 'pointwise+h st done', 5: 'bar+bulk issued', 6: 'LDONE waited', 7: 'argmax partial', 8: 'bar', 9: 'xchg sent', 10: 'TOK waited', 11: 'tok final', 12: 'bar (end step)', 16: 'mma: before HFULL wait', 17: 'mma: HFULL ok', 18: 'mma: L issued', 19: 'mma: G issued'}
+NAMES = {0: 'epiG start', 1: 'gtok loads issued', 2: 'GDONE waited', 3: 'tmem ld done', 4: 'pointwise+h st done', 5: 'bar+bulk issued', 6: 'LDONE waited', 7: 'argmax partial', 8: 'bar', 9: 'xchg sent', 10: 'TOK waited', 11: 'tok final', 12: 'bar (end step)', 13: 'xchg: combine done', 14: 'xchg: expect_tx done', 15: 'xchg: first st.async', 16: 'mma: before HFULL wait', 17: 'mma: HFULL ok', 18: 'mma: L issued', 19: 'mma: G issued'}
 if not dump:
     ts = dbg.cpu()[16 + 300000: 16 + 300000 + 64].view(torch.int64)
     t0 = int(ts[0])
-    for k in sorted(NAMES):
+    for k in sorted(NAMES, key=lambda k: int(ts[k])):
         print(f'  ts[{k:2d}] {NAMES[k]:28s} {int(ts[k]) - t0:8d} cyc')
     sys.exit(0)
 # oracle up to `step`
