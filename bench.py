@@ -93,6 +93,8 @@ def kernel_work(name, B, steps):
     out.  Decode: SURVEY 8d's per-step streaming figure W + B*S times the steps run."""
     E = H = 256; V = 512
     conv = {1: (3, 32, 64, 320), 2: (32, 64, 32, 160), 3: (64, 128, 16, 80)}
+    if name.startswith("cnn.conv1_u8in"):
+        return "hbm", B * (3 * 64 * 320 * 1 + 32 * 160 * 32 * 2)
     if name.startswith("cnn.conv1_bf16in"):
         return "hbm", B * (3 * 64 * 320 * 2 + 32 * 160 * 32 * 2)
     if name.startswith("cnn.conv1_bf16"):
@@ -149,15 +151,24 @@ def run_ours(args):
     model = model.to(dev).eval()
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
-    in_dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[args.input_dtype]
-    # two different batches, used alternately: 2 x B x 3x64x320 exceeds the 126 MB L2 in either dtype
-    x_master = [torch.randn(B, 3, 64, 320, generator=g) for _ in range(2)]
-    x_host = [xm.to(in_dtype).pin_memory() for xm in x_master]
+    # NB different batches, used in turn: NB x B x 3x64x320 exceeds the 126 MB L2 in every dtype.
+    # uint8 (default): raw RGB pixels = clamp(randn)/2 mapped to 0..255, normalised on the device as
+    # x/255*2-1 (Predictor._prepare_image, training/predictor.py:441-446) inside conv1; bf16 / fp32: the
+    # already normalised tensors (the reference model's own input dtype is fp32).
+    NB = 3
+    x_master = [torch.randn(B, 3, 64, 320, generator=g) for _ in range(NB)]
+
+    def to_dtype(xm, nm):
+        if nm == "uint8":
+            return ((xm.clamp(-2, 2) / 2 + 1) * 127.5).round().to(torch.uint8)
+        return xm.to({"bf16": torch.bfloat16, "fp32": torch.float32}[nm])
+
+    x_host = [to_dtype(xm, args.input_dtype).pin_memory() for xm in x_master]
     x_dev = [xh.to(dev) for xh in x_host]
     lib = N.lib()
 
     def step(inp):
-        enc = model.encoder(inp)
+        enc = model.encoder.forward_u8(inp) if inp.dtype == torch.uint8 else model.encoder(inp)
         tokens, lengths, steps = model.decoder.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_ALL_END_SAME_STEP)
         if world > 1:
             tokens, lengths, steps = gather_tokens(tokens, lengths, steps, B * world)
@@ -172,7 +183,7 @@ def run_ours(args):
         """n batches through Seq2SeqModel.greedy_stream from pinned HOST buffers; returns seconds."""
         def host_batches(k):
             for i in range(k):
-                yield hosts[i & 1]
+                yield hosts[i % len(hosts)]
         for _ in model.greedy_stream(host_batches(2), START, END, MAX_LEN):
             pass
         barrier()
@@ -185,7 +196,7 @@ def run_ours(args):
 
     with torch.no_grad():
         for i in range(max(args.warmup, 3)):
-            step(x_dev[i & 1])
+            step(x_dev[i % NB])
         barrier()
         # ---- device-resident timed region ------------------------------------------------
         sampler = ClockSampler(local); sampler.start()
@@ -194,7 +205,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
-            out = step(x_dev[i & 1])
+            out = step(x_dev[i % NB])
         e1.record()
         barrier()
         launches = lib.i2l_launch_count() - l0
@@ -210,11 +221,10 @@ def run_ours(args):
         # the same call with the other host element types (reported next to the headline e2e)
         e2e_other = {}
         if world == 1 and not args.no_extras:
-            for nm, mk in (("fp32", lambda xm: xm.float()), ("bf16", lambda xm: xm.bfloat16()),
-                           ("uint8", lambda xm: ((xm.clamp(-1, 1) + 1) * 127.5).round().to(torch.uint8))):
+            for nm in ("uint8", "bf16", "fp32"):
                 if nm == args.input_dtype:
                     continue
-                hosts = [mk(xm).pin_memory() for xm in x_master]
+                hosts = [to_dtype(xm, nm).pin_memory() for xm in x_master[:2]]
                 sec, _ = e2e_run(hosts, args.steps)
                 e2e_other[nm] = {"value": round(B * args.steps / sec, 1), "unit": "images/s",
                                  "h2d_bytes_per_step": hosts[0].numel() * hosts[0].element_size()}
@@ -223,7 +233,8 @@ def run_ours(args):
         beam = None
         if not args.no_extras:
             Bb, K = args.beam_batch, 5
-            encb = model.encoder(x_dev[0][:Bb])
+            enc_of = lambda inp: model.encoder.forward_u8(inp) if inp.dtype == torch.uint8 else model.encoder(inp)
+            encb = enc_of(x_dev[0][:Bb])
             for _ in range(2):
                 model.decoder.beam(encb, START, END, MAX_LEN, K)
             barrier()
@@ -232,7 +243,7 @@ def run_ours(args):
             nb = max(2, min(args.steps, 5))
             b0.record()
             for i in range(nb):
-                encb = model.encoder(x_dev[i & 1][:Bb])
+                encb = enc_of(x_dev[i % NB][:Bb])
                 model.decoder.beam(encb, START, END, MAX_LEN, K)
             b1.record()
             barrier()
@@ -241,6 +252,12 @@ def run_ours(args):
             bprof = N.prof_results()
             bdec = sum(v[1] for k, v in bprof.items() if k.startswith("dec.")) / nb
             beam = [bms, bdec, Bb, K, {k: round(v[1] / nb, 4) for k, v in sorted(bprof.items())}]
+        resnet = None
+        if world == 1 and not args.no_extras:
+            try:
+                resnet = resnet_lines(pkg, dev, B)
+            except Exception as e:                       # an extra line must never take the headline down
+                resnet = {"error": repr(e)[:300]}
     tms = torch.tensor([ms, e2e_s * 1e3, beam[0] if beam else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -281,9 +298,11 @@ def run_ours(args):
         "config": {"workload": "BASELINE configs[1]: CNN-LSTM greedy decode, batch %d per GPU, 3x64x320 %s images, "
                                "max_len 150, V=512, E=H=256, L=1, random init" % (B, args.input_dtype),
                    "global_batch": B * world, "parallelism": "dp%d (batch-sharded, token all-gather)" % world,
-                   "l2_policy": "two input batches used alternately (2 x %.0f MB of images) exceed the 126 MB L2; "
+                   "l2_policy": "%d input batches used in turn (%d x %.0f MB of images) exceed the 126 MB L2; "
                                 "the bf16 activations written per step (587 MB) flush it as well"
-                                % (x_dev[0].numel() * x_dev[0].element_size() / 1e6),
+                                % (NB, NB, x_dev[0].numel() * x_dev[0].element_size() / 1e6),
+                   "input": {"uint8": "raw uint8 RGB pixels, x/255*2-1 (Predictor._prepare_image) fused into conv1",
+                             "bf16": "normalised bf16 tensors", "fp32": "normalised fp32 tensors"}[args.input_dtype],
                    "decode_steps_run": steps_run, "host_input_dtype": args.input_dtype},
         "us_per_decode_step": None,
         "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items())},
@@ -309,6 +328,8 @@ def run_ours(args):
                                       "peak": pk["hbm"], "unit": "GB/s",
                                       "frac": round(bbytes / (bdec / 1e3) / 1e9 / pk["hbm"], 4)},
                          "workload": "BASELINE configs[2]: CNN-LSTM beam search, beam 5, batch %d per GPU, max_len 150" % Bb}
+    if resnet:
+        line.update(resnet)
     dk = [v[1] for k, v in prof.items() if k.startswith("dec.")]
     if dk and steps_run:
         line["us_per_decode_step"] = round(sum(dk) / args.steps / steps_run * 1e3, 3)
@@ -317,6 +338,77 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def resnet_lines(pkg, dev, B, reps=3):
+    """BASELINE configs[3] / configs[4] on one GPU (extra lines next to the headline):
+    ResNet18-LSTM greedy decode over width-bucketed images (widths uniform in {128,160,...,800}),
+    ResNet50-LSTM temperature / top-k / top-p sampling at 3x64x320.  E = H = 256, L = 1, V = 512,
+    bf16 tcgen05 trunk (resnet_bf16.cu); images are created on the device (no e2e figure here)."""
+    import torch
+    N = pkg._native
+    lib = N.lib()
+    out = {}
+    mk = lambda name: pkg.Seq2SeqModel("resnet_lstm", CFG["vocab_size"],
+                                       dict(img_height=64, img_width=320, channels=3, model_name=name, embedding_dim=256),
+                                       dict(hidden_dim=256, lstm_layers=1, attention=True), precision="bf16").to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    # ---- configs[3]: width buckets
+    m = mk("resnet18")
+    widths = (torch.randint(0, 22, (B,), generator=g) * 32 + 128).tolist()
+    buckets = {}
+    for w in widths:
+        buckets[w] = buckets.get(w, 0) + 1
+    xs = {w: torch.randn(n, 3, 64, w, device=dev) for w, n in sorted(buckets.items())}
+
+    def step18():
+        enc = torch.cat([m.encoder(x) for x in xs.values()], 0)
+        return m.decoder.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_ALL_END_SAME_STEP)
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        lib.i2l_prof_reset(); lib.i2l_prof_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        lib.i2l_prof_enable(0)
+        prof = N.prof_results()
+        return e0.elapsed_time(e1) / reps, {k: round(v[1] / reps, 4) for k, v in sorted(prof.items())}
+
+    ms, prof = timed(step18)
+    enc_ms = sum(v for k, v in prof.items() if k.startswith("rn."))
+    fl = 4.627e6 * sum(widths)
+    out["resnet18_bucketed_greedy"] = {
+        "workload": "BASELINE configs[3]: ResNet18-LSTM greedy decode, %d images, widths uniform in {128..800 step 32} "
+                    "(%d buckets), max_len 150" % (B, len(buckets)),
+        "value": round(B / ms * 1e3, 1), "unit": "images/s", "ms_per_step": round(ms, 3),
+        "encoder_ms": round(enc_ms, 3), "encoder_tflops": round(fl / enc_ms / 1e9, 1),
+        "encoder_frac_of_bf16_peak": round(fl / enc_ms / 1e9 / peaks()["tf_sust"], 3),
+        "decode_ms": round(sum(v for k, v in prof.items() if k.startswith("dec.")), 3)}
+    del m, xs
+    # ---- configs[4]: ResNet50 + sampling
+    m = mk("resnet50")
+    x = torch.randn(B, 3, 64, 320, device=dev)
+
+    def step50():
+        enc = m.encoder(x)
+        return m.decoder.sample(enc, START, END, MAX_LEN, temperature=0.8, top_k=50, top_p=0.9, seed=1)
+
+    ms, prof = timed(step50)
+    enc_ms = sum(v for k, v in prof.items() if k.startswith("rn."))
+    fl = 10.43e6 * 320 * B
+    out["resnet50_sampling"] = {
+        "workload": "BASELINE configs[4] on one GPU: ResNet50-LSTM sampling (temperature 0.8, top_k 50, top_p 0.9), "
+                    "batch %d, 3x64x320, max_len 150" % B,
+        "value": round(B / ms * 1e3, 1), "unit": "images/s", "ms_per_step": round(ms, 3),
+        "encoder_ms": round(enc_ms, 3), "encoder_tflops": round(fl / enc_ms / 1e9, 1),
+        "encoder_frac_of_bf16_peak": round(fl / enc_ms / 1e9 / peaks()["tf_sust"], 3),
+        "decode_ms": round(ms - enc_ms, 3)}
+    return out
 
 
 def cpu_baseline(model=None, sample_batch=32, budget_s=20.0, min_reps=1):
@@ -393,7 +485,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--input-dtype", default="bf16", choices=["bf16", "fp32"],
+    ap.add_argument("--input-dtype", default="uint8", choices=["uint8", "bf16", "fp32"],
                     help="element type of the image tensors (HBM-resident for `value`, pinned host for `e2e`)")
     ap.add_argument("--beam-batch", type=int, default=512, help="images per GPU for the beam-5 line")
     ap.add_argument("--no-extras", action="store_true", help="skip the beam-5 and other-host-dtype measurements")

@@ -22,7 +22,7 @@ MAX_RESNET_CONVS = 160
 FP32, BF16 = 0, 1
 STOP_NONE, STOP_ALL_END_SAME_STEP, STOP_ALL_FINISHED_STICKY = 0, 1, 2
 PRECISIONS = {"fp32": FP32, "bf16": BF16}
-IN_F32, IN_BF16 = 0, 1
+IN_F32, IN_BF16, IN_U8 = 0, 1, 2
 NORM_PM1, NORM_MEANSTD = 0, 1
 
 _fp = C.c_void_p  # all device pointers travel as void*
@@ -70,6 +70,8 @@ SIGNATURES = {
     "i2l_cnn_encoder_fwd": (C.c_int, [C.POINTER(CnnDesc), _fp, _fp, C.c_int32, _fp, _fp, C.c_size_t, _fp]),
     "i2l_cnn_encoder_fwd_in": (C.c_int, [C.POINTER(CnnDesc), _fp, _fp, C.c_int32, C.c_int32, _fp, _fp, C.c_size_t,
                                          _fp]),
+    "i2l_cnn_encoder_fwd_u8": (C.c_int, [C.POINTER(CnnDesc), _fp, _fp, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                         C.c_int32, _fp, _fp, C.c_size_t, _fp]),
     "i2l_normalize_u8": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_float), C.POINTER(C.c_float), _fp, C.c_int32, _fp]),
     "i2l_resnet_num_convs": (C.c_int32, [C.c_int32]),

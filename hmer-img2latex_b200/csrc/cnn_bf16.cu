@@ -91,6 +91,11 @@ constexpr int PATCH_H = 18;
 template <typename T> struct C1In;
 template <> struct C1In<float> { static constexpr int PATCH_W = 40, X0 = 3, ELT = 4; };
 template <> struct C1In<__nv_bfloat16> { static constexpr int PATCH_W = 48, X0 = 7, ELT = 2; };
+// raw uint8 pixels: y = a[c] * x + b[c] (the normalisation of load_image / _prepare_image, data/utils.py:68-80,
+// training/predictor.py:441-446) is applied while the im2col rows are built; out-of-image taps stay 0 in
+// NORMALISED space (the conv's zero padding), which the TMA zero fill of the raw pixels alone would not give
+template <> struct C1In<uint8_t> { static constexpr int PATCH_W = 64, X0 = 15, ELT = 1; };
+struct C1Norm { float a[3], b[3]; };
 constexpr int C1_PATCH_STRIDE = 9216;                  // ring slot (fp32 patch = 8640 B, bf16 patch = 5184 B)
 constexpr int C1_OFF_W = 0;                            // [32 co][32 k] bf16 SW64, 2 KB
 constexpr int C1_TC_ACC = 0, C1_TC_A = 256;            // TMEM columns: 2 x (4 x 32) accumulators, 2 x (4 x 16) im2col A tiles
@@ -101,7 +106,7 @@ constexpr int C1_SMEM = C1_OFF_BAR + 256;
 template <typename InT>
 __global__ void __launch_bounds__(C1_THREADS, 1)
 conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __restrict__ w1img,
-             const float* __restrict__ bias1, __nv_bfloat16* __restrict__ act1, int B, int n_tiles, int dbg) {
+             const float* __restrict__ bias1, __nv_bfloat16* __restrict__ act1, int B, int n_tiles, int dbg, const C1Norm nrm) {
   constexpr int PATCH_W = C1In<InT>::PATCH_W, PATCH_X0 = C1In<InT>::X0;
   constexpr int C1_PATCH_BYTES = 3 * PATCH_H * PATCH_W * C1In<InT>::ELT;
   static_assert(C1_PATCH_BYTES <= C1_PATCH_STRIDE, "patch ring slot too small");
@@ -229,7 +234,31 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
       // raw[ci][kh][j]: 32-bit words holding the 4 needed columns (qw + kw = 0..3) of patch row
       // (ci, 2*pl + qh + kh); fp32: one value per word, bf16: column e of the pair in half (e & 1)
       uint32_t raw[3][3][4];
-      if constexpr (sizeof(InT) == 4) {
+      if constexpr (sizeof(InT) == 1) {
+        // needed patch bytes 15 + 2*pwl + j (j = 0..3): an unaligned 4-byte window over two words
+        const int tw = tile % 10, th = (tile / 10) % 4;
+        const bool top = th == 0 && pl == 0 && qh == 0, bot = th == 3 && pl == 7 && qh == 1;      // kh = 0 / kh = 2 outside
+        const bool left = tw == 0 && pwl == 0, right = tw == 9 && pwl == 15;                      // j = 0 / j = 3 outside
+        const int b0 = C1In<uint8_t>::X0 + 2 * pwl;
+        const uint32_t* p0 = reinterpret_cast<const uint32_t*>(patch) + (2 * pl + qh) * (PATCH_W / 4) + (b0 >> 2);
+        const uint32_t sh = (uint32_t)(b0 & 3) * 8;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t* pp = p0 + (ci * PATCH_H + kh) * (PATCH_W / 4);
+            const uint32_t win = __funnelshift_r(pp[0], pp[1], sh);
+            const bool rz = (kh == 0 && top) || (kh == 2 && bot);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // byte j -> exact fp32 integer via the 2^23 magic constant, then the affine normalisation
+              float v = __uint_as_float(__byte_perm(win, 0x4B000000u, 0x7650u + j)) - 8388608.0f;
+              v = fmaf(v, nrm.a[ci], nrm.b[ci]);
+              if (rz || (j == 0 && left) || (j == 3 && right)) v = 0.f;
+              raw[ci][kh][j] = __float_as_uint(v);
+            }
+          }
+      } else if constexpr (sizeof(InT) == 4) {
         const float* p0 = reinterpret_cast<const float*>(patch) + (2 * pl + qh) * PATCH_W + 2 * pwl;
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci)
@@ -263,7 +292,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
         for (int k2 = 0; k2 < 16; ++k2) {
           const int ka = 2 * k2, kb = 2 * k2 + 1;
           const int ja = qw + ka % 3, jb = qw + kb % 3;       // column index 0..3 within raw[][][]
-          if constexpr (sizeof(InT) == 4) {
+          if constexpr (sizeof(InT) != 2) {
             float va = ka < 27 ? __uint_as_float(raw[ka / 9 % 3][(ka % 9) / 3][ja]) : 0.f;
             float vb = kb < 27 ? __uint_as_float(raw[kb / 9 % 3][(kb % 9) / 3][jb]) : 0.f;
             __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
@@ -630,7 +659,7 @@ static int dbg_sync(const char* what, cudaStream_t s) {
 }
 
 int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const void* x, int in_dtype, int B, float* out, void* ws,
-                 size_t ws_bytes, cudaStream_t s) {
+                 size_t ws_bytes, cudaStream_t s, const float* norm_a, const float* norm_b) {
   Ws w = carve(B, ws);
   if (ws_bytes < w.bytes) { set_error("cnn_bf16_fwd: workspace too small (%zu < %zu)", ws_bytes, w.bytes); return I2L_ERR_WORKSPACE; }
   Sec L = sec_layout();
@@ -642,24 +671,30 @@ int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const void* x, int in
   }
   // ---- conv1: input x (B,3,64,320) fp32 / bf16 NCHW read through a 4-D tensor map
   {
-    const bool in_bf16 = in_dtype == I2L_IN_BF16;
-    const uint64_t el = in_bf16 ? 2 : 4;
+    const bool in_bf16 = in_dtype == I2L_IN_BF16, in_u8 = in_dtype == I2L_IN_U8;
+    const uint64_t el = in_u8 ? 1 : (in_bf16 ? 2 : 4);
+    C1Norm nrm{};
+    if (in_u8) for (int c = 0; c < 3; ++c) { nrm.a[c] = norm_a[c]; nrm.b[c] = norm_b[c]; }
     CUtensorMap tm;
     uint64_t dims[4] = {IMG_W, IMG_H, C0, (uint64_t)B};
     uint64_t str[3] = {IMG_W * el, (uint64_t)IMG_W * IMG_H * el, (uint64_t)IMG_W * IMG_H * C0 * el};
-    uint32_t box[4] = {(uint32_t)(in_bf16 ? C1In<__nv_bfloat16>::PATCH_W : C1In<float>::PATCH_W), PATCH_H, C0, 1};
+    uint32_t box[4] = {(uint32_t)(in_u8 ? C1In<uint8_t>::PATCH_W : in_bf16 ? C1In<__nv_bfloat16>::PATCH_W : C1In<float>::PATCH_W), PATCH_H, C0, 1};
     I2L_TRY(make_tensor_map(&tm, x, 4, dims, str, box, 0, (int)el));
     const int n_tiles = B * 40;
     const int dbg = getenv("I2L_CONV1_DBG") ? atoi(getenv("I2L_CONV1_DBG")) : 0;
-    KernelTimer kt(in_bf16 ? "cnn.conv1_bf16in" : "cnn.conv1_bf16", s);
-    if (in_bf16) {
+    KernelTimer kt(in_u8 ? "cnn.conv1_u8in" : in_bf16 ? "cnn.conv1_bf16in" : "cnn.conv1_bf16", s);
+    if (in_u8) {
+      I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
+      conv1_kernel<uint8_t><<<min(n_tiles, sms), C1_THREADS, C1_SMEM, s>>>(
+          tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1), w.act1, Bp, n_tiles, dbg, nrm);
+    } else if (in_bf16) {
       I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
       conv1_kernel<__nv_bfloat16><<<min(n_tiles, sms), C1_THREADS, C1_SMEM, s>>>(
-          tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1), w.act1, Bp, n_tiles, dbg);
+          tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1), w.act1, Bp, n_tiles, dbg, nrm);
     } else {
       I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
       conv1_kernel<float><<<min(n_tiles, sms), C1_THREADS, C1_SMEM, s>>>(
-          tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1), w.act1, Bp, n_tiles, dbg);
+          tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1), w.act1, Bp, n_tiles, dbg, nrm);
     }
     I2L_LAUNCH_OK();
   }

@@ -263,6 +263,30 @@ extern "C" int i2l_cnn_encoder_fwd_in(const i2l_cnn_desc* d, const void* packed,
   return gemm_f32(g, s);
 }
 
+extern "C" int i2l_cnn_encoder_fwd_u8(const i2l_cnn_desc* d, const void* packed, const uint8_t* x, int32_t norm_mode,
+                                      const float* mean, const float* stdv, int32_t batch, float* out, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  I2L_TRY(device_check());
+  I2L_TRY(cnn_check(d));
+  I2L_REQUIRE(packed && batch >= 0, "i2l_cnn_encoder_fwd_u8: invalid argument");
+  I2L_REQUIRE(norm_mode == I2L_NORM_PM1 || (norm_mode == I2L_NORM_MEANSTD && mean && stdv), "i2l_cnn_encoder_fwd_u8: invalid normalisation");
+  if (batch == 0) return I2L_OK;
+  I2L_REQUIRE(x && out && workspace, "i2l_cnn_encoder_fwd_u8: null buffer");
+  CnnLayout L = cnn_layout(*d);
+  if (!L.bf16_section) {
+    set_error("i2l_cnn_encoder_fwd_u8: fused uint8 input needs precision == I2L_BF16 and the tcgen05 shape (3x64x320, 32/64/128, "
+              "E=256); use i2l_normalize_u8 + i2l_cnn_encoder_fwd otherwise");
+    return I2L_ERR_UNSUPPORTED;
+  }
+  float a[3], b[3];
+  for (int c = 0; c < 3; ++c) {
+    if (norm_mode == I2L_NORM_PM1) { a[c] = 2.0f / 255.0f; b[c] = -1.0f; }                  // x/255*2-1
+    else { a[c] = 1.0f / (255.0f * stdv[c]); b[c] = -mean[c] / stdv[c]; }                   // (x/255-mean)/std
+  }
+  return cnn_bf16_fwd(*d, reinterpret_cast<const char*>(packed) + L.bf16_section, x, I2L_IN_U8, batch, out, workspace,
+                      workspace_bytes, (cudaStream_t)stream, a, b);
+}
+
 // ====================================================================== ResNet C ABI
 extern "C" int32_t i2l_resnet_num_convs(int32_t depth) {
   RNet n = build_resnet(depth);

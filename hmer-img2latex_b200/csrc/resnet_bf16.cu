@@ -320,7 +320,13 @@ template <int BN, int KB>
 int launch_conv(const CUtensorMap& tm, const ConvArgs& a, cudaStream_t s) {
   using Cfg = IgCfg<BN, KB>;
   auto kern = conv_igemm_kernel<BN, KB>;
-  I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  static thread_local int attr_dev = -1;      // the attribute is per device; set it once per (thread, device)
+  int dev = 0;
+  I2L_CUDA_OK(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_dev = dev;
+  }
   const int n_tiles = a.n_mt * a.n_nt;
   kern<<<std::min(n_tiles, num_sms()), 192, Cfg::SMEM, s>>>(tm, a);
   I2L_LAUNCH_OK();

@@ -147,7 +147,7 @@ __host__ __device__ inline uint32_t swz_off(uint32_t row, uint32_t chunk, uint32
 
 // ------------------------------------------------------------------ host: tensor maps
 // dims / strides innermost first; strides[i] = byte stride of dim i+1 (rank-1 entries).
-// elem_bytes: 2 = bf16, 4 = fp32.  swizzle_bytes 0 = no swizzle.
+// elem_bytes: 1 = uint8, 2 = bf16, 4 = fp32.  swizzle_bytes 0 = no swizzle.
 int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, int swizzle_bytes, int elem_bytes);
 

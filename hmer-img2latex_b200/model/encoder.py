@@ -156,6 +156,42 @@ class CNNEncoder(nn.Module):
                                                N.ptr(ws), ws.numel(), N.stream_ptr(x.device)), "i2l_cnn_encoder_fwd")
         return out
 
+    def fused_u8_supported(self) -> bool:
+        """True when raw uint8 pixels can be fed straight to the first convolution (``forward_u8``)."""
+        return self.precision == "bf16" and self._bf16_shape()
+
+    def forward_u8(self, pixels: torch.Tensor, normalize: str = "pm1", mean=IMAGENET_MEAN, std=IMAGENET_STD
+                   ) -> torch.Tensor:
+        """(B, C, H, W) uint8 pixels -> (B, embedding_dim): ``forward(normalize_u8(pixels))`` with the
+        normalisation of the reference's ``load_image`` / ``_prepare_image`` fused into conv1
+        (``i2l_cnn_encoder_fwd_u8``) -- the image is read once, one byte per pixel.  Shapes / precisions
+        without the fused kernel run the two calls."""
+        require_cuda(pixels, "CNNEncoder.forward_u8")
+        if pixels.dtype != torch.uint8 or pixels.dim() != 4 or \
+                tuple(pixels.shape[1:]) != (self.channels, self.img_height, self.img_width):
+            raise RuntimeError(f"CNNEncoder.forward_u8 expected uint8 (B,{self.channels},{self.img_height},"
+                               f"{self.img_width}), got {pixels.dtype} {tuple(pixels.shape)}")
+        if normalize not in ("pm1", "meanstd"):
+            raise ValueError("normalize must be 'pm1' or 'meanstd'")
+        if not self.fused_u8_supported():
+            return self.forward(normalize_u8(pixels, normalize, mean, std,
+                                             out_dtype=torch.bfloat16 if self.precision == "bf16" else torch.float32))
+        with torch.cuda.device(pixels.device):
+            self._ensure_packed(pixels.device)
+            lib, d = N.lib(), self._desc()
+            x = pixels.contiguous()
+            B = x.shape[0]
+            out = torch.empty(B, self.embedding_dim, dtype=torch.float32, device=x.device)
+            if B == 0:
+                return out
+            m = (C.c_float * 4)(*([float(v) for v in mean[:3]] + [0.0]))
+            sd = (C.c_float * 4)(*([float(v) for v in std[:3]] + [1.0]))
+            ws = self._ws.get(lib.i2l_cnn_workspace_bytes(C.byref(d), B), x.device)
+            N.check(lib.i2l_cnn_encoder_fwd_u8(C.byref(d), N.ptr(self._packed), N.ptr(x),
+                                               N.NORM_PM1 if normalize == "pm1" else N.NORM_MEANSTD, m, sd, B, N.ptr(out),
+                                               N.ptr(ws), ws.numel(), N.stream_ptr(x.device)), "i2l_cnn_encoder_fwd_u8")
+        return out
+
     def _bf16_shape(self) -> bool:
         return ((self.channels, self.img_height, self.img_width) == (3, 64, 320) and self.conv_filters == [32, 64, 128]
                 and self.kernel_size == 3 and self.pool_size == 2 and self.embedding_dim == 256)

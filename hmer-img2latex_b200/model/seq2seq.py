@@ -121,41 +121,67 @@ class Seq2SeqModel(nn.Module):
         copy_stream = torch.cuda.Stream(dev)
         compute = torch.cuda.current_stream(dev)
         bufs: List[Optional[torch.Tensor]] = [None, None]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        out_tok = out_len = None
+        ready = [torch.cuda.Event(), torch.cuda.Event()]          # H2D copy of the slot has landed
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]       # the encoder has read the slot
+        done = [torch.cuda.Event(), torch.cuda.Event()]           # results of the slot are in host memory
+        used = [False, False]
+        out_tok: List[Optional[torch.Tensor]] = [None, None]
+        out_len: List[Optional[torch.Tensor]] = [None, None]
+        out_steps: List[Optional[torch.Tensor]] = [None, None]
 
         def stage(slot: int, xb: torch.Tensor) -> None:
             if bufs[slot] is None or bufs[slot].shape != xb.shape or bufs[slot].dtype != xb.dtype:
                 bufs[slot] = torch.empty(xb.shape, dtype=xb.dtype, device=dev)
             with torch.cuda.stream(copy_stream):
+                if used[slot]:
+                    copy_stream.wait_event(consumed[slot])        # the batch that used this buffer has been encoded
                 bufs[slot].copy_(xb, non_blocking=True)
                 ready[slot].record(copy_stream)
 
+        def collect(slot: int):
+            done[slot].synchronize()                              # the one host sync of the batch
+            return out_tok[slot], out_len[slot], int(out_steps[slot])
+
+        # Two batches are in flight: batch i+1 is copied while batch i computes, and the kernels of batch
+        # i+1 are enqueued BEFORE the host waits for the results of batch i, so the GPU never idles on the
+        # host.  A yielded triple lives in pinned buffers that are reused: it is valid until the generator is advanced.
         it = iter(host_batches)
         cur = next(it, None)
         if cur is None:
             return
         stage(0, cur)
         i = 0
+        prev = -1
         while cur is not None:
             nxt = next(it, None)
+            slot = i & 1
             if nxt is not None:
-                stage((i + 1) & 1, nxt)                  # overlaps with the compute below
-            compute.wait_event(ready[i & 1])
-            xin = bufs[i & 1]
-            if xin.dtype == torch.uint8:
-                xin = normalize_u8(xin, normalize, out_dtype=torch.bfloat16 if self.encoder.precision == "bf16"
-                                   else torch.float32)
-            enc = self.encoder(xin)
+                stage(slot ^ 1, nxt)                              # overlaps with the compute below
+            compute.wait_event(ready[slot])
+            xin = bufs[slot]
+            if xin.dtype == torch.uint8 and hasattr(self.encoder, "forward_u8"):
+                enc = self.encoder.forward_u8(xin, normalize)     # normalisation fused into conv1 where supported
+            else:
+                if xin.dtype == torch.uint8:
+                    xin = normalize_u8(xin, normalize, out_dtype=torch.bfloat16 if self.encoder.precision == "bf16"
+                                       else torch.float32)
+                enc = self.encoder(xin)
+            consumed[slot].record(compute)
+            used[slot] = True
             tokens, lengths, steps = self.decoder.greedy(enc, start_token_id, end_token_id, max_length, temperature,
                                                          stop_rule)
-            if out_tok is None or out_tok.shape != tokens.shape:
-                out_tok = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
-                out_len = torch.empty(lengths.shape, dtype=lengths.dtype).pin_memory()
-            out_tok.copy_(tokens, non_blocking=True)
-            out_len.copy_(lengths, non_blocking=True)
-            n = int(steps.item())                        # the one host sync of the batch
-            compute.synchronize()
-            yield out_tok, out_len, n
+            if out_tok[slot] is None or out_tok[slot].shape != tokens.shape:
+                out_tok[slot] = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
+                out_len[slot] = torch.empty(lengths.shape, dtype=lengths.dtype).pin_memory()
+                out_steps[slot] = torch.empty((), dtype=steps.dtype).pin_memory()
+            out_tok[slot].copy_(tokens, non_blocking=True)
+            out_len[slot].copy_(lengths, non_blocking=True)
+            out_steps[slot].copy_(steps, non_blocking=True)
+            done[slot].record(compute)
+            if prev >= 0:
+                yield collect(prev)
+            prev = slot
             cur = nxt
             i += 1
+        if prev >= 0:
+            yield collect(prev)

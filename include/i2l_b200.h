@@ -91,7 +91,7 @@ int i2l_cnn_encoder_fwd(const i2l_cnn_desc* d, const void* packed, const float* 
 /* Same call with the input element type stated: I2L_IN_F32 (the reference's tensor dtype)
  * or I2L_IN_BF16 (precision == I2L_BF16 only: halves the host->device and HBM bytes of the
  * image; the conv1 operand is bf16 either way).  SURVEY 8d: "fp32 master -> bf16 for the bf16 runs". */
-typedef enum { I2L_IN_F32 = 0, I2L_IN_BF16 = 1 } i2l_input_dtype;
+typedef enum { I2L_IN_F32 = 0, I2L_IN_BF16 = 1, I2L_IN_U8 = 2 /* i2l_cnn_encoder_fwd_u8 only */ } i2l_input_dtype;
 int i2l_cnn_encoder_fwd_in(const i2l_cnn_desc* d, const void* packed, const void* x, int32_t x_dtype,
                            int32_t batch, float* out, void* workspace, size_t workspace_bytes,
                            void* stream);
@@ -107,6 +107,15 @@ typedef enum { I2L_NORM_PM1 = 0, I2L_NORM_MEANSTD = 1 } i2l_norm_mode;
 int i2l_normalize_u8(const uint8_t* src, int32_t src_layout, int32_t batch, int32_t channels,
                      int32_t height, int32_t width, int32_t mode, const float* mean, const float* stdev,
                      void* dst, int32_t dst_dtype, void* stream);
+
+/* CNNEncoder.forward on RAW uint8 pixels (B,C,H,W) NCHW: the normalisation above is fused into the
+ * first convolution (the im2col operand is built from the pixels as a[c]*x + b[c]; out-of-image taps
+ * are zero in normalised space like the reference's padding), so the image crosses PCIe and HBM once,
+ * at one byte per pixel.  precision == I2L_BF16 and the tcgen05 shape only (else I2L_ERR_UNSUPPORTED:
+ * call i2l_normalize_u8 + i2l_cnn_encoder_fwd).  mean / stdev: HOST pointers (I2L_NORM_MEANSTD). */
+int i2l_cnn_encoder_fwd_u8(const i2l_cnn_desc* d, const void* packed, const uint8_t* x, int32_t norm_mode,
+                           const float* mean, const float* stdev, int32_t batch, float* out, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* ResNet encoder -- replaces ResNetEncoder.forward, model/encoder.py:231-249   */

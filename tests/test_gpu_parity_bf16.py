@@ -125,6 +125,25 @@ def test_normalize_u8(pkg, shape, mode, nhwc):
     assert torch.equal(out16.cpu(), ref.bfloat16())
 
 
+@pytest.mark.parametrize("B,mode", [(5, "pm1"), (4, "meanstd"), (1, "pm1")])
+def test_cnn_fused_uint8_conv1(pkg, B, mode):
+    """CNNEncoder.forward_u8 (normalisation fused into the tcgen05 conv1, i2l_cnn_encoder_fwd_u8) is bit-identical
+    to normalize_u8 -> bf16 -> forward (tests/test_oracle_golden.py::test_fused_affine_equals_reference_after_bf16
+    shows why: the affine form rounds to the same bf16 for all 256 pixel values), including the zero padding in
+    normalised space at the image border, and within the bf16 tolerance of the fp32 oracle."""
+    cfg = H.HEADLINE
+    p = oracle.make_params(cfg, 1)
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    g = torch.Generator().manual_seed(11 + B)
+    px = torch.randint(0, 256, (B, 3, 64, 320), dtype=torch.uint8, generator=g)
+    px[:, :, 0, :] = 0; px[:, :, -1, :] = 255; px[:, :, :, 0] = 0; px[:, :, :, -1] = 7      # borders: raw 0 is not padding
+    fused = m16.encoder.forward_u8(px.cuda(), mode)
+    two_step = m16.encoder(pkg.normalize_u8(px.cuda(), mode, out_dtype=torch.bfloat16))
+    torch.cuda.synchronize()
+    assert torch.equal(fused, two_step)
+    assert H.rel_err(fused, oracle.cnn_encoder(p, oracle.normalize_u8(px, mode))) < 3e-2
+
+
 def test_greedy_stream_uint8_and_bf16_hosts(pkg):
     """Seq2SeqModel.greedy_stream with raw uint8 pixels / bf16 tensors on the host gives the same
     tokens as the fp32-tensor call on the normalised images."""

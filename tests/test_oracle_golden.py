@@ -139,3 +139,23 @@ def test_load_image_golden():
     gray = torch.as_tensor(d["gray"]).unsqueeze(0)
     assert torch.equal(oracle.normalize_u8(rgb, "meanstd"), torch.as_tensor(d["out_rgb"]))
     assert torch.equal(oracle.normalize_u8(gray, "pm1"), torch.as_tensor(d["out_gray"]))
+
+
+def test_fused_affine_equals_reference_after_bf16():
+    """The uint8-input conv1 (cnn_bf16.cu) builds its operand as bf16(fma(x, a, b)); the reference arithmetic is
+    x/255*2-1 or (x/255-mean)/std in fp32 (data/utils.py:68-80, predictor.py:441-446).  For all 256 pixel values the
+    two agree after rounding to bf16, so the fused path equals normalize_u8 -> bf16 -> conv1 bit for bit."""
+    import numpy as np
+    x = torch.arange(256, dtype=torch.uint8).reshape(1, 1, 16, 16)
+    ref = oracle.normalize_u8(x, "pm1").flatten()
+    a = np.float32(2.0) / np.float32(255.0)
+    fused = (x.flatten().double() * float(a) - 1.0).float()          # fmaf: exact product, one rounding
+    assert torch.equal(ref.bfloat16(), fused.bfloat16())
+    rgb = torch.arange(256, dtype=torch.uint8).reshape(1, 1, 16, 16).repeat(1, 3, 1, 1)
+    ref3 = oracle.normalize_u8(rgb, "meanstd")
+    for c, (m, s) in enumerate(zip((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))):
+        m32, s32 = np.float32(m), np.float32(s)
+        a = np.float32(1.0) / (np.float32(255.0) * s32)
+        b = -m32 / s32
+        fused = (x.flatten().double() * float(a) + float(b)).float()
+        assert torch.equal(ref3[0, c].flatten().bfloat16(), fused.bfloat16())
