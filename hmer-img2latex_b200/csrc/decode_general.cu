@@ -348,6 +348,197 @@ __global__ void sample_select_kernel(const float* __restrict__ logits, int V, in
   }
 }
 
+// ------------------------------------------------------------------ sampling, V <= 512: one warp per row
+// Same arithmetic as sample_select_kernel, with the row held in registers (vocab index 16*lane + i) and ONE
+// warp-level bitonic sort on 64-bit (probability bits, ~index) keys instead of two block-wide sorts in shared
+// memory: top-k masking and renormalisation keep the order of the surviving entries, so the order found once is
+// also the order of the top-p pass (predictor.py:311-317 sorts again).  The kept set is a prefix of the sorted
+// order; it is carried back to index order as a threshold KEY, not as a scatter.
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+  return ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m) << 32) | __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
+}
+__device__ __forceinline__ double warp_excl_scan(double v, int lane, double* total) {
+  double inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { double n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+  *total = __shfl_sync(0xffffffffu, inc, 31);
+  return inc - v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sorted element at (warp-uniform) position pos of the 512-entry array held as key[16] per lane
+__device__ __forceinline__ unsigned long long sorted_at(const unsigned long long (&key)[16], int pos) {
+  unsigned long long sel = key[0];
+#pragma unroll
+  for (int i = 1; i < 16; ++i) if ((pos & 15) == i) sel = key[i];
+  return ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(sel >> 32), pos >> 4) << 32) | __shfl_sync(0xffffffffu, (unsigned)sel, pos >> 4);
+}
+
+__global__ void __launch_bounds__(256) sample_select_warp_kernel(const float* __restrict__ logits, int V, int rows, float temperature,
+                                                                int top_k, float top_p, int do_sample, uint64_t seed,
+                                                                uint64_t offset, const float* __restrict__ uniforms,
+                                                                float* __restrict__ probs_trace, int step, int T1, int end_id,
+                                                                int stop_rule, int64_t* tokens, int64_t* tok_cur,
+                                                                int* first_end, LoopState* st) {
+  if (st->done) return;
+  __shared__ int counter;
+  if (threadIdx.x == 0) counter = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row < rows) {
+    const float* x = logits + (size_t)row * V;
+    float po[16];                                             // probabilities in index order
+    // softmax(logits / T)                                               predictor.py:295-297
+    float lm = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int v = 16 * lane + i;
+      float val = -INFINITY;
+      if (v < V) { val = x[v]; if (temperature != 1.0f) val = val / temperature; }
+      po[i] = val;
+      lm = fmaxf(lm, val);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lm = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, o));
+    float ls = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float e = (16 * lane + i) < V ? expf(po[i] - lm) : 0.f; po[i] = e; ls += e; }
+    const float s = warp_sum(ls);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) po[i] = po[i] / s;
+
+    if (top_k > 0 || top_p > 0.0f) {
+      // ---- descending sort of (prob, index): key = prob bits (prob >= 0: unsigned order) : ~index
+      unsigned long long key[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) key[i] = ((unsigned long long)__float_as_uint(po[i]) << 32) | (0xFFFFFFFFu - (unsigned)(16 * lane + i));
+#pragma unroll
+      for (int lk = 1; lk <= 9; ++lk) {                         // canonical counted loops: fully unrolled, key[] stays in registers
+        const int k = 1 << lk;
+#pragma unroll
+        for (int lj = 8; lj >= 0; --lj) {
+          if (lj >= lk) continue;
+          const int j = 1 << lj;
+          if (j >= 16) {
+            const int lj = j >> 4;
+            const bool keep_max = ((lane & lj) == 0) == (((16 * lane) & k) == 0);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const unsigned long long o = shfl_xor_u64(key[i], lj);
+              const bool gt = o > key[i];
+              key[i] = (gt == keep_max) ? o : key[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (i & j) continue;
+              const unsigned long long a = key[i], b = key[i | j];
+              const bool desc = ((16 * lane + i) & k) == 0;      // static for k <= 16, per lane above
+              const bool sw = (b > a) == desc;
+              key[i] = sw ? b : a;
+              key[i | j] = sw ? a : b;
+            }
+          }
+        }
+      }
+      int R = V;                                                // kept entries = sorted positions [0, R)
+      float s2 = 1.f, s3 = 1.f, kth = 0.f;
+      bool renorm2 = false, renorm3 = false;
+      if (top_k > 0) {                                          // predictor.py:299-309 (ties with the k-th value are kept)
+        const int k = min(top_k, V);
+        kth = __uint_as_float((unsigned)(sorted_at(key, k - 1) >> 32));
+        float l2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (po[i] >= kth) l2 += po[i];
+        s2 = warp_sum(l2);
+        renorm2 = s2 > 0.f;
+      }
+      if (top_p > 0.0f) {                                       // predictor.py:311-327
+        // cumulative sum over the sorted, top-k-masked and renormalised probabilities (fp64, ATen CPU cumsum);
+        // sorted position t is removed iff t >= 1 and float(cum[t-1]) > top_p
+        double c[16], acc = 0.0;
+        float sp2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float v = __uint_as_float((unsigned)(key[i] >> 32));
+          if (top_k > 0) { v = v >= kth ? v : 0.f; if (renorm2) v = v / s2; }
+          sp2[i] = v;
+          acc += (double)v;
+          c[i] = acc;
+        }
+        double tot;
+        const double base = warp_excl_scan(acc, lane, &tot);
+        int keep = 0; float l3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const double prev = i == 0 ? base : base + c[i - 1];
+          const bool rem = (lane > 0 || i > 0) && (float)prev > top_p;
+          if (!rem) { ++keep; l3 += sp2[i]; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+        R = keep;
+        s3 = warp_sum(l3);
+        renorm3 = s3 > 0.f;
+      }
+      // ---- back to index order: entry v survives top-p iff its key >= the key at sorted position R-1
+      const unsigned long long kt = sorted_at(key, max(R, 1) - 1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float v = po[i];
+        if (top_k > 0) { v = v >= kth ? v : 0.f; if (renorm2) v = v / s2; }
+        if (top_p > 0.0f) {
+          const unsigned long long kv = ((unsigned long long)__float_as_uint(po[i]) << 32) | (0xFFFFFFFFu - (unsigned)(16 * lane + i));
+          if (kv < kt) v = 0.f;
+          if (renorm3) v = v / s3;
+        }
+        po[i] = v;
+      }
+    }
+    if (probs_trace) {
+      float* o = probs_trace + ((size_t)step * rows + row) * V;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (16 * lane + i < V) o[16 * lane + i] = po[i];
+    }
+    int chosen;
+    if (do_sample) {                                            // predictor.py:330-331 (restated inverse-CDF draw)
+      double c[16], acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { acc += (double)po[i]; c[i] = acc; }
+      double tot;
+      const double base = warp_excl_scan(acc, lane, &tot);
+      const float u = uniforms ? uniforms[(size_t)step * rows + row] : philox_uniform(seed, offset + (uint64_t)step * rows + row);
+      const double tgt = (double)u * tot;
+      int best = 0x7fffffff, lastpos = -1;
+#pragma unroll
+      for (int i = 15; i >= 0; --i) {
+        if (base + c[i] > tgt && 16 * lane + i < V) best = 16 * lane + i;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (po[i] > 0.f) lastpos = 16 * lane + i;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        lastpos = max(lastpos, __shfl_xor_sync(0xffffffffu, lastpos, o));
+      }
+      chosen = best != 0x7fffffff ? best : max(lastpos, 0);
+    } else {                                                    // predictor.py:333-335 argmax(probs)
+      float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (16 * lane + i < V && po[i] > bv) { bv = po[i]; bi = 16 * lane + i; }
+      warp_argmax(bv, bi);
+      chosen = bi == 0x7fffffff ? 0 : bi;
+    }
+    if (lane == 0) commit_token(row, chosen, step, T1, end_id, stop_rule, tokens, tok_cur, first_end, &counter);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) block_loop_exit(counter, rows, step, stop_rule, st);
+}
+
 // ------------------------------------------------------------------ beam (seq2seq.py:234-298)
 
 __global__ void beam_init_kernel(BeamState* bs, double* score, int64_t* tok_cur, int* live, int B, int K,
@@ -747,7 +938,11 @@ static int run_loop(const i2l_dec_desc* d, const void* packed, const float* enc,
   KernelTimer kt(sampling_path ? "dec.sample_loop_general" : "dec.greedy_loop_general", s);
   for (int step = 0; step < max_length; ++step) {
     I2L_TRY(step_rows(*d, pk, lay, w, w.h[0], w.c[0], batch, skip, s));
-    if (sampling_path) {
+    if (sampling_path && V <= 512) {
+      sample_select_warp_kernel<<<cdiv(batch, 8), 256, 0, s>>>(w.logits, V, batch, temperature, top_k, top_p, do_sample,
+                                                              seed, offset, uniforms, probs_trace, step, T1, end_id,
+                                                              stop_rule, tokens, w.tok_cur, w.first_end, w.st);
+    } else if (sampling_path) {
       sample_select_kernel<<<batch, 256, smem, s>>>(w.logits, V, n2, batch, temperature, top_k, top_p, do_sample,
                                                    seed, offset, uniforms, probs_trace, step, T1, end_id,
                                                    stop_rule, tokens, w.tok_cur, w.first_end, w.st);

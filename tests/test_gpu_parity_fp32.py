@@ -135,11 +135,13 @@ def test_greedy_b1_postprocess_and_all_end_stop(pkg):
         assert int(steps) == steps_ref
 
 
-@pytest.mark.parametrize("temperature,top_k,top_p", [(1.0, 0, 0.0), (0.7, 0, 0.0), (0.8, 5, 0.0), (1.0, 0, 0.9),
-                                                     (0.8, 50, 0.9), (1.3, 3, 0.5)])
-def test_sampling_loop(pkg, temperature, top_k, top_p):
-    cfg = H.SMALL
-    T, B = 20, 12
+@pytest.mark.parametrize("cfg,temperature,top_k,top_p", [
+    (H.SMALL, 1.0, 0, 0.0), (H.SMALL, 0.7, 0, 0.0), (H.SMALL, 0.8, 5, 0.0), (H.SMALL, 1.0, 0, 0.9), (H.SMALL, 0.8, 50, 0.9),
+    (H.SMALL, 1.3, 3, 0.5),
+    # V = 512: the full 16-entries-per-lane warp sort of sample_select_warp_kernel
+    (H.HEADLINE, 0.8, 50, 0.9), (H.HEADLINE, 1.0, 0, 0.95), (H.HEADLINE, 1.2, 7, 0.0)])
+def test_sampling_loop(pkg, cfg, temperature, top_k, top_p):
+    T, B = (20, 12) if cfg is H.SMALL else (12, 10)
     p = oracle.make_params(cfg, 1, sharp=True)
     m = H.build_model(pkg, cfg, p)
     x = H.make_images(cfg, B)
