@@ -282,7 +282,39 @@ class ResNetEncoder(nn.Module):
         torch.cuda.current_stream(device).synchronize()
         self._packed, self._packed_key = packed, key
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward_buckets(self, batches: List[torch.Tensor], n_streams: int = 4) -> List[torch.Tensor]:
+        """Width-bucketed encoding (BASELINE configs[3]): ``[forward(x) for x in batches]`` with the buckets spread
+        over ``n_streams`` CUDA streams, each with its own workspace.  A bucket of a few dozen images launches
+        ~26 (resnet18) small kernels whose grids fill a fraction of the 148 SMs; running buckets side by side fills
+        the machine.  Results are identical to ``forward`` (same kernels, same data)."""
+        if not batches:
+            return []
+        dev = batches[0].device
+        require_cuda(batches[0], "ResNetEncoder.forward_buckets")
+        if getattr(self, "_bucket_streams", None) is None or len(self._bucket_streams) != n_streams:
+            self._bucket_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+            self._bucket_ws = [Workspace() for _ in range(n_streams)]
+        cur = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(cur)
+        outs = []
+        with torch.cuda.device(dev):
+            self._ensure_packed(dev)
+        for i, x in enumerate(batches):
+            st = self._bucket_streams[i % n_streams]
+            if i < n_streams:
+                st.wait_event(start)
+            with torch.cuda.stream(st):
+                out = self.forward(x, _ws=self._bucket_ws[i % n_streams])
+            out.record_stream(cur)
+            outs.append(out)
+        for st in self._bucket_streams[: min(n_streams, len(batches))]:
+            done = torch.cuda.Event()
+            done.record(st)
+            cur.wait_event(done)
+        return outs
+
+    def forward(self, x: torch.Tensor, _ws: Optional[Workspace] = None) -> torch.Tensor:
         """(B, 3, H, W) -> (B, embedding_dim); any W (the trunk ends in adaptive average
         pooling), which is what width bucketing relies on.  reference encoder.py:231-249."""
         require_cuda(x, "ResNetEncoder.forward")
@@ -298,7 +330,7 @@ class ResNetEncoder(nn.Module):
             if B == 0:
                 return out
             wsb = lib.i2l_resnet_workspace_bytes(C.byref(d), B, W)
-            ws = self._ws.get(wsb, x.device)
+            ws = (_ws or self._ws).get(wsb, x.device)
             N.check(lib.i2l_resnet_encoder_fwd(C.byref(d), N.ptr(self._packed), N.ptr(x), B, W, N.ptr(out),
                                                N.ptr(ws), ws.numel(), N.stream_ptr(x.device)),
                     "i2l_resnet_encoder_fwd")

@@ -204,3 +204,17 @@ def test_resnet_bf16_odd_width_uses_fp32_path(pkg):
     x = H.make_images(cfg, 2, width=131)
     ref = oracle.resnet_encoder(p, x, cfg["model_name"])
     assert H.rel_err(m.encoder(x.cuda()), ref) < 1e-3
+
+
+def test_resnet_forward_buckets_matches_forward(pkg):
+    """Width buckets on several streams (ResNetEncoder.forward_buckets) give the same bits as one forward per bucket."""
+    cfg = H.R18
+    p = oracle.make_params(cfg, 0)
+    m = H.build_model(pkg, cfg, p, precision="bf16")
+    xs = [H.make_images(cfg, b, seed=w, width=w).cuda() for b, w in ((3, 128), (5, 160), (2, 320), (4, 224), (1, 96), (6, 192))]
+    ref = [m.encoder(x).clone() for x in xs]
+    for _ in range(2):
+        outs = m.encoder.forward_buckets(xs, n_streams=3)
+        torch.cuda.synchronize()
+        for a, b in zip(outs, ref):
+            assert torch.equal(a, b)
