@@ -4,6 +4,7 @@
 // The C-ABI entry points of the decoder live here; for the headline shape in bf16 they
 // route the greedy loop to the persistent cluster kernel (decode_persistent.cu).
 #include "decode_kernels.cuh"
+#include "gemm_bf16.cuh"
 #include <math.h>
 
 namespace i2l {
@@ -32,11 +33,29 @@ PackedDec dec_layout(const i2l_dec_desc& d) {
     L.bf16_section = bytes;
     bytes += persistent_packed_bytes(d);
   }
+  L.g16 = 0;
+  if (general_bf16_supported(d)) {
+    bytes = align_up(bytes, 1024);
+    L.g16 = bytes;
+    auto take16 = [&](size_t n) { size_t r = bytes; bytes = align_up(bytes + n * 2, 256); return r; };
+    for (int l = 0; l < d.lstm_layers; ++l) {
+      L.g16_w_hh[l] = take16(4 * H * H);
+      L.g16_w_ih[l] = l == 0 ? 0 : take16(4 * H * H);
+    }
+    L.g16_out_w = take16(V * H);
+  }
   L.total_bytes = bytes;
   return L;
 }
 
+bool general_bf16_supported(const i2l_dec_desc& d) { return d.precision == I2L_BF16 && (d.hidden_dim % 8) == 0; }
+
 namespace {
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
 
 __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -46,7 +65,7 @@ __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 __global__ void lstm_cell_kernel(const float* __restrict__ gates, float* __restrict__ h, float* __restrict__ c,
-                                 int rows, int H, const int* skip) {
+                                 int rows, int H, const int* skip, __nv_bfloat16* __restrict__ hb) {
   if (skip != nullptr && *skip != 0) return;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * H) return;
@@ -55,7 +74,9 @@ __global__ void lstm_cell_kernel(const float* __restrict__ gates, float* __restr
   float ig = sigmoidf_(g[j]), fg = sigmoidf_(g[H + j]), gg = tanhf(g[2 * H + j]), og = sigmoidf_(g[3 * H + j]);
   float cn = fg * c[i] + ig * gg;
   c[i] = cn;
-  h[i] = og * tanhf(cn);
+  const float hn = og * tanhf(cn);
+  h[i] = hn;
+  if (hb != nullptr) hb[i] = __float2bfloat16(hn);
 }
 
 __device__ __forceinline__ void warp_argmax(float& v, int& i) {
@@ -734,6 +755,7 @@ __global__ void attention_combine_kernel(const float* __restrict__ p1, const flo
 // ------------------------------------------------------------------ workspace carving
 struct DecWs {
   float *gctx, *gates, *logits, *h[2], *c[2];
+  __nv_bfloat16* hb;             // bf16 copy of h[0] (L,R,H): A operand of the tcgen05 GEMMs (precision bf16)
   int64_t* tok_cur;
   int* first_end;
   LoopState* st;
@@ -750,6 +772,7 @@ DecWs carve(const i2l_dec_desc& d, int rows, int max_length, void* ws) {
   w.gates = a.take<float>(R * 4 * H);
   w.logits = a.take<float>(R * V);
   for (int i = 0; i < 2; ++i) { w.h[i] = a.take<float>(L * R * H); w.c[i] = a.take<float>(L * R * H); }
+  w.hb = a.take<__nv_bfloat16>(L * R * H);
   w.tok_cur = a.take<int64_t>(R);
   w.first_end = a.take<int>(R);
   w.st = a.take<LoopState>(1);
@@ -802,6 +825,56 @@ int step_rows(const i2l_dec_desc& d, const float* pk, const PackedDec& lay, cons
   return gemm_f32(g, s);
 }
 
+// The same step with the products on tcgen05 (gemm_bf16.cu): bf16 weights (PackedDec::g16*) and the bf16 copy of h
+// written by the cell kernel; gate pre-activations, cell state, logits and every epilogue term stay fp32.
+struct StepBf16 { GemmBf16 gates[I2L_MAX_LSTM_LAYERS]; GemmBf16 logits; };
+
+int make_step_bf16(const i2l_dec_desc& d, const void* packed, const PackedDec& lay, const DecWs& w, int rows,
+                   const int* skip, StepBf16* st) {
+  const int H = d.hidden_dim, V = d.vocab_size;
+  const float* pk = reinterpret_cast<const float*>(packed);
+  const char* pb = reinterpret_cast<const char*>(packed);
+  for (int l = 0; l < d.lstm_layers; ++l) {
+    GemmBf16& g = st->gates[l];
+    g = GemmBf16{};
+    g.M = rows; g.N = 4 * H; g.C = w.gates; g.ldc = 4 * H; g.skip_flag = skip;
+    const __nv_bfloat16* hl = w.hb + (size_t)l * rows * H;
+    if (l == 0) {
+      I2L_TRY(gemm_bf16_a_map(&g.tmA1, hl, rows, H, H));
+      I2L_TRY(gemm_bf16_w_map(&g.tmW1, pb + lay.g16_w_hh[0], 4 * H, H, H));
+      g.K1 = H;
+      g.add_rows = w.gctx; g.ld_add = 4 * H;
+      g.add_table = pk + lay.gtok; g.ld_tab = 4 * H; g.tab_idx = w.tok_cur;
+    } else {
+      I2L_TRY(gemm_bf16_a_map(&g.tmA1, w.hb + (size_t)(l - 1) * rows * H, rows, H, H));
+      I2L_TRY(gemm_bf16_w_map(&g.tmW1, pb + lay.g16_w_ih[l], 4 * H, H, H));
+      I2L_TRY(gemm_bf16_a_map(&g.tmA2, hl, rows, H, H));
+      I2L_TRY(gemm_bf16_w_map(&g.tmW2, pb + lay.g16_w_hh[l], 4 * H, H, H));
+      g.K1 = H; g.K2 = H;
+      g.bias = pk + lay.bsum[l];
+    }
+  }
+  GemmBf16& g = st->logits;
+  g = GemmBf16{};
+  g.M = rows; g.N = V; g.C = w.logits; g.ldc = V; g.skip_flag = skip;
+  I2L_TRY(gemm_bf16_a_map(&g.tmA1, w.hb + (size_t)(d.lstm_layers - 1) * rows * H, rows, H, H));
+  I2L_TRY(gemm_bf16_w_map(&g.tmW1, pb + lay.g16_out_w, V, H, H));
+  g.K1 = H;
+  g.bias = pk + lay.out_b;
+  return I2L_OK;
+}
+
+int step_rows_bf16(const i2l_dec_desc& d, const StepBf16& st, const DecWs& w, float* h, float* c, int rows,
+                   const int* skip, cudaStream_t s) {
+  const int H = d.hidden_dim;
+  for (int l = 0; l < d.lstm_layers; ++l) {
+    I2L_TRY(gemm_bf16(st.gates[l], s));
+    I2L_TRY(lstm_cell_f32(w.gates, h + (size_t)l * rows * H, c + (size_t)l * rows * H, rows, H, skip, s,
+                          w.hb + (size_t)l * rows * H));
+  }
+  return gemm_bf16(st.logits, s);
+}
+
 // gctx (rows,4H) = enc W_ih0[:, E:2E]^T + b_ih0 + b_hh0 ; enc row index = row / rows_per_enc
 int make_gctx(const i2l_dec_desc& d, const float* pk, const PackedDec& lay, const float* enc, int n_enc,
               float* gctx, cudaStream_t s) {
@@ -824,10 +897,10 @@ __global__ void repeat_rows_kernel(const float* __restrict__ src, float* __restr
 }  // namespace
 
 int lstm_cell_f32(const float* gates, float* h, float* c, int rows, int H, const int* skip_flag,
-                  cudaStream_t s) {
+                  cudaStream_t s, __nv_bfloat16* hb) {
   size_t total = (size_t)rows * H;
   if (total == 0) return I2L_OK;
-  lstm_cell_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(gates, h, c, rows, H, skip_flag);
+  lstm_cell_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(gates, h, c, rows, H, skip_flag, hb);
   I2L_LAUNCH_OK();
   return I2L_OK;
 }
@@ -869,6 +942,19 @@ extern "C" int i2l_dec_pack(const i2l_dec_desc* d, const i2l_dec_params* p, void
   g.A1 = pk + lay.emb; g.lda1 = (int)E; g.W1 = pk + lay.w_ih0; g.ldw1 = 2 * (int)E; g.K1 = (int)E;
   I2L_TRY(gemm_f32(g, s));
   if (lay.bf16_section) I2L_TRY(persistent_pack(*d, *p, pk + lay.gtok, reinterpret_cast<char*>(packed) + lay.bf16_section, s));
+  if (lay.g16) {
+    char* pb = reinterpret_cast<char*>(packed);
+    auto conv = [&](const float* src, size_t off, size_t n) -> int {
+      f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(pb + off), n);
+      I2L_LAUNCH_OK();
+      return I2L_OK;
+    };
+    for (int l = 0; l < d->lstm_layers; ++l) {
+      I2L_TRY(conv(p->w_hh[l], lay.g16_w_hh[l], 4 * H * H));
+      if (l > 0) I2L_TRY(conv(p->w_ih[l], lay.g16_w_ih[l], 4 * H * H));
+    }
+    I2L_TRY(conv(p->out_w, lay.g16_out_w, V * H));
+  }
   return I2L_OK;
 }
 
@@ -935,9 +1021,16 @@ static int run_loop(const i2l_dec_desc* d, const void* packed, const float* enc,
     I2L_CUDA_OK(cudaFuncSetAttribute(sample_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   const int do_sample = temperature > 0.f && (top_k > 0 || top_p > 0.0f);   // predictor.py:330
+  const bool tc = lay.g16 != 0;                       // precision bf16: the per-step GEMMs run on tcgen05
+  StepBf16 st16;
+  if (tc) {
+    I2L_CUDA_OK(cudaMemsetAsync(w.hb, 0, (size_t)d->lstm_layers * batch * d->hidden_dim * 2, s));
+    I2L_TRY(make_step_bf16(*d, packed, lay, w, batch, skip, &st16));
+  }
   KernelTimer kt(sampling_path ? "dec.sample_loop_general" : "dec.greedy_loop_general", s);
   for (int step = 0; step < max_length; ++step) {
-    I2L_TRY(step_rows(*d, pk, lay, w, w.h[0], w.c[0], batch, skip, s));
+    if (tc) I2L_TRY(step_rows_bf16(*d, st16, w, w.h[0], w.c[0], batch, skip, s));
+    else I2L_TRY(step_rows(*d, pk, lay, w, w.h[0], w.c[0], batch, skip, s));
     if (sampling_path && V <= 512) {
       sample_select_warp_kernel<<<cdiv(batch, 8), 256, 0, s>>>(w.logits, V, batch, temperature, top_k, top_p, do_sample,
                                                               seed, offset, uniforms, probs_trace, step, T1, end_id,

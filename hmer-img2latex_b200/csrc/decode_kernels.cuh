@@ -31,12 +31,18 @@ struct PackedDec {     // offsets (in floats) into the packed decoder buffer, fp
   size_t emb, gtok, w_ih0, bsum[I2L_MAX_LSTM_LAYERS], w_hh[I2L_MAX_LSTM_LAYERS],
       w_ih[I2L_MAX_LSTM_LAYERS], out_w, out_b, end_f32;
   size_t bf16_section;  // byte offset of the persistent-kernel section (0 if absent)
+  // bf16 row-major copies of the per-step GEMM weights for the general path (byte offsets; g16 == 0 if absent):
+  // W_hh[l] (4H,H), W_ih[l >= 1] (4H,H), W_out (V,H) -- operands of gemm_bf16.cu
+  size_t g16, g16_w_hh[I2L_MAX_LSTM_LAYERS], g16_w_ih[I2L_MAX_LSTM_LAYERS], g16_out_w;
   size_t total_bytes;
 };
+// precision == I2L_BF16 and TMA-addressable rows (H % 8 == 0): the general loops run their GEMMs on tcgen05
+bool general_bf16_supported(const i2l_dec_desc& d);
 PackedDec dec_layout(const i2l_dec_desc& d);
 
+// hb: optional bf16 copy of the new h (A operand of the next bf16 GEMM)
 int lstm_cell_f32(const float* gates, float* h, float* c, int rows, int H, const int* skip_flag,
-                  cudaStream_t s);
+                  cudaStream_t s, __nv_bfloat16* hb = nullptr);
 
 // persistent bf16 greedy decode (decode_persistent.cu); returns I2L_ERR_UNSUPPORTED for
 // shapes it does not cover so that the caller can take the general path.

@@ -1,0 +1,168 @@
+// bf16 tensor-core GEMM for the per-step products of the GENERAL decode path (any V / E / H / L):
+//   C[M,N] (fp32) = A1[M,K1] W1[N,K1]^T (+ A2[M,K2] W2[N,K2]^T) + bias[N] + add_rows[M,N] + add_table[tab_idx[m], N]
+// A and W are bf16, K-major; TMA (SWIZZLE_128B) -> shared memory -> tcgen05.mma, fp32 accumulator in TMEM.
+// One 128 x 128 output tile per CTA, 4-stage pipeline: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 =
+// epilogue.  K and N tails are zero-filled by the tensor maps; M / N tails are masked in the epilogue.
+// Same epilogue terms as gemm_f32.cu (the gate GEMM of LSTMDecoder.decode_step, model/decoder.py:268-279, with
+// W_ih [emb ; ctx] hoisted into the token table / per-row constant).
+#include "gemm_bf16.cuh"
+
+namespace i2l {
+namespace {
+
+using namespace tc;
+
+constexpr int GB_BM = 128, GB_BN = 128, GB_BK = 64, GB_STAGES = 4;
+constexpr int GB_A_BYTES = GB_BM * GB_BK * 2, GB_B_BYTES = GB_BN * GB_BK * 2;
+constexpr int GB_STAGE = GB_A_BYTES + GB_B_BYTES;
+constexpr int GB_OFF_BAR = GB_STAGES * GB_STAGE;
+constexpr int GB_SMEM = GB_OFF_BAR + 128;
+
+__global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant__ GemmBf16 g) {
+  if (g.skip_flag != nullptr && *g.skip_flag != 0) return;          // device-side loop exit
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar = sbase + GB_OFF_BAR;
+  auto FULL = [&](int s) { return bar + 8u * s; };
+  auto EMPTY = [&](int s) { return bar + 8u * (GB_STAGES + s); };
+  const uint32_t TFULL = bar + 8u * (2 * GB_STAGES);
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + GB_OFF_BAR + 8 * (2 * GB_STAGES + 1));
+  if (tid == 0) {
+    for (int s = 0; s < GB_STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    mbar_init(TFULL, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&g.tmA1); tma_prefetch_desc(&g.tmW1);
+  }
+  if (warp == 1) tmem_alloc<GB_BN>(smem_u32(misc));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc[0];
+  const int m0 = blockIdx.x * GB_BM, n0 = blockIdx.y * GB_BN;
+  const int kb1 = (g.K1 + GB_BK - 1) / GB_BK, kb2 = (g.K2 + GB_BK - 1) / GB_BK;
+  const int nkb = kb1 + kb2;
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(EMPTY(stage), ph ^ 1);
+        mbar_arrive_expect_tx(FULL(stage), GB_STAGE);
+        const uint32_t a = sbase + stage * GB_STAGE;
+        const bool second = kb >= kb1;
+        const int k0 = (second ? kb - kb1 : kb) * GB_BK;
+        tma_load_2d(a, second ? &g.tmA2 : &g.tmA1, k0, m0, FULL(stage));
+        tma_load_2d(a + GB_A_BYTES, second ? &g.tmW2 : &g.tmW1, k0, n0, FULL(stage));
+        if (++stage == GB_STAGES) { stage = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t IDESC = idesc_bf16(GB_BM, GB_BN);
+    const uint64_t d0 = desc_base(sbase, 128);
+    int stage = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(FULL(stage), ph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < GB_BK / 16; ++ks) {
+          const uint64_t ad = d0 + (uint64_t)((stage * GB_STAGE + ks * 32) >> 4);
+          const uint64_t bd = d0 + (uint64_t)((stage * GB_STAGE + GB_A_BYTES + ks * 32) >> 4);
+          tc_mma_ss(tmem, ad, bd, IDESC, (kb | ks) ? 1u : 0u);
+        }
+        tc_commit(EMPTY(stage));
+        if (kb == nkb - 1) tc_commit(TFULL);
+      }
+      __syncwarp();
+      if (++stage == GB_STAGES) { stage = 0; ph ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + 32 * q + lane;
+    const bool mv = m < g.M;
+    const float* arow = (g.add_rows != nullptr && mv) ? g.add_rows + (size_t)m * g.ld_add : nullptr;
+    const float* trow = (g.add_table != nullptr && mv) ? g.add_table + (size_t)g.tab_idx[m] * g.ld_tab : nullptr;
+    mbar_wait(TFULL, 0);
+    tc_fence_after();
+    // 16 consecutive columns per tcgen05.ld: 64-byte row segments of C / add_rows / the token's table row, moved as
+    // float4 when the segment is complete and 16-byte aligned (always, for N % 16 == 0 and 4-float-aligned rows)
+    const bool vec_ok = (g.ldc % 4) == 0 && (g.ld_add % 4) == 0 && (g.ld_tab % 4) == 0 && (reinterpret_cast<uintptr_t>(g.C) % 16) == 0 &&
+                        (reinterpret_cast<uintptr_t>(g.add_rows) % 16) == 0 && (reinterpret_cast<uintptr_t>(g.add_table) % 16) == 0 &&
+                        (reinterpret_cast<uintptr_t>(g.bias) % 16) == 0;
+#pragma unroll 2
+    for (int cc = 0; cc < GB_BN / 16; ++cc) {
+      uint32_t r[16];
+      tc_ld16_nowait(tmem + ((uint32_t)(32 * q) << 16) + cc * 16, r);
+      const int nb = n0 + cc * 16;
+      const bool full = vec_ok && mv && nb + 16 <= g.N;
+      float4 ar[4] = {}, tr[4] = {}, bs[4] = {};
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (arow != nullptr) ar[i] = *reinterpret_cast<const float4*>(arow + nb + 4 * i);
+          if (trow != nullptr) tr[i] = __ldg(reinterpret_cast<const float4*>(trow + nb + 4 * i));
+          if (g.bias != nullptr) bs[i] = __ldg(reinterpret_cast<const float4*>(g.bias + nb + 4 * i));
+        }
+      }
+      tc_wait_ld();
+      if (!mv || nb >= g.N) continue;
+      float* dst = g.C + (size_t)m * g.ldc + nb;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 o;
+          o.x = __uint_as_float(r[4 * i]) + bs[i].x + ar[i].x + tr[i].x;
+          o.y = __uint_as_float(r[4 * i + 1]) + bs[i].y + ar[i].y + tr[i].y;
+          o.z = __uint_as_float(r[4 * i + 2]) + bs[i].z + ar[i].z + tr[i].z;
+          o.w = __uint_as_float(r[4 * i + 3]) + bs[i].w + ar[i].w + tr[i].w;
+          reinterpret_cast<float4*>(dst)[i] = o;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (nb + i < g.N) {
+            float v = __uint_as_float(r[i]);
+            if (g.bias != nullptr) v += __ldg(g.bias + nb + i);
+            if (arow != nullptr) v += arow[nb + i];
+            if (trow != nullptr) v += __ldg(trow + nb + i);
+            dst[i] = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<GB_BN>(tmem);
+}
+
+}  // namespace
+
+int gemm_bf16_operand_map(CUtensorMap* out, const void* base, int rows, int K, int ld_elems, int box_rows) {
+  I2L_REQUIRE((ld_elems % 8) == 0 && (reinterpret_cast<uintptr_t>(base) % 16) == 0,
+              "gemm_bf16: operand rows must be 16-byte aligned (leading dimension %d)", ld_elems);
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+  uint64_t str[1] = {(uint64_t)ld_elems * 2};
+  uint32_t box[2] = {GB_BK, (uint32_t)box_rows};
+  return make_tensor_map(out, base, 2, dims, str, box, 128, 2);
+}
+int gemm_bf16_a_map(CUtensorMap* out, const void* a, int M, int K, int lda) { return gemm_bf16_operand_map(out, a, M, K, lda, GB_BM); }
+int gemm_bf16_w_map(CUtensorMap* out, const void* w, int N, int K, int ldw) { return gemm_bf16_operand_map(out, w, N, K, ldw, GB_BN); }
+
+int gemm_bf16(const GemmBf16& g, cudaStream_t s) {
+  if (g.M <= 0 || g.N <= 0) return I2L_OK;
+  I2L_REQUIRE(g.K1 > 0 && g.C != nullptr, "gemm_bf16: invalid arguments");
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  I2L_CUDA_OK(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    I2L_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM));
+    attr_dev = dev;
+  }
+  gemm_bf16_kernel<<<dim3(cdiv(g.M, GB_BM), cdiv(g.N, GB_BN)), 192, GB_SMEM, s>>>(g);
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
+
+}  // namespace i2l

@@ -218,3 +218,44 @@ def test_resnet_forward_buckets_matches_forward(pkg):
         torch.cuda.synchronize()
         for a, b in zip(outs, ref):
             assert torch.equal(a, b)
+
+
+# ---- general decode loops with the per-step GEMMs on tcgen05 (gemm_bf16.cu): any E / H / L, precision "bf16"
+@pytest.mark.parametrize("cfg,B,T", [(H.SMALL, 12, 20), (H.R18, 9, 16), (H.HEADLINE, 140, 12)])
+def test_general_bf16_sampling_and_greedy(pkg, cfg, B, T):
+    """Sampling (always the general path) and, for shapes the persistent kernel does not cover, greedy: bf16 weights
+    and h on the tensor cores, fp32 accumulation / cell state / epilogue.  Filtered distributions within 6e-2 of the
+    oracle's per-row maximum up to the first divergence of a row (the bf16 rounding of h feeds back through the
+    recurrence: measured 3e-2 after 15 steps with the sharpened output layer); greedy rows may leave the oracle only
+    at near ties."""
+    p = oracle.make_params(cfg, 1, sharp=True)
+    m32 = H.build_model(pkg, cfg, p, precision="fp32")
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    x = H.make_images(cfg, min(B, 16))
+    enc_ref = oracle.encoder(p, x, cfg).repeat((B + 15) // 16, 1)[:B]
+    enc = m32.encoder(x.cuda()).repeat((B + 15) // 16, 1)[:B].contiguous()
+    u = torch.rand(T, B, generator=torch.Generator().manual_seed(4))
+    seqs, trimmed, steps_ref, ptrace = oracle.sample_loop(p, enc_ref, H.START, H.END, T, 0.9, 20, 0.9, cfg, uniforms=u,
+                                                          return_probs=True)
+    tokens, lengths, steps, probs = m16.decoder.sample(enc, H.START, H.END, T, 0.9, 20, 0.9, uniforms=u, return_probs=True)
+    tokens, probs = tokens.cpu(), probs.cpu()
+    same_rows = 0
+    for b in range(B):
+        ref_row = seqs[b].tolist()
+        got_row = tokens[b, : len(ref_row)].tolist()
+        t_div = next((i for i, (a, r) in enumerate(zip(got_row, ref_row)) if a != r), None)
+        same_rows += t_div is None
+        upto = min(len(ref_row) - 1 if t_div is None else t_div, steps_ref)
+        for t in range(upto):
+            # the kept SET may differ by entries at the top-k / top-p cut (bf16 logits): compare where both keep
+            both = (probs[t, b] > 0) & (ptrace[t][b] > 0)
+            assert both.any()
+            d = (probs[t, b] - ptrace[t][b]).abs()[both].max() / ptrace[t][b].max()
+            assert float(d) < 6e-2, (b, t, float(d))
+    assert same_rows >= 0.7 * B, f"only {same_rows}/{B} sampled rows follow the oracle"
+    if not pkg._native.lib().i2l_device_check() and cfg is not H.HEADLINE:     # greedy takes the general path too
+        ref, steps_ref, trace = oracle.greedy_search(p, enc_ref, H.START, H.END, T, 1.0, cfg, return_logits=True)
+        tok, _, _ = m16.decoder.greedy(enc, H.START, H.END, T)
+        exact, near, bad = divergence_report(tok.cpu()[:, : steps_ref + 1].tolist(), ref, trace)
+        assert not bad, f"rows diverging at a step with a clear margin: {bad}"
+        assert exact >= 0.6 * B
