@@ -282,6 +282,14 @@ def run_ours(args):
             roof = {"kernel": name, "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit,
                     "frac": round(ach / peak, 4), "traffic": None, "peak_source": pk["src"],
                     "launch_ms": round(tot / cnt, 4), "share_of_step": round(tot / ms, 4)}
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
+        if roof and roof["kernel"] in tr and B == 1024:
+            roof["traffic"] = tr[roof["kernel"]]["dram_bytes_per_launch"]
+            roof["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json)"
+    except Exception:
+        pass
     rooflines = {}
     for kname, (cnt, tot) in sorted(prof.items()):
         bound, work = kernel_work(kname, B, steps_run)

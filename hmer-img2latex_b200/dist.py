@@ -27,17 +27,21 @@ def gather_tokens(tokens: torch.Tensor, lengths: torch.Tensor, steps: torch.Tens
     ws = dist.get_world_size()
     T1 = tokens.shape[1]
     cap = (n_total + ws - 1) // ws
-    buf = torch.full((cap, T1 + 1), pad_id, dtype=torch.int64, device=tokens.device)
+    # ONE collective: rows [0, cap) = (tokens | length) of the shard, row cap = the rank's stop step
+    buf = torch.full((cap + 1, T1 + 1), pad_id, dtype=torch.int64, device=tokens.device)
     b = tokens.shape[0]
     buf[:b, :T1] = tokens
-    buf[:b, T1] = lengths.to(torch.int64)
-    out = torch.empty(ws * cap, T1 + 1, dtype=torch.int64, device=tokens.device)
-    dist.all_gather_into_tensor(out, buf)
-    rows: List[torch.Tensor] = []
-    for r in range(ws):
-        lo, hi = shard_bounds(n_total, ws, r)
-        rows.append(out[r * cap: r * cap + (hi - lo)])
-    full = torch.cat(rows, dim=0)
-    gsteps = steps.clone().to(torch.int32)
-    dist.all_reduce(gsteps, op=dist.ReduceOp.MAX)
+    buf[:b, T1] = lengths
+    buf[cap] = steps
+    out = torch.empty(ws, cap + 1, T1 + 1, dtype=torch.int64, device=tokens.device)
+    dist.all_gather_into_tensor(out.view(ws * (cap + 1), T1 + 1), buf)
+    gsteps = out[:, cap, 0].max().to(torch.int32)                  # the sticky stop composes as max over ranks
+    if n_total == ws * cap:
+        full = out[:, :cap].reshape(n_total, T1 + 1)
+    else:
+        rows: List[torch.Tensor] = []
+        for r in range(ws):
+            lo, hi = shard_bounds(n_total, ws, r)
+            rows.append(out[r, : hi - lo])
+        full = torch.cat(rows, dim=0)
     return full[:, :T1].contiguous(), full[:, T1].to(torch.int32), gsteps
