@@ -18,6 +18,17 @@ for rep in sys.argv[2:]:
     hdr, units = rows[0], rows[1]
     cols = [h for h in WANT if h in hdr]
     if first:
-        out.writerow(["report"] + cols); out.writerow(["(unit)"] + [units[hdr.index(c)] for c in cols]); first = False
+        out.writerow(["report"] + cols)
+        out.writerow(["(unit)"] + ["us" if c == "gpu__time_duration.sum" else ("byte" if "byte" in units[hdr.index(c)] else units[hdr.index(c)]) for c in cols])
+        first = False
+    SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for r in rows[2:]:
-        out.writerow([rep.split("/")[-1]] + [r[hdr.index(c)] for c in cols])
+        vals = []
+        for c in cols:
+            v, un = r[hdr.index(c)], units[hdr.index(c)]
+            if c == "gpu__time_duration.sum":
+                v = "%.3f" % (float(v) * SCALE[un])                      # always microseconds
+            elif un in ("byte", "Kbyte", "Mbyte", "Gbyte") and v not in ("", "n/a"):
+                v = "%.0f" % (float(v) * SCALE[un])                      # always bytes
+            vals.append(v)
+        out.writerow([rep.split("/")[-1]] + vals)
