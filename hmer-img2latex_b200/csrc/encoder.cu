@@ -298,7 +298,7 @@ extern "C" size_t i2l_resnet_packed_bytes(const i2l_resnet_desc* d) {
   RNet n = build_resnet(d->depth);
   if (!n.ok || d->embedding_dim <= 0) return 0;
   size_t bytes = resnet_layout(n, d->embedding_dim).end_f32 * 4;
-  if (d->precision == I2L_BF16) bytes = align_up(bytes, 1024) + resnet_bf16_packed_bytes(n);
+  if (d->precision == I2L_BF16) bytes = align_up(bytes, 1024) + resnet_bf16_packed_bytes(n, d->embedding_dim);
   return bytes;
 }
 
@@ -328,7 +328,7 @@ extern "C" int i2l_resnet_pack(const i2l_resnet_desc* d, const i2l_resnet_params
   I2L_CUDA_OK(cudaMemcpyAsync(pk + L.fc_w, p->fc_w, (size_t)d->embedding_dim * n.feat * 4, cudaMemcpyDeviceToDevice, s));
   I2L_CUDA_OK(cudaMemcpyAsync(pk + L.fc_b, p->fc_b, (size_t)d->embedding_dim * 4, cudaMemcpyDeviceToDevice, s));
   if (d->precision == I2L_BF16)
-    I2L_TRY(resnet_bf16_pack(n, pk, reinterpret_cast<char*>(packed) + align_up(L.end_f32 * 4, 1024), s));
+    I2L_TRY(resnet_bf16_pack(n, d->embedding_dim, pk, pk + L.fc_w, reinterpret_cast<char*>(packed) + align_up(L.end_f32 * 4, 1024), s));
   return I2L_OK;
 }
 

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant
           o.y = __uint_as_float(r[4 * i + 1]) + bs[i].y + ar[i].y + tr[i].y;
           o.z = __uint_as_float(r[4 * i + 2]) + bs[i].z + ar[i].z + tr[i].z;
           o.w = __uint_as_float(r[4 * i + 3]) + bs[i].w + ar[i].w + tr[i].w;
+          if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           reinterpret_cast<float4*>(dst)[i] = o;
         }
       } else {
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant
             if (g.bias != nullptr) v += __ldg(g.bias + nb + i);
             if (arow != nullptr) v += arow[nb + i];
             if (trow != nullptr) v += __ldg(trow + nb + i);
-            dst[i] = v;
+            dst[i] = g.relu ? fmaxf(v, 0.f) : v;
           }
         }
       }

@@ -13,6 +13,7 @@ struct GemmBf16 {
   const float* add_table = nullptr; int ld_tab = 0; const int64_t* tab_idx = nullptr;
   float* C = nullptr; int ldc = 0;
   int M = 0, N = 0;
+  int relu = 0;
   const int* skip_flag = nullptr;  // device flag: != 0 => the kernel exits at once
 };
 int gemm_bf16_a_map(CUtensorMap* out, const void* a, int M, int K, int lda);

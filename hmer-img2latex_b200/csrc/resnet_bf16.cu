@@ -18,7 +18,7 @@
 //                fetches a K = 32 operand block (7 x 32 = 224, 147 useful), SWIZZLE_64B.  Same kernel.
 //   maxpool 3x3/2, global average pool: bandwidth kernels; embedding Linear + ReLU: fp32 GEMM.
 #include "resnet_bf16.cuh"
-#include "tc_common.cuh"
+#include "gemm_bf16.cuh"
 
 namespace i2l {
 namespace {
@@ -72,23 +72,30 @@ struct ConvArgs {
   int relu, n_mt, n_nt;
 };
 
-template <int BN, int KB>     // KB = K elements per pipeline stage: 64 (generic, SWIZZLE_128B rows) or 32 (stem, SWIZZLE_64B)
+constexpr int WRES_MAX_KB = 9;                  // resident-weight variant: up to 9 K blocks (3x3, 64 channels) of a 64-wide N tile
+
+// KB = K elements per pipeline stage: 64 (generic, SWIZZLE_128B rows) or 32 (stem, SWIZZLE_64B).
+// WRES: the whole weight image of the (single) N tile stays in shared memory for the lifetime of the CTA and a
+// stage carries only the A tile -- for the Cout = 64 layers the weights are a third of the L2 -> SM traffic, and
+// those layers sit at the chip's L2 throughput cap.
+template <int BN, int KB, bool WRES>
 struct IgCfg {
   static constexpr int ROWB = KB * 2;
   static constexpr int A_ST = BM * ROWB;
   static constexpr int B_ST = BN * ROWB;
-  static constexpr int STAGE = A_ST + B_ST;
+  static constexpr int STAGE = WRES ? A_ST : A_ST + B_ST;
   static constexpr int STAGES = KB == 32 ? 12 : (BN == 128 ? 6 : 8);
-  static constexpr int OFF_BAR = STAGES * STAGE;
+  static constexpr int OFF_W = STAGES * STAGE;                       // resident weights (WRES)
+  static constexpr int OFF_BAR = OFF_W + (WRES ? WRES_MAX_KB * B_ST : 0);
   static constexpr int SMEM = OFF_BAR + 256;
   static constexpr int TMEM_COLS = 2 * BN;
   static_assert(STAGE % 1024 == 0, "stage alignment");
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-template <int BN, int KB>
+template <int BN, int KB, bool WRES>
 __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const ConvArgs a) {
-  using Cfg = IgCfg<BN, KB>;
+  using Cfg = IgCfg<BN, KB, WRES>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -98,11 +105,13 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   auto EMPTY = [&](int s) { return bar + 8u * (STAGES + s); };
   auto TFULL = [&](int i) { return bar + 8u * (2 * STAGES + i); };
   auto TEMPTY = [&](int i) { return bar + 8u * (2 * STAGES + 2 + i); };
-  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 8 * (2 * STAGES + 4));
+  const uint32_t WBAR = bar + 8u * (2 * STAGES + 4);
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + Cfg::OFF_BAR + 8 * (2 * STAGES + 5));
   if ((sbase & 1023u) != 0) __trap();
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), 1); mbar_init(TEMPTY(i), 128); }
+    mbar_init(WBAR, 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
   }
@@ -117,6 +126,10 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
+      if constexpr (WRES) {                                  // n_nt == 1: one weight image for every tile of this CTA
+        mbar_arrive_expect_tx(WBAR, (uint32_t)(nkb * Cfg::B_ST));
+        for (int kb = 0; kb < nkb; ++kb) bulk_g2s(sbase + Cfg::OFF_W + kb * Cfg::B_ST, a.wimg + (size_t)kb * Cfg::B_ST, Cfg::B_ST, WBAR);
+      }
       int stage = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int mt = tile / a.n_nt, nt = tile % a.n_nt;
@@ -133,7 +146,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
                 mbar_arrive_expect_tx(FULL(stage), Cfg::STAGE);
                 const uint32_t dst = sbase + stage * Cfg::STAGE;
                 tma_load_im2col(dst, &tmA, cb * KB, w0, h0, n0, kw, kh, FULL(stage));
-                bulk_g2s(dst + Cfg::A_ST, wt + (size_t)kb * Cfg::B_ST, Cfg::B_ST, FULL(stage));
+                if constexpr (!WRES) bulk_g2s(dst + Cfg::A_ST, wt + (size_t)kb * Cfg::B_ST, Cfg::B_ST, FULL(stage));
                 if (++stage == STAGES) { stage = 0; ph ^= 1; }
               }
         }
@@ -144,6 +157,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     // ===================== MMA issuer =====================
     constexpr uint32_t IDESC = idesc_bf16(128, BN);
     const int nstages = nkb;
+    if constexpr (WRES) { mbar_wait(WBAR, 0); tc_fence_after(); }
     int stage = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(TEMPTY(acc), aph ^ 1);
@@ -153,7 +167,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         mbar_wait(FULL(stage), ph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = sbase + stage * Cfg::STAGE, sb = sa + Cfg::A_ST;
+          const uint32_t sa = sbase + stage * Cfg::STAGE, sb = WRES ? sbase + Cfg::OFF_W + kb * Cfg::B_ST : sa + Cfg::A_ST;
           {
             const uint64_t ad = desc_base(sa, Cfg::ROWB), bd = desc_base(sb, Cfg::ROWB);
 #pragma unroll
@@ -275,15 +289,14 @@ __global__ void maxpool3s2_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv
   reinterpret_cast<uint4*>(y + pix * C)[cg] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// AdaptiveAvgPool2d(1) on NHWC bf16 -> fp32 [B][C]
-__global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int HW, int C) {
+// AdaptiveAvgPool2d(1) on NHWC bf16 -> bf16 [B][C] (fp32 sums; the A operand of the embedding GEMM)
+__global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int HW, int C) {
   const int b = blockIdx.x;
   for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
     float s0 = 0.f, s1 = 0.f;
     const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(x + (size_t)b * HW * C) + c2;
     for (int i = 0; i < HW; ++i) { __nv_bfloat162 v = p[(size_t)i * (C / 2)]; s0 += __low2float(v); s1 += __high2float(v); }
-    y[(size_t)b * C + 2 * c2] = s0 / (float)HW;
-    y[(size_t)b * C + 2 * c2 + 1] = s1 / (float)HW;
+    reinterpret_cast<__nv_bfloat162*>(y + (size_t)b * C)[c2] = __floats2bfloat162_rn(s0 / (float)HW, s1 / (float)HW);
   }
 }
 
@@ -291,35 +304,42 @@ __global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, float* 
 size_t conv_img_bytes(const RConv& c) { return (size_t)c.co * c.ci * c.k * c.k * 2; }   // generic convs: no padding elements
 constexpr size_t STEM_IMG_BYTES = 7 * 64 * 64;
 
-struct Sec { std::vector<size_t> off; size_t total; };
-Sec sec_layout(const RNet& n) {
+struct Sec { std::vector<size_t> off; size_t fc; size_t total; };
+Sec sec_layout(const RNet& n, int E) {
   Sec s; size_t o = 0;
   for (size_t i = 0; i < n.convs.size(); ++i) {
     s.off.push_back(o);
     o = align_up(o + (i == 0 ? STEM_IMG_BYTES : conv_img_bytes(n.convs[i])), 1024);
   }
+  s.fc = o;                                              // embedding_layer.weight (E, feat) bf16 row-major
+  o = align_up(o + (size_t)E * n.feat * 2, 1024);
   s.total = o;
   return s;
 }
 
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
+
 int out_dim(int v, int k, int st, int p) { return (v + 2 * p - k) / st + 1; }
 
-struct Ws { __nv_bfloat16* x4; __nv_bfloat16* buf[5]; float* pooled; size_t bytes; };
+struct Ws { __nv_bfloat16* x4; __nv_bfloat16* buf[5]; __nv_bfloat16* pooled; size_t bytes; };
 Ws carve(const RNet& n, int B, int H, int W, void* ws) {
   Arena a(ws, (size_t)-1);
   Ws w{};
   w.x4 = a.take<__nv_bfloat16>((size_t)B * H * (W + 2 * (STEM_PADL + STEM_PADR)) * 4);
   const size_t act = resnet_max_act(n, H, W) * (size_t)B;
   for (int i = 0; i < 5; ++i) w.buf[i] = a.take<__nv_bfloat16>(act);
-  w.pooled = a.take<float>((size_t)B * n.feat);
+  w.pooled = a.take<__nv_bfloat16>((size_t)B * n.feat);
   w.bytes = align_up(a.off, 256);
   return w;
 }
 
-template <int BN, int KB>
+template <int BN, int KB, bool WRES = false>
 int launch_conv(const CUtensorMap& tm, const ConvArgs& a, cudaStream_t s) {
-  using Cfg = IgCfg<BN, KB>;
-  auto kern = conv_igemm_kernel<BN, KB>;
+  using Cfg = IgCfg<BN, KB, WRES>;
+  auto kern = conv_igemm_kernel<BN, KB, WRES>;
   static thread_local int attr_dev = -1;      // the attribute is per device; set it once per (thread, device)
   int dev = 0;
   I2L_CUDA_OK(cudaGetDevice(&dev));
@@ -339,10 +359,16 @@ bool resnet_bf16_supported(const i2l_resnet_desc& d, int img_width) {
   return d.precision == I2L_BF16 && d.img_height >= 2 && img_width >= 2 && (img_width % 2) == 0;
 }
 
-size_t resnet_bf16_packed_bytes(const RNet& n) { return sec_layout(n).total; }
+size_t resnet_bf16_packed_bytes(const RNet& n, int E) { return sec_layout(n, E).total; }
 
-int resnet_bf16_pack(const RNet& n, const float* folded /* fp32 packed region */, void* section, cudaStream_t s) {
-  Sec L = sec_layout(n);
+int resnet_bf16_pack(const RNet& n, int E, const float* folded /* fp32 packed region */, const float* fc_w, void* section,
+                     cudaStream_t s) {
+  Sec L = sec_layout(n, E);
+  {
+    const size_t tot = (size_t)E * n.feat;
+    f32_to_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(fc_w, reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(section) + L.fc), tot);
+    I2L_LAUNCH_OK();
+  }
   unsigned char* sec = reinterpret_cast<unsigned char*>(section);
   pack_stem_kernel<<<cdiv(7 * 64 * 32, 256), 256, 0, s>>>(folded + n.convs[0].w_off, sec + L.off[0]);
   I2L_LAUNCH_OK();
@@ -363,7 +389,7 @@ int resnet_bf16_fwd(const RNet& n, const i2l_resnet_desc& d, const float* folded
   const int H = d.img_height;
   Ws w = carve(n, B, H, W, ws);
   if (ws_bytes < w.bytes) { set_error("resnet_bf16_fwd: workspace too small (%zu < %zu)", ws_bytes, w.bytes); return I2L_ERR_WORKSPACE; }
-  Sec L = sec_layout(n);
+  Sec L = sec_layout(n, d.embedding_dim);
   const unsigned char* sec = reinterpret_cast<const unsigned char*>(section);
   char tag[40];
   snprintf(tag, sizeof tag, "resnet%d", d.depth);
@@ -412,6 +438,7 @@ int resnet_bf16_fwd(const RNet& n, const i2l_resnet_desc& d, const float* folded
     char nm[48];
     snprintf(nm, sizeof nm, "rn.conv%dx%d_c%d", c.k, c.k, c.co);
     KernelTimer kt(nm, s);
+    if (bn == 64 && a.n_nt == 1 && a.KH * a.KW * a.cblocks <= WRES_MAX_KB) return launch_conv<64, 64, true>(tm, a, s);
     if (bn == 64) return launch_conv<64, 64>(tm, a, s);
     return launch_conv<128, 64>(tm, a, s);
   };
@@ -438,12 +465,16 @@ int resnet_bf16_fwd(const RNet& n, const i2l_resnet_desc& d, const float* folded
     avgpool_nhwc_kernel<<<B, 256, 0, s>>>(cur, w.pooled, h * wd, n.feat);
     I2L_LAUNCH_OK();
   }
-  GemmF32 g;
+  // embedding Linear + ReLU (encoder.py:245-247) on the tensor cores
+  (void)fc_w;
+  GemmBf16 g;
   g.M = B; g.N = d.embedding_dim; g.C = out; g.ldc = d.embedding_dim;
-  g.A1 = w.pooled; g.lda1 = n.feat; g.W1 = fc_w; g.ldw1 = n.feat; g.K1 = n.feat;
+  I2L_TRY(gemm_bf16_a_map(&g.tmA1, w.pooled, B, n.feat, n.feat));
+  I2L_TRY(gemm_bf16_w_map(&g.tmW1, sec + L.fc, d.embedding_dim, n.feat, n.feat));
+  g.K1 = n.feat;
   g.bias = fc_b; g.relu = 1;
-  KernelTimer kt("rn.fc_f32", s);
-  return gemm_f32(g, s);
+  KernelTimer kt("rn.fc_bf16", s);
+  return gemm_bf16(g, s);
 }
 
 }  // namespace i2l
