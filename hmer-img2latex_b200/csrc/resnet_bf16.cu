@@ -19,6 +19,7 @@
 //   maxpool 3x3/2, global average pool: bandwidth kernels; embedding Linear + ReLU: fp32 GEMM.
 #include "resnet_bf16.cuh"
 #include "gemm_bf16.cuh"
+#include <stdlib.h>
 
 namespace i2l {
 namespace {
@@ -28,7 +29,9 @@ using namespace tc;
 constexpr int BM = 128;                       // output pixels per tile
 constexpr int STEM_PADL = 2, STEM_PADR = 2;   // zero pixel pairs stored left / right of every image row
 
-__host__ __device__ constexpr int conv_bn(int co) { return co == 64 ? 64 : 128; }
+// N tile: the tcgen05 pipe runs a 128 x N x 16 MMA in roughly 50 + 0.75 N cycles (measured: N = 64 -> ~100, N = 128 -> ~150),
+// so wide tiles are what approaches the tensor peak
+__host__ __device__ constexpr int conv_bn(int co) { return co == 64 ? 64 : (co % 256 == 0 ? 256 : 128); }
 
 // ------------------------------------------------------------------ packing
 // generic conv: image [n_nt][n_kb][BN rows][64 k] bf16, rows 128 B, SWIZZLE_128B; k block kb = tap * (Ci/64) + cb
@@ -84,7 +87,7 @@ struct IgCfg {
   static constexpr int A_ST = BM * ROWB;
   static constexpr int B_ST = BN * ROWB;
   static constexpr int STAGE = WRES ? A_ST : A_ST + B_ST;
-  static constexpr int STAGES = KB == 32 ? 12 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = KB == 32 ? 12 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int OFF_W = STAGES * STAGE;                       // resident weights (WRES)
   static constexpr int OFF_BAR = OFF_W + (WRES ? WRES_MAX_KB * B_ST : 0);
   static constexpr int SMEM = OFF_BAR + 256;
@@ -238,6 +241,158 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
+// ------------------------------------------------------------------ stem, row-window variant
+// The 7x7/2 stem WITHOUT an im2col: for output row ho and filter row kh, the 4 pixel pairs that output column wo
+// needs (wo-2 .. wo+1, physical wo .. wo+3) are 64 contiguous bytes of ONE image row, and column wo+1 needs the
+// same bytes shifted by 16.  A no-swizzle K-major UMMA descriptor with a 16-byte ROW pitch (SBO = 128) and a
+// 16-byte K-chunk pitch (LBO = 16) reads exactly those overlapping windows: row m, chunk c -> byte 16 (m + c).
+// So the A operand of (tile, kh) is just a 1 KB slice of the image row, fetched with one plain bulk copy; a
+// tile is 2 output rows x 61 columns (M = 128: rows 0-63 / 64-127 are the two slices, 1 KB apart; columns 61-63
+// of each half read past their slice and are masked).  14 bulk copies of 1 KB and 14 MMAs (128x64x16) per tile,
+// instead of 7 im2col loads of 128 unaligned 64-byte windows (the TMA unit processes ~0.2 windows per cycle).
+constexpr int SR_COLS = 61;                      // valid output columns per half tile
+constexpr int SR_STAGE = 2048, SR_STAGES = 28;   // one stage = (kh, both output rows)
+constexpr int SR_OFF_W = SR_STAGES * SR_STAGE;   // resident weights: 7 x [64 co][32 k] SWIZZLE_64B
+constexpr int SR_OFF_BAR = SR_OFF_W + 7 * 4096;
+constexpr int SR_SMEM = SR_OFF_BAR + 512;
+
+struct StemArgs {
+  const unsigned char* x4;       // [B][H][Wpp pairs][8] bf16 (zero pairs stored left / right)
+  const unsigned char* zero_row; // >= 1 KB of zeros: source of out-of-image rows
+  const unsigned char* wimg;
+  const float* bias;
+  __nv_bfloat16* out;            // [B][Ho][Wo][64]
+  int B, H, Wpp, Ho, Wo, tiles_w, n_tiles;
+};
+
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+         ((uint64_t)1 << 46);
+}
+
+__global__ void __launch_bounds__(256, 1) stem_rows_kernel(const StemArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar = sbase + SR_OFF_BAR;
+  auto FULL = [&](int s) { return bar + 8u * s; };
+  auto EMPTY = [&](int s) { return bar + 8u * (SR_STAGES + s); };
+  auto TFULL = [&](int i) { return bar + 8u * (2 * SR_STAGES + i); };
+  auto TEMPTY = [&](int i) { return bar + 8u * (2 * SR_STAGES + 2 + i); };
+  const uint32_t WBAR = bar + 8u * (2 * SR_STAGES + 4);
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + SR_OFF_BAR + 8 * (2 * SR_STAGES + 5));
+  if ((sbase & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int s = 0; s < SR_STAGES; ++s) { mbar_init(FULL(s), 2); mbar_init(EMPTY(s), 1); }     // two producers per stage
+    for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), 1); mbar_init(TEMPTY(i), 128); }
+    mbar_init(WBAR, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<128>(smem_u32(misc));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc[0];
+  const int hop = a.Ho / 2;                                    // output row pairs per image
+
+  if (warp == 0 || warp == 6 || warp == 7) {
+    // ===================== producers: plain bulk copies of image-row slices =====================
+    // a bulk copy costs ~100+ cycles of issue in its thread: warp 0 feeds output row 0 of every tile, warp 6 row 1
+    // (warp 7 only pads the block to whole warp quads and idles)
+    const int seg = warp == 0 ? 0 : 1;
+    if (warp != 7 && elect_one()) {
+      if (warp == 0) {
+        mbar_arrive_expect_tx(WBAR, 7 * 4096);
+        for (int kh = 0; kh < 7; ++kh) bulk_g2s(sbase + SR_OFF_W + kh * 4096, a.wimg + kh * 4096, 4096, WBAR);
+      }
+      int stage = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int tw = tile % a.tiles_w, rp = (tile / a.tiles_w) % hop, n = tile / (a.tiles_w * hop);
+        const int wo0 = tw * SR_COLS, ho0 = 2 * rp;
+        for (int kh = 0; kh < 7; ++kh) {
+          mbar_wait(EMPTY(stage), ph ^ 1);
+          mbar_arrive_expect_tx(FULL(stage), SR_STAGE / 2);
+          const uint32_t dst = sbase + stage * SR_STAGE;
+          const int h = 2 * (ho0 + seg) - 3 + kh;
+          const unsigned char* src = (h >= 0 && h < a.H) ? a.x4 + (((size_t)n * a.H + h) * a.Wpp + wo0) * 16 : a.zero_row;
+          bulk_g2s(dst + seg * 1024, src, 1024, FULL(stage));
+          if (++stage == SR_STAGES) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t IDESC = idesc_bf16(128, 64);
+    mbar_wait(WBAR, 0);
+    tc_fence_after();
+    int stage = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      mbar_wait(TEMPTY(acc), aph ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem + (uint32_t)(acc * 64);
+      for (int kh = 0; kh < 7; ++kh) {
+        mbar_wait(FULL(stage), ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = sbase + stage * SR_STAGE;
+          const uint64_t bd = desc_base(sbase + SR_OFF_W + kh * 4096, 64);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            tc_mma_ss(d, desc_nosw(sa + ks * 32, 16, 128), bd + (uint64_t)((ks * 32) >> 4), IDESC, (kh | ks) ? 1u : 0u);
+          tc_commit(EMPTY(stage));
+          if (kh == 6) tc_commit(TFULL(acc));
+        }
+        __syncwarp();
+        if (++stage == SR_STAGES) { stage = 0; ph ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue warps 2..5: BN shift + ReLU -> bf16 NHWC =====================
+    const int q = warp & 3;
+    const int m = 32 * q + lane;
+    const int seg = m >> 6, i = m & 63;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    int acc = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int tw = tile % a.tiles_w, rp = (tile / a.tiles_w) % hop, n = tile / (a.tiles_w * hop);
+      const int wo = tw * SR_COLS + i, ho = 2 * rp + seg;
+      const bool valid = i < SR_COLS && wo < a.Wo;
+      __nv_bfloat16* dst = a.out + (((size_t)n * a.Ho + ho) * a.Wo + wo) * 64;
+      mbar_wait(TFULL(acc), aph);
+      tc_fence_after();
+      const uint32_t ta = tmem + lane_addr + (uint32_t)(acc * 64);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+        tc_ld16_nowait(ta + cc * 32, r);
+        tc_ld16_nowait(ta + cc * 32 + 16, r + 16);
+        tc_wait_ld();
+        uint32_t ov[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float v0 = fmaxf(__uint_as_float(r[2 * k]) + __ldg(a.bias + cc * 32 + 2 * k), 0.f);
+          const float v1 = fmaxf(__uint_as_float(r[2 * k + 1]) + __ldg(a.bias + cc * 32 + 2 * k + 1), 0.f);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+          ov[k] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        if (valid) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + cc * 32);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) d4[k] = make_uint4(ov[4 * k], ov[4 * k + 1], ov[4 * k + 2], ov[4 * k + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(TEMPTY(acc));
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem);
+}
+
 // ------------------------------------------------------------------ bandwidth kernels
 // (B,3,H,W) fp32 NCHW -> [B][H][Wp][4] bf16, Wp = W + 2 (PADL + PADR) pixels per row (zero columns), channel 3 = 0
 __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ x, uint2* __restrict__ y, int H, int W, int Wp, size_t total /*B*H*Wp*/) {
@@ -324,11 +479,12 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 
 int out_dim(int v, int k, int st, int p) { return (v + 2 * p - k) / st + 1; }
 
-struct Ws { __nv_bfloat16* x4; __nv_bfloat16* buf[5]; __nv_bfloat16* pooled; size_t bytes; };
+struct Ws { __nv_bfloat16* x4; unsigned char* zero_row; __nv_bfloat16* buf[5]; __nv_bfloat16* pooled; size_t bytes; };
 Ws carve(const RNet& n, int B, int H, int W, void* ws) {
   Arena a(ws, (size_t)-1);
   Ws w{};
-  w.x4 = a.take<__nv_bfloat16>((size_t)B * H * (W + 2 * (STEM_PADL + STEM_PADR)) * 4);
+  w.x4 = a.take<__nv_bfloat16>((size_t)B * H * (W + 2 * (STEM_PADL + STEM_PADR)) * 4 + 1024);   // + slack: the last row slice over-reads
+  w.zero_row = a.take<unsigned char>(2048);
   const size_t act = resnet_max_act(n, H, W) * (size_t)B;
   for (int i = 0; i < 5; ++i) w.buf[i] = a.take<__nv_bfloat16>(act);
   w.pooled = a.take<__nv_bfloat16>((size_t)B * n.feat);
@@ -413,7 +569,19 @@ int resnet_bf16_fwd(const RNet& n, const i2l_resnet_desc& d, const float* folded
     a.P = B * h * wd; a.HoWo = h * wd; a.Wo = wd; a.Co = 64; a.KH = 7; a.KW = 1; a.cblocks = 1;
     a.stride_w = 1; a.stride_h = 2; a.pad_w = 0; a.pad_h = 3; a.relu = 1; a.n_mt = cdiv(a.P, BM); a.n_nt = 1;
     KernelTimer kt("rn.stem_conv7x7", s);
-    I2L_TRY((launch_conv<64, 32>(tm, a, s)));
+    if ((h % 2) == 0 && getenv("I2L_STEM_IM2COL") == nullptr) {
+      // row-window stem (stem_rows_kernel): needs an even number of output rows
+      I2L_CUDA_OK(cudaMemsetAsync(w.zero_row, 0, 2048, s));
+      StemArgs sa{};
+      sa.x4 = reinterpret_cast<const unsigned char*>(w.x4); sa.zero_row = w.zero_row; sa.wimg = sec + L.off[0];
+      sa.bias = folded + n.convs[0].b_off; sa.out = w.buf[1];
+      sa.B = B; sa.H = H; sa.Wpp = Wpp; sa.Ho = h; sa.Wo = wd; sa.tiles_w = cdiv(wd, SR_COLS); sa.n_tiles = B * (h / 2) * sa.tiles_w;
+      I2L_CUDA_OK(cudaFuncSetAttribute(stem_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SR_SMEM));
+      stem_rows_kernel<<<std::min(sa.n_tiles, num_sms()), 256, SR_SMEM, s>>>(sa);
+      I2L_LAUNCH_OK();
+    } else {
+      I2L_TRY((launch_conv<64, 32>(tm, a, s)));
+    }
   }
   // ---- maxpool 3x3/2
   {
@@ -440,6 +608,7 @@ int resnet_bf16_fwd(const RNet& n, const i2l_resnet_desc& d, const float* folded
     KernelTimer kt(nm, s);
     if (bn == 64 && a.n_nt == 1 && a.KH * a.KW * a.cblocks <= WRES_MAX_KB) return launch_conv<64, 64, true>(tm, a, s);
     if (bn == 64) return launch_conv<64, 64>(tm, a, s);
+    if (bn == 256) return launch_conv<256, 64>(tm, a, s);
     return launch_conv<128, 64>(tm, a, s);
   };
   __nv_bfloat16 *cur = w.buf[0], *nxt = w.buf[1], *t1 = w.buf[2], *t2 = w.buf[3], *idt = w.buf[4];
