@@ -43,18 +43,26 @@ PackedDec dec_layout(const i2l_dec_desc& d) {
       L.g16_w_ih[l] = l == 0 ? 0 : take16(4 * H * H);
     }
     L.g16_out_w = take16(V * H);
+    L.g16_w_ctx = take16(4 * H * E);
   }
   L.total_bytes = bytes;
   return L;
 }
 
-bool general_bf16_supported(const i2l_dec_desc& d) { return d.precision == I2L_BF16 && (d.hidden_dim % 8) == 0; }
+bool general_bf16_supported(const i2l_dec_desc& d) {
+  return d.precision == I2L_BF16 && (d.hidden_dim % 8) == 0 && (d.embedding_dim % 8) == 0;
+}
 
 namespace {
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
+// dst (rows, cols) contiguous <- src (rows, cols) with leading dimension ld
+__global__ void f32_to_bf16_ld_kernel(const float* __restrict__ src, int ld, __nv_bfloat16* __restrict__ dst, int cols, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16(src[(i / cols) * ld + (i % cols)]);
 }
 
 __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
@@ -905,6 +913,22 @@ int lstm_cell_f32(const float* gates, float* h, float* c, int rows, int H, const
   return I2L_OK;
 }
 
+int make_gctx_bf16(const i2l_dec_desc& d, const void* packed, const PackedDec& lay, const float* enc, int n, float* gctx,
+                   __nv_bfloat16* encb, cudaStream_t s) {
+  const int E = d.embedding_dim, H = d.hidden_dim;
+  const size_t tot = (size_t)n * E;
+  if (tot == 0) return I2L_OK;
+  f32_to_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(enc, encb, tot);
+  I2L_LAUNCH_OK();
+  GemmBf16 g;
+  g.M = n; g.N = 4 * H; g.C = gctx; g.ldc = 4 * H;
+  I2L_TRY(gemm_bf16_a_map(&g.tmA1, encb, n, E, E));
+  I2L_TRY(gemm_bf16_w_map(&g.tmW1, reinterpret_cast<const char*>(packed) + lay.g16_w_ctx, 4 * H, E, E));
+  g.K1 = E;
+  g.bias = reinterpret_cast<const float*>(packed) + lay.bsum[0];
+  return gemm_bf16(g, s);
+}
+
 }  // namespace i2l
 
 using namespace i2l;
@@ -954,6 +978,11 @@ extern "C" int i2l_dec_pack(const i2l_dec_desc* d, const i2l_dec_params* p, void
       if (l > 0) I2L_TRY(conv(p->w_ih[l], lay.g16_w_ih[l], 4 * H * H));
     }
     I2L_TRY(conv(p->out_w, lay.g16_out_w, V * H));
+    {
+      const size_t n = 4 * H * E;
+      f32_to_bf16_ld_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->w_ih[0] + E, 2 * (int)E, reinterpret_cast<__nv_bfloat16*>(pb + lay.g16_w_ctx), (int)E, n);
+      I2L_LAUNCH_OK();
+    }
   }
   return I2L_OK;
 }

@@ -34,10 +34,14 @@ struct PackedDec {     // offsets (in floats) into the packed decoder buffer, fp
   // bf16 row-major copies of the per-step GEMM weights for the general path (byte offsets; g16 == 0 if absent):
   // W_hh[l] (4H,H), W_ih[l >= 1] (4H,H), W_out (V,H) -- operands of gemm_bf16.cu
   size_t g16, g16_w_hh[I2L_MAX_LSTM_LAYERS], g16_w_ih[I2L_MAX_LSTM_LAYERS], g16_out_w;
+  size_t g16_w_ctx;     // W_ih0[:, E:2E] (4H,E): the per-sequence constant gate term gctx = enc W_ctx^T + b_ih0 + b_hh0
   size_t total_bytes;
 };
-// precision == I2L_BF16 and TMA-addressable rows (H % 8 == 0): the general loops run their GEMMs on tcgen05
+// precision == I2L_BF16 and TMA-addressable rows (H % 8 == 0, E % 8 == 0): the general loops run their GEMMs on tcgen05
 bool general_bf16_supported(const i2l_dec_desc& d);
+// gctx (n,4H) = enc (n,E) W_ih0[:, E:2E]^T + b_ih0 + b_hh0 on the tensor cores; encb: scratch for n*E bf16
+int make_gctx_bf16(const i2l_dec_desc& d, const void* packed, const PackedDec& lay, const float* enc, int n, float* gctx,
+                   __nv_bfloat16* encb, cudaStream_t s);
 PackedDec dec_layout(const i2l_dec_desc& d);
 
 // hb: optional bf16 copy of the new h (A operand of the next bf16 GEMM)

@@ -481,12 +481,13 @@ __global__ void persistent_finalize_kernel(const int* first_end, const unsigned 
     }
 }
 
-struct PWs { float* gctx; int* first_end; unsigned char* allend; int* cluster_steps; size_t bytes; };
+struct PWs { float* gctx; __nv_bfloat16* encb; int* first_end; unsigned char* allend; int* cluster_steps; size_t bytes; };
 PWs pcarve(int rows, int T, void* ws) {
   Arena a(ws, (size_t)-1);
   PWs w{};
   int ncl = cdiv(rows, NB);
   w.gctx = a.take<float>((size_t)rows * 1024);
+  w.encb = a.take<__nv_bfloat16>((size_t)rows * E);
   w.first_end = a.take<int>(rows);
   w.allend = a.take<unsigned char>((size_t)ncl * (T > 0 ? T : 1));
   w.cluster_steps = a.take<int>(ncl);
@@ -543,13 +544,10 @@ int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* p
     persistent_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(tokens, T1, batch, start_id);
     I2L_LAUNCH_OK();
   }
-  // per-sequence constant gates: enc W_ih[:, E:2E]^T + b_ih + b_hh  (fp32 GEMM)
+  // per-sequence constant gates: enc W_ih[:, E:2E]^T + b_ih + b_hh  (tcgen05 GEMM, bf16 operands)
   {
-    GemmF32 g;
-    g.M = batch; g.N = 4 * H; g.C = w.gctx; g.ldc = 4 * H;
-    g.A1 = enc; g.lda1 = E; g.W1 = packed_f32 + lay.w_ih0 + E; g.ldw1 = 2 * E; g.K1 = E; g.bias = packed_f32 + lay.bsum[0];
     KernelTimer kt("dec.gctx_gemm", s);
-    I2L_TRY(gemm_f32(g, s));
+    I2L_TRY(make_gctx_bf16(d, packed_f32, lay, enc, batch, w.gctx, w.encb, s));
   }
   const int ncl = cdiv(batch, NB);
   if (max_length > 0) {
