@@ -49,11 +49,12 @@ constexpr int OFF_PART = OFF_H + 2 * HB_BYTES;      // [8 warps][16 cols] (float
 constexpr int OFF_XCHG = OFF_PART + 8 * 16 * 8;     // [4 ctas][32 cols] (float,int)
 constexpr int OFF_TOK = OFF_XCHG + CL * NB * 8;     // [32] int tokens of the current step
 constexpr int OFF_BAR = OFF_TOK + NB * 4;           // mbarriers
-constexpr int OFF_MISC = OFF_BAR + 8 * 8;           // tmem base, exit flag
+constexpr int OFF_MISC = OFF_BAR + 16 * 8;           // tmem base, exit flag
 constexpr int SMEM_BYTES = OFF_MISC + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 
-enum { BAR_W = 0, BAR_HFULL0 = 1, BAR_HFULL1 = 2, BAR_LDONE = 3, BAR_GDONE = 4, BAR_TOK = 5, BAR_FINAL = 6 };
+// BAR_HS + 4 * buf + d: K-block of h buffer `buf` written by the CTA at cluster distance d (rank - d; d = 0: this CTA)
+enum { BAR_W = 0, BAR_LDONE = 3, BAR_GDONE = 4, BAR_TOK = 5, BAR_FINAL = 6, BAR_HS = 8 };
 
 // debug build of the kernel only (tools/debug_persistent.py): per-phase clock64() stamps of one
 // step of cluster 0 / rank 0, and optional dumps of gates / h / logits of that step
@@ -98,8 +99,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
   if ((sbase & 1023u) != 0) __trap();
 
   if (tid == 0) {
-    mbar_init(BAR(BAR_HFULL0), 1);
-    mbar_init(BAR(BAR_HFULL1), 1);
+    for (int i = 0; i < 8; ++i) mbar_init(BAR(BAR_HS + i), 1);
     mbar_init(BAR(BAR_LDONE), 1);
     mbar_init(BAR(BAR_GDONE), 1);
     mbar_init(BAR(BAR_TOK), 1);
@@ -169,23 +169,38 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       tc_commit(BAR(BAR_GDONE));
     }
     __syncwarp();
-    for (int s = 0; s < P.T; ++s) {
+    // The 16 logits MMAs cost ~45 cycles each on the tensor pipe (tools/probes/mma_rate_probe.cu: that is the floor of
+    // a 128xNx16 MMA for N <= 64): the 4 of a K-block are issued as soon as THAT block of h has arrived -- the CTA's
+    // own block first, then the peers' in the order their bulk copies were sent -- so most of the chain runs under
+    // the DSMEM exchange instead of after it.
+    bool stop = false;
+    for (int s = 0; s < P.T && !stop; ++s) {
       const bool dbg_ts = DBG && cluster == 0 && rank == 0 && s == P.dbg_step && lane == 0;
       const int nb = (s + 1) & 1;                       // buffer holding h_{s+1}
-      I2L_TS(16);
-      mbar_wait(BAR(BAR_HFULL0 + nb), (uint32_t)((s >> 1) & 1));     // h_j (j = s+1) is use (j-1)/2 of its buffer
-      I2L_TS(17);
-      if (*reinterpret_cast<volatile uint32_t*>(&misc[1])) break;
-      tc_fence_after();
       const uint32_t hb = OFF_H + nb * HB_BYTES;
-      if (elect_one()) {
-        issue_tile(TM_L, TC_WO, hb);                    // logits_s = W_out h_{s+1}
-        tc_commit(BAR(BAR_LDONE));
-        if (s + 1 < P.T) {
-          issue_tile(TM_G0, TC_WG0, hb);                // gates of step s+1
-          issue_tile(TM_G1, TC_WG1, hb);
-          tc_commit(BAR(BAR_GDONE));
+      I2L_TS(16);
+#pragma unroll
+      for (uint32_t d = 0; d < CL; ++d) {
+        mbar_wait(BAR(BAR_HS + 4 * nb + d), (uint32_t)((s >> 1) & 1));     // h_j (j = s+1) is use (j-1)/2 of its buffer
+        if (d == 0 && *reinterpret_cast<volatile uint32_t*>(&misc[1])) { stop = true; break; }
+        tc_fence_after();
+        const uint32_t kb = (rank - d) & (CL - 1);      // K-block = rank of the CTA that produced it
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t bd = dbase + (uint64_t)((hb + kb * HSLICE_BYTES + k * 32) >> 4);
+            tc_mma_ts(TM_L, tmem + TC_WO + (kb * 4 + k) * 8, bd, IDESC, (d | (uint32_t)k) ? 1u : 0u);
+          }
+          if (d == CL - 1) tc_commit(BAR(BAR_LDONE));
         }
+        __syncwarp();
+      }
+      if (stop) break;
+      I2L_TS(17);
+      if (s + 1 < P.T && elect_one()) {
+        issue_tile(TM_G0, TC_WG0, hb);                  // gates of step s+1
+        issue_tile(TM_G1, TC_WG1, hb);
+        tc_commit(BAR(BAR_GDONE));
       }
       __syncwarp();
       I2L_TS(18);
@@ -292,11 +307,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       epi_bar_sync();
       if (tid == 0) {
         const uint32_t src = sbase + OFF_H + nb * HB_BYTES + rank * HSLICE_BYTES;
-        mbar_arrive_expect_tx(BAR(BAR_HFULL0 + nb), (I2L_ABL & 8) ? 0 : (CL - 1) * HSLICE_BYTES);
+        mbar_arrive(BAR(BAR_HS + 4 * nb));                          // own K-block is in place
 #pragma unroll
-        for (uint32_t d = 1; d < ((I2L_ABL & 8) ? 1 : CL); ++d) {
-          uint32_t peer = (rank + d) & (CL - 1);
-          bulk_s2peer(mapa(src, peer), src, HSLICE_BYTES, mapa(BAR(BAR_HFULL0 + nb), peer));
+        for (uint32_t d = 1; d < CL; ++d) {
+          // arm the barrier of the block that arrives from distance d, send ours to the CTA at distance d
+          if (I2L_ABL & 8) { mbar_arrive(BAR(BAR_HS + 4 * nb + d)); continue; }
+          mbar_arrive_expect_tx(BAR(BAR_HS + 4 * nb + d), HSLICE_BYTES);
+          const uint32_t peer = (rank + d) & (CL - 1);
+          bulk_s2peer(mapa(src, peer), src, HSLICE_BYTES, mapa(BAR(BAR_HS + 4 * nb + d), peer));
         }
       }
       // ---------------- Epi-L(s): logits -> tok_{s+1} ----------------
@@ -394,7 +412,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
     }
     if (*reinterpret_cast<volatile uint32_t*>(&misc[1]) && tid == 0) {
       // early exit: release the MMA thread that is waiting for an h buffer that will never fill
-      mbar_arrive(BAR(BAR_HFULL0 + ((s + 1) & 1)));
+      mbar_arrive(BAR(BAR_HS + 4 * ((s + 1) & 1)));
     }
   }
   // ---- teardown: peers may still be reading / writing our shared memory ----
