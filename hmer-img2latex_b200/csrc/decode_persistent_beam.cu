@@ -41,7 +41,7 @@ struct Geo {
   static constexpr int OFF_NEW = OFF_ROW + NB * 16;        // [32] (double score, int parent slot, int tok)
   static constexpr int OFF_PUB = OFF_NEW + NB * 16;        // [32] (int parent column in group, int tok)
   static constexpr int OFF_BAR = OFF_PUB + NB * 8;
-  static constexpr int OFF_MISC = OFF_BAR + 8 * 8;
+  static constexpr int OFF_MISC = OFF_BAR + 16 * 8;
   static constexpr int SMEM = OFF_MISC + 16;
   static_assert(K >= 1 && K <= 16 && SMEM <= 232448, "beam geometry");
 };
@@ -51,7 +51,8 @@ struct Geo {
 // otherwise just wait for them.
 constexpr int BT = EPI_THREADS;
 
-enum { BAR_HFULL0 = 1, BAR_HFULL1 = 2, BAR_LDONE = 3, BAR_GDONE = 4, BAR_TOK = 5, BAR_FINAL = 6 };
+// BAR_HS + 4 * buf + d: K-block of h buffer `buf` written by the CTA at cluster distance d (rank - d; d = 0: this CTA)
+enum { BAR_LDONE = 3, BAR_GDONE = 4, BAR_TOK = 5, BAR_FINAL = 6, BAR_HS = 8 };
 
 __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
                                             uint32_t cluster_bar) {
@@ -125,8 +126,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
 
   if ((sbase & 1023u) != 0) __trap();
   if (tid == 0) {
-    mbar_init(BAR(BAR_HFULL0), 1);
-    mbar_init(BAR(BAR_HFULL1), 1);
+    for (int i = 0; i < 8; ++i) mbar_init(BAR(BAR_HS + i), 1);
     mbar_init(BAR(BAR_LDONE), 1);
     mbar_init(BAR(BAR_GDONE), 1);
     mbar_init(BAR(BAR_TOK), 1);
@@ -317,25 +317,38 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
       epi_bar_sync();
       if (tid == 0) {
         const uint32_t src = sbase + G::OFF_H + nb * HB_BYTES + rank * HSLICE_BYTES;
-        mbar_arrive_expect_tx(BAR(BAR_HFULL0 + nb), (CL - 1) * HSLICE_BYTES);
+        mbar_arrive(BAR(BAR_HS + 4 * nb));                          // own K-block is in place
 #pragma unroll
         for (uint32_t d = 1; d < CL; ++d) {
-          uint32_t peer = (rank + d) & (CL - 1);
-          bulk_s2peer(mapa(src, peer), src, HSLICE_BYTES, mapa(BAR(BAR_HFULL0 + nb), peer));
+          // arm the barrier of the block that arrives from distance d, send ours to the CTA at distance d
+          mbar_arrive_expect_tx(BAR(BAR_HS + 4 * nb + d), HSLICE_BYTES);
+          const uint32_t peer = (rank + d) & (CL - 1);
+          bulk_s2peer(mapa(src, peer), src, HSLICE_BYTES, mapa(BAR(BAR_HS + 4 * nb + d), peer));
         }
       }
-      if (warp == 0) {   // MMA-L(s) and MMA-G(s+1) as soon as the four h slices are in place
-        mbar_wait(BAR(BAR_HFULL0 + nb), (uint32_t)((s >> 1) & 1));
-        tc_fence_after();
+      if (warp == 0) {
+        // MMA-L(s): the 4 MMAs of a K-block as soon as THAT block of h arrived (own block first, then the peers' in
+        // the order their copies were sent; a 128x32x16 MMA costs ~45 cycles of the tensor pipe), then MMA-G(s+1)
         const uint32_t hb = G::OFF_H + nb * HB_BYTES;
-        if (elect_one()) {
-          issue_tile(TM_L, TC_WO, hb);                      // logits_s = W_out h_{s+1}
-          tc_commit(BAR(BAR_LDONE));
-          if (s + 1 < P.T) {
-            issue_tile(TM_G0, TC_WG0, hb);                  // gates of step s+1
-            issue_tile(TM_G1, TC_WG1, hb);
-            tc_commit(BAR(BAR_GDONE));
+#pragma unroll
+        for (uint32_t d = 0; d < CL; ++d) {
+          mbar_wait(BAR(BAR_HS + 4 * nb + d), (uint32_t)((s >> 1) & 1));
+          tc_fence_after();
+          const uint32_t kb = (rank - d) & (CL - 1);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t bd = dbase + (uint64_t)((hb + kb * HSLICE_BYTES + k * 32) >> 4);
+              tc_mma_ts(TM_L, tmem + TC_WO + (kb * 4 + k) * 8, bd, IDESC, (d | (uint32_t)k) ? 1u : 0u);
+            }
+            if (d == CL - 1) tc_commit(BAR(BAR_LDONE));
           }
+          __syncwarp();
+        }
+        if (s + 1 < P.T && elect_one()) {
+          issue_tile(TM_G0, TC_WG0, hb);                  // gates of step s+1
+          issue_tile(TM_G1, TC_WG1, hb);
+          tc_commit(BAR(BAR_GDONE));
         }
         __syncwarp();
       }
