@@ -370,7 +370,7 @@ def resnet_lines(pkg, dev, B, reps=3):
     xs = {w: torch.randn(n, 3, 64, w, device=dev) for w, n in sorted(buckets.items())}
 
     def step18():
-        enc = torch.cat(m.encoder.forward_buckets(list(xs.values())), 0)
+        enc = torch.cat(m.encoder.forward_buckets(list(xs.values()), n_streams=int(os.environ.get('I2L_BUCKET_STREAMS', '4'))), 0)
         return m.decoder.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_ALL_END_SAME_STEP)
 
     def timed(fn):
@@ -397,7 +397,7 @@ def resnet_lines(pkg, dev, B, reps=3):
                     "(%d buckets), max_len 150" % (B, len(buckets)),
         "value": round(B / ms * 1e3, 1), "unit": "images/s", "ms_per_step": round(ms, 3),
         "decode_ms": round(sum(v for k, v in prof.items() if k.startswith("dec.")), 3),
-        "note": "buckets run on 4 streams (ResNetEncoder.forward_buckets)"}
+        "note": "buckets replayed as CUDA graphs on 4 streams (ResNetEncoder.forward_buckets)"}
     r = out["resnet18_bucketed_greedy"]
     r["encoder_ms"] = round(ms - r["decode_ms"], 3)
     r["encoder_tflops"] = round(fl / r["encoder_ms"] / 1e9, 1)

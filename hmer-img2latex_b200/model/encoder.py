@@ -282,11 +282,15 @@ class ResNetEncoder(nn.Module):
         torch.cuda.current_stream(device).synchronize()
         self._packed, self._packed_key = packed, key
 
-    def forward_buckets(self, batches: List[torch.Tensor], n_streams: int = 4) -> List[torch.Tensor]:
+    def forward_buckets(self, batches: List[torch.Tensor], n_streams: int = 4, use_graphs: bool = True
+                        ) -> List[torch.Tensor]:
         """Width-bucketed encoding (BASELINE configs[3]): ``[forward(x) for x in batches]`` with the buckets spread
-        over ``n_streams`` CUDA streams, each with its own workspace.  A bucket of a few dozen images launches
-        ~26 (resnet18) small kernels whose grids fill a fraction of the 148 SMs; running buckets side by side fills
-        the machine.  Results are identical to ``forward`` (same kernels, same data)."""
+        over ``n_streams`` CUDA streams.  A bucket of a few dozen images launches ~26 (resnet18) small kernels whose
+        grids fill a fraction of the 148 SMs; running buckets side by side fills the machine.  With ``use_graphs``
+        the launch sequence of every (batch, width) shape is captured once into a CUDA graph with its own workspace
+        and static input / output buffers, so a bucket costs one graph launch on the host instead of ~26 kernel
+        launches and tensor-map encodes.  Results are identical to ``forward`` (same kernels, same data); the
+        returned tensors are owned by the graphs and are overwritten by the next call with the same shape."""
         if not batches:
             return []
         dev = batches[0].device
@@ -294,25 +298,61 @@ class ResNetEncoder(nn.Module):
         if getattr(self, "_bucket_streams", None) is None or len(self._bucket_streams) != n_streams:
             self._bucket_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
             self._bucket_ws = [Workspace() for _ in range(n_streams)]
+        if getattr(self, "_bucket_graphs", None) is None:
+            self._bucket_graphs = {}
+        with torch.cuda.device(dev):
+            self._ensure_packed(dev)
+        key_w = self._packed_key
         cur = torch.cuda.current_stream(dev)
+        if use_graphs:
+            seen = set()
+            for x in batches:                    # capture the shapes that are new (or whose weights changed), serially
+                k = (tuple(x.shape), x.dtype)
+                if k in seen:
+                    raise RuntimeError("forward_buckets(use_graphs=True) needs one batch per (shape, dtype)")
+                seen.add(k)
+                g = self._bucket_graphs.get(k)
+                if g is None or g["weights"] != key_w:
+                    self._bucket_graphs[k] = self._capture_bucket(x, key_w)
         start = torch.cuda.Event()
         start.record(cur)
         outs = []
-        with torch.cuda.device(dev):
-            self._ensure_packed(dev)
         for i, x in enumerate(batches):
             st = self._bucket_streams[i % n_streams]
             if i < n_streams:
                 st.wait_event(start)
             with torch.cuda.stream(st):
-                out = self.forward(x, _ws=self._bucket_ws[i % n_streams])
-            out.record_stream(cur)
+                if use_graphs:
+                    g = self._bucket_graphs[(tuple(x.shape), x.dtype)]
+                    g["x"].copy_(x, non_blocking=True)
+                    g["graph"].replay()
+                    out = g["out"]
+                else:
+                    out = self.forward(x, _ws=self._bucket_ws[i % n_streams])
+                    out.record_stream(cur)
             outs.append(out)
         for st in self._bucket_streams[: min(n_streams, len(batches))]:
             done = torch.cuda.Event()
             done.record(st)
             cur.wait_event(done)
         return outs
+
+    def _capture_bucket(self, x: torch.Tensor, key_w) -> dict:
+        """One CUDA graph per (shape, dtype): static input, private workspace, static output."""
+        dev = x.device
+        ws = Workspace()
+        xs = torch.empty_like(x)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            xs.copy_(x)
+            self.forward(xs, _ws=ws)             # warm-up: allocates the workspace, sets function attributes
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.forward(xs, _ws=ws)
+        return {"graph": graph, "x": xs, "out": out, "ws": ws, "weights": key_w}
 
     def forward(self, x: torch.Tensor, _ws: Optional[Workspace] = None) -> torch.Tensor:
         """(B, 3, H, W) -> (B, embedding_dim); any W (the trunk ends in adaptive average

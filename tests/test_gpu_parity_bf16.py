@@ -213,11 +213,17 @@ def test_resnet_forward_buckets_matches_forward(pkg):
     m = H.build_model(pkg, cfg, p, precision="bf16")
     xs = [H.make_images(cfg, b, seed=w, width=w).cuda() for b, w in ((3, 128), (5, 160), (2, 320), (4, 224), (1, 96), (6, 192))]
     ref = [m.encoder(x).clone() for x in xs]
-    for _ in range(2):
-        outs = m.encoder.forward_buckets(xs, n_streams=3)
+    for use_graphs in (False, True, True):          # second graph pass = pure replays
+        outs = m.encoder.forward_buckets(xs, n_streams=3, use_graphs=use_graphs)
         torch.cuda.synchronize()
         for a, b in zip(outs, ref):
             assert torch.equal(a, b)
+    # replays pick up new data in the static inputs
+    xs2 = [x.flip(0).contiguous() for x in xs]
+    outs = m.encoder.forward_buckets(xs2, n_streams=3)
+    torch.cuda.synchronize()
+    for a, b in zip(outs, ref):
+        assert torch.equal(a, b.flip(0))
 
 
 # ---- general decode loops with the per-step GEMMs on tcgen05 (gemm_bf16.cu): any E / H / L, precision "bf16"
