@@ -441,6 +441,104 @@ __global__ void __launch_bounds__(256) sample_select_warp_kernel(const float* __
     for (int i = 0; i < 16; ++i) po[i] = po[i] / s;
 
     if (top_k > 0 || top_p > 0.0f) {
+      int R = V;                                                // kept entries = sorted positions [0, R)
+      float s2 = 1.f, s3 = 1.f, kth = 0.f;
+      bool renorm2 = false, renorm3 = false;
+      unsigned long long kt = 0ull;                             // key at sorted position R-1
+      bool fast = false;
+      if (top_k > 0 && min(top_k, V) <= 64) {
+        // ---- fast path (top_k <= 64): the k-th largest probability by a bitwise radix select over the warp
+        // (30 x count-and-reduce), then ONLY the survivors (>= k-th, ties kept: predictor.py:302-306) are compacted
+        // and sorted -- 64 keys, 2 per lane -- for the top-p pass.  Falls back to the full sort when ties push the
+        // survivor count beyond 64.
+        const int k = min(top_k, V);
+        uint32_t bits[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bits[i] = (16 * lane + i) < V ? __float_as_uint(po[i]) : 0u;
+        uint32_t pref = 0u;
+#pragma unroll 1
+        for (int b = 29; b >= 0; --b) {                         // p <= 1.0f = 0x3F800000: bits 31 and 30 are never set
+          const uint32_t cand = pref | (1u << b);
+          int cn = 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) cn += bits[i] >= cand ? 1 : 0;
+          cn = __reduce_add_sync(0xffffffffu, cn);
+          if (cn >= k) pref = cand;
+        }
+        unsigned m16 = 0u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m16 |= (bits[i] >= pref && (16 * lane + i) < V ? 1u : 0u) << i;
+        const int cnt = __popc(m16);
+        const int kp = __reduce_add_sync(0xffffffffu, cnt);     // survivors of top-k (>= k with ties)
+        if (kp <= 64) {
+          fast = true;
+          kth = __uint_as_float(pref);
+          float l2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (po[i] >= kth) l2 += po[i];
+          s2 = warp_sum(l2);
+          renorm2 = s2 > 0.f;
+          if (top_p > 0.0f) {
+            __shared__ unsigned long long cand_s[8][64];
+            unsigned long long* slot = cand_s[warp];
+            slot[lane] = 0ull; slot[lane + 32] = 0ull;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+            int pos = incl - cnt;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if ((m16 >> i) & 1u) slot[pos++] = ((unsigned long long)bits[i] << 32) | (0xFFFFFFFFu - (unsigned)(16 * lane + i));
+            __syncwarp();
+            unsigned long long e[2] = {slot[lane], slot[lane + 32]};      // sorted position t = lane + 32 i after the network
+            __syncwarp();
+#pragma unroll
+            for (int lk = 1; lk <= 6; ++lk) {
+              const int kk = 1 << lk;
+#pragma unroll
+              for (int lj = 5; lj >= 0; --lj) {
+                if (lj >= lk) continue;
+                const int j = 1 << lj;
+                if (j == 32) {                                             // kk == 64: descending over the register pair
+                  const unsigned long long x0 = e[0], x1 = e[1];
+                  const bool sw = x1 > x0;
+                  e[0] = sw ? x1 : x0; e[1] = sw ? x0 : x1;
+                } else {
+                  const bool lower = (lane & j) == 0;
+#pragma unroll
+                  for (int i = 0; i < 2; ++i) {
+                    const bool desc = kk == 64 ? true : (kk == 32 ? i == 0 : (lane & kk) == 0);
+                    const unsigned long long o = shfl_xor_u64(e[i], j);
+                    const bool gt = o > e[i];
+                    e[i] = (gt == (lower == desc)) ? o : e[i];
+                  }
+                }
+              }
+            }
+            // top-p over the sorted survivors (positions >= kp carry probability 0)
+            float v[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              float x = (lane + 32 * i) < kp ? __uint_as_float((unsigned)(e[i] >> 32)) : 0.f;
+              if (renorm2) x = x / s2;
+              v[i] = x;
+            }
+            double tot0, tot1;
+            const double b0 = warp_excl_scan((double)v[0], lane, &tot0);
+            const double b1 = tot0 + warp_excl_scan((double)v[1], lane, &tot1);
+            const bool keep0 = lane < kp && !(lane > 0 && (float)b0 > top_p);
+            const bool keep1 = (lane + 32) < kp && !((float)b1 > top_p);
+            R = __reduce_add_sync(0xffffffffu, (keep0 ? 1 : 0) + (keep1 ? 1 : 0));
+            s3 = warp_sum((keep0 ? v[0] : 0.f) + (keep1 ? v[1] : 0.f));
+            renorm3 = s3 > 0.f;
+            const int rp = max(R, 1) - 1;
+            const unsigned long long sel = rp < 32 ? e[0] : e[1];
+            kt = ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(sel >> 32), rp & 31) << 32) | __shfl_sync(0xffffffffu, (unsigned)sel, rp & 31);
+          }
+        }
+      }
+      if (!fast) {
       // ---- descending sort of (prob, index): key = prob bits (prob >= 0: unsigned order) : ~index
       unsigned long long key[16];
 #pragma unroll
@@ -474,9 +572,6 @@ __global__ void __launch_bounds__(256) sample_select_warp_kernel(const float* __
           }
         }
       }
-      int R = V;                                                // kept entries = sorted positions [0, R)
-      float s2 = 1.f, s3 = 1.f, kth = 0.f;
-      bool renorm2 = false, renorm3 = false;
       if (top_k > 0) {                                          // predictor.py:299-309 (ties with the k-th value are kept)
         const int k = min(top_k, V);
         kth = __uint_as_float((unsigned)(sorted_at(key, k - 1) >> 32));
@@ -514,8 +609,9 @@ __global__ void __launch_bounds__(256) sample_select_warp_kernel(const float* __
         s3 = warp_sum(l3);
         renorm3 = s3 > 0.f;
       }
+      kt = sorted_at(key, max(R, 1) - 1);
+      }
       // ---- back to index order: entry v survives top-p iff its key >= the key at sorted position R-1
-      const unsigned long long kt = sorted_at(key, max(R, 1) - 1);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float v = po[i];
