@@ -28,8 +28,10 @@ def gather_tokens(tokens: torch.Tensor, lengths: torch.Tensor, steps: torch.Tens
     T1 = tokens.shape[1]
     cap = (n_total + ws - 1) // ws
     # ONE collective: rows [0, cap) = (tokens | length) of the shard, row cap = the rank's stop step
-    buf = torch.full((cap + 1, T1 + 1), pad_id, dtype=torch.int64, device=tokens.device)
     b = tokens.shape[0]
+    buf = torch.empty((cap + 1, T1 + 1), dtype=torch.int64, device=tokens.device)
+    if b < cap:
+        buf[b:cap].fill_(pad_id)
     buf[:b, :T1] = tokens
     buf[:b, T1] = lengths
     buf[cap] = steps
@@ -44,4 +46,4 @@ def gather_tokens(tokens: torch.Tensor, lengths: torch.Tensor, steps: torch.Tens
             lo, hi = shard_bounds(n_total, ws, r)
             rows.append(out[r, : hi - lo])
         full = torch.cat(rows, dim=0)
-    return full[:, :T1].contiguous(), full[:, T1].to(torch.int32), gsteps
+    return full[:, :T1], full[:, T1].to(torch.int32), gsteps        # tokens: a view of the gathered buffer
