@@ -88,6 +88,9 @@ SIGNATURES = {
     "i2l_dec_workspace_bytes": (C.c_size_t, [C.POINTER(DecDesc), C.c_int32, C.c_int32]),
     "i2l_decode_step": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp,
                                   C.c_size_t, _fp]),
+    "i2l_dec_forward_workspace_bytes": (C.c_size_t, [C.POINTER(DecDesc), C.c_int32, C.c_int32]),
+    "i2l_decoder_forward": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp, _fp,
+                                      _fp, _fp, C.c_size_t, _fp]),
     "i2l_decode_greedy": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_float, C.c_int32, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "i2l_decode_sample": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -73,7 +73,8 @@ __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 __global__ void lstm_cell_kernel(const float* __restrict__ gates, float* __restrict__ h, float* __restrict__ c,
-                                 int rows, int H, const int* skip, __nv_bfloat16* __restrict__ hb) {
+                                 int rows, int H, const int* skip, __nv_bfloat16* __restrict__ hb,
+                                 float* __restrict__ h_seq, __nv_bfloat16* __restrict__ hb_seq, size_t seq_ld) {
   if (skip != nullptr && *skip != 0) return;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * H) return;
@@ -85,6 +86,9 @@ __global__ void lstm_cell_kernel(const float* __restrict__ gates, float* __restr
   const float hn = og * tanhf(cn);
   h[i] = hn;
   if (hb != nullptr) hb[i] = __float2bfloat16(hn);
+  // teacher-forced forward: the top layer's h of this time step, row r at r * seq_ld
+  if (h_seq != nullptr) h_seq[(size_t)r * seq_ld + j] = hn;
+  if (hb_seq != nullptr) hb_seq[(size_t)r * seq_ld + j] = __float2bfloat16(hn);
 }
 
 __device__ __forceinline__ void warp_argmax(float& v, int& i) {
@@ -1001,10 +1005,11 @@ __global__ void repeat_rows_kernel(const float* __restrict__ src, float* __restr
 }  // namespace
 
 int lstm_cell_f32(const float* gates, float* h, float* c, int rows, int H, const int* skip_flag,
-                  cudaStream_t s, __nv_bfloat16* hb) {
+                  cudaStream_t s, __nv_bfloat16* hb, float* h_seq, __nv_bfloat16* hb_seq, size_t seq_ld) {
   size_t total = (size_t)rows * H;
   if (total == 0) return I2L_OK;
-  lstm_cell_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(gates, h, c, rows, H, skip_flag, hb);
+  lstm_cell_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(gates, h, c, rows, H, skip_flag, hb, h_seq, hb_seq,
+                                                                   seq_ld);
   I2L_LAUNCH_OK();
   return I2L_OK;
 }
@@ -1265,6 +1270,137 @@ extern "C" int i2l_decode_beam(const i2l_dec_desc* d, const void* packed, const 
   beam_finalize_kernel<<<cdiv(batch, 128), 128, 0, s>>>(w.bstate, w.score, trp, trt, batch, K, max_length, end_id,
                                                         out_tokens, out_len, out_score);
   I2L_LAUNCH_OK();
+  return I2L_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Teacher-forced pass over a known token sequence (LSTMDecoder.forward in eval mode,
+// decoder.py:100-195; both of its branches are the recurrence of decode_step -- attention over the
+// single encoder vector is the identity).  Per step: one gate GEMM per layer (token term
+// gathered from Gtok, context term from gctx) + the cell kernel, which also records the top layer's
+// h at [b, t, :]; the vocabulary projection of ALL steps is ONE (B*T, H) x (H, V) GEMM at the end.
+namespace i2l {
+namespace {
+struct FwdWs { DecWs w; int64_t* tok_t; float* h_seq; __nv_bfloat16* hb_seq; size_t bytes; };
+FwdWs carve_fwd(const i2l_dec_desc& d, int batch, int seq_len, void* ws) {
+  FwdWs f{};
+  f.w = carve(d, batch, 1, ws);
+  Arena a(ws, (size_t)-1);
+  a.off = f.w.bytes;
+  const size_t n = (size_t)batch * seq_len;
+  f.tok_t = a.take<int64_t>(n);
+  f.h_seq = a.take<float>(n * d.hidden_dim);
+  f.hb_seq = a.take<__nv_bfloat16>(n * d.hidden_dim);
+  f.bytes = align_up(a.off, 256);
+  return f;
+}
+// (B,T) -> (T,B); ids outside [0,V) raise the device flag (nn.Embedding would raise IndexError) and read row 0
+__global__ void transpose_tokens_kernel(const int64_t* __restrict__ src, int64_t* __restrict__ dst, int B, int T, int V,
+                                        int* bad) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * T) return;
+  int t = (int)(i / B), b = (int)(i % B);
+  int64_t v = src[(size_t)b * T + t];
+  if (v < 0 || v >= V) { if (bad) atomicExch(bad, 1); v = 0; }
+  dst[i] = v;
+}
+}  // namespace
+}  // namespace i2l
+
+extern "C" size_t i2l_dec_forward_workspace_bytes(const i2l_dec_desc* d, int32_t batch, int32_t seq_len) {
+  if (!d || batch <= 0 || seq_len <= 0) return 0;
+  return carve_fwd(*d, batch, seq_len, nullptr).bytes;
+}
+
+extern "C" int i2l_decoder_forward(const i2l_dec_desc* d, const void* packed, const float* enc,
+                                   const int64_t* target, int32_t batch, int32_t seq_len, const float* h_in,
+                                   const float* c_in, float* logits, float* h_out, float* c_out,
+                                   int32_t* bad_token_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  I2L_TRY(check_common(d, packed));
+  I2L_REQUIRE(batch >= 0 && seq_len >= 0, "i2l_decoder_forward: negative sizes");
+  I2L_REQUIRE((h_in == nullptr) == (c_in == nullptr), "i2l_decoder_forward: h_in and c_in must both be given or both NULL");
+  I2L_REQUIRE((h_out == nullptr) == (c_out == nullptr), "i2l_decoder_forward: h_out and c_out must both be given or both NULL");
+  if (batch == 0 || seq_len == 0) return I2L_OK;
+  I2L_REQUIRE(enc && target && logits, "i2l_decoder_forward: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int B = batch, T = seq_len, H = d->hidden_dim, V = d->vocab_size, L = d->lstm_layers;
+  PackedDec lay = dec_layout(*d);
+  FwdWs f = carve_fwd(*d, B, T, workspace);
+  if (workspace_bytes < f.bytes) { set_error("i2l_decoder_forward: workspace too small (%zu < %zu)", workspace_bytes, f.bytes); return I2L_ERR_WORKSPACE; }
+  const DecWs& w = f.w;
+  const float* pk = reinterpret_cast<const float*>(packed);
+  const char* pb = reinterpret_cast<const char*>(packed);
+  const size_t n_state = (size_t)L * B * H * sizeof(float);
+  float *h = w.h[0], *c = w.c[0];
+  if (h_in) {
+    I2L_CUDA_OK(cudaMemcpyAsync(h, h_in, n_state, cudaMemcpyDeviceToDevice, s));
+    I2L_CUDA_OK(cudaMemcpyAsync(c, c_in, n_state, cudaMemcpyDeviceToDevice, s));
+  } else {                                                         // decoder.py:145-158
+    I2L_CUDA_OK(cudaMemsetAsync(h, 0, n_state, s));
+    I2L_CUDA_OK(cudaMemsetAsync(c, 0, n_state, s));
+  }
+  {
+    size_t tot = (size_t)B * T;
+    transpose_tokens_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(target, f.tok_t, B, T, V, bad_token_flag);
+    I2L_LAUNCH_OK();
+  }
+  const bool tc = lay.g16 != 0;
+  KernelTimer kt("dec.forward_teacher", s);
+  if (tc) {
+    I2L_TRY(make_gctx(*d, pk, lay, enc, B, w.gctx, s));       // fp32, as in the general decode loops
+    size_t tot = (size_t)L * B * H;
+    f32_to_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(h, w.hb, tot);
+    I2L_LAUNCH_OK();
+    StepBf16 st;
+    I2L_TRY(make_step_bf16(*d, packed, lay, w, B, nullptr, &st));
+    for (int t = 0; t < T; ++t) {
+      for (int l = 0; l < L; ++l) {
+        GemmBf16 g = st.gates[l];
+        if (l == 0) g.tab_idx = f.tok_t + (size_t)t * B;
+        I2L_TRY(gemm_bf16(g, s));
+        const bool top = l == L - 1;
+        I2L_TRY(lstm_cell_f32(w.gates, h + (size_t)l * B * H, c + (size_t)l * B * H, B, H, nullptr, s,
+                              w.hb + (size_t)l * B * H, nullptr, top ? f.hb_seq + (size_t)t * H : nullptr,
+                              (size_t)T * H));
+      }
+    }
+    GemmBf16 g;
+    g.M = B * T; g.N = V; g.C = logits; g.ldc = V; g.K1 = H;
+    I2L_TRY(gemm_bf16_a_map(&g.tmA1, f.hb_seq, B * T, H, H));
+    I2L_TRY(gemm_bf16_w_map(&g.tmW1, pb + lay.g16_out_w, V, H, H));
+    g.bias = pk + lay.out_b;
+    I2L_TRY(gemm_bf16(g, s));
+  } else {
+    I2L_TRY(make_gctx(*d, pk, lay, enc, B, w.gctx, s));
+    for (int t = 0; t < T; ++t) {
+      for (int l = 0; l < L; ++l) {
+        GemmF32 g;
+        g.M = B; g.N = 4 * H; g.C = w.gates; g.ldc = 4 * H;
+        float* hl = h + (size_t)l * B * H;
+        if (l == 0) {
+          g.A1 = hl; g.lda1 = H; g.W1 = pk + lay.w_hh[0]; g.ldw1 = H; g.K1 = H;
+          g.add_rows = w.gctx; g.ld_add = 4 * H;
+          g.add_table = pk + lay.gtok; g.ld_tab = 4 * H; g.tab_idx = f.tok_t + (size_t)t * B;
+        } else {
+          g.A1 = h + (size_t)(l - 1) * B * H; g.lda1 = H; g.W1 = pk + lay.w_ih[l]; g.ldw1 = H; g.K1 = H;
+          g.A2 = hl; g.lda2 = H; g.W2 = pk + lay.w_hh[l]; g.ldw2 = H; g.K2 = H;
+          g.bias = pk + lay.bsum[l];
+        }
+        I2L_TRY(gemm_f32(g, s));
+        const bool top = l == L - 1;
+        I2L_TRY(lstm_cell_f32(w.gates, hl, c + (size_t)l * B * H, B, H, nullptr, s, nullptr,
+                              top ? f.h_seq + (size_t)t * H : nullptr, nullptr, (size_t)T * H));
+      }
+    }
+    GemmF32 g;
+    g.M = B * T; g.N = V; g.C = logits; g.ldc = V;
+    g.A1 = f.h_seq; g.lda1 = H; g.W1 = pk + lay.out_w; g.ldw1 = H; g.K1 = H; g.bias = pk + lay.out_b;
+    I2L_TRY(gemm_f32(g, s));
+  }
+  if (h_out) {
+    I2L_CUDA_OK(cudaMemcpyAsync(h_out, h, n_state, cudaMemcpyDeviceToDevice, s));
+    I2L_CUDA_OK(cudaMemcpyAsync(c_out, c, n_state, cudaMemcpyDeviceToDevice, s));
+  }
   return I2L_OK;
 }
 

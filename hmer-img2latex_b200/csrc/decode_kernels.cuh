@@ -44,9 +44,11 @@ int make_gctx_bf16(const i2l_dec_desc& d, const void* packed, const PackedDec& l
                    __nv_bfloat16* encb, cudaStream_t s);
 PackedDec dec_layout(const i2l_dec_desc& d);
 
-// hb: optional bf16 copy of the new h (A operand of the next bf16 GEMM)
+// hb: optional bf16 copy of the new h (A operand of the next bf16 GEMM); h_seq / hb_seq: optional extra copies
+// with row stride seq_ld (the (B,T,H) hidden-state record of the teacher-forced forward)
 int lstm_cell_f32(const float* gates, float* h, float* c, int rows, int H, const int* skip_flag,
-                  cudaStream_t s, __nv_bfloat16* hb = nullptr);
+                  cudaStream_t s, __nv_bfloat16* hb = nullptr, float* h_seq = nullptr,
+                  __nv_bfloat16* hb_seq = nullptr, size_t seq_ld = 0);
 
 // persistent bf16 greedy decode (decode_persistent.cu); returns I2L_ERR_UNSUPPORTED for
 // shapes it does not cover so that the caller can take the general path.

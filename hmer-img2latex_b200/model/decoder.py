@@ -114,10 +114,42 @@ class LSTMDecoder(nn.Module):
         return self._ws.get(N.lib().i2l_dec_workspace_bytes(C.byref(d), rows, max_length), device)
 
     # -- reference API ---------------------------------------------------
-    def forward(self, encoder_output, target_sequence, hidden=None):
-        raise NotImplementedError(
-            "teacher-forced training forward (decoder.py:100-195) is outside the inference hot path "
-            "(SURVEY.md 8f-4); use decode_step / the decode loops")
+    def forward(self, encoder_output: torch.Tensor, target_sequence: torch.Tensor, hidden=None,
+                return_hidden: bool = False):
+        """Teacher-forced pass, reference decoder.py:100-195 in eval mode (dropout is the identity; the
+        backward pass stays out of scope): (B,E), (B,T) int64 -> logits (B,T,V).  ``return_hidden=True``
+        additionally returns the final (h, c)."""
+        require_cuda(encoder_output, "LSTMDecoder.forward")
+        if self.training and self.dropout > 0:
+            raise RuntimeError("LSTMDecoder.forward: only the eval-mode forward runs on the native path "
+                               "(call .eval(); training with dropout / autograd is out of scope)")
+        if target_sequence.dim() != 2:
+            raise ValueError(f"target_sequence must be (B,T), got {tuple(target_sequence.shape)}")
+        dev = encoder_output.device
+        with torch.cuda.device(dev):
+            self._ensure_packed(dev)
+            lib, d = N.lib(), self._desc()
+            B, T = target_sequence.shape
+            enc = f32c(encoder_output)
+            tgt = target_sequence.to(device=dev, dtype=torch.int64).contiguous()
+            h_in = c_in = None
+            if hidden is not None:
+                h_in, c_in = f32c(hidden[0]), f32c(hidden[1])
+            logits = torch.empty(B, T, self.vocab_size, dtype=torch.float32, device=dev)
+            h_out = torch.empty(self.lstm_layers, B, self.hidden_dim, dtype=torch.float32, device=dev)
+            c_out = torch.empty_like(h_out)
+            bad = torch.zeros((), dtype=torch.int32, device=dev)
+            wsb = lib.i2l_dec_forward_workspace_bytes(C.byref(d), B, T)
+            ws = self._ws.get(wsb, dev)
+            N.check(lib.i2l_decoder_forward(C.byref(d), N.ptr(self._packed), N.ptr(enc), N.ptr(tgt), B, T,
+                                            N.ptr(h_in), N.ptr(c_in), N.ptr(logits), N.ptr(h_out), N.ptr(c_out),
+                                            N.ptr(bad), N.ptr(ws), ws.numel(), N.stream_ptr(dev)),
+                    "i2l_decoder_forward")
+            if int(bad.item()):                                      # nn.Embedding: IndexError
+                raise IndexError("index out of range in self (token id outside [0, vocab_size))")
+        if return_hidden:
+            return logits, (h_out, c_out)
+        return logits
 
     def decode_step(self, encoder_output: torch.Tensor, input_token: torch.Tensor, hidden=None
                     ) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:

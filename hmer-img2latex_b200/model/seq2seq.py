@@ -53,8 +53,11 @@ class Seq2SeqModel(nn.Module):
         self.decoder.precision = precision
         return self
 
-    def forward(self, images, target_sequences):
-        raise NotImplementedError("training forward (seq2seq.py:98-122) is outside the inference hot path")
+    def forward(self, images: torch.Tensor, target_sequences: torch.Tensor) -> torch.Tensor:
+        """reference seq2seq.py:98-122 in eval mode: encoder, then the teacher-forced decoder pass over
+        ``target_sequences[:, :-1]`` -> logits (B, T-1, V) (validation loss / accuracy, trainer.py:508-533)."""
+        encoder_output = self.encoder(images)
+        return self.decoder(encoder_output, target_sequences[:, :-1])
 
     @torch.no_grad()
     def inference(self, image: torch.Tensor, start_token_id: int, end_token_id: int, max_length: int = None,

@@ -192,6 +192,19 @@ int i2l_decode_step(const i2l_dec_desc* d, const void* packed, const float* enc,
                     int32_t batch, const float* h_in, const float* c_in, float* logits, float* h_out,
                     float* c_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* replaces LSTMDecoder.forward in eval mode (dropout = identity), model/decoder.py:100-195:
+ * the teacher-forced pass over a known token sequence (validation loss / accuracy path,
+ * training/trainer.py:508-533).  enc (B,E) fp32; target (B,T) int64;
+ * h_in/c_in (L,B,H) or NULL (= zeros, decoder.py:145-158); logits (B,T,V) fp32;
+ * h_out/c_out (L,B,H) optional (both or neither).  bad_token_flag: optional device int32 set
+ * to 1 when a token id lies outside [0,V) (nn.Embedding raises IndexError there; the kernel
+ * reads row 0 instead and the host wrapper raises). */
+size_t i2l_dec_forward_workspace_bytes(const i2l_dec_desc* d, int32_t batch, int32_t seq_len);
+int i2l_decoder_forward(const i2l_dec_desc* d, const void* packed, const float* enc, const int64_t* target,
+                        int32_t batch, int32_t seq_len, const float* h_in, const float* c_in, float* logits,
+                        float* h_out, float* c_out, int32_t* bad_token_flag, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* replaces Seq2SeqModel._greedy_search, model/seq2seq.py:192-232 (stop rule
  * ALL_END_SAME_STEP) -- the whole loop runs on the device, no host sync per token.
  * tokens (B, max_length+1) int64, column 0 = start; lengths (B) int32 = position

@@ -25,7 +25,7 @@ __all__ = [
     "make_params", "cnn_encoder", "resnet_encoder", "encoder", "attention",
     "lstm_step", "decode_step", "greedy_search", "inference_postprocess",
     "filter_probs", "sample_loop", "beam_search", "beam_search_batched",
-    "RESNET_LAYERS", "trim_at_end", "inverse_cdf_draw", "normalize_u8",
+    "RESNET_LAYERS", "trim_at_end", "inverse_cdf_draw", "normalize_u8", "decoder_forward", "seq2seq_forward",
 ]
 
 RESNET_LAYERS = {
@@ -292,6 +292,24 @@ def decode_step(p: Params, encoder_output: torch.Tensor, input_token: torch.Tens
     top, hn, cn = lstm_step(p, x, h, c, L)                                     # :247 / :277
     logits = F.linear(top, p["decoder.output_layer.weight"], p["decoder.output_layer.bias"])  # :250/:280
     return logits.unsqueeze(1), (hn, cn)
+
+
+def decoder_forward(p: Params, encoder_output: torch.Tensor, target_sequence: torch.Tensor, cfg: dict,
+                    hidden: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
+    """`LSTMDecoder.forward` in eval mode (decoder.py:100-195: dropout is the identity): the teacher-forced pass
+    over a known token sequence.  encoder_output (B,E), target_sequence (B,T) int64 -> logits (B,T,V).  Both
+    branches of the reference (one nn.LSTM call over the whole sequence without attention, 121-144; a per-step
+    loop with attention over the single encoder vector, 145-193) are the recurrence of `decode_step`."""
+    outs = []
+    for t in range(target_sequence.shape[1]):
+        logits, hidden = decode_step(p, encoder_output, target_sequence[:, t:t + 1], hidden, cfg)
+        outs.append(logits)
+    return torch.cat(outs, dim=1)
+
+
+def seq2seq_forward(p: Params, images: torch.Tensor, target_sequences: torch.Tensor, cfg: dict) -> torch.Tensor:
+    """`Seq2SeqModel.forward` (seq2seq.py:98-122): encoder, then the decoder on target_sequences[:, :-1]."""
+    return decoder_forward(p, encoder(p, images, cfg), target_sequences[:, :-1], cfg)
 
 
 # --------------------------------------------------------------------------

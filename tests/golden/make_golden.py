@@ -122,6 +122,24 @@ def predict_batch_case(name, temperature, top_k, top_p, T=16, B=5):
     save(name, **arrs)
 
 
+@torch.no_grad()
+def teacher_forced_case(name):
+    """Reference `Seq2SeqModel.forward` in eval mode (seq2seq.py:98-122 -> decoder.py:100-195): both decoder
+    branches (per-step loop with attention; one nn.LSTM call over the sequence without)."""
+    arrs = {}
+    for tag, cfg, seed, B, T in (("headline", H.HEADLINE, 1, 3, 12), ("small_l2", H.SMALL, 2, 5, 9),
+                                 ("small_l2_noattn", dict(H.SMALL, attention=False), 2, 5, 9)):
+        p = oracle.make_params(cfg, seed, sharp=True)
+        m = ref_shim.build_reference_model(cfg, p)
+        x = H.make_images(cfg, B)
+        tgt = torch.randint(0, cfg["vocab_size"], (B, T + 1), generator=torch.Generator().manual_seed(21))
+        arrs[f"{tag}_checksum"] = checksum(p, x)
+        arrs[f"{tag}_target"] = tgt
+        arrs[f"{tag}_logits"] = m(x, tgt)
+        arrs[f"{tag}_meta"] = np.array([seed, B, T])
+    save(name, **arrs)
+
+
 def load_image_case(name):
     """Reference `load_image` (data/utils.py:18-90) on PNG files whose size already equals the
     target size (ResizeWithAspectRatio is then the identity, transforms.py:38-43)."""
@@ -148,6 +166,7 @@ if __name__ == "__main__":
     resnet_case("resnet50.npz", H.R50, [96])
     attention_case("attention_L5.npz")
     load_image_case("load_image.npz")
+    teacher_forced_case("teacher_forced.npz")
     predict_batch_case("predict_batch_greedy.npz", 1.0, 0, 0.0)
     predict_batch_case("predict_batch_topk_topp.npz", 0.8, 5, 0.9)
     predict_batch_case("predict_batch_topp.npz", 1.2, 0, 0.7)

@@ -1,0 +1,84 @@
+"""Teacher-forced decoder pass (`LSTMDecoder.forward` / `Seq2SeqModel.forward` in eval mode,
+reference decoder.py:100-195, seq2seq.py:98-122) through the C-ABI
+(`i2l_decoder_forward`) against the CPU oracle and the live-reference golden vectors.
+fp32: logits within 1e-3 relative.  bf16: within 3e-2 of max|logit| (stated bf16 tolerance)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from helpers import oracle
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("tag,cfg", [("headline", H.HEADLINE), ("small_l2", H.SMALL),
+                                     ("small_l2_noattn", dict(H.SMALL, attention=False))])
+def test_forward_matches_reference_golden(pkg, tag, cfg):
+    d = np.load(os.path.join(G, "teacher_forced.npz"))
+    seed, B, T = (int(v) for v in d[f"{tag}_meta"])
+    p = oracle.make_params(cfg, seed, sharp=True)
+    m = H.build_model(pkg, cfg, p)
+    x = H.make_images(cfg, B)
+    tgt = torch.as_tensor(d[f"{tag}_target"])
+    out = m(x.cuda(), tgt.cuda())
+    assert out.shape == (B, T, cfg["vocab_size"])
+    assert H.rel_err(out, torch.as_tensor(d[f"{tag}_logits"])) < 1e-3
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 3e-2)])
+@pytest.mark.parametrize("cfg,B,T", [(H.HEADLINE, 37, 24), (H.SMALL, 9, 17)])
+def test_forward_vs_oracle(pkg, precision, tol, cfg, B, T):
+    p = oracle.make_params(cfg, 4, sharp=True)
+    m = H.build_model(pkg, cfg, p, precision=precision)
+    g = torch.Generator().manual_seed(8)
+    enc = torch.randn(B, cfg["embedding_dim"], generator=g).relu()
+    tgt = torch.randint(0, cfg["vocab_size"], (B, T), generator=g)
+    L, Hd = cfg["lstm_layers"], cfg["hidden_dim"]
+    h0, c0 = torch.randn(L, B, Hd, generator=g) * 0.3, torch.randn(L, B, Hd, generator=g) * 0.3
+    for hidden in (None, (h0, c0)):
+        ref = oracle.decoder_forward(p, enc, tgt, cfg, hidden)
+        hid = None if hidden is None else (h0.cuda(), c0.cuda())
+        out, (h, c) = m.decoder(enc.cuda(), tgt.cuda(), hid, return_hidden=True)
+        assert H.rel_err(out, ref) < tol
+        # the final state equals T chained decode_step calls
+        hh = hidden
+        for t in range(T):
+            _, hh = oracle.decode_step(p, enc, tgt[:, t:t + 1], hh, cfg)
+        assert H.rel_err(h, hh[0]) < tol and H.rel_err(c, hh[1]) < tol
+
+
+def test_forward_consistent_with_decode_step(pkg):
+    """One teacher-forced pass == the chain of decode_step calls on the same tokens (fp32, same kernels)."""
+    cfg = H.SMALL
+    p = oracle.make_params(cfg, 1)
+    m = H.build_model(pkg, cfg, p)
+    g = torch.Generator().manual_seed(2)
+    B, T = 4, 6
+    enc = torch.randn(B, cfg["embedding_dim"], generator=g).cuda()
+    tgt = torch.randint(0, cfg["vocab_size"], (B, T), generator=g).cuda()
+    out = m.decoder(enc, tgt)
+    hid, rows = None, []
+    for t in range(T):
+        lg, hid = m.decoder.decode_step(enc, tgt[:, t:t + 1], hid)
+        rows.append(lg)
+    assert H.rel_err(out, torch.cat(rows, 1)) < 1e-5
+
+
+def test_forward_edge_cases(pkg):
+    cfg = H.SMALL
+    p = oracle.make_params(cfg, 1)
+    m = H.build_model(pkg, cfg, p)
+    enc = torch.zeros(3, cfg["embedding_dim"], device="cuda")
+    assert m.decoder(enc, torch.zeros(3, 0, dtype=torch.long, device="cuda")).shape == (3, 0, cfg["vocab_size"])
+    assert m.decoder(enc[:0], torch.zeros(0, 5, dtype=torch.long, device="cuda")).shape == (0, 5, cfg["vocab_size"])
+    bad = torch.full((3, 4), cfg["vocab_size"], dtype=torch.long, device="cuda")
+    with pytest.raises(IndexError):                     # nn.Embedding's behaviour in the reference
+        m.decoder(enc, bad)
+    m.train()
+    with pytest.raises(RuntimeError, match="eval"):
+        m.decoder(enc, bad)

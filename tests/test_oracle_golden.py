@@ -159,3 +159,20 @@ def test_fused_affine_equals_reference_after_bf16():
         b = -m32 / s32
         fused = (x.flatten().double() * float(a) + float(b)).float()
         assert torch.equal(ref3[0, c].flatten().bfloat16(), fused.bfloat16())
+
+
+@pytest.mark.parametrize("tag,cfg", [("headline", H.HEADLINE), ("small_l2", H.SMALL),
+                                     ("small_l2_noattn", dict(H.SMALL, attention=False))])
+def test_teacher_forced_golden(tag, cfg):
+    """`Seq2SeqModel.forward` of the live reference in eval mode (both decoder branches) against the
+    restated recurrence (oracle.seq2seq_forward)."""
+    d = load("teacher_forced.npz")
+    seed, B, T = (int(v) for v in d[f"{tag}_meta"])
+    p = oracle.make_params(cfg, seed, sharp=True)
+    x = H.make_images(cfg, B)
+    check_inputs(d, p, x, key=f"{tag}_checksum")
+    tgt = torch.as_tensor(d[f"{tag}_target"])
+    with torch.no_grad():
+        out = oracle.seq2seq_forward(p, x, tgt, cfg)
+    assert out.shape == (B, T, cfg["vocab_size"])
+    close(out, d[f"{tag}_logits"])
