@@ -24,6 +24,8 @@ STOP_NONE, STOP_ALL_END_SAME_STEP, STOP_ALL_FINISHED_STICKY = 0, 1, 2
 PRECISIONS = {"fp32": FP32, "bf16": BF16}
 IN_F32, IN_BF16, IN_U8 = 0, 1, 2
 NORM_PM1, NORM_MEANSTD = 0, 1
+FILTER_LANCZOS, FILTER_BICUBIC = 0, 1
+RESIZE_ASPECT_PAD_CROP, RESIZE_STRETCH = 0, 1
 
 _fp = C.c_void_p  # all device pointers travel as void*
 
@@ -47,6 +49,10 @@ class ResnetParams(C.Structure):
     _fields_ = [("n_convs", C.c_int32), ("conv_w", _fp * MAX_RESNET_CONVS), ("bn_weight", _fp * MAX_RESNET_CONVS),
                 ("bn_bias", _fp * MAX_RESNET_CONVS), ("bn_mean", _fp * MAX_RESNET_CONVS),
                 ("bn_var", _fp * MAX_RESNET_CONVS), ("fc_w", _fp), ("fc_b", _fp)]
+
+
+class ImageDesc(C.Structure):
+    _fields_ = [("src_offset", C.c_int64), ("height", C.c_int32), ("width", C.c_int32)]
 
 
 class DecDesc(C.Structure):
@@ -74,6 +80,12 @@ SIGNATURES = {
                                          C.c_int32, _fp, _fp, C.c_size_t, _fp]),
     "i2l_normalize_u8": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_float), C.POINTER(C.c_float), _fp, C.c_int32, _fp]),
+    "i2l_resize_plan_bytes": (C.c_size_t, [C.POINTER(ImageDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_int32]),
+    "i2l_resize_plan_build": (C.c_int, [C.POINTER(ImageDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, _fp, C.c_size_t]),
+    "i2l_resize_workspace_bytes": (C.c_size_t, [_fp]),
+    "i2l_resize_pad_u8": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "i2l_resnet_num_convs": (C.c_int32, [C.c_int32]),
     "i2l_resnet_packed_bytes": (C.c_size_t, [C.POINTER(ResnetDesc)]),
     "i2l_resnet_pack": (C.c_int, [C.POINTER(ResnetDesc), C.POINTER(ResnetParams), _fp, C.c_size_t, _fp]),

@@ -2,17 +2,23 @@
 hot path: ``predict`` / ``predict_batch`` on image *tensors* with the reference's loop
 semantics (sampling only when temperature > 0 and (top_k > 0 or top_p > 0), sticky
 finished flags, cut at the first END, beam clamped to greedy -- predictor.py:163-167,
-231-235).  File / PIL loading (``_prepare_image`` 396-462) is host-side I/O outside the
-hot path; tensors of the wrong size are resized bilinearly as in ``_preprocess_tensor``
-(464-499) but to the MODEL's size (the reference hard-codes 64x800)."""
+231-235).  ``_prepare_image`` (396-462) takes the reference's four input kinds: paths go
+through the batched device-side ``load_image`` (aspect-preserving LANCZOS resize + pad / crop +
+normalisation, ``preprocess.load_images``), PIL images through the device-side plain resize
+(Pillow's default bicubic) and x/255*2-1, arrays / tensors of the wrong size are resized bilinearly
+as in ``_preprocess_tensor`` (464-499).  Every branch resizes to the MODEL's size (the reference
+hard-codes 64x800); only file decoding runs on the host."""
 from __future__ import annotations
 
 import logging
 from typing import List, Optional, Sequence, Union
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import preprocess as P
+from .model.encoder import normalize_u8
 from .model.seq2seq import Seq2SeqModel
 from .tokenizer import LaTeXTokenizer
 
@@ -40,16 +46,69 @@ class Predictor:
         model.load_state_dict(ck["model_state_dict"])
         return cls(model, tok, device)
 
-    def _prepare_image(self, image: torch.Tensor) -> torch.Tensor:
-        if not isinstance(image, torch.Tensor):
-            raise TypeError(f"Unsupported image type: {type(image)} (tensor inputs only on the hot path)")  # cf. predictor.py:448-452
+    def _prepare_image(self, image) -> torch.Tensor:
+        """predictor.py:396-462 for one input; see `_prepare_images` for the batched form."""
+        return self._prepare_images([image])
+
+    def _prepare_images(self, images: Sequence) -> torch.Tensor:
+        """predictor.py:396-462 applied to a chunk: (n, C, H, W) fp32 on the device.  Inputs of one kind are
+        prepared together (one H2D copy + two launches for all paths / all PIL images of the chunk)."""
         enc = self.model.encoder
-        x = image.to(self.device, dtype=torch.float32)
-        if x.dim() == 3:
-            x = x.unsqueeze(0)
-        if x.shape[-2:] != (enc.img_height, enc.img_width):
-            x = F.interpolate(x, size=(enc.img_height, enc.img_width), mode="bilinear", align_corners=False)
-        return x
+        size, channels = (enc.img_height, enc.img_width), enc.channels
+        out: List[Optional[torch.Tensor]] = [None] * len(images)
+        paths = [i for i, im in enumerate(images) if isinstance(im, str)]
+        pils = [i for i, im in enumerate(images)
+                if not isinstance(im, (str, torch.Tensor, np.ndarray)) and hasattr(im, "mode") and hasattr(im, "size")]
+        if paths:                                                  # predictor.py:417-419 -> data/utils.py:18-90
+            arrs = [P.open_image(images[i], channels) for i in paths]
+            for mode_gray in (True, False):                        # a chunk may mix L and RGB files
+                sel = [j for j, a in enumerate(arrs) if (a.ndim == 2) == mode_gray]
+                if sel:
+                    x = P.load_images([arrs[j] for j in sel], size, channels, device=self.device)
+                    for j, row in zip(sel, x):
+                        out[paths[j]] = row
+        if pils:                                                   # predictor.py:427-446
+            arrs = []
+            for i in pils:
+                im = images[i]
+                if channels == 1 and im.mode != "L":
+                    im = im.convert("L")
+                elif channels == 3 and im.mode != "RGB":
+                    im = im.convert("RGB")
+                arrs.append(np.asarray(im))
+            u8 = P.ResizePlan(arrs, size[0], size[1], resample="bicubic", mode="stretch").run(self.device)
+            x = normalize_u8(u8, "pm1")
+            for i, row in zip(pils, x):
+                out[i] = row
+        for i, im in enumerate(images):
+            if out[i] is not None:
+                continue
+            if isinstance(im, np.ndarray):                         # predictor.py:423-426, 500-520
+                a = im
+                if a.ndim == 2:
+                    a = a[None]
+                elif a.ndim == 3 and a.shape[0] not in (1, 3):
+                    a = np.transpose(a, (2, 0, 1))
+                im = torch.from_numpy(np.ascontiguousarray(a)).float()
+            if not isinstance(im, torch.Tensor):
+                raise TypeError(f"Unsupported image type: {type(im)}. Expected str, torch.Tensor, numpy.ndarray, "
+                                f"or PIL.Image.Image.")            # predictor.py:448-452
+            x = im.to(self.device, dtype=torch.float32)
+            if x.dim() == 2:
+                x = x.unsqueeze(0)
+            if x.dim() == 3:
+                x = x.unsqueeze(0)
+            if x.shape[-2:] != size:                               # predictor.py:483-492
+                x = F.interpolate(x, size=size, mode="bilinear", align_corners=False)
+            needs = (x.amin() < 0) | (x.amax() > 1)                 # predictor.py:494-497, decided on the device
+            x = torch.where(needs, (x / 255.0) * 2.0 - 1.0, x)
+            out[i] = x[0]
+        rows = []
+        for r in out:
+            if self.model.model_type == "resnet_lstm" and r.shape[0] == 1:          # predictor.py:454-456
+                r = r.repeat(3, 1, 1)
+            rows.append(r)
+        return torch.stack(rows)
 
     @torch.no_grad()
     def predict_batch(self, images: Union[torch.Tensor, Sequence[torch.Tensor]], beam_size: int = 0,
@@ -64,7 +123,7 @@ class Predictor:
         n = len(images)
         for i in range(0, n, batch_size):                          # predictor.py:240-246
             chunk = images[i:i + batch_size]
-            batch = torch.cat([self._prepare_image(im) for im in chunk], dim=0)
+            batch = self._prepare_images(list(chunk))
             enc = self.model.encoder(batch)
             u = None if uniforms is None else uniforms[:, i:i + batch.shape[0]]
             tokens, lengths, steps = self.model.decoder.sample(enc, start, end, max_length, temperature, top_k, top_p,

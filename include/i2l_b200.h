@@ -118,6 +118,39 @@ int i2l_cnn_encoder_fwd_u8(const i2l_cnn_desc* d, const void* packed, const uint
                            size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Image geometry on the device -- replaces the PIL calls of load_image           */
+/* (data/utils.py:37-48) and Predictor._prepare_image (training/predictor.py:     */
+/* 427-436) for a RAGGED batch of uint8 images: optional convert("L"), Pillow     */
+/* resize (8-bit resampler, bit-exact), then ResizeWithAspectRatio's white right  */
+/* padding / centre crop (data/transforms.py:26-56).  SURVEY 8f-1.                */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int64_t src_offset;      /* byte offset of the image inside the packed source buffer            */
+  int32_t height, width;   /* source size; pixels are HWC interleaved uint8 (np.array(PIL image)) */
+} i2l_image_desc;
+typedef enum { I2L_FILTER_LANCZOS = 0, I2L_FILTER_BICUBIC = 1 } i2l_resize_filter;
+typedef enum {
+  I2L_RESIZE_ASPECT_PAD_CROP = 0, /* ResizeWithAspectRatio.__call__, data/transforms.py:26-56: new_w = round(Ht*w/h),
+                                     resize to (new_w,Ht), pad right with Image.new(mode,size,255) (L: white; RGB: (255,0,0), as Pillow reads the int) or centre-crop to Wt; h == 0 => all padding */
+  I2L_RESIZE_STRETCH = 1          /* image.resize((Wt,Ht)), training/predictor.py:436 (Pillow's default filter = BICUBIC) */
+} i2l_resize_mode;
+
+/* HOST side, no CUDA: the plan holds per-image geometry and the fixed-point filter weights, computed in
+ * double precision exactly like Pillow's precompute_coeffs / normalize_coeffs_8bpc.  The caller copies the
+ * plan to the device next to the pixels (one H2D), keeps the host copy for the launch call.
+ * Errors: an image whose resized width would be 0 (Pillow: ValueError) => I2L_ERR_INVALID. */
+size_t i2l_resize_plan_bytes(const i2l_image_desc* imgs, int32_t n, int32_t src_channels, int32_t to_gray,
+                             int32_t target_h, int32_t target_w, int32_t filter, int32_t mode);   /* 0 on error */
+int i2l_resize_plan_build(const i2l_image_desc* imgs, int32_t n, int32_t src_channels, int32_t to_gray,
+                          int32_t target_h, int32_t target_w, int32_t filter, int32_t mode, void* plan_host,
+                          size_t plan_bytes);
+size_t i2l_resize_workspace_bytes(const void* plan_host);
+/* src: packed uint8 source images (device); dst: (n, C_out, target_h, target_w) uint8 NCHW (device), the input
+ * layout of i2l_normalize_u8 / i2l_cnn_encoder_fwd_u8.  Two launches for the whole batch, no host sync. */
+int i2l_resize_pad_u8(const uint8_t* src, const void* plan_host, const void* plan_dev, uint8_t* dst,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* ResNet encoder -- replaces ResNetEncoder.forward, model/encoder.py:231-249   */
 /* (torchvision trunk minus fc, model/encoder.py:184-199; eval-mode BN folded). */
 /* ------------------------------------------------------------------------- */

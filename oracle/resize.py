@@ -45,12 +45,28 @@ def _lanczos(x: float) -> float:
     return 0.0
 
 
-def lanczos_coeffs(in_size: int, out_size: int) -> Tuple[int, np.ndarray, np.ndarray]:
+def _bicubic(x: float) -> float:
+    """Resample.c bicubic_filter (Keys, a = -0.5, support 2): Pillow's default for `Image.resize(size)`."""
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+_FILTERS = {"lanczos": (_lanczos, LANCZOS_SUPPORT), "bicubic": (_bicubic, 2.0)}
+
+
+def lanczos_coeffs(in_size: int, out_size: int, resample: str = "lanczos") -> Tuple[int, np.ndarray, np.ndarray]:
     """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the full box (in0 = 0, in1 = in_size).
     Returns ksize, bounds (out_size, 2) int32 = (xmin, count), kk (out_size, ksize) int32."""
+    _filter, fsupport = _FILTERS[resample]
     scale = float(in_size) / out_size
     filterscale = max(scale, 1.0)
-    support = LANCZOS_SUPPORT * filterscale
+    support = fsupport * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
     bounds = np.zeros((out_size, 2), np.int32)
     kk = np.zeros((out_size, ksize), np.int32)
@@ -64,7 +80,7 @@ def lanczos_coeffs(in_size: int, out_size: int) -> Tuple[int, np.ndarray, np.nda
         if xmax > in_size:
             xmax = in_size
         xmax -= xmin
-        w = [_lanczos((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        w = [_filter((x + xmin - center + 0.5) * ss) for x in range(xmax)]
         ww = 0.0
         for v in w:
             ww += v
@@ -79,10 +95,10 @@ def _clip8(acc: np.ndarray) -> np.ndarray:
     return np.clip(acc >> PRECISION_BITS, 0, 255).astype(np.uint8)       # arithmetic shift, clip8_lookups
 
 
-def _pass(img: np.ndarray, out_size: int, axis: int) -> np.ndarray:
+def _pass(img: np.ndarray, out_size: int, axis: int, resample: str = "lanczos") -> np.ndarray:
     """One resampling pass along `axis` of an (H, W, C) uint8 array."""
     in_size = img.shape[axis]
-    _, bounds, kk = lanczos_coeffs(in_size, out_size)
+    _, bounds, kk = lanczos_coeffs(in_size, out_size, resample)
     src = np.moveaxis(img, axis, 0).astype(np.int64)
     out = np.empty((out_size,) + src.shape[1:], np.uint8)
     for xx in range(out_size):
@@ -93,8 +109,9 @@ def _pass(img: np.ndarray, out_size: int, axis: int) -> np.ndarray:
     return np.moveaxis(out, 0, axis)
 
 
-def resize_lanczos_u8(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
-    """`Image.resize((out_w, out_h), LANCZOS)` for modes L / RGB.  img: (H, W) or (H, W, C) uint8.
+def resize_lanczos_u8(img: np.ndarray, out_w: int, out_h: int, resample: str = "lanczos") -> np.ndarray:
+    """`Image.resize((out_w, out_h), LANCZOS)` for modes L / RGB (resample="bicubic": `Image.resize(size)`,
+    the PIL branch of Predictor._prepare_image, training/predictor.py:436).  img: (H, W) or (H, W, C) uint8.
     Resample.c ImagingResample: horizontal pass first (skipped when the width is unchanged), then the
     vertical pass (skipped when the height is unchanged)."""
     squeeze = img.ndim == 2
@@ -102,9 +119,9 @@ def resize_lanczos_u8(img: np.ndarray, out_w: int, out_h: int) -> np.ndarray:
     if out_w <= 0 or out_h <= 0:
         raise ValueError("height and width must be > 0")                 # Pillow raises ValueError
     if a.shape[1] != out_w:
-        a = _pass(a, out_w, 1)
+        a = _pass(a, out_w, 1, resample)
     if a.shape[0] != out_h:
-        a = _pass(a, out_h, 0)
+        a = _pass(a, out_h, 0, resample)
     a = np.ascontiguousarray(a)
     return a[:, :, 0] if squeeze else a
 
@@ -114,17 +131,29 @@ def aspect_width(width: int, height: int, target_height: int) -> int:
     return int(round(target_height * (width / height)))
 
 
+def _blank(img: np.ndarray, target_height: int, target_width: int) -> np.ndarray:
+    """`Image.new(img.mode, size, 255)` (transforms.py:29,45-47): for mode L that is white, but for mode RGB
+    Pillow reads the integer colour 255 as 0x0000FF = (R=255, G=0, B=0) -- the reference pads RGB images
+    with RED (pinned by tests/golden/resize.npz)."""
+    out = np.zeros((target_height, target_width) + img.shape[2:], np.uint8)
+    if img.ndim == 2:
+        out[:] = 255
+    else:
+        out[:, :, 0] = 255
+    return out
+
+
 def resize_with_aspect_ratio(img: np.ndarray, target_height: int, target_width: int) -> np.ndarray:
     """transforms.py:26-56 on an (H, W) / (H, W, C) uint8 array."""
     height, width = img.shape[0], img.shape[1]
     if height == 0:                                                      # transforms.py:28-29
-        return np.full((target_height, target_width) + img.shape[2:], 255, np.uint8)
+        return _blank(img, target_height, target_width)
     new_width = aspect_width(width, height, target_height)
     r = resize_lanczos_u8(img, new_width, target_height)
     if new_width == target_width:
         return r
-    if new_width < target_width:                                         # white right padding, 44-50
-        out = np.full((target_height, target_width) + img.shape[2:], 255, np.uint8)
+    if new_width < target_width:                                         # right padding, 44-50
+        out = _blank(img, target_height, target_width)
         out[:, :new_width] = r
         return out
     left = (new_width - target_width) // 2                               # centre crop, 51-56

@@ -157,6 +157,61 @@ def load_image_case(name):
     save(name, rgb=rgb, gray=gray, out_rgb=out_rgb, out_gray=out_gray)
 
 
+def formula_like(rng, h, w, c):
+    """White page with dark strokes and a little grey (compressible, but exercises ringing / clipping)."""
+    a = np.full((h, w, c), 255, np.uint8)
+    for _ in range(max(1, (h * w) // 150)):
+        y, x = int(rng.integers(0, h)), int(rng.integers(0, w))
+        dh, dw = int(rng.integers(1, max(2, h // 4))), int(rng.integers(1, max(2, w // 8)))
+        a[y:y + dh, x:x + dw] = rng.integers(0, 120, size=c if rng.random() < 0.3 else 1)
+    return a if c == 3 else a[:, :, 0]
+
+
+def resize_case(name):
+    """Reference `ResizeWithAspectRatio` (data/transforms.py:9-56; live Pillow), `load_image`
+    (data/utils.py:18-90, through PNG files) and the PIL branch of `Predictor._prepare_image`
+    (training/predictor.py:427-446) on seeded ragged images."""
+    import tempfile
+    from PIL import Image
+    RWA = ref_shim.reference_module("img2latex.data.transforms").ResizeWithAspectRatio
+    load_image = ref_shim.reference_module("img2latex.data.utils").load_image
+    rng = np.random.default_rng(12)
+    arrs = {}
+    # (h, w, channels): pad, crop, identity width, identity height, up- and down-scaling, 1-pixel edges
+    sizes = [(20, 90, 1), (50, 400, 1), (64, 300, 1), (33, 700, 1), (100, 330, 1), (7, 9, 1), (1, 40, 1), (40, 1, 1),
+             (16, 100, 1), (30, 160, 3), (80, 200, 3), (12, 300, 3), (64, 64, 3), (45, 211, 3)]
+    TH, TW = 32, 160
+    shapes, flat, outs_l, outs_rgb = [], [], [], []
+    for i, (h, w, c) in enumerate(sizes):
+        a = formula_like(rng, h, w, c) if i % 3 else rng.integers(0, 256, size=(h, w, c) if c == 3 else (h, w), dtype=np.uint8)
+        shapes.append((h, w, c)); flat.append(a.reshape(-1))
+        img = Image.fromarray(a, "L" if c == 1 else "RGB")
+        out = np.array(RWA(TH, TW)(img))
+        (outs_l if c == 1 else outs_rgb).append(out)
+    arrs.update(shapes=np.array(shapes), pixels=np.concatenate(flat), target=np.array([TH, TW]),
+                out_l=np.stack(outs_l), out_rgb=np.stack(outs_rgb))
+    # load_image through files: RGB file read with channels=1 (convert L on the way) and channels=3 (ImageNet norm)
+    with tempfile.TemporaryDirectory() as td:
+        li = []
+        for j, (h, w) in enumerate([(24, 150), (50, 90)]):
+            a = formula_like(rng, h, w, 3)
+            Image.fromarray(a, "RGB").save(os.path.join(td, f"f{j}.png"))
+            arrs[f"file{j}"] = a
+            arrs[f"file{j}_load1"] = load_image(os.path.join(td, f"f{j}.png"), (TH, TW), 1)
+            arrs[f"file{j}_load3"] = load_image(os.path.join(td, f"f{j}.png"), (TH, TW), 3)
+    # PIL branch of _prepare_image: plain resize with Pillow's default filter (bicubic), /255*2-1
+    ref = ref_shim.load()
+    cfg = dict(model_type="cnn_lstm", vocab_size=46, embedding_dim=32, hidden_dim=48, lstm_layers=1, attention=True,
+               img_height=64, img_width=800, channels=1, conv_filters=[4, 8, 8])
+    m = ref_shim.build_reference_model(cfg, oracle.make_params(cfg, 3))
+    tok = ref["LaTeXTokenizer"](); tok.default_init()
+    pred = ref["Predictor"](m, tok, device=torch.device("cpu"), model_type="cnn_lstm")
+    a = formula_like(rng, 40, 230, 3)
+    arrs["pil_in"] = a
+    arrs["pil_prepared"] = pred._prepare_image(Image.fromarray(a, "RGB"))        # (1,1,64,800) fp32
+    save(name, **arrs)
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "the live reference is needed to (re)generate golden vectors"
     seq2seq_case("cnn_headline_sharp.npz", H.HEADLINE, seed=1, sharp=True, B=4, T=30)
@@ -167,6 +222,7 @@ if __name__ == "__main__":
     attention_case("attention_L5.npz")
     load_image_case("load_image.npz")
     teacher_forced_case("teacher_forced.npz")
+    resize_case("resize.npz")
     predict_batch_case("predict_batch_greedy.npz", 1.0, 0, 0.0)
     predict_batch_case("predict_batch_topk_topp.npz", 0.8, 5, 0.9)
     predict_batch_case("predict_batch_topp.npz", 1.2, 0, 0.7)

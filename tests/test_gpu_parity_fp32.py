@@ -183,8 +183,10 @@ def test_predict_batch_strings(pkg):
     tok = pkg.LaTeXTokenizer(); tok.default_init()
     assert tok.vocab_size == 46
     pred = pkg.Predictor(m, tok)
-    x = H.make_images(cfg, 6)
-    enc_ref = oracle.encoder(p, x, cfg)
+    x = H.make_images(cfg, 6) * 40.0
+    x[4] = x[4].abs().clamp(max=1.0)          # already in [0,1]: left untouched by _preprocess_tensor (predictor.py:494-497)
+    x_ref = torch.stack([xi if (xi.min() >= 0 and xi.max() <= 1) else (xi / 255.0) * 2.0 - 1.0 for xi in x])
+    enc_ref = oracle.encoder(p, x_ref, cfg)
     _, trimmed, _ = oracle.sample_loop(p, enc_ref, H.START, H.END, 20, 1.0, 0, 0.0, cfg)
     got = pred.predict_batch(list(x), max_length=20, batch_size=4, return_ids=True)
     assert got == [t[1:] for t in trimmed]

@@ -176,3 +176,66 @@ def test_teacher_forced_golden(tag, cfg):
         out = oracle.seq2seq_forward(p, x, tgt, cfg)
     assert out.shape == (B, T, cfg["vocab_size"])
     close(out, d[f"{tag}_logits"])
+
+
+def _resize_golden_images(d):
+    out, off = [], 0
+    for h, w, c in d["shapes"]:
+        n = int(h) * int(w) * int(c)
+        a = d["pixels"][off:off + n]
+        out.append(a.reshape(h, w, c) if c == 3 else a.reshape(h, w))
+        off += n
+    return out
+
+
+def test_resize_with_aspect_ratio_golden():
+    """oracle/resize.py (Pillow's 8-bit resampler restated) against the reference's ResizeWithAspectRatio run on
+    live Pillow: identical bytes."""
+    d = load("resize.npz")
+    TH, TW = (int(v) for v in d["target"])
+    imgs = _resize_golden_images(d)
+    got = [oracle.resize.resize_with_aspect_ratio(a, TH, TW) for a in imgs]
+    assert np.array_equal(np.stack([g for g in got if g.ndim == 2]), d["out_l"])
+    assert np.array_equal(np.stack([g for g in got if g.ndim == 3]), d["out_rgb"])
+
+
+def test_load_image_geometry_golden():
+    """Reference load_image through PNG files (convert -> resize/pad -> /255 -> normalise) restated end to end."""
+    d = load("resize.npz")
+    TH, TW = (int(v) for v in d["target"])
+    for j in range(2):
+        rgb = d[f"file{j}"]
+        g = oracle.resize.resize_with_aspect_ratio(oracle.resize.rgb_to_l(rgb), TH, TW)
+        assert torch.equal(oracle.normalize_u8(torch.from_numpy(g)[None], "pm1"), torch.from_numpy(d[f"file{j}_load1"]))
+        c = oracle.resize.resize_with_aspect_ratio(rgb, TH, TW)
+        out3 = oracle.normalize_u8(torch.from_numpy(c).permute(2, 0, 1).contiguous(), "meanstd")
+        assert torch.equal(out3, torch.from_numpy(d[f"file{j}_load3"]))
+    # PIL branch of Predictor._prepare_image: convert L, plain bicubic stretch to 64x800, /255*2-1
+    g = oracle.resize.resize_lanczos_u8(oracle.resize.rgb_to_l(d["pil_in"]), 800, 64, "bicubic")
+    assert torch.equal(oracle.normalize_u8(torch.from_numpy(g)[None, None], "pm1"), torch.from_numpy(d["pil_prepared"]))
+
+
+def test_resize_plan_host_tables(pkg):
+    """Host half of the C-ABI resize path (i2l_resize_plan_build, no GPU needed): geometry and 22-bit filter
+    tables of a ragged batch equal the oracle's restatement of Pillow's precompute_coeffs."""
+    P = pkg.preprocess
+    d = load("resize.npz")
+    TH, TW = (int(v) for v in d["target"])
+    imgs = [a for a in _resize_golden_images(d) if a.ndim == 2]
+    for resample in ("lanczos", "bicubic"):
+        plan = P.ResizePlan(imgs, TH, TW, resample=resample)
+        for a, pl in zip(imgs, plan.describe()):
+            nw = oracle.resize.aspect_width(a.shape[1], a.shape[0], TH)
+            assert (pl["new_w"], pl["new_h"]) == (nw, TH)
+            assert pl["left"] == (max(nw - TW, 0) // 2) and pl["kept_w"] == min(nw, TW)
+            for tag, n_in, n_out in (("h", a.shape[1], nw), ("v", a.shape[0], TH)):
+                if n_in == n_out:
+                    assert pl[f"weights_{tag}"] is None          # Resample.c: identity pass is skipped
+                    continue
+                ks, bnd, kk = oracle.resize.lanczos_coeffs(n_in, n_out, resample)
+                assert np.array_equal(pl[f"bounds_{tag}"], bnd)
+                assert np.array_equal(pl[f"weights_{tag}"][:, :ks], kk) and not pl[f"weights_{tag}"][:, ks:].any()
+    with pytest.raises(ValueError):                               # Pillow: "height and width must be > 0"
+        P.ResizePlan([np.zeros((200, 1), np.uint8)], 16, 100)
+    white = P.ResizePlan([np.zeros((0, 7), np.uint8)], 16, 100).describe()[0]
+    assert white["kept_w"] == 0                                   # transforms.py:28-29: all-white output
