@@ -4,11 +4,11 @@ Hand-written CUDA kernels behind a C-ABI (include/i2l_b200.h); PyTorch only prov
 device memory, streams and torch.distributed.  CUDA only: no CPU fallback."""
 from . import _native
 from .model import Attention, CNNEncoder, LSTMDecoder, ResNetEncoder, Seq2SeqModel, normalize_u8
-from . import preprocess
+from . import metrics, preprocess
 from .predictor import Predictor
 from .preprocess import ResizeWithAspectRatio, load_images
 from .tokenizer import LaTeXTokenizer
 
 __all__ = ["Attention", "CNNEncoder", "LSTMDecoder", "ResNetEncoder", "Seq2SeqModel", "Predictor",
-           "LaTeXTokenizer", "normalize_u8", "ResizeWithAspectRatio", "load_images", "preprocess", "_native"]
+           "LaTeXTokenizer", "normalize_u8", "ResizeWithAspectRatio", "load_images", "preprocess", "metrics", "_native"]
 __version__ = "0.1.0"

@@ -110,6 +110,8 @@ SIGNATURES = {
                                     _fp, _fp, C.c_size_t, _fp]),
     "i2l_decode_beam": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "i2l_sequence_metrics": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, _fp, _fp]),
+    "i2l_filter_ids": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, C.POINTER(C.c_int64), C.c_int32, _fp, C.c_int32, _fp, _fp]),
     "i2l_launch_count": (C.c_longlong, []),
     "i2l_prof_enable": (None, [C.c_int]),
     "i2l_prof_reset": (None, []),

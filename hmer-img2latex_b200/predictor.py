@@ -139,6 +139,25 @@ class Predictor:
         return results
 
     @torch.no_grad()
+    def evaluate_batch(self, images, target_ids: torch.Tensor, max_length: Optional[int] = None, batch_size: int = 1024):
+        """One batch of the ``img2latex evaluate`` loop (cli.py:448-495) kept on the device end to end: prepare ->
+        encoder -> greedy ``predict_batch`` loop -> special-token filtering -> BLEU-4 / Levenshtein counts.  Returns
+        the same dict as ``calculate_metrics``; the only device -> host read is the (B,8) count matrix."""
+        from . import metrics as M
+        max_length = self.tokenizer.max_sequence_length if max_length is None else max_length      # cli.py:458
+        start, end = self.tokenizer.start_token_id, self.tokenizer.end_token_id
+        counts = []
+        for i in range(0, len(images), batch_size):
+            batch = self._prepare_images(list(images[i:i + batch_size]))
+            enc = self.model.encoder(batch)
+            tokens, lengths, _ = self.model.decoder.sample(enc, start, end, max_length, 1.0, 0, 0.0)
+            counts.append(M.evaluate_ids(tokens, lengths, target_ids[i:i + batch_size], self.tokenizer, return_counts=True))
+        rows = torch.cat(counts).tolist()
+        both = [M.scores_from_counts(r, 4) for r in rows]
+        return {"bleu": sum(b for _, b in both) / len(rows), "levenshtein": sum(l for l, _ in both) / len(rows),
+                "batch_size": len(rows)}
+
+    @torch.no_grad()
     def predict(self, image: torch.Tensor, beam_size: int = 0, max_length: int = 141, temperature: float = 1.0,
                 top_k: int = 0, top_p: float = 0.0) -> str:
         """predictor.py:139-203 (greedy through Seq2SeqModel.inference; beam clamped to 0)."""

@@ -45,6 +45,11 @@ class LaTeXTokenizer:
         t.vocab_size = len(t.token_to_id)
         return t
 
+    def encode(self, text: str, add_special_tokens: bool = False) -> List[int]:  # tokenizer.py:143-164
+        if add_special_tokens:
+            text = f"{self.special_tokens['START']} {text} {self.special_tokens['END']}"
+        return [self.token_to_id.get(tok, self.unk_token_id) for tok in text.split()]
+
     def decode(self, ids: List[int], skip_special_tokens: bool = True) -> str:   # tokenizer.py:166-194
         special = set(self.token_to_id[t] for t in self.special_tokens.values()) if skip_special_tokens else set()
         toks = [self.id_to_token.get(i, self.special_tokens["UNK"]) for i in ids if i not in special]

@@ -271,6 +271,27 @@ int i2l_decode_beam(const i2l_dec_desc* d, const void* packed, const float* enc,
                     void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* Evaluation metrics -- the integer work of levenshtein_distance / bleu_n_score  */
+/* (training/metrics.py:49-94, 97-179; calculate_metrics 182-223, cli.py:493-495) */
+/* for a batch of (prediction, target) id sequences.  SURVEY 8f-3.                */
+/* pred (B, ld_pred) / tgt (B, ld_tgt) int64 id matrices, pred_len / tgt_len (B)  */
+/* int32 (clamped to [0, ld]).  out (B, 8) int32 per pair: [0] edit distance      */
+/* D[rows][cols] of metrics.py:60-85, [1..4] clipped n-gram matches for n = 1..4  */
+/* (metrics.py:131-152; 0 beyond max_n), [5] pred_len, [6] tgt_len, [7] 0.  The   */
+/* float formulas (metrics.py:87-94, 160-179) are applied by the host wrapper.    */
+/* ------------------------------------------------------------------------- */
+int i2l_sequence_metrics(const int64_t* pred, int32_t ld_pred, const int32_t* pred_len, const int64_t* tgt,
+                         int32_t ld_tgt, const int32_t* tgt_len, int32_t batch, int32_t max_n, int32_t* out,
+                         void* stream);
+
+/* Per-row stable compaction out[b] = [x for x in ids[b, :len[b]] if x not in drop]: the id-level effect of
+ * tokenizer.decode (drops the four specials, data/tokenizer.py:177-189) + tokenizer.encode on the predictions
+ * (cli.py:476-479) and of the padding filter on the targets (cli.py:471-474).  len: NULL => every row has ld
+ * ids.  drop_host: HOST pointer to n_drop <= 8 ids.  out (B, ld_out) int64, out_len (B) int32. */
+int i2l_filter_ids(const int64_t* ids, int32_t ld, const int32_t* len, int32_t batch, const int64_t* drop_host,
+                   int32_t n_drop, int64_t* out, int32_t ld_out, int32_t* out_len, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* Measurement aids (bench.py): count of kernel launches issued by the library  */
 /* and optional CUDA-event timing of its named kernels on the launching stream. */
 /* ------------------------------------------------------------------------- */

@@ -12,4 +12,5 @@ executed in the build container (``oracle/ref_shim.py`` +
 ``tests/golden/`` and re-checked by ``tests/test_oracle_golden.py``.
 """
 from .port import *  # noqa: F401,F403
+from . import metrics  # noqa: F401  (evaluate metrics restated; pinned against the live reference)
 from . import resize  # noqa: F401  (Pillow resampling restated; pinned against live Pillow)

@@ -212,6 +212,38 @@ def resize_case(name):
     save(name, **arrs)
 
 
+def metrics_pairs(seed=31, n=48):
+    """Seeded (prediction, target) id lists: small vocabularies (many repeated n-grams), empty / one-token /
+    identical / prefix / long cases."""
+    rng = np.random.default_rng(seed)
+    pairs = [([], []), ([], [5, 6]), ([5], []), ([7], [7]), ([3, 3, 3, 3, 3], [3, 3, 3]), ([1, 2, 3, 4], [1, 2, 3, 4]),
+             ([1, 2, 3], [1, 2, 3, 4, 5, 6]), ([9, 8, 7, 6, 5, 4], [4, 5, 6, 7, 8, 9])]
+    while len(pairs) < n:
+        V = int(rng.choice([2, 3, 6, 40]))
+        t = rng.integers(0, V, size=int(rng.integers(1, 60))).tolist()
+        kind = rng.random()
+        if kind < 0.5:                      # noisy copy of the target
+            p = [x for x in t if rng.random() > 0.15]
+            p = [int(rng.integers(0, V)) if rng.random() < 0.15 else x for x in p]
+        else:
+            p = rng.integers(0, V, size=int(rng.integers(1, 60))).tolist()
+        pairs.append((p, t))
+    pairs.append((rng.integers(0, 5, size=300).tolist(), rng.integers(0, 5, size=270).tolist()))   # > 256 columns
+    return pairs
+
+
+def metrics_case(name):
+    """Reference training/metrics.py (levenshtein_distance 49-94, bleu_n_score 97-179, calculate_metrics 182-223)."""
+    M = ref_shim.reference_module("img2latex.training.metrics")
+    pairs = metrics_pairs()
+    lev = np.array([M.levenshtein_distance(p, t) for p, t in pairs], np.float64)
+    bleu4 = np.array([M.bleu_n_score(p, t, 4) for p, t in pairs], np.float64)
+    bleu2 = np.array([M.bleu_n_score(p, t, 2) for p, t in pairs], np.float64)
+    res = M.calculate_metrics([p for p, _ in pairs[2:]], [t for _, t in pairs[2:]])
+    save(name, pred=pad_rows([p for p, _ in pairs] + [[0]])[:-1], tgt=pad_rows([t for _, t in pairs] + [[0]])[:-1],
+         lev=lev, bleu4=bleu4, bleu2=bleu2, mean=np.array([res["bleu"], res["levenshtein"], res["batch_size"]], np.float64))
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "the live reference is needed to (re)generate golden vectors"
     seq2seq_case("cnn_headline_sharp.npz", H.HEADLINE, seed=1, sharp=True, B=4, T=30)
@@ -223,6 +255,7 @@ if __name__ == "__main__":
     load_image_case("load_image.npz")
     teacher_forced_case("teacher_forced.npz")
     resize_case("resize.npz")
+    metrics_case("metrics.npz")
     predict_batch_case("predict_batch_greedy.npz", 1.0, 0, 0.0)
     predict_batch_case("predict_batch_topk_topp.npz", 0.8, 5, 0.9)
     predict_batch_case("predict_batch_topp.npz", 1.2, 0, 0.7)

@@ -239,3 +239,15 @@ def test_resize_plan_host_tables(pkg):
         P.ResizePlan([np.zeros((200, 1), np.uint8)], 16, 100)
     white = P.ResizePlan([np.zeros((0, 7), np.uint8)], 16, 100).describe()[0]
     assert white["kept_w"] == 0                                   # transforms.py:28-29: all-white output
+
+
+def test_metrics_golden():
+    """oracle/metrics.py against the live reference's training/metrics.py: identical floats."""
+    d = load("metrics.npz")
+    preds, tgts = unpad(d["pred"]), unpad(d["tgt"])
+    M = oracle.metrics
+    assert [M.levenshtein_distance(p, t) for p, t in zip(preds, tgts)] == d["lev"].tolist()
+    assert [M.bleu_n_score(p, t, 4) for p, t in zip(preds, tgts)] == d["bleu4"].tolist()
+    assert [M.bleu_n_score(p, t, 2) for p, t in zip(preds, tgts)] == d["bleu2"].tolist()
+    res = M.calculate_metrics(preds[2:], tgts[2:])
+    assert [res["bleu"], res["levenshtein"], float(res["batch_size"])] == d["mean"].tolist()
