@@ -253,11 +253,16 @@ def run_ours(args):
             bdec = sum(v[1] for k, v in bprof.items() if k.startswith("dec.")) / nb
             beam = [bms, bdec, Bb, K, {k: round(v[1] / nb, 4) for k, v in sorted(bprof.items())}]
         resnet = None
+        nxt = None
         if world == 1 and not args.no_extras:
             try:
                 resnet = resnet_lines(pkg, dev, B)
             except Exception as e:                       # an extra line must never take the headline down
                 resnet = {"error": repr(e)[:300]}
+            try:
+                nxt = next_row_lines(pkg, dev, B)
+            except Exception as e:
+                nxt = {"error": repr(e)[:300]}
     tms = torch.tensor([ms, e2e_s * 1e3, beam[0] if beam else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -338,6 +343,8 @@ def run_ours(args):
                          "workload": "BASELINE configs[2]: CNN-LSTM beam search, beam 5, batch %d per GPU, max_len 150" % Bb}
     if resnet:
         line.update(resnet)
+    if nxt:
+        line["next_rows"] = nxt
     dk = [v[1] for k, v in prof.items() if k.startswith("dec.")]
     if dk and steps_run:
         line["us_per_decode_step"] = round(sum(dk) / args.steps / steps_run * 1e3, 3)
@@ -421,6 +428,122 @@ def resnet_lines(pkg, dev, B, reps=3):
         "encoder_ms": round(enc_ms, 3), "encoder_tflops": round(fl / enc_ms / 1e9, 1),
         "encoder_frac_of_bf16_peak": round(fl / enc_ms / 1e9 / peaks()["tf_sust"], 3),
         "decode_ms": round(ms - enc_ms, 3)}
+    return out
+
+
+def next_row_lines(pkg, dev, B):
+    """SURVEY 8f rows next to the headline (one GPU): device-side image preparation (f1), evaluation metrics
+    (f3) and the teacher-forced decoder pass (f4), each with its algorithmic-bytes roofline and the reference's
+    CPU arithmetic (Pillow / the pure-Python port) timed on a bounded sample of the same work."""
+    import ctypes as C
+    import time
+    import numpy as np
+    import torch
+    N = pkg._native
+    lib = N.lib()
+    pk = peaks()
+    out = {}
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # ---- f1: ragged grey images -> 64 x 800 (the size load_image / Predictor use), LANCZOS + pad / crop
+    P = pkg.preprocess
+    rng = np.random.default_rng(0)
+    imgs = []
+    for _ in range(B):
+        h = int(rng.integers(32, 128)); w = int(h * rng.uniform(2.0, 14.0))
+        imgs.append(rng.integers(0, 256, size=(h, w), dtype=np.uint8))
+    plan = P.ResizePlan(imgs, 64, 800)
+    dplan = plan.host.to(dev)
+    o = torch.empty(B, 1, 64, 800, dtype=torch.uint8, device=dev)
+    ws = torch.empty(plan.workspace_bytes, dtype=torch.uint8, device=dev)
+
+    def resize():
+        N.check(lib.i2l_resize_pad_u8(N.ptr(dplan), C.c_void_p(plan.plan_ptr), C.c_void_p(dplan.data_ptr() + plan.pixel_bytes),
+                                      N.ptr(o), N.ptr(ws), ws.numel(), N.stream_ptr(dev)), "i2l_resize_pad_u8")
+    ms = timed(resize)
+    src = sum(a.size for a in imgs)
+    alg = src + 2 * (plan.workspace_bytes - 512) + o.numel()          # source + intermediate write/read + output
+    t0 = time.perf_counter()
+    for _ in range(3):
+        P.ResizePlan(imgs, 64, 800).run(dev)
+    torch.cuda.synchronize(dev)
+    e2e = (time.perf_counter() - t0) / 3
+    row = {"workload": "SURVEY 8f-1: %d ragged grey images (h 32-127, aspect 2-14) -> 64x800, Pillow LANCZOS + pad/crop, "
+                       "bit-exact" % B,
+           "value": round(B / ms * 1e3, 1), "unit": "images/s", "ms": round(ms, 4),
+           "roofline": {"bound": "hbm", "achieved": round(alg / ms / 1e6, 1), "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": round(alg / ms / 1e6 / pk["hbm"], 4), "algorithmic_bytes": int(alg)},
+           "e2e": {"value": round(B / e2e, 1), "unit": "images/s", "h2d_bytes_per_step": int(plan.host.numel()),
+                   "note": "host arrays -> filter-weight plan on the host cores -> one H2D -> two launches"}}
+    try:
+        from PIL import Image
+        n = min(B, 128)
+        t0 = time.perf_counter()
+        for a in imgs[:n]:
+            im = Image.fromarray(a, "L")
+            nw = int(round(64 * (a.shape[1] / a.shape[0])))
+            r = im.resize((nw, 64), Image.Resampling.LANCZOS)
+            if nw < 800:
+                q = Image.new("L", (800, 64), 255); q.paste(r, (0, 0)); r = q
+            elif nw > 800:
+                l = (nw - 800) // 2; r = r.crop((l, 0, l + 800, 64))
+        row["cpu_baseline"] = {"value": round(n / (time.perf_counter() - t0), 1), "unit": "images/s", "cores": 1,
+                               "kind": "reference", "sample": "Pillow (the reference's own resampler) on the first %d images" % n}
+    except ImportError:
+        pass
+    out["preprocess_resize"] = row
+    del dplan, o, ws
+
+    # ---- f3: BLEU-4 + Levenshtein counts of B (prediction, target) pairs of ~150 tokens
+    M = pkg.metrics
+    g = torch.Generator().manual_seed(0)
+    T = MAX_LEN + 1
+    t = torch.randint(0, 100, (B, T), generator=g)
+    p = torch.where(torch.rand(B, T, generator=g) < 0.15, torch.randint(0, 100, (B, T), generator=g), t)
+    lt = torch.randint(100, T + 1, (B,), generator=g, dtype=torch.int32)
+    lp = (lt - torch.randint(0, 10, (B,), generator=g, dtype=torch.int32)).clamp(min=1)
+    pc, tc, lpc, ltc = p.to(dev), t.to(dev), lp.to(dev), lt.to(dev)
+    ms = timed(lambda: M.sequence_counts(pc, lpc, tc, ltc))
+    cells = float((lp.double() * lt.double()).sum())
+    row = {"workload": "SURVEY 8f-3: edit distance + clipped 1..4-gram matches of %d id-sequence pairs (100-151 tokens)" % B,
+           "value": round(B / ms * 1e3, 1), "unit": "pairs/s", "ms": round(ms, 4),
+           "dp_cells_per_s": round(cells / ms * 1e3, 1),
+           "note": "integer DP held in registers / shared memory: neither HBM- nor tensor-bound (16 B of ids per token "
+                   "in, 32 B per pair out); the rate is set by dependent shared-memory reads"}
+    from oracle import metrics as OM                       # cpu_baseline leg: the reference's pure-Python loops restated
+    n = min(B, 16)
+    t0 = time.perf_counter()
+    OM.calculate_metrics([p[i, : lp[i]].tolist() for i in range(n)], [t[i, : lt[i]].tolist() for i in range(n)])
+    row["cpu_baseline"] = {"value": round(n / (time.perf_counter() - t0), 1), "unit": "pairs/s", "cores": 1, "kind": "port",
+                           "sample": "first %d pairs, pure-Python port of training/metrics.py" % n}
+    out["evaluate_metrics"] = row
+
+    # ---- f4: teacher-forced decoder pass, headline decoder, B x 150 tokens
+    m = pkg.Seq2SeqModel("cnn_lstm", CFG["vocab_size"], dict(img_height=64, img_width=320, channels=3, embedding_dim=256),
+                         dict(hidden_dim=256, lstm_layers=1, attention=True), precision="bf16").to(dev).eval()
+    enc = torch.relu(torch.randn(B, 256, generator=g)).to(dev)
+    tg = torch.randint(0, CFG["vocab_size"], (B, MAX_LEN), generator=g).to(dev)
+    ms = timed(lambda: m.decoder(enc, tg), reps=5)
+    W = 2 * (4 * 256 * 768 + 8 * 256 + 512 * 256 + 512)
+    S = 16 * 256 + 2 * 256 + 2 * 256 + 8
+    alg = MAX_LEN * (W + B * S) + B * MAX_LEN * 512 * 4                 # SURVEY 8d per-step bytes + the fp32 logits written
+    out["teacher_forced_forward"] = {
+        "workload": "SURVEY 8f-4: LSTMDecoder.forward (eval), %d x %d tokens, E=H=256, L=1, V=512, bf16 GEMMs" % (B, MAX_LEN),
+        "value": round(B * MAX_LEN / ms * 1e3, 1), "unit": "tokens/s", "ms": round(ms, 3),
+        "us_per_step": round(ms / MAX_LEN * 1e3, 2),
+        "roofline": {"bound": "hbm", "achieved": round(alg / ms / 1e6, 1), "peak": pk["hbm"], "unit": "GB/s",
+                     "frac": round(alg / ms / 1e6 / pk["hbm"], 4)},
+        "note": "one stream-ordered gate GEMM + cell launch per step, one (B*T,H)x(H,V) logits GEMM for all steps"}
     return out
 
 

@@ -36,13 +36,20 @@ class Predictor:
         self.tokenizer = tokenizer
 
     @classmethod
-    def from_checkpoint(cls, checkpoint_path: str, device=None) -> "Predictor":
-        """Checkpoint layout of training/trainer.py:209-221, consumed as in predictor.py:61-137."""
+    def from_checkpoint(cls, checkpoint_path: str, device=None, precision: Optional[str] = None) -> "Predictor":
+        """Reference checkpoints (layout written by training/trainer.py:207-221) consumed exactly as
+        training/predictor.py:61-137 does: tokenizer from ``tokenizer_config``, encoder parameters from
+        ``config.model.encoder.{cnn|resnet}``, ``config.model.embedding_dim`` (default 256) for both halves,
+        ``model_state_dict`` loaded strictly."""
         ck = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
-        mc = ck["config"]["model"]
-        tok = LaTeXTokenizer.from_config(ck["tokenizer_config"])
-        model = Seq2SeqModel(mc["name"], tok.vocab_size, dict(mc.get("encoder", {}), embedding_dim=mc.get("embedding_dim", 256)),
-                             mc.get("decoder", {}))
+        config = ck.get("config", {})
+        model_config = config.get("model", {})
+        model_type = model_config.get("name", "cnn_lstm")
+        tok = LaTeXTokenizer.from_config(ck.get("tokenizer_config", {}))
+        encoder_params = dict(model_config.get("encoder", {}).get("cnn" if model_type == "cnn_lstm" else "resnet", {}))
+        encoder_params["embedding_dim"] = model_config.get("embedding_dim", 256)
+        model = Seq2SeqModel(model_type=model_type, vocab_size=tok.vocab_size, encoder_params=encoder_params,
+                             decoder_params=model_config.get("decoder", {}), precision=precision)
         model.load_state_dict(ck["model_state_dict"])
         return cls(model, tok, device)
 

@@ -38,11 +38,16 @@ class LaTeXTokenizer:
 
     @classmethod
     def from_config(cls, cfg: dict) -> "LaTeXTokenizer":
-        """Rebuild from a checkpoint's tokenizer_config (training/predictor.py:88-105)."""
-        t = cls(cfg.get("special_tokens"), cfg.get("max_sequence_length"))
-        t.token_to_id = dict(cfg["token_to_id"])
+        """Rebuild from a checkpoint's tokenizer_config (training/predictor.py:86-105): the special ids are
+        looked up in the stored ``token_to_id``."""
+        t = cls(cfg.get("special_tokens"), cfg.get("max_sequence_length", 141))
+        t.token_to_id = dict(cfg.get("token_to_id", {}))
         t.id_to_token = {int(i): tok for tok, i in t.token_to_id.items()}
         t.vocab_size = len(t.token_to_id)
+        t.pad_token_id = t.token_to_id[t.special_tokens["PAD"]]
+        t.start_token_id = t.token_to_id[t.special_tokens["START"]]
+        t.end_token_id = t.token_to_id[t.special_tokens["END"]]
+        t.unk_token_id = t.token_to_id[t.special_tokens["UNK"]]
         return t
 
     def encode(self, text: str, add_special_tokens: bool = False) -> List[int]:  # tokenizer.py:143-164

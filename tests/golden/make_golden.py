@@ -212,6 +212,28 @@ def resize_case(name):
     save(name, **arrs)
 
 
+def checkpoint_case(name):
+    """Reference `Predictor.from_checkpoint` + `predict` / `predict_batch` (training/predictor.py:61-203) on a
+    checkpoint file in the reference's own layout."""
+    import tempfile
+    ref = ref_shim.load()
+    p = oracle.make_params(H.CKPT_CFG, 2, sharp=True)
+    g = torch.Generator().manual_seed(13)
+    imgs = [torch.rand(1, 64, 800, generator=g) for _ in range(4)]
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "best_checkpoint_epoch_3_step_7.pt")
+        H.make_checkpoint(path, p)
+        pred = ref["Predictor"].from_checkpoint(path, device=torch.device("cpu"))
+        singles = []
+        for im in imgs:
+            try:
+                singles.append(pred.predict(im, max_length=24))
+            except IndexError:        # predictor.py:194 indexes an EMPTY sequence when the first token is END
+                singles.append("<IndexError>")
+        batch = pred.predict_batch(imgs, max_length=24, batch_size=4)
+    save(name, singles=np.array(singles), batch=np.array(batch), vocab_size=np.array(pred.tokenizer.vocab_size))
+
+
 def metrics_pairs(seed=31, n=48):
     """Seeded (prediction, target) id lists: small vocabularies (many repeated n-grams), empty / one-token /
     identical / prefix / long cases."""
@@ -256,6 +278,7 @@ if __name__ == "__main__":
     teacher_forced_case("teacher_forced.npz")
     resize_case("resize.npz")
     metrics_case("metrics.npz")
+    checkpoint_case("checkpoint.npz")
     predict_batch_case("predict_batch_greedy.npz", 1.0, 0, 0.0)
     predict_batch_case("predict_batch_topk_topp.npz", 0.8, 5, 0.9)
     predict_batch_case("predict_batch_topp.npz", 1.2, 0, 0.7)

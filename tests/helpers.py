@@ -46,3 +46,33 @@ def build_model(pkg, cfg, params, precision="fp32", device="cuda"):
 def rel_err(a, b):
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def default_vocab():
+    """The 42 non-special tokens of the reference tokenizer's `default_init` (data/tokenizer.py:323-385), in id order."""
+    import i2l_import
+    t = i2l_import.load().LaTeXTokenizer()
+    t.default_init()
+    return [t.id_to_token[i] for i in range(4, t.vocab_size)]
+
+
+CKPT_CFG = dict(model_type="cnn_lstm", vocab_size=46, embedding_dim=32, hidden_dim=48, lstm_layers=2, attention=True,
+                img_height=64, img_width=800, channels=1, conv_filters=[4, 8, 8])
+
+
+def make_checkpoint(path, params):
+    """A checkpoint in the layout training/trainer.py:207-221 writes (config in configs/config.yaml's layout)."""
+    ref_tok_ids = {"<PAD>": 0, "<START>": 1, "<END>": 2, "<UNK>": 3}
+    for t in default_vocab():
+        ref_tok_ids[t] = len(ref_tok_ids)
+    c = CKPT_CFG
+    config = {"model": {"name": "cnn_lstm", "embedding_dim": c["embedding_dim"],
+                        "encoder": {"cnn": dict(img_height=64, img_width=800, channels=1, conv_filters=c["conv_filters"],
+                                                kernel_size=3, pool_size=2, padding="same"),
+                                    "resnet": dict(img_height=64, img_width=800, channels=3, model_name="resnet18")},
+                        "decoder": dict(hidden_dim=c["hidden_dim"], lstm_layers=c["lstm_layers"], dropout=0.3, attention=True)}}
+    torch.save({"epoch": 3, "step": 7, "model_state_dict": params, "optimizer_state_dict": {}, "metrics": {},
+                "config": config,
+                "tokenizer_config": {"token_to_id": ref_tok_ids,
+                                     "special_tokens": {"PAD": "<PAD>", "START": "<START>", "END": "<END>", "UNK": "<UNK>"},
+                                     "max_sequence_length": 30}}, path)

@@ -69,3 +69,20 @@ def test_predict_batch_vs_reference_golden(pkg, name):
     got = pred.predict_batch(list(x), max_length=T, temperature=float(d["temperature"]), top_k=int(d["top_k"]),
                              top_p=float(d["top_p"]), batch_size=int(d["B"]), uniforms=torch.as_tensor(d["u"]))
     assert got == [str(s) for s in d["strings"]]
+
+
+def test_from_checkpoint_vs_reference_golden(pkg, tmp_path):
+    """a checkpoint file in the reference's layout (training/trainer.py:207-221) loaded by
+    Predictor.from_checkpoint gives the strings the reference's Predictor.from_checkpoint(...).predict /
+    predict_batch produced from the same file contents (tests/golden/checkpoint.npz)."""
+    d = load("checkpoint.npz")
+    p = oracle.make_params(H.CKPT_CFG, 2, sharp=True)
+    path = str(tmp_path / "best_checkpoint_epoch_3_step_7.pt")
+    H.make_checkpoint(path, p)
+    pred = pkg.Predictor.from_checkpoint(path)
+    assert pred.tokenizer.vocab_size == int(d["vocab_size"]) and pred.tokenizer.max_sequence_length == 30
+    assert pred.model.decoder.lstm_layers == 2 and pred.model.encoder.img_width == 800
+    g = torch.Generator().manual_seed(13)
+    imgs = [torch.rand(1, 64, 800, generator=g) for _ in range(4)]
+    assert pred.predict_batch(imgs, max_length=24, batch_size=4) == d["batch"].tolist()
+    assert [pred.predict(im, max_length=24) for im in imgs] == d["singles"].tolist()
