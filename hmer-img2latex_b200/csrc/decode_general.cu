@@ -4,8 +4,10 @@
 // The C-ABI entry points of the decoder live here; for the headline shape in bf16 they
 // route the greedy loop to the persistent cluster kernel (decode_persistent.cu).
 #include "decode_kernels.cuh"
+#include "sample_select.cuh"
 #include "gemm_bf16.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace i2l {
 
@@ -91,15 +93,6 @@ __global__ void lstm_cell_kernel(const float* __restrict__ gates, float* __restr
   if (hb_seq != nullptr) hb_seq[(size_t)r * seq_ld + j] = __float2bfloat16(hn);
 }
 
-__device__ __forceinline__ void warp_argmax(float& v, int& i) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    float ov = __shfl_xor_sync(0xffffffffu, v, o);
-    int oi = __shfl_xor_sync(0xffffffffu, i, o);
-    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
-  }
-}
-
 __global__ void loop_init_kernel(int64_t* tokens, int T1, int rows, int start_id, int64_t* tok_cur,
                                  int* first_end, LoopState* st) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,25 +174,6 @@ __global__ void loop_finalize_kernel(const int* first_end, int rows, int max_len
 }
 
 // ------------------------------------------------------------------ sampling (predictor.py:295-335)
-__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
-  uint64_t p = (uint64_t)a * b;
-  *hi = (uint32_t)(p >> 32);
-  return (uint32_t)p;
-}
-__device__ float philox_uniform(uint64_t seed, uint64_t ctr) {
-  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0, c3 = 0;
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t h0, h1;
-    uint32_t l0 = mulhilo(0xD2511F53u, c0, &h0), l1 = mulhilo(0xCD9E8D57u, c2, &h1);
-    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
-    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return (float)(c0 >> 8) * (1.0f / 16777216.0f);
-}
-
 __device__ __forceinline__ float block_reduce_max(float v, float* scratch) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -382,34 +356,7 @@ __global__ void sample_select_kernel(const float* __restrict__ logits, int V, in
 }
 
 // ------------------------------------------------------------------ sampling, V <= 512: one warp per row
-// Same arithmetic as sample_select_kernel, with the row held in registers (vocab index 16*lane + i) and ONE
-// warp-level bitonic sort on 64-bit (probability bits, ~index) keys instead of two block-wide sorts in shared
-// memory: top-k masking and renormalisation keep the order of the surviving entries, so the order found once is
-// also the order of the top-p pass (predictor.py:311-317 sorts again).  The kept set is a prefix of the sorted
-// order; it is carried back to index order as a threshold KEY, not as a scatter.
-__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
-  return ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m) << 32) | __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
-}
-__device__ __forceinline__ double warp_excl_scan(double v, int lane, double* total) {
-  double inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { double n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
-  *total = __shfl_sync(0xffffffffu, inc, 31);
-  return inc - v;
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// sorted element at (warp-uniform) position pos of the 512-entry array held as key[16] per lane
-__device__ __forceinline__ unsigned long long sorted_at(const unsigned long long (&key)[16], int pos) {
-  unsigned long long sel = key[0];
-#pragma unroll
-  for (int i = 1; i < 16; ++i) if ((pos & 15) == i) sel = key[i];
-  return ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(sel >> 32), pos >> 4) << 32) | __shfl_sync(0xffffffffu, (unsigned)sel, pos >> 4);
-}
-
+// (arithmetic in sample_select.cuh: warp_sample_select)
 __global__ void __launch_bounds__(256) sample_select_warp_kernel(const float* __restrict__ logits, int V, int rows, float temperature,
                                                                 int top_k, float top_p, int do_sample, uint64_t seed,
                                                                 uint64_t offset, const float* __restrict__ uniforms,
@@ -424,244 +371,13 @@ __global__ void __launch_bounds__(256) sample_select_warp_kernel(const float* __
   const int row = blockIdx.x * 8 + warp;
   if (row < rows) {
     const float* x = logits + (size_t)row * V;
-    float po[16];                                             // probabilities in index order
-    // softmax(logits / T)                                               predictor.py:295-297
-    float lm = -INFINITY;
+    float lg[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int v = 16 * lane + i;
-      float val = -INFINITY;
-      if (v < V) { val = x[v]; if (temperature != 1.0f) val = val / temperature; }
-      po[i] = val;
-      lm = fmaxf(lm, val);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lm = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, o));
-    float ls = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { const float e = (16 * lane + i) < V ? expf(po[i] - lm) : 0.f; po[i] = e; ls += e; }
-    const float s = warp_sum(ls);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) po[i] = po[i] / s;
-
-    if (top_k > 0 || top_p > 0.0f) {
-      int R = V;                                                // kept entries = sorted positions [0, R)
-      float s2 = 1.f, s3 = 1.f, kth = 0.f;
-      bool renorm2 = false, renorm3 = false;
-      unsigned long long kt = 0ull;                             // key at sorted position R-1
-      bool fast = false;
-      if (top_k > 0 && min(top_k, V) <= 64) {
-        // ---- fast path (top_k <= 64): the k-th largest probability by a bitwise radix select over the warp
-        // (30 x count-and-reduce), then ONLY the survivors (>= k-th, ties kept: predictor.py:302-306) are compacted
-        // and sorted -- 64 keys, 2 per lane -- for the top-p pass.  Falls back to the full sort when ties push the
-        // survivor count beyond 64.
-        const int k = min(top_k, V);
-        uint32_t bits[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) bits[i] = (16 * lane + i) < V ? __float_as_uint(po[i]) : 0u;
-        uint32_t pref = 0u;
-#pragma unroll 1
-        for (int b = 29; b >= 0; --b) {                         // p <= 1.0f = 0x3F800000: bits 31 and 30 are never set
-          const uint32_t cand = pref | (1u << b);
-          int cn = 0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) cn += bits[i] >= cand ? 1 : 0;
-          cn = __reduce_add_sync(0xffffffffu, cn);
-          if (cn >= k) pref = cand;
-        }
-        unsigned m16 = 0u;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) m16 |= (bits[i] >= pref && (16 * lane + i) < V ? 1u : 0u) << i;
-        const int cnt = __popc(m16);
-        const int kp = __reduce_add_sync(0xffffffffu, cnt);     // survivors of top-k (>= k with ties)
-        if (kp <= 64) {
-          fast = true;
-          kth = __uint_as_float(pref);
-          float l2 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) if (po[i] >= kth) l2 += po[i];
-          s2 = warp_sum(l2);
-          renorm2 = s2 > 0.f;
-          if (top_p > 0.0f) {
-            __shared__ unsigned long long cand_s[8][64];
-            unsigned long long* slot = cand_s[warp];
-            slot[lane] = 0ull; slot[lane + 32] = 0ull;
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
-            int pos = incl - cnt;
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if ((m16 >> i) & 1u) slot[pos++] = ((unsigned long long)bits[i] << 32) | (0xFFFFFFFFu - (unsigned)(16 * lane + i));
-            __syncwarp();
-            unsigned long long e[2] = {slot[lane], slot[lane + 32]};      // sorted position t = lane + 32 i after the network
-            __syncwarp();
-#pragma unroll
-            for (int lk = 1; lk <= 6; ++lk) {
-              const int kk = 1 << lk;
-#pragma unroll
-              for (int lj = 5; lj >= 0; --lj) {
-                if (lj >= lk) continue;
-                const int j = 1 << lj;
-                if (j == 32) {                                             // kk == 64: descending over the register pair
-                  const unsigned long long x0 = e[0], x1 = e[1];
-                  const bool sw = x1 > x0;
-                  e[0] = sw ? x1 : x0; e[1] = sw ? x0 : x1;
-                } else {
-                  const bool lower = (lane & j) == 0;
-#pragma unroll
-                  for (int i = 0; i < 2; ++i) {
-                    const bool desc = kk == 64 ? true : (kk == 32 ? i == 0 : (lane & kk) == 0);
-                    const unsigned long long o = shfl_xor_u64(e[i], j);
-                    const bool gt = o > e[i];
-                    e[i] = (gt == (lower == desc)) ? o : e[i];
-                  }
-                }
-              }
-            }
-            // top-p over the sorted survivors (positions >= kp carry probability 0)
-            float v[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              float x = (lane + 32 * i) < kp ? __uint_as_float((unsigned)(e[i] >> 32)) : 0.f;
-              if (renorm2) x = x / s2;
-              v[i] = x;
-            }
-            double tot0, tot1;
-            const double b0 = warp_excl_scan((double)v[0], lane, &tot0);
-            const double b1 = tot0 + warp_excl_scan((double)v[1], lane, &tot1);
-            const bool keep0 = lane < kp && !(lane > 0 && (float)b0 > top_p);
-            const bool keep1 = (lane + 32) < kp && !((float)b1 > top_p);
-            R = __reduce_add_sync(0xffffffffu, (keep0 ? 1 : 0) + (keep1 ? 1 : 0));
-            s3 = warp_sum((keep0 ? v[0] : 0.f) + (keep1 ? v[1] : 0.f));
-            renorm3 = s3 > 0.f;
-            const int rp = max(R, 1) - 1;
-            const unsigned long long sel = rp < 32 ? e[0] : e[1];
-            kt = ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(sel >> 32), rp & 31) << 32) | __shfl_sync(0xffffffffu, (unsigned)sel, rp & 31);
-          }
-        }
-      }
-      if (!fast) {
-      // ---- descending sort of (prob, index): key = prob bits (prob >= 0: unsigned order) : ~index
-      unsigned long long key[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) key[i] = ((unsigned long long)__float_as_uint(po[i]) << 32) | (0xFFFFFFFFu - (unsigned)(16 * lane + i));
-#pragma unroll
-      for (int lk = 1; lk <= 9; ++lk) {                         // canonical counted loops: fully unrolled, key[] stays in registers
-        const int k = 1 << lk;
-#pragma unroll
-        for (int lj = 8; lj >= 0; --lj) {
-          if (lj >= lk) continue;
-          const int j = 1 << lj;
-          if (j >= 16) {
-            const int lj = j >> 4;
-            const bool keep_max = ((lane & lj) == 0) == (((16 * lane) & k) == 0);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const unsigned long long o = shfl_xor_u64(key[i], lj);
-              const bool gt = o > key[i];
-              key[i] = (gt == keep_max) ? o : key[i];
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (i & j) continue;
-              const unsigned long long a = key[i], b = key[i | j];
-              const bool desc = ((16 * lane + i) & k) == 0;      // static for k <= 16, per lane above
-              const bool sw = (b > a) == desc;
-              key[i] = sw ? b : a;
-              key[i | j] = sw ? a : b;
-            }
-          }
-        }
-      }
-      if (top_k > 0) {                                          // predictor.py:299-309 (ties with the k-th value are kept)
-        const int k = min(top_k, V);
-        kth = __uint_as_float((unsigned)(sorted_at(key, k - 1) >> 32));
-        float l2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) if (po[i] >= kth) l2 += po[i];
-        s2 = warp_sum(l2);
-        renorm2 = s2 > 0.f;
-      }
-      if (top_p > 0.0f) {                                       // predictor.py:311-327
-        // cumulative sum over the sorted, top-k-masked and renormalised probabilities (fp64, ATen CPU cumsum);
-        // sorted position t is removed iff t >= 1 and float(cum[t-1]) > top_p
-        double c[16], acc = 0.0;
-        float sp2[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float v = __uint_as_float((unsigned)(key[i] >> 32));
-          if (top_k > 0) { v = v >= kth ? v : 0.f; if (renorm2) v = v / s2; }
-          sp2[i] = v;
-          acc += (double)v;
-          c[i] = acc;
-        }
-        double tot;
-        const double base = warp_excl_scan(acc, lane, &tot);
-        int keep = 0; float l3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const double prev = i == 0 ? base : base + c[i - 1];
-          const bool rem = (lane > 0 || i > 0) && (float)prev > top_p;
-          if (!rem) { ++keep; l3 += sp2[i]; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
-        R = keep;
-        s3 = warp_sum(l3);
-        renorm3 = s3 > 0.f;
-      }
-      kt = sorted_at(key, max(R, 1) - 1);
-      }
-      // ---- back to index order: entry v survives top-p iff its key >= the key at sorted position R-1
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float v = po[i];
-        if (top_k > 0) { v = v >= kth ? v : 0.f; if (renorm2) v = v / s2; }
-        if (top_p > 0.0f) {
-          const unsigned long long kv = ((unsigned long long)__float_as_uint(po[i]) << 32) | (0xFFFFFFFFu - (unsigned)(16 * lane + i));
-          if (kv < kt) v = 0.f;
-          if (renorm3) v = v / s3;
-        }
-        po[i] = v;
-      }
-    }
-    if (probs_trace) {
-      float* o = probs_trace + ((size_t)step * rows + row) * V;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) if (16 * lane + i < V) o[16 * lane + i] = po[i];
-    }
-    int chosen;
-    if (do_sample) {                                            // predictor.py:330-331 (restated inverse-CDF draw)
-      double c[16], acc = 0.0;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { acc += (double)po[i]; c[i] = acc; }
-      double tot;
-      const double base = warp_excl_scan(acc, lane, &tot);
-      const float u = uniforms ? uniforms[(size_t)step * rows + row] : philox_uniform(seed, offset + (uint64_t)step * rows + row);
-      const double tgt = (double)u * tot;
-      int best = 0x7fffffff, lastpos = -1;
-#pragma unroll
-      for (int i = 15; i >= 0; --i) {
-        if (base + c[i] > tgt && 16 * lane + i < V) best = 16 * lane + i;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) if (po[i] > 0.f) lastpos = 16 * lane + i;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-        lastpos = max(lastpos, __shfl_xor_sync(0xffffffffu, lastpos, o));
-      }
-      chosen = best != 0x7fffffff ? best : max(lastpos, 0);
-    } else {                                                    // predictor.py:333-335 argmax(probs)
-      float bv = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) if (16 * lane + i < V && po[i] > bv) { bv = po[i]; bi = 16 * lane + i; }
-      warp_argmax(bv, bi);
-      chosen = bi == 0x7fffffff ? 0 : bi;
-    }
+    for (int i = 0; i < 16; ++i) lg[i] = (16 * lane + i) < V ? x[16 * lane + i] : 0.f;
+    float u = 0.f;
+    if (do_sample) u = uniforms ? uniforms[(size_t)step * rows + row] : philox_uniform(seed, offset + (uint64_t)step * rows + row);
+    const int chosen = warp_sample_select(lg, V, lane, temperature, top_k, top_p, do_sample, u,
+                                          probs_trace ? probs_trace + ((size_t)step * rows + row) * V : nullptr);
     if (lane == 0) commit_token(row, chosen, step, T1, end_id, stop_rule, tokens, tok_cur, first_end, &counter);
   }
   __syncthreads();
@@ -1205,9 +921,28 @@ extern "C" int i2l_decode_sample(const i2l_dec_desc* d, const void* packed, cons
                                  int32_t top_k, float top_p, uint64_t seed, uint64_t offset,
                                  const float* uniforms, int64_t* tokens, int32_t* lengths, int32_t* steps_run,
                                  float* probs_trace, void* workspace, size_t workspace_bytes, void* stream) {
+  I2L_TRY(check_common(d, packed));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool no_persistent = getenv("I2L_NO_PERSISTENT_SAMPLE") != nullptr;          // A/B switch (tests, tools)
+  if (!no_persistent && d->precision == I2L_BF16 && persistent_supported(*d) && batch > 0 && max_length > 0 &&
+      end_id >= 0 && end_id < d->vocab_size && tokens != nullptr) {
+    // headline decoder shape in bf16: the whole sampling loop runs inside the persistent cluster kernel
+    PackedDec lay = dec_layout(*d);
+    size_t gen = carve(*d, batch, max_length, nullptr).bytes;
+    I2L_REQUIRE(workspace_bytes >= gen + persistent_workspace_bytes(*d, batch, max_length),
+                "i2l_decode_sample: workspace too small");
+    PersistentSampleArgs sa{};
+    sa.top_k = top_k; sa.top_p = top_p;
+    sa.do_sample = temperature > 0.f && (top_k > 0 || top_p > 0.0f);               // predictor.py:330
+    sa.seed = seed; sa.offset = offset; sa.uniforms = uniforms; sa.probs_trace = probs_trace;
+    return persistent_greedy(*d, reinterpret_cast<const char*>(packed) + lay.bf16_section,
+                             reinterpret_cast<const float*>(packed), lay, enc, batch, start_id, end_id, max_length,
+                             temperature, I2L_STOP_ALL_FINISHED_STICKY, tokens, lengths, steps_run,
+                             reinterpret_cast<char*>(workspace) + gen, workspace_bytes - gen, s, &sa);
+  }
   return run_loop(d, packed, enc, batch, start_id, end_id, max_length, temperature,
                   I2L_STOP_ALL_FINISHED_STICKY, true, top_k, top_p, seed, offset, uniforms, tokens, lengths,
-                  steps_run, probs_trace, workspace, workspace_bytes, (cudaStream_t)stream);
+                  steps_run, probs_trace, workspace, workspace_bytes, s);
 }
 
 extern "C" int i2l_decode_beam(const i2l_dec_desc* d, const void* packed, const float* enc, int32_t batch,

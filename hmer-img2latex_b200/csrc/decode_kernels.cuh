@@ -57,10 +57,19 @@ size_t persistent_packed_bytes(const i2l_dec_desc& d);
 int persistent_pack(const i2l_dec_desc& d, const i2l_dec_params& p, const float* gtok_f32, void* section,
                     cudaStream_t s);
 size_t persistent_workspace_bytes(const i2l_dec_desc& d, int rows, int max_length);
+// sample != nullptr: the same kernel in sampling mode (Predictor.predict_batch, training/predictor.py:295-335): warp-level
+// temperature / top-k / top-p selection instead of the argmax, one warp of the cluster per sequence.
+struct PersistentSampleArgs {
+  int top_k; float top_p; int do_sample;
+  unsigned long long seed, offset;
+  const float* uniforms;      // (T,B) or null
+  float* probs_trace;         // (T,B,V) or null
+};
 int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* packed_f32,
                       const PackedDec& lay, const float* enc, int batch, int start_id, int end_id,
                       int max_length, float temperature, int stop_rule, int64_t* tokens, int32_t* lengths,
-                      int32_t* steps_run, void* ws, size_t ws_bytes, cudaStream_t s);
+                      int32_t* steps_run, void* ws, size_t ws_bytes, cudaStream_t s,
+                      const PersistentSampleArgs* sample = nullptr);
 
 // persistent bf16 beam search (decode_persistent_beam.cu): same resident-weight cluster kernel with
 // log-softmax + top-K, per-image candidate merge, back-pointers and state reorder on the device.

@@ -30,6 +30,7 @@
 // Seq2SeqModel._greedy_search (model/seq2seq.py:192-232); attention with src_len == 1 is the
 // identity and W_ih [emb ; ctx] is hoisted into the Gtok table / Gctx (F4).
 #include "decode_persistent_common.cuh"
+#include "sample_select.cuh"
 #include <limits.h>
 
 // Timing ablations (tools/ablate_greedy.sh builds one library per mask; results are WRONG by design):
@@ -51,10 +52,15 @@ constexpr int OFF_TOK = OFF_XCHG + CL * NB * 8;     // [32] int tokens of the cu
 constexpr int OFF_BAR = OFF_TOK + NB * 4;           // mbarriers
 constexpr int OFF_MISC = OFF_BAR + 16 * 8;           // tmem base, exit flag
 constexpr int SMEM_BYTES = OFF_MISC + 16;
-static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+// sampling mode only: the logits of a step are regrouped so that ONE warp holds a whole row
+constexpr int LG_BLOCK_BYTES = (NB / CL) * 128 * 4;  // 8 sequences x 128 vocabulary rows, fp32 = 4 KB
+constexpr int OFF_STAGE = (SMEM_BYTES + 127) / 128 * 128;          // [32 sequences][128 own vocab rows] fp32 (bulk-copy source)
+constexpr int OFF_RX = OFF_STAGE + CL * LG_BLOCK_BYTES;            // [4 source CTAs][8 own sequences][128] fp32
+constexpr int SMEM_BYTES_SAMPLE = OFF_RX + CL * LG_BLOCK_BYTES;
+static_assert(SMEM_BYTES_SAMPLE <= 232448, "shared memory budget exceeded");
 
 // BAR_HS + 4 * buf + d: K-block of h buffer `buf` written by the CTA at cluster distance d (rank - d; d = 0: this CTA)
-enum { BAR_W = 0, BAR_LDONE = 3, BAR_GDONE = 4, BAR_TOK = 5, BAR_FINAL = 6, BAR_HS = 8 };
+enum { BAR_W = 0, BAR_LDONE = 3, BAR_GDONE = 4, BAR_TOK = 5, BAR_FINAL = 6, BAR_LG = 7, BAR_HS = 8 };
 
 // debug build of the kernel only (tools/debug_persistent.py): per-phase clock64() stamps of one
 // step of cluster 0 / rank 0, and optional dumps of gates / h / logits of that step
@@ -82,9 +88,19 @@ struct Params {
   float temperature;
   float* dbg;                    // debug kernel only
   int dbg_step, dbg_dump;
+  // sampling mode (Predictor.predict_batch, training/predictor.py:295-335)
+  int V, top_k, do_sample;
+  float top_p;
+  unsigned long long seed, offset;
+  const float* uniforms;         // [T][B] or null (Philox)
+  float* probs_trace;            // [T][B][V] or null
 };
 
-template <int DBG>   // 0 = production, 1 = clock stamps, 2 = stamps + value dumps
+// DBG: 0 = production, 1 = clock stamps, 2 = stamps + value dumps.  MODE: 0 = greedy argmax (partials combined across
+// the cluster), 1 = temperature / top-k / top-p sampling: every CTA ships its 128-row logits slice of 8 sequences to the
+// CTA that owns them (3 x 4 KB DSMEM bulk copies, the h-exchange pattern), each of the 32 epilogue warps of the cluster
+// then runs the warp-level selection (sample_select.cuh) for ONE sequence and broadcasts its token with st.async.
+template <int DBG, int MODE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persistent_greedy_kernel(Params P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -104,6 +120,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
     mbar_init(BAR(BAR_GDONE), 1);
     mbar_init(BAR(BAR_TOK), 1);
     mbar_init(BAR(BAR_FINAL), 1);
+    mbar_init(BAR(BAR_LG), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     misc[1] = 0;
   }
@@ -329,8 +346,49 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       for (int j = 0; j < 16; ++j) {
         lg[j] += bias;
         if (DBG == 2 && dbg_dump) P.dbg[16 + 131072 + ((cluster * 4 + rank) * 128 + p) * 32 + col0 + j] = lg[j];
-        if (P.temperature != 1.0f) lg[j] = lg[j] / P.temperature;   // seq2seq.py:213-214
+        if (MODE == 0 && P.temperature != 1.0f) lg[j] = lg[j] / P.temperature;   // seq2seq.py:213-214
       }
+      if (MODE == 1) {
+        // ---- regroup: this CTA's [128 vocab rows] x [32 sequences] slice -> whole rows at the owning warps
+        float* stage = reinterpret_cast<float*>(smem + OFF_STAGE);
+        const float* rx = reinterpret_cast<const float*>(smem + OFF_RX);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) stage[(col0 + j) * 128 + p] = lg[j];
+        if (xt == 0) mbar_arrive_expect_tx(BAR(BAR_TOK), NB * 4);     // 32 tokens will be stored here this step
+        fence_proxy_async();
+        epi_bar_sync();
+        if (tid == 0) {
+          mbar_arrive_expect_tx(BAR(BAR_LG), (CL - 1) * LG_BLOCK_BYTES);
+#pragma unroll
+          for (uint32_t d = 1; d < CL; ++d) {
+            const uint32_t peer = (rank + d) & (CL - 1);              // owner of sequences [8 peer, 8 peer + 8)
+            bulk_s2peer(mapa(sbase + OFF_RX + rank * LG_BLOCK_BYTES, peer), sbase + OFF_STAGE + peer * LG_BLOCK_BYTES,
+                        LG_BLOCK_BYTES, mapa(BAR(BAR_LG), peer));
+          }
+        }
+        mbar_wait(BAR(BAR_LG), s & 1);
+        // warp w owns sequence n = 8 rank + w; vocabulary entry 16 lane + i lives in source CTA lane / 8, row 16 (lane % 8) + i
+        const int n = (NB / CL) * (int)rank + warp;
+        const int srcr = lane >> 3;
+        const float* src = (srcr == (int)rank) ? stage + n * 128 : rx + (srcr * (NB / CL) + warp) * 128;
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v4 = *reinterpret_cast<const float4*>(src + 16 * (lane & 7) + 4 * i);
+          x[4 * i] = v4.x; x[4 * i + 1] = v4.y; x[4 * i + 2] = v4.z; x[4 * i + 3] = v4.w;
+        }
+        const int row = row0 + n;
+        float u = 0.f;
+        if (P.do_sample && row < P.B)
+          u = P.uniforms ? P.uniforms[(size_t)s * P.B + row] : philox_uniform(P.seed, P.offset + (uint64_t)s * P.B + row);
+        float* pout = (P.probs_trace && row < P.B) ? P.probs_trace + ((size_t)s * P.B + row) * P.V : nullptr;
+        const int chosen = warp_sample_select(x, P.V, lane, P.temperature, P.top_k, P.top_p, P.do_sample, u, pout);
+        if (lane == 0) {
+#pragma unroll
+          for (uint32_t d = 0; d < CL; ++d)
+            st_async_b32(mapa(sbase + OFF_TOK + n * 4, d), (uint32_t)chosen, mapa(BAR(BAR_TOK), d));
+        }
+      } else
       // per-column argmax over the warp's 32 vocab rows: order-preserving integer keys, one
       // redux.sync.max.s32 + one ballot per column (uniform results, ~6 instructions per column).
       // The ballot keeps every row holding the maximum; the lowest one wins later (torch.argmax:
@@ -351,12 +409,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
           for (int j = 0; j < 8; ++j) dst[j] = make_uint4((uint32_t)kmax[2 * j], bal[2 * j], (uint32_t)kmax[2 * j + 1], bal[2 * j + 1]);
         }
       }
-      epi_bar_sync();
+      if (MODE == 0) epi_bar_sync();
       if (tid == 0) I2L_TS(8);
       if (xt >= 0 && xt < NB) {
+        int bk = INT_MIN, bi = 0;
+        if (MODE == 1) {
+          mbar_wait_cluster(BAR(BAR_TOK), s & 1);
+          bi = *reinterpret_cast<volatile int*>(tok_s + xt);
+        } else {
         const int cgrp = xt >> 4, j = xt & 15;
         const int2* pp = reinterpret_cast<const int2*>(part);
-        int bk = INT_MIN, bi = 0;
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {                             // ascending row order: strict > keeps the first maximum
           const int2 e = pp[(cgrp * 4 + qq) * 16 + j];
@@ -384,6 +446,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
           if (r == 0 || e.x > bk) { bk = e.x; bi = e.y; }
         }
         tok_s[xt] = bi;
+        }
         // token append + EOS bookkeeping (seq2seq.py:216-221 / predictor.py:338-347)
         const int row = row0 + xt;
         const bool valid = row < P.B;
@@ -550,8 +613,8 @@ size_t persistent_workspace_bytes(const i2l_dec_desc&, int rows, int max_length)
 int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* packed_f32, const PackedDec& lay,
                       const float* enc, int batch, int start_id, int end_id, int max_length, float temperature,
                       int stop_rule, int64_t* tokens, int32_t* lengths, int32_t* steps_run, void* ws, size_t ws_bytes,
-                      cudaStream_t s) {
-  I2L_REQUIRE(start_id >= 0 && start_id < d.vocab_size, "decode_greedy: start token out of range");
+                      cudaStream_t s, const PersistentSampleArgs* sample) {
+  I2L_REQUIRE(start_id >= 0 && start_id < d.vocab_size, "decode loop: start token out of range");
   PWs w = pcarve(batch, max_length, ws);
   if (ws_bytes < w.bytes) { set_error("persistent_greedy: workspace too small"); return I2L_ERR_WORKSPACE; }
   PSection ps = psection(d.vocab_size);
@@ -575,22 +638,30 @@ int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* p
     P.gctx = w.gctx; P.tokens = tokens; P.first_end = w.first_end; P.allend = w.allend; P.cluster_steps = w.cluster_steps;
     P.B = batch; P.T = max_length; P.start_id = start_id; P.end_id = end_id; P.stop_rule = stop_rule;
     P.temperature = temperature;
-    KernelTimer kt("dec.greedy_persistent", s);
-    if (g_dbg_buf != nullptr) {
+    P.V = d.vocab_size;
+    if (sample) {
+      P.top_k = sample->top_k; P.top_p = sample->top_p; P.do_sample = sample->do_sample;
+      P.seed = sample->seed; P.offset = sample->offset; P.uniforms = sample->uniforms; P.probs_trace = sample->probs_trace;
+    }
+    KernelTimer kt(sample ? "dec.sample_persistent" : "dec.greedy_persistent", s);
+    if (sample) {
+      I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SAMPLE));
+      persistent_greedy_kernel<0, 1><<<ncl * CL, THREADS, SMEM_BYTES_SAMPLE, s>>>(P);
+    } else if (g_dbg_buf != nullptr) {
       float hdr[2];
       I2L_CUDA_OK(cudaMemcpyAsync(hdr, g_dbg_buf, sizeof(hdr), cudaMemcpyDeviceToHost, s));
       I2L_CUDA_OK(cudaStreamSynchronize(s));
       P.dbg = g_dbg_buf; P.dbg_step = (int)hdr[0]; P.dbg_dump = (int)hdr[1];
       if (P.dbg_dump) {
-        I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        persistent_greedy_kernel<2><<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
+        I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        persistent_greedy_kernel<2, 0><<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
       } else {
-        I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        persistent_greedy_kernel<1><<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
+        I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        persistent_greedy_kernel<1, 0><<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
       }
     } else {
-      I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      persistent_greedy_kernel<0><<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
+      I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      persistent_greedy_kernel<0, 0><<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
     }
     I2L_LAUNCH_OK();
   } else {

@@ -80,6 +80,11 @@ __device__ __forceinline__ void st_async_v2(uint32_t cluster_addr, uint32_t a, u
                "r"(a), "r"(b), "r"(cluster_bar)
                : "memory");
 }
+__device__ __forceinline__ void st_async_b32(uint32_t cluster_addr, uint32_t a, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(a),
+               "r"(cluster_bar)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)

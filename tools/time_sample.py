@@ -1,23 +1,29 @@
-"""GPU box: time the sampling loop (general path) for the headline decoder, fp32 vs bf16 GEMMs."""
+"""GPU box: time the sampling decode loop (headline decoder, B=1024, 150 steps): persistent kernel vs the
+stream-ordered general path (I2L_NO_PERSISTENT_SAMPLE=1)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import i2l_import
 pkg = i2l_import.load()
-B, T = 1024, 150
-for prec in ("bf16", "fp32"):
-    torch.manual_seed(0)
-    m = pkg.Seq2SeqModel("cnn_lstm", 512, dict(img_height=64, img_width=320, channels=3, embedding_dim=256),
-                         dict(hidden_dim=256, lstm_layers=1, attention=True), precision=prec).cuda().eval()
-    enc = torch.relu(torch.randn(B, 256)).cuda()
-    for _ in range(2):
-        m.decoder.sample(enc, 1, 2, T, temperature=0.8, top_k=50, top_p=0.9, seed=1)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        m.decoder.sample(enc, 1, 2, T, temperature=0.8, top_k=50, top_p=0.9, seed=1)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
-    print(f"sample loop {prec}: {ms:.3f} ms  {ms / T * 1e3:.1f} us/step")
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 150
+torch.manual_seed(0)
+m = pkg.Seq2SeqModel("cnn_lstm", 512, dict(img_height=64, img_width=320, channels=3, embedding_dim=256),
+                     dict(hidden_dim=256, lstm_layers=1, attention=True), precision="bf16").cuda().eval()
+enc = torch.relu(torch.randn(B, 256)).cuda()
+for label, env in (("persistent", None), ("general", "1")):
+    if env: os.environ["I2L_NO_PERSISTENT_SAMPLE"] = env
+    else: os.environ.pop("I2L_NO_PERSISTENT_SAMPLE", None)
+    for args in ((0.8, 50, 0.9), (1.0, 0, 0.9), (1.0, 200, 0.0), (0.7, 0, 0.0)):
+        for _ in range(2):
+            m.decoder.sample(enc, 1, 2, T, *args, seed=1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            tok, ln, st = m.decoder.sample(enc, 1, 2, T, *args, seed=1)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        n = int(st)
+        print(f"{label:10s} T={args[0]} k={args[1]} p={args[2]}: {ms:.3f} ms, {n} steps, {ms / max(n, 1) * 1e3:.2f} us/step")
