@@ -1016,7 +1016,7 @@ extern "C" int i2l_decode_beam(const i2l_dec_desc* d, const void* packed, const 
 // h at [b, t, :]; the vocabulary projection of ALL steps is ONE (B*T, H) x (H, V) GEMM at the end.
 namespace i2l {
 namespace {
-struct FwdWs { DecWs w; int64_t* tok_t; float* h_seq; __nv_bfloat16* hb_seq; size_t bytes; };
+struct FwdWs { DecWs w; int64_t* tok_t; float* h_seq; __nv_bfloat16* hb_seq; char* pws; size_t pws_bytes; size_t bytes; };
 FwdWs carve_fwd(const i2l_dec_desc& d, int batch, int seq_len, void* ws) {
   FwdWs f{};
   f.w = carve(d, batch, 1, ws);
@@ -1026,6 +1026,8 @@ FwdWs carve_fwd(const i2l_dec_desc& d, int batch, int seq_len, void* ws) {
   f.tok_t = a.take<int64_t>(n);
   f.h_seq = a.take<float>(n * d.hidden_dim);
   f.hb_seq = a.take<__nv_bfloat16>(n * d.hidden_dim);
+  f.pws_bytes = (d.precision == I2L_BF16 && persistent_supported(d)) ? persistent_workspace_bytes(d, batch, seq_len) : 0;
+  f.pws = a.take<char>(f.pws_bytes);
   f.bytes = align_up(a.off, 256);
   return f;
 }
@@ -1080,6 +1082,12 @@ extern "C" int i2l_decoder_forward(const i2l_dec_desc* d, const void* packed, co
     I2L_LAUNCH_OK();
   }
   const bool tc = lay.g16 != 0;
+  if (f.pws_bytes != 0 && h_in == nullptr && getenv("I2L_NO_PERSISTENT_FORWARD") == nullptr) {
+    // headline decoder shape in bf16, zero initial state: all T steps inside the persistent cluster kernel
+    float* ho = h_out ? h_out : nullptr;
+    return persistent_forward(*d, reinterpret_cast<const char*>(packed) + lay.bf16_section, pk, lay, enc, f.tok_t, B, T,
+                              logits, ho, c_out, f.pws, f.pws_bytes, s);
+  }
   KernelTimer kt("dec.forward_teacher", s);
   if (tc) {
     I2L_TRY(make_gctx(*d, pk, lay, enc, B, w.gctx, s));       // fp32, as in the general decode loops

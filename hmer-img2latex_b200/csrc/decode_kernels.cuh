@@ -71,6 +71,11 @@ int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* p
                       int32_t* steps_run, void* ws, size_t ws_bytes, cudaStream_t s,
                       const PersistentSampleArgs* sample = nullptr);
 
+// teacher-forced pass on the same kernel (mode 2): tok_t (T,B) given tokens, logits (B,T,V), zero initial state
+int persistent_forward(const i2l_dec_desc& d, const void* section, const float* packed_f32, const PackedDec& lay,
+                       const float* enc, const int64_t* tok_t, int batch, int seq_len, float* logits, float* h_out,
+                       float* c_out, void* ws, size_t ws_bytes, cudaStream_t s);
+
 // persistent bf16 beam search (decode_persistent_beam.cu): same resident-weight cluster kernel with
 // log-softmax + top-K, per-image candidate merge, back-pointers and state reorder on the device.
 bool persistent_beam_supported(const i2l_dec_desc& d, int beam_size);

@@ -94,12 +94,18 @@ struct Params {
   unsigned long long seed, offset;
   const float* uniforms;         // [T][B] or null (Philox)
   float* probs_trace;            // [T][B][V] or null
+  // teacher-forced mode (LSTMDecoder.forward, model/decoder.py:100-195)
+  const int64_t* tok_t;          // [T][B] given input tokens (already range-checked)
+  float* logits_out;             // [B][T][V]
+  float* h_out; float* c_out;    // [B][H] final state, or null
 };
 
 // DBG: 0 = production, 1 = clock stamps, 2 = stamps + value dumps.  MODE: 0 = greedy argmax (partials combined across
 // the cluster), 1 = temperature / top-k / top-p sampling: every CTA ships its 128-row logits slice of 8 sequences to the
 // CTA that owns them (3 x 4 KB DSMEM bulk copies, the h-exchange pattern), each of the 32 epilogue warps of the cluster
-// then runs the warp-level selection (sample_select.cuh) for ONE sequence and broadcasts its token with st.async.
+// then runs the warp-level selection (sample_select.cuh) for ONE sequence and broadcasts its token with st.async;
+// 2 = teacher forcing: the input token of every step is given, the logits of every step are written out, and there is
+// no token exchange at all.
 template <int DBG, int MODE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persistent_greedy_kernel(Params P) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -259,11 +265,28 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
     int* tok_s = reinterpret_cast<int*>(smem + OFF_TOK);
     const float2* gt_base = reinterpret_cast<const float2*>(P.gtok + (size_t)rank * 256) + p;   // [V][rank][128 rows][tile 0,1]
     int s = 0;
+    float hlast[16];                                      // MODE 2: h of the last step (fp32, before the bf16 rounding)
+    if (MODE == 2) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int row = row0 + col0 + j;
+        tok[j] = row < P.B ? (int)P.tok_t[row] : 0;
+        hlast[j] = 0.f;
+      }
+    }
     for (; s < P.T; ++s) {
       const bool dbg_ts = DBG && cluster == 0 && rank == 0 && s == P.dbg_step;
       const bool dbg_dump = DBG == 2 && s == P.dbg_step;
       // ---------------- Epi-G(s): gates -> c_{s+1}, h_{s+1} ----------------
       if (tid == 0) I2L_TS(0);
+      int tok_n[16];                                      // MODE 2: next step's tokens, fetched a step ahead
+      if (MODE == 2 && s + 1 < P.T) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int row = row0 + col0 + j;
+          tok_n[j] = row < P.B ? (int)P.tok_t[(size_t)(s + 1) * P.B + row] : 0;
+        }
+      }
       float gt0[16], gt1[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {                      // token -> gate table rows (L2 resident)
@@ -308,6 +331,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
         float cn = fmaf(y0[j], c[j], pg[j]);
         c[j] = cn;
         hn[j] = y1[j] * TANH(cn);
+        if (MODE == 2) hlast[j] = hn[j];
       }
       if (hi) {
 #pragma unroll
@@ -347,6 +371,20 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
         lg[j] += bias;
         if (DBG == 2 && dbg_dump) P.dbg[16 + 131072 + ((cluster * 4 + rank) * 128 + p) * 32 + col0 + j] = lg[j];
         if (MODE == 0 && P.temperature != 1.0f) lg[j] = lg[j] / P.temperature;   // seq2seq.py:213-214
+      }
+      if (MODE == 2) {
+        // ---- teacher forcing: logits of this step straight to (B,T,V); lanes = consecutive vocabulary rows
+        const int v = 128 * (int)rank + p;
+        if (v < P.V) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int row = row0 + col0 + j;
+            if (row < P.B) P.logits_out[((size_t)row * P.T + s) * P.V + v] = lg[j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) tok[j] = tok_n[j];
+        continue;
       }
       if (MODE == 1) {
         // ---- regroup: this CTA's [128 vocab rows] x [32 sequences] slice -> whole rows at the owning warps
@@ -468,7 +506,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       for (int j = 0; j < 16; ++j) tok[j] = tok_s[col0 + j];
       if (*reinterpret_cast<volatile uint32_t*>(&misc[1])) { ++s; break; }
     }
-    if (rank == 0 && xt >= 0 && xt < NB) {
+    if (MODE == 2) {
+      if (P.h_out != nullptr && hi) {                      // lanes 16..31 own (h, c) of unit u for 16 sequences
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int row = row0 + col0 + j;
+          if (row < P.B) {
+            P.h_out[(size_t)row * H + 64 * rank + u] = hlast[j];
+            P.c_out[(size_t)row * H + 64 * rank + u] = c[j];
+          }
+        }
+      }
+    } else if (rank == 0 && xt >= 0 && xt < NB) {
       const int row = row0 + xt;
       if (row < P.B) P.first_end[row] = fe;
       if (xt == 0) P.cluster_steps[cluster] = s;
@@ -670,6 +719,27 @@ int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* p
   }
   persistent_finalize_kernel<<<1, 256, 0, s>>>(w.first_end, w.allend, w.cluster_steps, ncl, batch, max_length, stop_rule,
                                                lengths, steps_run);
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
+
+// Teacher-forced pass (LSTMDecoder.forward in eval mode) on the persistent kernel: zero initial state only.
+int persistent_forward(const i2l_dec_desc& d, const void* section, const float* packed_f32, const PackedDec& lay,
+                       const float* enc, const int64_t* tok_t, int batch, int seq_len, float* logits, float* h_out,
+                       float* c_out, void* ws, size_t ws_bytes, cudaStream_t s) {
+  PWs w = pcarve(batch, seq_len, ws);
+  if (ws_bytes < w.bytes) { set_error("persistent_forward: workspace too small"); return I2L_ERR_WORKSPACE; }
+  PSection ps = psection(d.vocab_size);
+  const unsigned char* sec = reinterpret_cast<const unsigned char*>(section);
+  I2L_TRY(make_gctx_bf16(d, packed_f32, lay, enc, batch, w.gctx, w.encb, s));
+  Params P{};
+  P.wimg = sec + ps.wimg; P.gtok = reinterpret_cast<const float*>(sec + ps.gtok);
+  P.bias = reinterpret_cast<const float*>(sec + ps.bias);
+  P.gctx = w.gctx; P.B = batch; P.T = seq_len; P.V = d.vocab_size; P.temperature = 1.0f;
+  P.tok_t = tok_t; P.logits_out = logits; P.h_out = h_out; P.c_out = c_out;
+  KernelTimer kt("dec.forward_persistent", s);
+  I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  persistent_greedy_kernel<0, 2><<<cdiv(batch, NB) * CL, THREADS, SMEM_BYTES, s>>>(P);
   I2L_LAUNCH_OK();
   return I2L_OK;
 }

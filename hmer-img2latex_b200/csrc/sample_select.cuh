@@ -82,13 +82,16 @@ __device__ __forceinline__ uint32_t sorted_at32(const uint32_t (&key)[16], int p
 __device__ __forceinline__ int warp_sample_select(const float (&logit)[16], int V, int lane, float temperature, int top_k,
                                                   float top_p, int do_sample, float u, float* probs_out) {
   float po[16];                                             // probabilities in index order
+  const RowDiv dt = row_div(temperature);
   // softmax(logits / T)                                               predictor.py:295-297
+  // (exp through ex2.approx: relative error <= ~5e-6 for the arguments of a softmax, far inside the 1e-3 the
+  // distributions are compared at; the libm-accurate expf costs 17 instructions per entry)
   float lm = -INFINITY;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int v = 16 * lane + i;
     float val = -INFINITY;
-    if (v < V) { val = logit[i]; if (temperature != 1.0f) val = val / temperature; }
+    if (v < V) { val = logit[i]; if (temperature != 1.0f) val = div_by(val, dt); }
     po[i] = val;
     lm = fmaxf(lm, val);
   }
@@ -96,7 +99,7 @@ __device__ __forceinline__ int warp_sample_select(const float (&logit)[16], int 
   for (int o = 16; o > 0; o >>= 1) lm = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, o));
   float ls = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { const float e = (16 * lane + i) < V ? expf(po[i] - lm) : 0.f; po[i] = e; ls += e; }
+  for (int i = 0; i < 16; ++i) { const float e = (16 * lane + i) < V ? __expf(po[i] - lm) : 0.f; po[i] = e; ls += e; }
   const float s = warp_sum(ls);
 #pragma unroll
   const RowDiv ds = row_div(s);

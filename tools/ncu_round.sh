@@ -11,3 +11,9 @@ ncu --set full --clock-control none --import-source on -k regex:'persistent_beam
 # ResNet trunk: the generic conv kernel of one resnet18 forward (stem + the 3x3 / 1x1 convs)
 ncu --set full --clock-control none --import-source on -k regex:'conv_igemm_kernel' -s 63 -c 21 -o gpurun_out/prof_resnet_$TAG -f python tools/bench_resnet.py resnet18 1024 320 > gpurun_out/ncu_full3_$TAG.log 2>&1
 ls -la gpurun_out/ | tail -8
+# sampling mode of the persistent kernel (decode_persistent.cu, MODE = 1)
+ncu --set full --clock-control none --import-source on -k regex:'persistent_greedy_kernel' -s 2 -c 1 -o gpurun_out/prof_sample_$TAG -f python tools/time_sample.py 256 30 > gpurun_out/ncu_full4_$TAG.log 2>&1
+# image preparation and evaluation metrics
+ncu --set full --clock-control none --import-source on -k regex:'resize_rows_kernel|resize_cols_kernel' -s 6 -c 2 -o gpurun_out/prof_pre_$TAG -f python tools/time_preprocess.py > gpurun_out/ncu_full5_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'sequence_metrics_kernel' -s 3 -c 1 -o gpurun_out/prof_metrics_$TAG -f python tools/time_metrics.py > gpurun_out/ncu_full6_$TAG.log 2>&1
+ls -la gpurun_out/ | tail -8
