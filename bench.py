@@ -545,6 +545,17 @@ def next_row_lines(pkg, dev, B):
                      "frac": round(alg / ms / 1e6 / pk["hbm"], 4)},
         "note": "all steps inside the persistent cluster kernel (mode 2: given tokens, logits written per step, no "
                 "token exchange); the stream-ordered path (3 launches per step) measured 3.1 ms"}
+    # validation step of the reference trainer (trainer.py:517-529): forward + label-smoothed CE + masked accuracy
+    lg = m.decoder(enc, tg)
+    tgt_next = torch.roll(tg, -1, dims=1)
+    ms_x = timed(lambda: pkg.metrics.cross_entropy_metrics(lg, tgt_next, 0, 0.1, sync=False), reps=10)
+    row_bytes = B * MAX_LEN * 512 * 4
+    out["validation_loss_accuracy"] = {
+        "workload": "SURVEY 8f-4: CrossEntropyLoss(ignore_index, mean, label_smoothing 0.1) + masked_accuracy over "
+                    "%d x %d x 512 fp32 logits" % (B, MAX_LEN),
+        "value": round(B * MAX_LEN / ms_x * 1e3, 1), "unit": "tokens/s", "ms": round(ms_x, 4),
+        "roofline": {"bound": "hbm", "achieved": round(row_bytes / ms_x / 1e6, 1), "peak": pk["hbm"], "unit": "GB/s",
+                     "frac": round(row_bytes / ms_x / 1e6 / pk["hbm"], 4), "algorithmic_bytes": row_bytes}}
     return out
 
 

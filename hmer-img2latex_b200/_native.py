@@ -111,6 +111,8 @@ SIGNATURES = {
     "i2l_decode_beam": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "i2l_sequence_metrics": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, _fp, _fp]),
+    "i2l_xent_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "i2l_xent_metrics": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int64, C.c_float, _fp, _fp, _fp, C.c_size_t, _fp]),
     "i2l_filter_ids": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, C.POINTER(C.c_int64), C.c_int32, _fp, C.c_int32, _fp, _fp]),
     "i2l_launch_count": (C.c_longlong, []),
     "i2l_prof_enable": (None, [C.c_int]),

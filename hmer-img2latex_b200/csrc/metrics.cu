@@ -150,10 +150,104 @@ __global__ void __launch_bounds__(256) filter_ids_kernel(const int64_t* __restri
   if (lane == 0) out_len[row] = min(kept, ld_out);
 }
 
+// Validation loss / accuracy of the teacher-forced pass (training/trainer.py:111-115, 517-529; training/metrics.py:
+// 226-238): nn.CrossEntropyLoss(ignore_index = pad, reduction = "mean", label_smoothing = eps) over the logits rows
+// and masked_accuracy (argmax == target on non-pad positions).  One warp per (sequence, position) row: the row is read
+// ONCE (HBM-bound: V * 4 bytes per row) for the log-sum-exp, the target logit, the sum of logits and the argmax.
+//   loss = (1 - eps) * mean_i(lse_i - x_i[t_i]) + (eps / V) * mean_i(V * lse_i - sum_c x_i[c])     over rows with t_i != pad
+// Per-row terms go to the workspace and ONE block reduces them in a fixed order in fp64 (deterministic).
+__global__ void __launch_bounds__(256) xent_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets,
+                                                        int N, int V, int64_t ignore_index, float* __restrict__ row_nll,
+                                                        float* __restrict__ row_smooth, int* __restrict__ row_flag) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* x = logits + (size_t)row * V;
+  const int64_t t = targets[row];
+  float mx = -INFINITY, sum = 0.f;
+  int am = 0x7fffffff;
+  for (int c = lane; c < V; c += 32) {
+    const float v = x[c];
+    if (v > mx) { mx = v; am = c; }                       // first maximum of this lane's ascending indices
+    sum += v;
+  }
+  float bm = mx; int bi = am;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(kFull, bm, o);
+    const int oi = __shfl_xor_sync(kFull, bi, o);
+    if (ov > bm || (ov == bm && oi < bi)) { bm = ov; bi = oi; }        // torch.argmax: first index wins
+  }
+  float se = 0.f;
+  for (int c = lane; c < V; c += 32) se += expf(x[c] - bm);            // second pass hits L1
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(kFull, se, o); sum += __shfl_xor_sync(kFull, sum, o); }
+  if (lane == 0) {
+    const bool valid = t != ignore_index;
+    const float lse = bm + logf(se);
+    const float xt = (valid && t >= 0 && t < V) ? x[t] : 0.f;
+    row_nll[row] = valid ? lse - xt : 0.f;
+    row_smooth[row] = valid ? (float)V * lse - sum : 0.f;
+    row_flag[row] = (valid ? 1 : 0) | ((valid && (int64_t)bi == t) ? 2 : 0) | ((valid && (t < 0 || t >= V)) ? 4 : 0);
+  }
+}
+
+__global__ void __launch_bounds__(1024) xent_reduce_kernel(const float* __restrict__ row_nll, const float* __restrict__ row_smooth,
+                                                           const int* __restrict__ row_flag, int N, int V, float eps,
+                                                           float* __restrict__ loss, int32_t* __restrict__ counts) {
+  __shared__ double s_nll[1024], s_sm[1024];
+  __shared__ int s_tok[1024], s_cor[1024], s_bad[1024];
+  double a = 0.0, b = 0.0; int tk = 0, co = 0, bad = 0;
+  for (int i = threadIdx.x; i < N; i += 1024) {           // fixed assignment + fixed tree below: deterministic
+    a += (double)row_nll[i]; b += (double)row_smooth[i];
+    const int f = row_flag[i];
+    tk += f & 1; co += (f >> 1) & 1; bad += (f >> 2) & 1;
+  }
+  s_nll[threadIdx.x] = a; s_sm[threadIdx.x] = b; s_tok[threadIdx.x] = tk; s_cor[threadIdx.x] = co; s_bad[threadIdx.x] = bad;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_nll[threadIdx.x] += s_nll[threadIdx.x + o]; s_sm[threadIdx.x] += s_sm[threadIdx.x + o];
+      s_tok[threadIdx.x] += s_tok[threadIdx.x + o]; s_cor[threadIdx.x] += s_cor[threadIdx.x + o];
+      s_bad[threadIdx.x] += s_bad[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = (double)s_tok[0];                     // 0 non-pad tokens: 0 / 0 = NaN, like torch
+    *loss = (float)((1.0 - (double)eps) * (s_nll[0] / n) + ((double)eps / V) * (s_sm[0] / n));
+    counts[0] = s_cor[0]; counts[1] = s_tok[0]; counts[2] = s_bad[0]; counts[3] = 0;
+  }
+}
+
 }  // namespace
 }  // namespace i2l
 
 using namespace i2l;
+
+extern "C" size_t i2l_xent_workspace_bytes(int32_t rows) { return rows > 0 ? align_up((size_t)rows * 12, 256) + 256 : 0; }
+
+extern "C" int i2l_xent_metrics(const float* logits, const int64_t* targets, int32_t rows, int32_t vocab, int64_t ignore_index,
+                                float label_smoothing, float* loss, int32_t* counts, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  I2L_TRY(device_check());
+  I2L_REQUIRE(rows >= 0 && vocab >= 1, "i2l_xent_metrics: invalid sizes");
+  I2L_REQUIRE(label_smoothing >= 0.f && label_smoothing <= 1.f, "i2l_xent_metrics: label_smoothing must be in [0,1]");
+  I2L_REQUIRE(loss && counts, "i2l_xent_metrics: null output");
+  I2L_REQUIRE(rows == 0 || (logits && targets && workspace), "i2l_xent_metrics: null argument");
+  if (workspace_bytes < i2l_xent_workspace_bytes(rows)) { set_error("i2l_xent_metrics: workspace too small"); return I2L_ERR_WORKSPACE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  float* nll = reinterpret_cast<float*>(workspace);
+  float* sm = nll + rows;
+  int* flag = reinterpret_cast<int*>(sm + rows);
+  KernelTimer kt("eval.xent_metrics", s);
+  if (rows > 0) {
+    xent_rows_kernel<<<cdiv(rows, 8), 256, 0, s>>>(logits, targets, rows, vocab, ignore_index, nll, sm, flag);
+    I2L_LAUNCH_OK();
+  }
+  xent_reduce_kernel<<<1, 1024, 0, s>>>(nll, sm, flag, rows, vocab, label_smoothing, loss, counts);
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
 
 extern "C" int i2l_filter_ids(const int64_t* ids, int32_t ld, const int32_t* len, int32_t batch, const int64_t* drop_host,
                               int32_t n_drop, int64_t* out, int32_t ld_out, int32_t* out_len, void* stream) {

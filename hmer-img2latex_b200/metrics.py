@@ -14,7 +14,7 @@ import torch
 
 from . import _native as N
 
-__all__ = ["filter_ids", "evaluate_ids", "sequence_counts", "levenshtein_distance", "bleu_n_score", "calculate_metrics", "scores_from_counts"]
+__all__ = ["cross_entropy_metrics", "masked_accuracy", "filter_ids", "evaluate_ids", "sequence_counts", "levenshtein_distance", "bleu_n_score", "calculate_metrics", "scores_from_counts"]
 
 
 def _pad(seqs: Sequence[Sequence[int]]) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -46,6 +46,43 @@ def sequence_counts(pred: torch.Tensor, pred_len: torch.Tensor, tgt: torch.Tenso
                                              N.ptr(tgt_len), B, int(max_n), N.ptr(out), N.stream_ptr(dev)),
                 "i2l_sequence_metrics")
     return out
+
+
+def cross_entropy_metrics(logits: torch.Tensor, targets: torch.Tensor, pad_token_id: int, label_smoothing: float = 0.1,
+                          sync: bool = True):
+    """Validation step of the reference trainer (training/trainer.py:517-529) on device-resident logits:
+    ``nn.CrossEntropyLoss(ignore_index=pad, reduction="mean", label_smoothing=0.1)`` (trainer.py:111-115) and
+    ``masked_accuracy`` (training/metrics.py:226-238) in one pass over the logits.  logits (B,T,V) fp32 (what
+    ``Seq2SeqModel.forward`` returns), targets (B,T) int64.  Returns (loss tensor, correct, tokens) -- with
+    ``sync=False`` correct / tokens stay on the device as an int32[4] tensor."""
+    if not logits.is_cuda:
+        raise RuntimeError("cross_entropy_metrics needs CUDA tensors; there is no CPU fallback")
+    dev = logits.device
+    V = logits.shape[-1]
+    lg = logits.to(torch.float32).contiguous().view(-1, V)
+    tg = targets.to(device=dev, dtype=torch.int64).contiguous().view(-1)
+    if tg.numel() != lg.shape[0]:
+        raise ValueError(f"Expected {lg.shape[0]} targets, got {tg.numel()}")
+    n = lg.shape[0]
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    counts = torch.zeros(4, dtype=torch.int32, device=dev)
+    lib = N.lib()
+    ws = torch.empty(max(lib.i2l_xent_workspace_bytes(n), 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(lib.i2l_xent_metrics(N.ptr(lg), N.ptr(tg), n, V, int(pad_token_id), float(label_smoothing), N.ptr(loss),
+                                     N.ptr(counts), N.ptr(ws), ws.numel(), N.stream_ptr(dev)), "i2l_xent_metrics")
+    if not sync:
+        return loss, counts
+    c = counts.tolist()
+    if c[2]:
+        raise IndexError("Target out of bounds")            # what torch's cross_entropy raises on the CPU
+    return loss, c[0], c[1]
+
+
+def masked_accuracy(logits: torch.Tensor, targets: torch.Tensor, pad_token_id: int) -> Tuple[int, int]:
+    """training/metrics.py:226-238: (correct, total) over the non-pad positions."""
+    _, correct, total = cross_entropy_metrics(logits, targets, pad_token_id, 0.0)
+    return correct, total
 
 
 def filter_ids(ids: torch.Tensor, lengths: Optional[torch.Tensor], drop: Sequence[int]) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -284,6 +284,16 @@ int i2l_sequence_metrics(const int64_t* pred, int32_t ld_pred, const int32_t* pr
                          int32_t ld_tgt, const int32_t* tgt_len, int32_t batch, int32_t max_n, int32_t* out,
                          void* stream);
 
+/* Validation loss / accuracy over teacher-forced logits -- replaces nn.CrossEntropyLoss(ignore_index = pad,
+ * reduction = "mean", label_smoothing) as configured in training/trainer.py:111-115 and applied at 517-522, and
+ * masked_accuracy (training/metrics.py:226-238).  logits (rows, vocab) fp32 row-major (rows = B*T of the (B,T,V)
+ * tensor i2l_decoder_forward writes), targets (rows) int64.  loss: device float (NaN when no row counts, like torch);
+ * counts: device int32[4] = {correct, non-pad tokens, targets outside [0,vocab) (torch raises), 0}. */
+size_t i2l_xent_workspace_bytes(int32_t rows);
+int i2l_xent_metrics(const float* logits, const int64_t* targets, int32_t rows, int32_t vocab, int64_t ignore_index,
+                     float label_smoothing, float* loss, int32_t* counts, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 /* Per-row stable compaction out[b] = [x for x in ids[b, :len[b]] if x not in drop]: the id-level effect of
  * tokenizer.decode (drops the four specials, data/tokenizer.py:177-189) + tokenizer.encode on the predictions
  * (cli.py:476-479) and of the padding filter on the targets (cli.py:471-474).  len: NULL => every row has ld

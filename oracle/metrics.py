@@ -11,7 +11,7 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Sequence
 
-__all__ = ["edit_distance", "clipped_matches", "similarity_from_distance", "bleu_from_matches",
+__all__ = ["validation_loss_accuracy", "edit_distance", "clipped_matches", "similarity_from_distance", "bleu_from_matches",
            "levenshtein_distance", "bleu_n_score", "calculate_metrics"]
 
 
@@ -90,3 +90,16 @@ def calculate_metrics(predictions: List[List[int]], targets: List[List[int]]) ->
     bleu = [bleu_n_score(predictions[i], targets[i], 4) for i in range(num)]
     lev = [levenshtein_distance(predictions[i], targets[i]) for i in range(num)]
     return {"bleu": sum(bleu) / num, "levenshtein": sum(lev) / num, "batch_size": num}
+
+
+def validation_loss_accuracy(logits, targets, pad_token_id: int, label_smoothing: float = 0.1):
+    """training/trainer.py:111-115 + 517-529 and training/metrics.py:226-238 restated with torch functional ops on the
+    CPU (test infrastructure): loss = CrossEntropyLoss(ignore_index=pad, reduction="mean", label_smoothing) over
+    logits (B,T,V) / targets (B,T); (correct, total) = masked_accuracy."""
+    import torch
+    import torch.nn.functional as F
+    loss = F.cross_entropy(logits.transpose(1, 2), targets, ignore_index=pad_token_id, reduction="mean",
+                           label_smoothing=label_smoothing)
+    pred = torch.argmax(logits, dim=-1)
+    mask = targets.ne(pad_token_id)
+    return loss, int(torch.logical_and(pred.eq(targets), mask).sum()), int(mask.sum())

@@ -140,6 +140,32 @@ def teacher_forced_case(name):
     save(name, **arrs)
 
 
+@torch.no_grad()
+def validation_case(name):
+    """One validation step of the reference trainer (training/trainer.py:517-529): model(images, formulas) ->
+    CrossEntropyLoss(ignore_index=pad, reduction="mean", label_smoothing=0.1) (trainer.py:111-115) and
+    masked_accuracy (training/metrics.py:226-238)."""
+    masked_accuracy = ref_shim.reference_module("img2latex.training.metrics").masked_accuracy
+    cfg, B, T = H.SMALL, 6, 12
+    p = oracle.make_params(cfg, 2, sharp=True)
+    m = ref_shim.build_reference_model(cfg, p)
+    x = H.make_images(cfg, B)
+    g = torch.Generator().manual_seed(33)
+    formulas = torch.randint(4, cfg["vocab_size"], (B, T + 1), generator=g)
+    formulas[:, 0] = H.START
+    for b in range(B):
+        e = int(torch.randint(3, T + 1, (1,), generator=g))
+        formulas[b, e] = H.END
+        formulas[b, e + 1:] = 0                                   # PAD
+    outputs = m(x, formulas)
+    targets = formulas[:, 1:]
+    crit = torch.nn.CrossEntropyLoss(ignore_index=0, reduction="mean", label_smoothing=0.1)
+    loss = crit(outputs.transpose(1, 2), targets)
+    correct, total = masked_accuracy(outputs, targets, 0)
+    save(name, formulas=formulas, outputs=outputs, loss=np.array(float(loss)), correct=np.array(correct), total=np.array(total),
+         checksum=checksum(p, x))
+
+
 def load_image_case(name):
     """Reference `load_image` (data/utils.py:18-90) on PNG files whose size already equals the
     target size (ResizeWithAspectRatio is then the identity, transforms.py:38-43)."""
@@ -279,6 +305,7 @@ if __name__ == "__main__":
     resize_case("resize.npz")
     metrics_case("metrics.npz")
     checkpoint_case("checkpoint.npz")
+    validation_case("validation.npz")
     predict_batch_case("predict_batch_greedy.npz", 1.0, 0, 0.0)
     predict_batch_case("predict_batch_topk_topp.npz", 0.8, 5, 0.9)
     predict_batch_case("predict_batch_topp.npz", 1.2, 0, 0.7)

@@ -113,3 +113,46 @@ def test_persistent_forward_vs_general_and_oracle(pkg, monkeypatch, B, T):
         _, hh = oracle.decode_step(p, enc, tgt[:, t:t + 1], hh, cfg)
     assert H.rel_err(h, hh[0]) < TOL_STATE and H.rel_err(c, hh[1]) < TOL_STATE
     assert H.rel_err(h, h_g) < TOL_STATE and H.rel_err(c, c_g) < TOL_STATE
+
+
+def test_validation_step_vs_reference_golden(pkg):
+    """One validation step (trainer.py:517-529) on the device: Seq2SeqModel.forward -> i2l_xent_metrics, against the
+    live reference's loss / masked_accuracy (tests/golden/validation.npz)."""
+    d = np.load(os.path.join(G, "validation.npz"))
+    cfg = H.SMALL
+    formulas = torch.as_tensor(d["formulas"])
+    p = oracle.make_params(cfg, 2, sharp=True)
+    m = H.build_model(pkg, cfg, p)
+    x = H.make_images(cfg, formulas.shape[0])
+    out = m(x.cuda(), formulas.cuda())
+    assert H.rel_err(out, torch.as_tensor(d["outputs"])) < 1e-3
+    loss, correct, total = pkg.metrics.cross_entropy_metrics(out, formulas[:, 1:].cuda(), 0, 0.1)
+    assert abs(float(loss) - float(d["loss"])) < 1e-3 * abs(float(d["loss"]))
+    assert total == int(d["total"]) and abs(correct - int(d["correct"])) <= 1       # an argmax near tie may flip one token
+    # on the reference's own logits the kernel reproduces the reference numbers
+    loss2, correct2, total2 = pkg.metrics.cross_entropy_metrics(torch.as_tensor(d["outputs"]).cuda(), formulas[:, 1:].cuda(), 0, 0.1)
+    assert abs(float(loss2) - float(d["loss"])) < 1e-5 * abs(float(d["loss"]))
+    assert (correct2, total2) == (int(d["correct"]), int(d["total"]))
+    assert pkg.metrics.masked_accuracy(torch.as_tensor(d["outputs"]).cuda(), formulas[:, 1:].cuda(), 0) == (correct2, total2)
+
+
+@pytest.mark.parametrize("B,T,V,eps", [(64, 150, 512, 0.1), (5, 7, 46, 0.0), (1024, 150, 512, 0.1), (3, 4, 1000, 0.3)])
+def test_xent_metrics_vs_oracle(pkg, B, T, V, eps):
+    g = torch.Generator().manual_seed(B + V)
+    logits = torch.randn(B, T, V, generator=g) * 4
+    tg = torch.randint(1, V, (B, T), generator=g)
+    ln = torch.randint(1, T + 1, (B,), generator=g)
+    for b in range(B):
+        tg[b, ln[b]:] = 0
+    logits[0, 0, 5] = logits[0, 0, 9] = logits[0, 0].max() + 1.0                # exact tie: first index wins
+    ref_loss, rc, rt = oracle.metrics.validation_loss_accuracy(logits, tg, 0, eps)
+    loss, c, t = pkg.metrics.cross_entropy_metrics(logits.cuda(), tg.cuda(), 0, eps)
+    assert (c, t) == (rc, rt)
+    assert abs(float(loss) - float(ref_loss)) < 2e-6 * abs(float(ref_loss))
+    again = pkg.metrics.cross_entropy_metrics(logits.cuda(), tg.cuda(), 0, eps)
+    assert float(again[0]) == float(loss)                                       # deterministic reduction
+    empty = pkg.metrics.cross_entropy_metrics(logits[:2].cuda(), torch.zeros(2, T, dtype=torch.long).cuda(), 0, eps)
+    assert empty[2] == 0 and torch.isnan(empty[0])                              # torch: mean over no tokens = NaN
+    bad = tg.clone(); bad[0, 0] = V
+    with pytest.raises(IndexError):
+        pkg.metrics.cross_entropy_metrics(logits.cuda(), bad.cuda(), 0, eps)

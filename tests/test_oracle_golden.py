@@ -251,3 +251,19 @@ def test_metrics_golden():
     assert [M.bleu_n_score(p, t, 2) for p, t in zip(preds, tgts)] == d["bleu2"].tolist()
     res = M.calculate_metrics(preds[2:], tgts[2:])
     assert [res["bleu"], res["levenshtein"], float(res["batch_size"])] == d["mean"].tolist()
+
+
+def test_validation_step_golden():
+    """oracle.metrics.validation_loss_accuracy (+ oracle.seq2seq_forward) against one validation step of the live
+    reference trainer's arithmetic (CrossEntropyLoss with label smoothing, masked_accuracy)."""
+    d = load("validation.npz")
+    cfg = H.SMALL
+    formulas = torch.as_tensor(d["formulas"])
+    p = oracle.make_params(cfg, 2, sharp=True)
+    x = H.make_images(cfg, formulas.shape[0])
+    check_inputs(d, p, x)
+    with torch.no_grad():
+        out = oracle.seq2seq_forward(p, x, formulas, cfg)
+    close(out, d["outputs"])
+    loss, correct, total = oracle.metrics.validation_loss_accuracy(torch.as_tensor(d["outputs"]), formulas[:, 1:], 0)
+    assert abs(float(loss) - float(d["loss"])) < 1e-6 and (correct, total) == (int(d["correct"]), int(d["total"]))
