@@ -155,56 +155,96 @@ __global__ void __launch_bounds__(256) filter_ids_kernel(const int64_t* __restri
 // and masked_accuracy (argmax == target on non-pad positions).  One warp per (sequence, position) row: the row is read
 // ONCE (HBM-bound: V * 4 bytes per row) for the log-sum-exp, the target logit, the sum of logits and the argmax.
 //   loss = (1 - eps) * mean_i(lse_i - x_i[t_i]) + (eps / V) * mean_i(V * lse_i - sum_c x_i[c])     over rows with t_i != pad
-// Per-row terms go to the workspace and ONE block reduces them in a fixed order in fp64 (deterministic).
+// A CTA handles 64 rows and writes ONE fp64 partial; one block reduces the partials in a fixed order (deterministic).
+struct XentPartial { double nll, smooth; int tok, cor, bad, pad; };
+constexpr int kXentRowsPerWarp = 8;
 __global__ void __launch_bounds__(256) xent_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets,
-                                                        int N, int V, int64_t ignore_index, float* __restrict__ row_nll,
-                                                        float* __restrict__ row_smooth, int* __restrict__ row_flag) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= N) return;
+                                                        int N, int V, int64_t ignore_index, XentPartial* __restrict__ part) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double w_nll = 0.0, w_sm = 0.0;
+  int w_tok = 0, w_cor = 0, w_bad = 0;
+  for (int rr = 0; rr < kXentRowsPerWarp; ++rr) {
+  const int row = (blockIdx.x * 8 + warp) * kXentRowsPerWarp + rr;
+  if (row >= N) break;
   const float* x = logits + (size_t)row * V;
   const int64_t t = targets[row];
-  float mx = -INFINITY, sum = 0.f;
+  float mx = -INFINITY, sum = 0.f, se = 0.f;
   int am = 0x7fffffff;
-  for (int c = lane; c < V; c += 32) {
-    const float v = x[c];
-    if (v > mx) { mx = v; am = c; }                       // first maximum of this lane's ascending indices
-    sum += v;
-  }
-  float bm = mx; int bi = am;
+  float bm; int bi;
+  if (V <= 512 && (V & 3) == 0) {
+    // the whole row in registers: 128-bit loads, lane holds entries 4 lane + 128 k + {0..3}; read from HBM once
+    float4 r[4];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(kFull, bm, o);
-    const int oi = __shfl_xor_sync(kFull, bi, o);
-    if (ov > bm || (ov == bm && oi < bi)) { bm = ov; bi = oi; }        // torch.argmax: first index wins
+    for (int k = 0; k < 4; ++k) {
+      const int c = 4 * lane + 128 * k;
+      r[k] = c < V ? *reinterpret_cast<const float4*>(x + c) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      const float v4[4] = {r[k].x, r[k].y, r[k].z, r[k].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (c < V) { if (v4[q] > mx) { mx = v4[q]; am = c + q; } sum += v4[q]; }
+    }
+    bm = mx; bi = am;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(kFull, bm, o);
+      const int oi = __shfl_xor_sync(kFull, bi, o);
+      if (ov > bm || (ov == bm && oi < bi)) { bm = ov; bi = oi; }      // torch.argmax: first index wins
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (4 * lane + 128 * k < V) se += expf(r[k].x - bm) + expf(r[k].y - bm) + expf(r[k].z - bm) + expf(r[k].w - bm);
+  } else {
+    for (int c = lane; c < V; c += 32) {
+      const float v = x[c];
+      if (v > mx) { mx = v; am = c; }                     // first maximum of this lane's ascending indices
+      sum += v;
+    }
+    bm = mx; bi = am;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(kFull, bm, o);
+      const int oi = __shfl_xor_sync(kFull, bi, o);
+      if (ov > bm || (ov == bm && oi < bi)) { bm = ov; bi = oi; }      // torch.argmax: first index wins
+    }
+    for (int c = lane; c < V; c += 32) se += expf(x[c] - bm);          // second pass hits L1
   }
-  float se = 0.f;
-  for (int c = lane; c < V; c += 32) se += expf(x[c] - bm);            // second pass hits L1
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(kFull, se, o); sum += __shfl_xor_sync(kFull, sum, o); }
-  if (lane == 0) {
+  {
     const bool valid = t != ignore_index;
+    const bool inb = t >= 0 && t < V;
     const float lse = bm + logf(se);
-    const float xt = (valid && t >= 0 && t < V) ? x[t] : 0.f;
-    row_nll[row] = valid ? lse - xt : 0.f;
-    row_smooth[row] = valid ? (float)V * lse - sum : 0.f;
-    row_flag[row] = (valid ? 1 : 0) | ((valid && (int64_t)bi == t) ? 2 : 0) | ((valid && (t < 0 || t >= V)) ? 4 : 0);
+    const float xt = (valid && inb) ? x[t] : 0.f;
+    if (valid) {                                           // per-row terms in fp32 (as torch computes them), sums in fp64
+      w_nll += (double)(lse - xt);
+      w_sm += (double)((float)V * lse - sum);
+      w_tok += 1; w_cor += ((int64_t)bi == t) ? 1 : 0; w_bad += inb ? 0 : 1;
+    }
+  }
+  }
+  // CTA partial in a fixed order: warp 0..7 (every lane of a warp holds the same sums)
+  __shared__ XentPartial sp[8];
+  if (lane == 0) sp[warp] = XentPartial{w_nll, w_sm, w_tok, w_cor, w_bad, 0};
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    XentPartial a = sp[0];
+    for (int w = 1; w < 8; ++w) { a.nll += sp[w].nll; a.smooth += sp[w].smooth; a.tok += sp[w].tok; a.cor += sp[w].cor; a.bad += sp[w].bad; }
+    part[blockIdx.x] = a;
   }
 }
 
-__global__ void __launch_bounds__(1024) xent_reduce_kernel(const float* __restrict__ row_nll, const float* __restrict__ row_smooth,
-                                                           const int* __restrict__ row_flag, int N, int V, float eps,
-                                                           float* __restrict__ loss, int32_t* __restrict__ counts) {
-  __shared__ double s_nll[1024], s_sm[1024];
-  __shared__ int s_tok[1024], s_cor[1024], s_bad[1024];
+__global__ void __launch_bounds__(256) xent_reduce_kernel(const XentPartial* __restrict__ part, int n_part, int V, float eps,
+                                                          float* __restrict__ loss, int32_t* __restrict__ counts) {
+  __shared__ double s_nll[256], s_sm[256];
+  __shared__ int s_tok[256], s_cor[256], s_bad[256];
   double a = 0.0, b = 0.0; int tk = 0, co = 0, bad = 0;
-  for (int i = threadIdx.x; i < N; i += 1024) {           // fixed assignment + fixed tree below: deterministic
-    a += (double)row_nll[i]; b += (double)row_smooth[i];
-    const int f = row_flag[i];
-    tk += f & 1; co += (f >> 1) & 1; bad += (f >> 2) & 1;
+  for (int i = threadIdx.x; i < n_part; i += 256) {        // fixed assignment + fixed tree below: deterministic
+    const XentPartial p = part[i];
+    a += p.nll; b += p.smooth; tk += p.tok; co += p.cor; bad += p.bad;
   }
   s_nll[threadIdx.x] = a; s_sm[threadIdx.x] = b; s_tok[threadIdx.x] = tk; s_cor[threadIdx.x] = co; s_bad[threadIdx.x] = bad;
   __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
+  for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) {
       s_nll[threadIdx.x] += s_nll[threadIdx.x + o]; s_sm[threadIdx.x] += s_sm[threadIdx.x + o];
       s_tok[threadIdx.x] += s_tok[threadIdx.x + o]; s_cor[threadIdx.x] += s_cor[threadIdx.x + o];
@@ -224,7 +264,10 @@ __global__ void __launch_bounds__(1024) xent_reduce_kernel(const float* __restri
 
 using namespace i2l;
 
-extern "C" size_t i2l_xent_workspace_bytes(int32_t rows) { return rows > 0 ? align_up((size_t)rows * 12, 256) + 256 : 0; }
+static int xent_ctas(int rows) { return cdiv(rows, 8 * kXentRowsPerWarp); }
+extern "C" size_t i2l_xent_workspace_bytes(int32_t rows) {
+  return rows > 0 ? align_up((size_t)xent_ctas(rows) * sizeof(XentPartial), 256) + 256 : 256;
+}
 
 extern "C" int i2l_xent_metrics(const float* logits, const int64_t* targets, int32_t rows, int32_t vocab, int64_t ignore_index,
                                 float label_smoothing, float* loss, int32_t* counts, void* workspace, size_t workspace_bytes,
@@ -233,18 +276,18 @@ extern "C" int i2l_xent_metrics(const float* logits, const int64_t* targets, int
   I2L_REQUIRE(rows >= 0 && vocab >= 1, "i2l_xent_metrics: invalid sizes");
   I2L_REQUIRE(label_smoothing >= 0.f && label_smoothing <= 1.f, "i2l_xent_metrics: label_smoothing must be in [0,1]");
   I2L_REQUIRE(loss && counts, "i2l_xent_metrics: null output");
-  I2L_REQUIRE(rows == 0 || (logits && targets && workspace), "i2l_xent_metrics: null argument");
+  I2L_REQUIRE(rows == 0 || (logits && targets), "i2l_xent_metrics: null argument");
+  I2L_REQUIRE(workspace != nullptr, "i2l_xent_metrics: null workspace");
   if (workspace_bytes < i2l_xent_workspace_bytes(rows)) { set_error("i2l_xent_metrics: workspace too small"); return I2L_ERR_WORKSPACE; }
   cudaStream_t s = (cudaStream_t)stream;
-  float* nll = reinterpret_cast<float*>(workspace);
-  float* sm = nll + rows;
-  int* flag = reinterpret_cast<int*>(sm + rows);
+  XentPartial* part = reinterpret_cast<XentPartial*>(workspace);
+  const int n_cta = rows > 0 ? xent_ctas(rows) : 0;
   KernelTimer kt("eval.xent_metrics", s);
   if (rows > 0) {
-    xent_rows_kernel<<<cdiv(rows, 8), 256, 0, s>>>(logits, targets, rows, vocab, ignore_index, nll, sm, flag);
+    xent_rows_kernel<<<n_cta, 256, 0, s>>>(logits, targets, rows, vocab, ignore_index, part);
     I2L_LAUNCH_OK();
   }
-  xent_reduce_kernel<<<1, 1024, 0, s>>>(nll, sm, flag, rows, vocab, label_smoothing, loss, counts);
+  xent_reduce_kernel<<<1, 256, 0, s>>>(part, n_cta, vocab, label_smoothing, loss, counts);
   I2L_LAUNCH_OK();
   return I2L_OK;
 }
