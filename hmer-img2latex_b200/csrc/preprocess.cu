@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(256) resize_rows_kernel(const uint8_t* __restr
         for (int c = 0; c < CO; ++c) acc[r][c] = 1 << (kPrecisionBits - 1);
       const uint8_t* p0 = s + (size_t)y0 * row_bytes + (size_t)b.x * CS;
       if (rows == kRowGroup) {
+#pragma unroll 4
         for (int x = 0; x < b.y; ++x, p0 += CS) {
           const int k = kk[(size_t)x * ip.new_w + gx];
 #pragma unroll
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(256) resize_cols_kernel(const uint8_t* __restr
       if (SPT == 16) *reinterpret_cast<uint4*>(w) = *reinterpret_cast<const uint4*>(in + (size_t)yy * ip.pitch + s0);
       else w[0] = *reinterpret_cast<const uint32_t*>(in + (size_t)yy * ip.pitch + s0);
 #pragma unroll
-      for (int j = 0; j < SPT; ++j) v[j] = (w[j >> 2] >> (8 * (j & 3))) & 0xff;
+      for (int j = 0; j < SPT; ++j) v[j] = (int)__byte_perm(w[j >> 2], 0u, 0x4440u + (j & 3));   // byte j & 3, zero-extended: one PRMT
     } else {
       const int2 b = bnd[yy];
 #pragma unroll
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(256) resize_cols_kernel(const uint8_t* __restr
         if (SPT == 16) *reinterpret_cast<uint4*>(w) = *reinterpret_cast<const uint4*>(p);
         else w[0] = *reinterpret_cast<const uint32_t*>(p);
 #pragma unroll
-        for (int j = 0; j < SPT; ++j) v[j] += (int)((w[j >> 2] >> (8 * (j & 3))) & 0xff) * k;
+        for (int j = 0; j < SPT; ++j) v[j] += (int)__byte_perm(w[j >> 2], 0u, 0x4440u + (j & 3)) * k;
       }
 #pragma unroll
       for (int j = 0; j < SPT; ++j) v[j] = clip8(v[j]);
