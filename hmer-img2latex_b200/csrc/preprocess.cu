@@ -430,7 +430,12 @@ extern "C" int i2l_resize_pad_u8(const uint8_t* src, const void* plan_host, cons
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   if (hd.max_inter_pixels > 0) {
     KernelTimer kt("pre.resize_rows", s);
-    dim3 grid((unsigned)cdiv(hd.max_inter_pixels, 256), (unsigned)hd.n);
+    // a few CTAs per image, each looping over its share of the (column, row group) items: sizing the grid for the
+    // largest image of a ragged batch leaves half of the CTAs with nothing to do and the rest with ~350 issue cycles
+    int per_image = cdiv(hd.max_inter_pixels, 256);
+    const int cap = getenv("I2L_RESIZE_CTAS") ? atoi(getenv("I2L_RESIZE_CTAS")) : 6;
+    if (per_image > cap) per_image = cap;
+    dim3 grid((unsigned)per_image, (unsigned)hd.n);
     if (hd.src_channels == 1) resize_rows_kernel<1, 1><<<grid, 256, 0, s>>>(src, plan, ws);
     else if (hd.to_gray) resize_rows_kernel<3, 1><<<grid, 256, 0, s>>>(src, plan, ws);
     else resize_rows_kernel<3, 3><<<grid, 256, 0, s>>>(src, plan, ws);
@@ -438,11 +443,12 @@ extern "C" int i2l_resize_pad_u8(const uint8_t* src, const void* plan_host, cons
   }
   {
     KernelTimer kt("pre.resize_cols_pad", s);
+    const int cap = getenv("I2L_RESIZE_CTAS2") ? atoi(getenv("I2L_RESIZE_CTAS2")) : 6;
     if (hd.out_channels == 1) {
-      dim3 grid((unsigned)cdiv(hd.target_h * cdiv(hd.target_w, 16), 256), (unsigned)hd.n);
+      dim3 grid((unsigned)min(cdiv(hd.target_h * cdiv(hd.target_w, 16), 256), cap), (unsigned)hd.n);
       resize_cols_kernel<1, 16><<<grid, 256, 0, s>>>(ws, plan, dst);
     } else {
-      dim3 grid((unsigned)cdiv(hd.target_h * cdiv(hd.target_w * 3, 4), 256), (unsigned)hd.n);
+      dim3 grid((unsigned)min(cdiv(hd.target_h * cdiv(hd.target_w * 3, 4), 256), 4 * cap), (unsigned)hd.n);
       resize_cols_kernel<3, 4><<<grid, 256, 0, s>>>(ws, plan, dst);
     }
     I2L_LAUNCH_OK();
