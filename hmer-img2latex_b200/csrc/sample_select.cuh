@@ -42,9 +42,6 @@ __device__ float philox_uniform(uint64_t seed, uint64_t ctr) {
 // keep the order of the surviving entries, so the order found once is also the order of the top-p pass
 // (predictor.py:311-317 sorts again).  The kept set is a prefix of the sorted order; it is carried back to index
 // order as a threshold VALUE plus a rank among equal values, not as a scatter.
-__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
-  return ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m) << 32) | __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
-}
 __device__ __forceinline__ double warp_excl_scan(double v, int lane, double* total) {
   double inc = v;
 #pragma unroll
