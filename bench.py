@@ -195,11 +195,13 @@ def run_ours(args):
         return time.perf_counter() - t0, last
 
     with torch.no_grad():
+        # clocks / throttle reasons are sampled by one `nvidia-smi -lms 50` child from the warm-up on (the tool needs
+        # ~0.1-0.3 s before its first line, longer when 8 ranks start one each) through both timed regions
+        sampler = ClockSampler(local); sampler.start()
         for i in range(max(args.warmup, 3)):
             step(x_dev[i % NB])
         barrier()
         # ---- device-resident timed region ------------------------------------------------
-        sampler = ClockSampler(local); sampler.start()
         lib.i2l_prof_reset(); lib.i2l_prof_enable(1)
         l0 = lib.i2l_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -217,6 +219,11 @@ def run_ours(args):
         # Seq2SeqModel.greedy_stream: every step copies its own images from pinned host memory
         # (the copy of step i+1 overlaps the compute of step i) and reads the token ids back.
         e2e_s, (tok_h, lens_h, _) = e2e_run(x_host, args.steps)
+        # short runs: keep the same load up until the sampler has lines.  The count depends on the arguments only --
+        # every rank must run the same number of steps (a step ends in the token all-gather)
+        for i in range(max(0, 600 - 2 * args.steps)):
+            step(x_dev[i % NB])
+        torch.cuda.synchronize()
         sampler.stop()
         # the same call with the other host element types (reported next to the headline e2e)
         e2e_other = {}
