@@ -47,3 +47,38 @@ def gather_tokens(tokens: torch.Tensor, lengths: torch.Tensor, steps: torch.Tens
             rows.append(out[r, : hi - lo])
         full = torch.cat(rows, dim=0)
     return full[:, :T1], full[:, T1].to(torch.int32), gsteps        # tokens: a view of the gathered buffer
+
+
+def gather_counts(counts: torch.Tensor, n_total: int) -> torch.Tensor:
+    """Sharded `img2latex evaluate`: all-gather the per-rank (b_r, 8) int32 count matrices of
+    `metrics.sequence_counts` / `metrics.evaluate_ids` into the (n_total, 8) matrix in global image order, so that
+    `metrics.scores_from_counts` + the running sums of `calculate_metrics` (training/metrics.py:205-218) see the pairs
+    in the same order as a single process does (the means are then bit-identical)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return counts
+    ws = dist.get_world_size()
+    cap = (n_total + ws - 1) // ws
+    b = counts.shape[0]
+    buf = torch.zeros((cap, counts.shape[1]), dtype=counts.dtype, device=counts.device)
+    buf[:b] = counts
+    out = torch.empty(ws * cap, counts.shape[1], dtype=counts.dtype, device=counts.device)
+    dist.all_gather_into_tensor(out, buf)
+    rows = []
+    for r in range(ws):
+        lo, hi = shard_bounds(n_total, ws, r)
+        rows.append(out[r * cap: r * cap + (hi - lo)])
+    return torch.cat(rows, dim=0)
+
+
+def reduce_validation(loss: torch.Tensor, correct: int, tokens: int) -> Tuple[float, int, int]:
+    """Sharded validation step: every rank holds the token-mean loss of its shard (`metrics.cross_entropy_metrics`,
+    reduction "mean" over non-pad tokens) and its (correct, tokens) counts.  The global mean over tokens is the
+    token-weighted mean of the shard means (both terms of the label-smoothed loss are normalised by the same
+    count); combined in fp64.  Returns (loss, correct, tokens) of the whole batch on every rank."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(loss), int(correct), int(tokens)
+    v = torch.tensor([float(loss) * tokens if tokens else 0.0, float(correct), float(tokens)], dtype=torch.float64,
+                     device=loss.device)
+    dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    tot = int(v[2].item())
+    return (float(v[0].item()) / tot if tot else float("nan")), int(v[1].item()), tot

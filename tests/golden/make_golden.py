@@ -260,6 +260,24 @@ def checkpoint_case(name):
     save(name, singles=np.array(singles), batch=np.array(batch), vocab_size=np.array(pred.tokenizer.vocab_size))
 
 
+def tokenizer_case(name):
+    """Reference `LaTeXTokenizer` (data/tokenizer.py): default vocabulary, encode / decode round trips, special-token
+    handling -- the detokenise half of SURVEY 8f-2."""
+    ref = ref_shim.load()
+    tok = ref["LaTeXTokenizer"]()
+    tok.default_init()
+    vocab = [tok.id_to_token[i] for i in range(tok.vocab_size)]
+    texts = ["\\frac { a } { b } + \\sum _ { x = 0 } ^ { \\infty } x", "x ^ 2 + unknown_token - y", "", "<START> a <END> <PAD>"]
+    enc = [tok.encode(t) for t in texts]
+    enc_sp = [tok.encode(t, add_special_tokens=True) for t in texts]
+    ids = [[1, 16, 4, 19, 2, 0, 0], [3, 45, 44, 7, 2], [], [1, 2], [99, 5]]
+    dec = [tok.decode(i) for i in ids]
+    dec_keep = [tok.decode(i, skip_special_tokens=False) for i in ids]
+    save(name, vocab=np.array(vocab), texts=np.array(texts), enc=pad_rows(enc + [[0]])[:-1], enc_sp=pad_rows(enc_sp + [[0]])[:-1],
+         ids=pad_rows(ids + [[0]])[:-1], dec=np.array(dec), dec_keep=np.array(dec_keep),
+         specials=np.array([tok.pad_token_id, tok.start_token_id, tok.end_token_id, tok.unk_token_id, tok.max_sequence_length]))
+
+
 def metrics_pairs(seed=31, n=48):
     """Seeded (prediction, target) id lists: small vocabularies (many repeated n-grams), empty / one-token /
     identical / prefix / long cases."""
@@ -306,6 +324,7 @@ if __name__ == "__main__":
     metrics_case("metrics.npz")
     checkpoint_case("checkpoint.npz")
     validation_case("validation.npz")
+    tokenizer_case("tokenizer.npz")
     predict_batch_case("predict_batch_greedy.npz", 1.0, 0, 0.0)
     predict_batch_case("predict_batch_topk_topp.npz", 0.8, 5, 0.9)
     predict_batch_case("predict_batch_topp.npz", 1.2, 0, 0.7)

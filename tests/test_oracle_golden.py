@@ -267,3 +267,24 @@ def test_validation_step_golden():
     close(out, d["outputs"])
     loss, correct, total = oracle.metrics.validation_loss_accuracy(torch.as_tensor(d["outputs"]), formulas[:, 1:], 0)
     assert abs(float(loss) - float(d["loss"])) < 1e-6 and (correct, total) == (int(d["correct"]), int(d["total"]))
+
+
+def test_tokenizer_golden(pkg):
+    """SURVEY 8f-2 (host side): the drop-in LaTeXTokenizer against the live reference's (data/tokenizer.py) default
+    vocabulary, encode (with / without specials, unknown tokens -> UNK) and decode (specials skipped or kept,
+    unknown ids -> the UNK string)."""
+    d = load("tokenizer.npz")
+    tok = pkg.LaTeXTokenizer()
+    tok.default_init()
+    assert [tok.id_to_token[i] for i in range(tok.vocab_size)] == d["vocab"].tolist()
+    assert [tok.pad_token_id, tok.start_token_id, tok.end_token_id, tok.unk_token_id, tok.max_sequence_length] == d["specials"].tolist()
+    texts = d["texts"].tolist()
+    assert [tok.encode(t) for t in texts] == unpad(d["enc"])
+    assert [tok.encode(t, add_special_tokens=True) for t in texts] == unpad(d["enc_sp"])
+    ids = unpad(d["ids"])
+    assert [tok.decode(i) for i in ids] == d["dec"].tolist()
+    assert [tok.decode(i, skip_special_tokens=False) for i in ids] == d["dec_keep"].tolist()
+    # from_config round trip (training/predictor.py:86-105)
+    t2 = pkg.LaTeXTokenizer.from_config({"token_to_id": tok.token_to_id, "special_tokens": tok.special_tokens,
+                                         "max_sequence_length": 77})
+    assert t2.vocab_size == 46 and t2.max_sequence_length == 77 and t2.decode(ids[0]) == d["dec"][0]
