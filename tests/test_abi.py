@@ -84,3 +84,15 @@ def test_state_dict_keys_match_reference(pkg):
         pkg.Seq2SeqModel("vit_lstm", 46)
     with pytest.raises(ValueError, match="Invalid ResNet model name"):
         pkg.ResNetEncoder(model_name="resnet19")
+
+
+def test_cli_predict_surface(pkg):
+    """`img2latex predict` option surface (reference cli.py:253-270): same positionals, option names and defaults."""
+    from hmer_img2latex_b200.cli import build_parser, main
+    a = build_parser().parse_args(["predict", "ckpt.pt", "img.png"])
+    assert (a.beam_size, a.max_length, a.temperature, a.top_k, a.top_p, a.device) == (0, 141, 1.0, 0, 0.0, None)
+    a = build_parser().parse_args(["predict", "c", "i", "--beam-size", "5", "--max-length", "50", "--temperature", "0.8",
+                                   "--top-k", "40", "--top-p", "0.9", "--device", "cuda:0"])
+    assert (a.beam_size, a.max_length, a.temperature, a.top_k, a.top_p, a.device) == (5, 50, 0.8, 40, 0.9, "cuda:0")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        main(["predict", "c", "i", "--device", "cpu"])

@@ -86,3 +86,32 @@ def test_from_checkpoint_vs_reference_golden(pkg, tmp_path):
     imgs = [torch.rand(1, 64, 800, generator=g) for _ in range(4)]
     assert pred.predict_batch(imgs, max_length=24, batch_size=4) == d["batch"].tolist()
     assert [pred.predict(im, max_length=24) for im in imgs] == d["singles"].tolist()
+
+
+def test_cli_predict_on_reference_checkpoint(pkg, tmp_path, capsys):
+    """`img2latex predict CKPT IMG` end to end: checkpoint file in the trainer's layout + PNG on disk -> the string
+    Predictor.predict gives for the same path (device-side load_image: convert L, LANCZOS resize, pad, x/255*2-1)."""
+    from PIL import Image
+    from hmer_img2latex_b200.cli import main
+    p = oracle.make_params(H.CKPT_CFG, 2, sharp=True)
+    ck = str(tmp_path / "best_checkpoint_epoch_3_step_7.pt")
+    H.make_checkpoint(ck, p)
+    rng = np.random.default_rng(5)
+    img = np.full((40, 300, 3), 255, np.uint8)
+    for _ in range(40):
+        y, x = int(rng.integers(0, 36)), int(rng.integers(0, 290))
+        img[y:y + 3, x:x + 8] = 0
+    path = str(tmp_path / "formula.png")
+    Image.fromarray(img, "RGB").save(path)
+    assert main(["predict", ck, path, "--max-length", "24"]) == 0
+    out = capsys.readouterr().out.strip().splitlines()
+    assert out[0] == "Generated LaTeX:"
+    pred = pkg.Predictor.from_checkpoint(ck)
+    assert out[1] == pred.predict(path, max_length=24)
+    # the oracle on the reference's load_image arithmetic gives the same ids
+    g = oracle.resize.resize_with_aspect_ratio(oracle.resize.rgb_to_l(img), 64, 800)
+    x = oracle.normalize_u8(torch.from_numpy(g)[None, None], "pm1")
+    enc = oracle.encoder(p, x, H.CKPT_CFG)
+    ids = oracle.inference_postprocess(oracle.greedy_search(p, enc, H.START, H.END, 24, 1.0, H.CKPT_CFG)[0], H.START, H.END)
+    ids = ids[0] if ids and isinstance(ids[0], list) else ids
+    assert out[1] == pred.tokenizer.decode([i for i in ids if i != H.END])
