@@ -13,6 +13,7 @@ fallback: without the CUDA library every call raises.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -116,11 +117,23 @@ class ResizePlan:
             raise ValueError(f"resize plan rejected: {N.last_error()}")     # Pillow raises ValueError for empty targets
         self._slot, self.host = _POOL.get(self.pixel_bytes + self.plan_bytes)
         hv = self.host.numpy()
+        self.plan_ptr = self.host.data_ptr() + self.pixel_bytes
+        # the weight tables are built by the library's own threads (ctypes releases the GIL for the call) while this
+        # thread packs the pixels into the other half of the staging buffer
+        status = []
+
+        def build():                                     # the error text is thread-local: read it on this thread
+            rc = lib.i2l_resize_plan_build(*args, C.c_void_p(self.plan_ptr), self.plan_bytes)
+            status.append((rc, N.last_error() if rc else ""))
+
+        builder = threading.Thread(target=build)
+        builder.start()
         for i, a in enumerate(arrs):
             o = descs[i].src_offset
             hv[o:o + a.size] = a.reshape(-1)
-        self.plan_ptr = self.host.data_ptr() + self.pixel_bytes
-        N.check(lib.i2l_resize_plan_build(*args, C.c_void_p(self.plan_ptr), self.plan_bytes), "i2l_resize_plan_build")
+        builder.join()
+        if not status or status[0][0] != 0:
+            raise RuntimeError(f"i2l_resize_plan_build failed: {status[0][1] if status else 'builder thread died'}")
         self.workspace_bytes = lib.i2l_resize_workspace_bytes(C.c_void_p(self.plan_ptr))
 
     def describe(self) -> List[dict]:
