@@ -366,19 +366,29 @@ int layout_plan(const i2l_image_desc* imgs, int n, int src_channels, int to_gray
     // the double-precision weight tables are the host cost of a batch (two sin() per weight, as in Pillow):
     // independent jobs, spread over the host cores
     std::atomic<size_t> next{0};
+    std::atomic<bool> failed{false};
     auto worker = [&]() {
-      for (size_t j = next.fetch_add(1); j < jobs.size(); j = next.fetch_add(1))
-        build_table(jobs[j].in, jobs[j].out, filter, reinterpret_cast<int32_t*>(blob + jobs[j].k_off),
-                    reinterpret_cast<int32_t*>(blob + jobs[j].b_off));
+      for (size_t j = next.fetch_add(1); j < jobs.size(); j = next.fetch_add(1)) {
+        try {
+          build_table(jobs[j].in, jobs[j].out, filter, reinterpret_cast<int32_t*>(blob + jobs[j].k_off),
+                      reinterpret_cast<int32_t*>(blob + jobs[j].b_off));
+        } catch (...) {
+          failed.store(true);
+        }
+      }
     };
     unsigned nt = std::thread::hardware_concurrency();
     if (const char* e = getenv("I2L_PLAN_THREADS")) nt = (unsigned)atoi(e);     // 1 = build the tables on the calling thread
     if (nt > 32) nt = 32;
     if (nt > jobs.size() / 4) nt = (unsigned)(jobs.size() / 4);
     std::vector<std::thread> pool;
-    for (unsigned t = 1; t < nt; ++t) pool.emplace_back(worker);
+    try {                                               // nothing may throw across the C ABI: a thread that cannot be
+      for (unsigned t = 1; t < nt; ++t) pool.emplace_back(worker);   // created just leaves its jobs to the others
+    } catch (...) {
+    }
     worker();
     for (auto& t : pool) t.join();
+    if (failed.load()) { set_error("i2l_resize_plan_build: out of host memory while building a weight table"); return I2L_ERR_INVALID; }
     PlanHeader hd{};
     hd.magic = kPlanMagic; hd.n = n; hd.src_channels = src_channels; hd.out_channels = co; hd.to_gray = to_gray;
     hd.target_h = target_h; hd.target_w = target_w; hd.filter = filter; hd.mode = mode; hd.max_inter_pixels = max_inter;
@@ -396,7 +406,12 @@ using namespace i2l;
 extern "C" size_t i2l_resize_plan_bytes(const i2l_image_desc* imgs, int32_t n, int32_t src_channels, int32_t to_gray,
                                         int32_t target_h, int32_t target_w, int32_t filter, int32_t mode) {
   size_t need = 0;
-  if (layout_plan(imgs, n, src_channels, to_gray, target_h, target_w, filter, mode, nullptr, 0, &need) != I2L_OK) return 0;
+  try {
+    if (layout_plan(imgs, n, src_channels, to_gray, target_h, target_w, filter, mode, nullptr, 0, &need) != I2L_OK) return 0;
+  } catch (...) {                                      // std::bad_alloc of the host containers: never across the ABI
+    set_error("i2l_resize_plan_bytes: out of host memory");
+    return 0;
+  }
   return need;
 }
 
@@ -405,8 +420,13 @@ extern "C" int i2l_resize_plan_build(const i2l_image_desc* imgs, int32_t n, int3
                                      void* plan_host, size_t plan_bytes) {
   I2L_REQUIRE(plan_host != nullptr, "i2l_resize_plan_build: null plan buffer");
   size_t need = 0;
-  return layout_plan(imgs, n, src_channels, to_gray, target_h, target_w, filter, mode, reinterpret_cast<char*>(plan_host),
-                     plan_bytes, &need);
+  try {
+    return layout_plan(imgs, n, src_channels, to_gray, target_h, target_w, filter, mode, reinterpret_cast<char*>(plan_host),
+                       plan_bytes, &need);
+  } catch (...) {
+    set_error("i2l_resize_plan_build: out of host memory");
+    return I2L_ERR_INVALID;
+  }
 }
 
 extern "C" size_t i2l_resize_workspace_bytes(const void* plan_host) {
