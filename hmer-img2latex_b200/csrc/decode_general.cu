@@ -922,6 +922,8 @@ extern "C" int i2l_decode_sample(const i2l_dec_desc* d, const void* packed, cons
                                  const float* uniforms, int64_t* tokens, int32_t* lengths, int32_t* steps_run,
                                  float* probs_trace, void* workspace, size_t workspace_bytes, void* stream) {
   I2L_TRY(check_common(d, packed));
+  // predictor.py:295 divides the logits by the temperature: 0 gives +-inf / NaN "probabilities" in the reference; refused here
+  I2L_REQUIRE(temperature != 0.f, "i2l_decode_sample: temperature must be non-zero (the logits are divided by it)");
   cudaStream_t s = (cudaStream_t)stream;
   const bool no_persistent = getenv("I2L_NO_PERSISTENT_SAMPLE") != nullptr;          // A/B switch (tests, tools)
   if (!no_persistent && d->precision == I2L_BF16 && persistent_supported(*d) && batch > 0 && max_length > 0 &&

@@ -251,7 +251,8 @@ int i2l_decode_greedy(const i2l_dec_desc* d, const void* packed, const float* en
 /* replaces the batched loop of Predictor.predict_batch, training/predictor.py:283-347
  * (temperature / top-k / top-p filter 295-327, draw 330-335, sticky finished 343-347).
  * uniforms: optional (max_length,B) fp32 in [0,1) used for the inverse-CDF draw;
- * NULL => Philox4x32-10 keyed by (seed, offset + step*B + row).
+ * NULL => Philox4x32-10 keyed by (seed, offset + step*B + row).  temperature == 0 is refused (I2L_ERR_INVALID):
+ * the reference divides the logits by it.
  * probs_trace: optional (max_length,B,V) fp32 dump of the filtered distribution. */
 int i2l_decode_sample(const i2l_dec_desc* d, const void* packed, const float* enc, int32_t batch,
                       int32_t start_id, int32_t end_id, int32_t max_length, float temperature,

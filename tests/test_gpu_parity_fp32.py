@@ -231,3 +231,12 @@ def test_beam_search(pkg, cfg, K, T, sharp):
     assert one == out[0, : int(olen[0])].tolist()
     fallback = m.inference(x.cuda(), H.START, H.END, max_length=T, beam_size=K)      # B>1 -> greedy (244-247)
     assert fallback == m.inference(x.cuda(), H.START, H.END, max_length=T)
+
+
+def test_sample_refuses_zero_temperature(pkg):
+    """predictor.py:295 divides the logits by the temperature; 0 is refused instead of producing NaN probabilities."""
+    cfg = H.SMALL
+    m = H.build_model(pkg, cfg, oracle.make_params(cfg, 1))
+    enc = torch.zeros(2, cfg["embedding_dim"], device="cuda")
+    with pytest.raises(RuntimeError, match="temperature"):
+        m.decoder.sample(enc, H.START, H.END, 5, 0.0, 5, 0.9)
