@@ -84,6 +84,7 @@ SIGNATURES = {
                                            C.c_int32, C.c_int32]),
     "i2l_resize_plan_build": (C.c_int, [C.POINTER(ImageDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, _fp, C.c_size_t]),
+    "i2l_pack_images": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(ImageDesc), C.c_int32, C.c_int32, _fp]),
     "i2l_resize_workspace_bytes": (C.c_size_t, [_fp]),
     "i2l_resize_pad_u8": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
     "i2l_resnet_num_convs": (C.c_int32, [C.c_int32]),

@@ -116,7 +116,6 @@ class ResizePlan:
         if self.plan_bytes == 0:
             raise ValueError(f"resize plan rejected: {N.last_error()}")     # Pillow raises ValueError for empty targets
         self._slot, self.host = _POOL.get(self.pixel_bytes + self.plan_bytes)
-        hv = self.host.numpy()
         self.plan_ptr = self.host.data_ptr() + self.pixel_bytes
         # the weight tables are built by the library's own threads (ctypes releases the GIL for the call) while this
         # thread packs the pixels into the other half of the staging buffer
@@ -128,9 +127,10 @@ class ResizePlan:
 
         builder = threading.Thread(target=build)
         builder.start()
-        for i, a in enumerate(arrs):
-            o = descs[i].src_offset
-            hv[o:o + a.size] = a.reshape(-1)
+        if self.n:
+            ptrs = (C.c_void_p * self.n)(*[a.ctypes.data for a in arrs])
+            N.check(lib.i2l_pack_images(ptrs, descs, self.n, self.src_channels, C.c_void_p(self.host.data_ptr())),
+                    "i2l_pack_images")
         builder.join()
         if not status or status[0][0] != 0:
             raise RuntimeError(f"i2l_resize_plan_build failed: {status[0][1] if status else 'builder thread died'}")

@@ -144,6 +144,9 @@ size_t i2l_resize_plan_bytes(const i2l_image_desc* imgs, int32_t n, int32_t src_
 int i2l_resize_plan_build(const i2l_image_desc* imgs, int32_t n, int32_t src_channels, int32_t to_gray,
                           int32_t target_h, int32_t target_w, int32_t filter, int32_t mode, void* plan_host,
                           size_t plan_bytes);
+/* HOST: gather n separately allocated HWC uint8 images (images[i] -> descs[i].height x width x channels bytes) into
+ * the packed source buffer at descs[i].src_offset; the copies are spread over a few host threads. */
+int i2l_pack_images(const void* const* images, const i2l_image_desc* descs, int32_t n, int32_t channels, void* dst_host);
 size_t i2l_resize_workspace_bytes(const void* plan_host);
 /* src: packed uint8 source images (device); dst: (n, C_out, target_h, target_w) uint8 NCHW (device), the input
  * layout of i2l_normalize_u8 / i2l_cnn_encoder_fwd_u8.  Two launches for the whole batch, no host sync. */
