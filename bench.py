@@ -39,6 +39,31 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank's host threads (and thereby the first-touch placement of its pinned staging buffers) to the CPU
+    cores NVML reports as local to GPU `index`, when the process is allowed to run there; else leave the affinity
+    alone.  Returns a short description for the bench line."""
+    info = {"allowed_cpus": len(os.sched_getaffinity(0))}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        ideal = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        both = ideal & allowed
+        info["gpu_local_cpus"] = len(ideal)
+        if both and both != allowed:
+            os.sched_setaffinity(0, both)
+            info["bound_to"] = "%d cores local to GPU %d" % (len(both), index)
+        else:
+            info["bound_to"] = "unchanged (%s)" % ("already local" if both else "GPU-local cores not in the allowed set")
+    except Exception as e:                                   # binding is an optimisation, never a failure
+        info["bound_to"] = "unchanged (%s)" % type(e).__name__
+    return info
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons while the timed region runs: ONE long-running
     `nvidia-smi -lms` child (no fork per sample, nothing competing with the launch thread)."""
@@ -128,6 +153,7 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    binding = bind_to_gpu_numa(local)                    # before any pinned allocation
     if world > 1:
         # NCCL may print its version banner to stdout at communicator creation (NCCL_DEBUG=VERSION on
         # some boxes): keep stdout to the one JSON line by pointing fd 1 at stderr until the first collective ran
@@ -142,7 +168,7 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    from hmer_img2latex_b200.dist import gather_tokens
+    from hmer_img2latex_b200.dist import TokenExchange, gather_tokens
 
     torch.manual_seed(0)
     model = pkg.Seq2SeqModel("cnn_lstm", CFG["vocab_size"],
@@ -167,11 +193,31 @@ def run_ours(args):
     x_dev = [xh.to(dev) for xh in x_host]
     lib = N.lib()
 
-    def step(inp):
+    # N > 1: the token all-gather runs as direct peer stores into symmetric memory (dist.TokenExchange,
+    # csrc/token_exchange.cu), pipelined one step behind the compute; NCCL all_gather_into_tensor (gather_tokens) is the
+    # checked reference of that path and the fallback when symmetric memory cannot be set up on this box.
+    xchg, exchange_kind = None, "none"
+    if world > 1 and not args.nccl_gather:
+        try:
+            xchg = TokenExchange(B * world, MAX_LEN + 1, dev)
+            exchange_kind = "p2p stores into symmetric memory + flags (i2l_token_exchange_*), read one step behind"
+        except Exception as e:
+            print("TokenExchange unavailable (%r): NCCL all-gather instead" % (e,), file=sys.stderr)
+    if world > 1 and xchg is None:
+        exchange_kind = "NCCL all_gather_into_tensor on the compute stream"
+
+    def step(inp, xc=None, rows=None):
+        """one pass of the hot path over one batch; N > 1 returns the global result of the PREVIOUS step (p2p path)"""
+        xc = xchg if xc is None else xc
+        if rows is not None:
+            inp = inp[:rows]
         enc = model.encoder.forward_u8(inp) if inp.dtype == torch.uint8 else model.encoder(inp)
         tokens, lengths, steps = model.decoder.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_ALL_END_SAME_STEP)
         if world > 1:
-            tokens, lengths, steps = gather_tokens(tokens, lengths, steps, B * world)
+            if xc is not None:
+                prev = xc.step(tokens, lengths, steps)
+                return prev if prev is not None else (tokens, lengths, steps)
+            tokens, lengths, steps = gather_tokens(tokens, lengths, steps, inp.shape[0] * world)
         return tokens, lengths, steps
 
     def barrier():
@@ -184,15 +230,28 @@ def run_ours(args):
         def host_batches(k):
             for i in range(k):
                 yield hosts[i % len(hosts)]
-        for _ in model.greedy_stream(host_batches(2), START, END, MAX_LEN):
+        for _ in model.greedy_stream(host_batches(2), START, END, MAX_LEN, exchange=xchg):
             pass
         barrier()
         t0 = time.perf_counter()
         last = None
-        for last in model.greedy_stream(host_batches(n), START, END, MAX_LEN):
-            pass   # ranks decode independent shards; the id all-gather is part of `value`, not of e2e
+        for last in model.greedy_stream(host_batches(n), START, END, MAX_LEN, exchange=xchg):
+            pass   # N > 1: the yielded triples are the GLOBAL id matrices (exchange + D2H inside the timed region)
         barrier()
         return time.perf_counter() - t0, last
+
+    def h2d_only(hosts, n):
+        """ceiling of the end-to-end path: the same pinned batches copied to the device, nothing else; seconds"""
+        dst = [torch.empty_like(hosts[0], device=dev) for _ in range(2)]
+        cs = torch.cuda.Stream(dev)
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(cs):
+            for i in range(n):
+                dst[i & 1].copy_(hosts[i % len(hosts)], non_blocking=True)
+        cs.synchronize()
+        barrier()
+        return time.perf_counter() - t0
 
     with torch.no_grad():
         # clocks / throttle reasons are sampled by one `nvidia-smi -lms 50` child from the warm-up on (the tool needs
@@ -200,6 +259,17 @@ def run_ours(args):
         sampler = ClockSampler(local); sampler.start()
         for i in range(max(args.warmup, 3)):
             step(x_dev[i % NB])
+        if xchg is not None:
+            # parity of the p2p exchange with the library collective on the same shard results (every rank checks)
+            xchg.flush()
+            enc = model.encoder.forward_u8(x_dev[0]) if x_dev[0].dtype == torch.uint8 else model.encoder(x_dev[0])
+            t_, l_, s_ = model.decoder.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_ALL_END_SAME_STEP)
+            ref_t, ref_l, ref_s = gather_tokens(t_, l_, s_, B * world)
+            xchg.write(t_, l_, s_)
+            got_t, got_l, got_s = xchg.read()
+            xchg.check()
+            assert torch.equal(got_t, ref_t) and torch.equal(got_l, ref_l) and int(got_s) == int(ref_s), \
+                "p2p token exchange differs from the NCCL all-gather"
         barrier()
         # ---- device-resident timed region ------------------------------------------------
         lib.i2l_prof_reset(); lib.i2l_prof_enable(1)
@@ -208,6 +278,8 @@ def run_ours(args):
         e0.record()
         for i in range(args.steps):
             out = step(x_dev[i % NB])
+        if xchg is not None:
+            out = xchg.flush()                                # the last step's global result: inside the timed region
         e1.record()
         barrier()
         launches = lib.i2l_launch_count() - l0
@@ -219,10 +291,36 @@ def run_ours(args):
         # Seq2SeqModel.greedy_stream: every step copies its own images from pinned host memory
         # (the copy of step i+1 overlaps the compute of step i) and reads the token ids back.
         e2e_s, (tok_h, lens_h, _) = e2e_run(x_host, args.steps)
+        h2d_s = h2d_only(x_host, args.steps)
+        # ---- strong scaling (N > 1): BASELINE configs[1]'s global batch of 1024 split over the ranks ----------------
+        strong = None
+        if world > 1 and B % world == 0 and not args.no_extras:
+            Bs = B // world
+            xs = None
+            try:
+                xs = TokenExchange(B, MAX_LEN + 1, dev) if xchg is not None else None
+            except Exception:
+                xs = None
+            for i in range(3):
+                step(x_dev[i % NB], xs, Bs)
+            if xs is not None:
+                xs.flush()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(args.steps):
+                step(x_dev[i % NB], xs, Bs)
+            if xs is not None:
+                xs.flush()
+            s1.record()
+            barrier()
+            strong = s0.elapsed_time(s1)
         # short runs: keep the same load up until the sampler has lines.  The count depends on the arguments only --
         # every rank must run the same number of steps (a step ends in the token all-gather)
         for i in range(max(0, 600 - 2 * args.steps)):
             step(x_dev[i % NB])
+        if xchg is not None:
+            xchg.flush(); xchg.check()
         torch.cuda.synchronize()
         sampler.stop()
         # the same call with the other host element types (reported next to the headline e2e)
@@ -261,19 +359,20 @@ def run_ours(args):
             beam = [bms, bdec, Bb, K, {k: round(v[1] / nb, 4) for k, v in sorted(bprof.items())}]
         resnet = None
         nxt = None
-        if world == 1 and not args.no_extras:
+        if not args.no_extras:
             try:
-                resnet = resnet_lines(pkg, dev, B)
+                resnet = resnet_lines(pkg, dev, B, world=world)
             except Exception as e:                       # an extra line must never take the headline down
                 resnet = {"error": repr(e)[:300]}
             try:
-                nxt = next_row_lines(pkg, dev, B)
+                nxt = next_row_lines(pkg, dev, B) if world == 1 else None
             except Exception as e:
                 nxt = {"error": repr(e)[:300]}
-    tms = torch.tensor([ms, e2e_s * 1e3, beam[0] if beam else 0.0], device=dev, dtype=torch.float64)
+    tms = torch.tensor([ms, e2e_s * 1e3, beam[0] if beam else 0.0, h2d_s * 1e3, strong or 0.0], device=dev,
+                       dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, beam_ms = float(tms[0]), float(tms[1]), float(tms[2])
+    ms, e2e_ms, beam_ms, h2d_ms, strong_ms = (float(v) for v in tms)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -315,9 +414,10 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: CNN-LSTM greedy decode, batch %d per GPU, 3x64x320 %s images, "
-                               "max_len 150, V=512, E=H=256, L=1, random init" % (B, args.input_dtype),
+        "config": {"workload": "BASELINE configs[1]: CNN-LSTM greedy decode, batch %d per GPU, 3x64x320 images, "
+                               "max_len 150, V=512, E=H=256, L=1, random init" % B,
                    "global_batch": B * world, "parallelism": "dp%d (batch-sharded, token all-gather)" % world,
+                   "token_exchange": exchange_kind, "host_binding": binding,
                    "l2_policy": "%d input batches used in turn (%d x %.0f MB of images) exceed the 126 MB L2; "
                                 "the bf16 activations written per step (587 MB) flush it as well"
                                 % (NB, NB, x_dev[0].numel() * x_dev[0].element_size() / 1e6),
@@ -330,10 +430,24 @@ def run_ours(args):
         "roofline_all_kernels": rooflines,
         "e2e": {"value": round(world * B * args.steps / (e2e_ms / 1e3), 1), "unit": "images/s",
                 "h2d_bytes_per_step": x_host[0].numel() * x_host[0].element_size(),
-                "d2h_bytes_per_step": tok_h.numel() * 8 + lens_h.numel() * 4, "host_dtype": args.input_dtype},
+                "d2h_bytes_per_step": tok_h.numel() * 8 + lens_h.numel() * 4, "host_dtype": args.input_dtype,
+                "h2d_only_ceiling": {"value": round(world * B * args.steps / (h2d_ms / 1e3), 1), "unit": "images/s",
+                                     "GB_per_s_per_gpu": round(x_host[0].numel() * x_host[0].element_size() * args.steps
+                                                               / (h2d_ms / 1e3) / 1e9, 2),
+                                     "note": "the same pinned host batches copied to the device and nothing else "
+                                             "(max over ranks): the PCIe / host-memory bound of e2e"},
+                "frac_of_h2d_ceiling": round(h2d_ms / e2e_ms, 3)},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
+    if strong_ms > 0:
+        line["strong_scaling"] = {
+            "workload": "BASELINE configs[1] with the GLOBAL batch fixed at %d (%d images per GPU), token exchange "
+                        "included" % (B, B // world),
+            "value": round(B * args.steps / (strong_ms / 1e3), 1), "unit": "images/s", "scaling": "strong",
+            "ms_per_step": round(strong_ms / args.steps, 4),
+            "note": "the 150-step decode is a latency chain whose step time does not shrink with the batch (one "
+                    "cluster of 4 SMs per 32 sequences either way); only the encoder scales with 1/N"}
     if e2e_other:
         line["e2e_other_host_dtypes"] = e2e_other
     if beam:
@@ -362,8 +476,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def resnet_lines(pkg, dev, B, reps=3):
-    """BASELINE configs[3] / configs[4] on one GPU (extra lines next to the headline):
+def resnet_lines(pkg, dev, B, reps=3, world=1):
+    """BASELINE configs[3] / configs[4] (extra lines next to the headline; N > 1: B images per GPU, ids all-gathered over
+    NCCL inside the timed step, max time over ranks, whole-job images/s):
     ResNet18-LSTM greedy decode over width-bucketed images (widths uniform in {128,160,...,800}),
     ResNet50-LSTM temperature / top-k / top-p sampling at 3x64x320.  E = H = 256, L = 1, V = 512,
     bf16 tcgen05 trunk (resnet_bf16.cu); images are created on the device (no e2e figure here)."""
@@ -383,9 +498,15 @@ def resnet_lines(pkg, dev, B, reps=3):
         buckets[w] = buckets.get(w, 0) + 1
     xs = {w: torch.randn(n, 3, 64, w, device=dev) for w, n in sorted(buckets.items())}
 
+    import torch.distributed as dist
+    from hmer_img2latex_b200.dist import gather_tokens
+
+    def gathered(res):
+        return gather_tokens(res[0], res[1], res[2], B * world) if world > 1 else res
+
     def step18():
         enc = torch.cat(m.encoder.forward_buckets(list(xs.values()), n_streams=int(os.environ.get('I2L_BUCKET_STREAMS', '4'))), 0)
-        return m.decoder.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_ALL_END_SAME_STEP)
+        return gathered(m.decoder.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_ALL_END_SAME_STEP))
 
     def timed(fn):
         for _ in range(2):
@@ -397,6 +518,10 @@ def resnet_lines(pkg, dev, B, reps=3):
             fn()
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
+        if world > 1:                                      # max over ranks
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
         lib.i2l_prof_reset(); lib.i2l_prof_enable(1)       # separate pass for the per-kernel split (event records cost host time)
         fn()
         torch.cuda.synchronize()
@@ -409,7 +534,7 @@ def resnet_lines(pkg, dev, B, reps=3):
     out["resnet18_bucketed_greedy"] = {
         "workload": "BASELINE configs[3]: ResNet18-LSTM greedy decode, %d images, widths uniform in {128..800 step 32} "
                     "(%d buckets), max_len 150" % (B, len(buckets)),
-        "value": round(B / ms * 1e3, 1), "unit": "images/s", "ms_per_step": round(ms, 3),
+        "value": round(world * B / ms * 1e3, 1), "unit": "images/s", "n_gpus": world, "ms_per_step": round(ms, 3),
         "decode_ms": round(sum(v for k, v in prof.items() if k.startswith("dec.")), 3),
         "note": "buckets replayed as CUDA graphs on 4 streams (ResNetEncoder.forward_buckets)"}
     r = out["resnet18_bucketed_greedy"]
@@ -423,15 +548,15 @@ def resnet_lines(pkg, dev, B, reps=3):
 
     def step50():
         enc = m.encoder(x)
-        return m.decoder.sample(enc, START, END, MAX_LEN, temperature=0.8, top_k=50, top_p=0.9, seed=1)
+        return gathered(m.decoder.sample(enc, START, END, MAX_LEN, temperature=0.8, top_k=50, top_p=0.9, seed=1))
 
     ms, prof = timed(step50)
     enc_ms = sum(v for k, v in prof.items() if k.startswith("rn."))
     fl = 10.43e6 * 320 * B
     out["resnet50_sampling"] = {
-        "workload": "BASELINE configs[4] on one GPU: ResNet50-LSTM sampling (temperature 0.8, top_k 50, top_p 0.9), "
-                    "batch %d, 3x64x320, max_len 150" % B,
-        "value": round(B / ms * 1e3, 1), "unit": "images/s", "ms_per_step": round(ms, 3),
+        "workload": "BASELINE configs[4]: ResNet50-LSTM sampling (temperature 0.8, top_k 50, top_p 0.9), "
+                    "batch %d per GPU on %d GPU(s), 3x64x320, max_len 150" % (B, world),
+        "value": round(world * B / ms * 1e3, 1), "unit": "images/s", "n_gpus": world, "ms_per_step": round(ms, 3),
         "encoder_ms": round(enc_ms, 3), "encoder_tflops": round(fl / enc_ms / 1e9, 1),
         "encoder_frac_of_bf16_peak": round(fl / enc_ms / 1e9 / peaks()["tf_sust"], 3),
         "decode_ms": round(ms - enc_ms, 3)}
@@ -569,67 +694,83 @@ def next_row_lines(pkg, dev, B):
     return out
 
 
-def cpu_baseline(model=None, sample_batch=32, budget_s=20.0, min_reps=1):
-    """The CPU oracle port of the reference path (oracle/port.py: the same ATen CPU kernels the
-    reference calls) timed on the host cores on a bounded sample: BASELINE configs[0]
-    (batch 32, 150 greedy steps), repeated until ~budget_s of CPU work."""
+def reference_runner(params=None):
+    """(step_fn(x) -> None, kind, label): the LIVE reference's own `Seq2SeqModel.inference` (encoder +
+    `_greedy_search`, model/seq2seq.py:124-232, with its per-row `.item()` host syncs) from the travelling copy under
+    oracle/_ref (oracle/make_ref.py) when it is present -- kind "reference" -- else the oracle port of the same path
+    (the same ATen CPU kernels) -- kind "port"."""
     import torch
     import oracle
+    from oracle import ref_shim
     torch.set_num_threads(os.cpu_count())
-    if model is not None:
-        p = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
-    else:
-        p = oracle.make_params(CFG, 0)
+    p = params if params is not None else oracle.make_params(CFG, 0)
+    if ref_shim.available():
+        try:
+            m = ref_shim.build_reference_model(CFG, p)
+            return (lambda x: m.inference(x, START, END, max_length=MAX_LEN)), "reference", \
+                "the reference's own Seq2SeqModel.inference (greedy), fp32, torch CPU"
+        except Exception as e:
+            print("live reference unavailable (%r): timing the oracle port" % (e,), file=sys.stderr)
+
+    def port_step(x):
+        enc = oracle.encoder(p, x, CFG)
+        oracle.greedy_search(p, enc, START, END, MAX_LEN, 1.0, CFG)
+    return port_step, "port", "oracle port of encoder + _greedy_search, fp32, torch CPU"
+
+
+def cpu_baseline(model=None, sample_batch=32, budget_s=20.0, min_reps=1):
+    """The reference's CPU implementation of the path timed on the host cores on a bounded sample: BASELINE configs[0]
+    (batch 32, 150 greedy steps), repeated until ~budget_s of CPU work."""
+    import torch
+    p = {k: v.detach().float().cpu() for k, v in model.state_dict().items()} if model is not None else None
+    step, kind, label = reference_runner(p)
     x = torch.randn(sample_batch, 3, 64, 320, generator=torch.Generator().manual_seed(7))
     times = []
     with torch.no_grad():
-        enc = oracle.encoder(p, x, CFG); oracle.greedy_search(p, enc, START, END, 10, 1.0, CFG)   # warm-up
+        step(x[:4])                                                                              # warm-up
         t_all = time.perf_counter()
         while True:
             t0 = time.perf_counter()
-            enc = oracle.encoder(p, x, CFG)
-            oracle.greedy_search(p, enc, START, END, MAX_LEN, 1.0, CFG)
+            step(x)
             times.append(time.perf_counter() - t0)
             if len(times) >= min_reps and time.perf_counter() - t_all > budget_s:
                 break
     med = statistics.median(times)
     return {"value": round(sample_batch / med, 2), "unit": "images/s", "cores": torch.get_num_threads(),
-            "kind": "port", "sample": "batch %d x %d greedy steps (BASELINE configs[0]), median of %d passes, fp32"
-                                      % (sample_batch, MAX_LEN, len(times))}
+            "kind": kind, "sample": "batch %d x %d greedy steps (BASELINE configs[0]), median of %d passes; %s"
+                                    % (sample_batch, MAX_LEN, len(times), label)}
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path = the oracle port
-    (the reference is pure Python on torch CPU ops and cannot travel to the GPU box; the port
-    calls the same ATen kernels).  Rank 0 only."""
+    """Reference arm: the reference's own CPU implementation of the path on the box's host cores, all threads, on OUR
+    arm's workload -- every step is one full batch of `--batch` (1024) images through encoder + 150 greedy steps.
+    Rank 0 only; the other ranks exit 0 without work."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import torch
-    import oracle
-    torch.set_num_threads(os.cpu_count())
-    p = oracle.make_params(CFG, 0)
-    sb = 32
-    x = torch.randn(sb, 3, 64, 320, generator=torch.Generator().manual_seed(7))
-
-    def step():
-        enc = oracle.encoder(p, x, CFG)
-        oracle.greedy_search(p, enc, START, END, MAX_LEN, 1.0, CFG)
-
+    step, kind, label = reference_runner()
+    B = args.batch
+    x = torch.randn(B, 3, 64, 320, generator=torch.Generator().manual_seed(7))
+    W = max(args.warmup, 1)
     with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 2))):
-            step()
+        # the driver passes our arm's --steps / --warmup; a CPU step takes seconds, so the warm-up runs on a slice of
+        # the batch (it only has to fault in the weights and spin up the thread pool) and the timed steps are full
+        for _ in range(W):
+            step(x[:32])
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            step()
+            step(x)
         dt = time.perf_counter() - t0
-    v = round(sb * args.steps / dt, 2)
-    sample = "each step = batch %d slice of the workload, encoder + %d greedy steps, fp32, torch CPU" % (sb, MAX_LEN)
+    v = round(B * args.steps / dt, 2)
+    sample = "each step = the full batch of %d images, encoder + %d greedy steps; %s" % (B, MAX_LEN, label)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(dt / args.steps * 1e3, 2),
+        "steps": args.steps, "warmup": W, "ms_per_step": round(dt / args.steps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1] sampled: CNN-LSTM greedy decode, 3x64x320, max_len 150, V=512; " + sample},
-        "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "config": {"workload": "BASELINE configs[1]: CNN-LSTM greedy decode, batch %d per GPU, 3x64x320 images, "
+                               "max_len 150, V=512, E=H=256, L=1, random init" % B,
+                   "global_batch": B, "note": "CPU arm: rank 0 only, fp32 normalised images (the reference's input dtype)"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -647,6 +788,8 @@ def main():
                     help="element type of the image tensors (HBM-resident for `value`, pinned host for `e2e`)")
     ap.add_argument("--beam-batch", type=int, default=512, help="images per GPU for the beam-5 line")
     ap.add_argument("--no-extras", action="store_true", help="skip the beam-5 and other-host-dtype measurements")
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="N > 1: token all-gather through NCCL on the compute stream (the checked reference of the p2p exchange)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

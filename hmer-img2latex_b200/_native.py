@@ -19,7 +19,7 @@ MAX_CONV = 8
 MAX_LSTM = 8
 MAX_RESNET_CONVS = 160
 
-FP32, BF16 = 0, 1
+FP32, BF16, BF16_STREAMED = 0, 1, 2
 STOP_NONE, STOP_ALL_END_SAME_STEP, STOP_ALL_FINISHED_STICKY = 0, 1, 2
 PRECISIONS = {"fp32": FP32, "bf16": BF16}
 IN_F32, IN_BF16, IN_U8 = 0, 1, 2
@@ -99,7 +99,7 @@ SIGNATURES = {
     "i2l_dec_packed_bytes": (C.c_size_t, [C.POINTER(DecDesc)]),
     "i2l_dec_pack": (C.c_int, [C.POINTER(DecDesc), C.POINTER(DecParams), _fp, C.c_size_t, _fp]),
     "i2l_dec_workspace_bytes": (C.c_size_t, [C.POINTER(DecDesc), C.c_int32, C.c_int32]),
-    "i2l_decode_step": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp,
+    "i2l_decode_step": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, _fp, C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                                   C.c_size_t, _fp]),
     "i2l_dec_forward_workspace_bytes": (C.c_size_t, [C.POINTER(DecDesc), C.c_int32, C.c_int32]),
     "i2l_decoder_forward": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, _fp, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp, _fp,
@@ -110,7 +110,11 @@ SIGNATURES = {
                                     C.c_float, C.c_int32, C.c_float, C.c_uint64, C.c_uint64, _fp, _fp, _fp, _fp,
                                     _fp, _fp, C.c_size_t, _fp]),
     "i2l_decode_beam": (C.c_int, [C.POINTER(DecDesc), _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                  C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+                                  C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "i2l_token_exchange_buffer_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "i2l_token_exchange_write": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                           C.POINTER(C.c_void_p), C.c_uint32, _fp]),
+    "i2l_token_exchange_read": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, _fp, _fp, _fp, _fp, _fp]),
     "i2l_sequence_metrics": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     "i2l_xent_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "i2l_xent_metrics": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int64, C.c_float, _fp, _fp, _fp, C.c_size_t, _fp]),

@@ -642,7 +642,11 @@ size_t cnn_bf16_workspace_bytes(const i2l_cnn_desc&, int batch) { return carve(b
 
 // I2L_DEBUG_SYNC=1: synchronise after every encoder kernel so that a device fault is attributed
 static int dbg_sync(const char* what, cudaStream_t s) {
+#ifdef I2L_DIAG
   static const bool on = getenv("I2L_DEBUG_SYNC") != nullptr;
+#else
+  constexpr bool on = false;   // production library: never synchronises the host
+#endif
   if (!on) return I2L_OK;
   cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return I2L_ERR_CUDA; }
@@ -672,7 +676,11 @@ int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const void* x, int in
     uint32_t box[4] = {(uint32_t)(in_u8 ? C1In<uint8_t>::PATCH_W : in_bf16 ? C1In<__nv_bfloat16>::PATCH_W : C1In<float>::PATCH_W), PATCH_H, C0, 1};
     I2L_TRY(make_tensor_map(&tm, x, 4, dims, str, box, 0, (int)el));
     const int n_tiles = B * 40;
+#ifdef I2L_DIAG
     const int dbg = getenv("I2L_CONV1_DBG") ? atoi(getenv("I2L_CONV1_DBG")) : 0;
+#else
+    const int dbg = 0;
+#endif
     KernelTimer kt(in_u8 ? "cnn.conv1_u8in" : in_bf16 ? "cnn.conv1_bf16in" : "cnn.conv1_bf16", s);
     if (in_u8) {
       I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));

@@ -67,6 +67,17 @@ __global__ void f32_to_bf16_ld_kernel(const float* __restrict__ src, int ld, __n
   if (i < n) dst[i] = __float2bfloat16(src[(i / cols) * ld + (i % cols)]);
 }
 
+// (B,T) -> (T,B) with the nn.Embedding range check: ids outside [0,V) set *bad and are read as 0
+__global__ void transpose_tokens_kernel(const int64_t* __restrict__ src, int64_t* __restrict__ dst, int B, int T, int V,
+                                        int* bad) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * T) return;
+  int t = (int)(i / B), b = (int)(i % B);
+  int64_t v = src[(size_t)b * T + t];
+  if (v < 0 || v >= V) { if (bad) atomicExch(bad, 1); v = 0; }
+  dst[i] = v;
+}
+
 __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) o[i] = a[i] + b[i];
@@ -612,6 +623,16 @@ DecWs carve(const i2l_dec_desc& d, int rows, int max_length, void* ws) {
   return w;
 }
 
+// I2L_BF16_STREAMED = bf16 arithmetic on the stream-ordered path only (no persistent cluster kernel): same packed
+// layout and workspace as I2L_BF16, so one packed model serves both; the entry points work on the normalised copy.
+struct DescN {
+  i2l_dec_desc d;
+  bool streamed;
+  explicit DescN(const i2l_dec_desc* in) : d(in ? *in : i2l_dec_desc{}), streamed(in && in->precision == I2L_BF16_STREAMED) {
+    if (streamed) d.precision = I2L_BF16;
+  }
+};
+
 int check_common(const i2l_dec_desc* d, const void* packed) {
   I2L_TRY(device_check());
   I2L_REQUIRE(d != nullptr && packed != nullptr, "decoder: null descriptor / packed weights");
@@ -753,11 +774,13 @@ using namespace i2l;
 // ====================================================================== C ABI
 extern "C" size_t i2l_dec_packed_bytes(const i2l_dec_desc* d) {
   if (!d) return 0;
-  return dec_layout(*d).total_bytes;
+  return dec_layout(DescN(d).d).total_bytes;
 }
 
-extern "C" int i2l_dec_pack(const i2l_dec_desc* d, const i2l_dec_params* p, void* packed, size_t packed_bytes,
+extern "C" int i2l_dec_pack(const i2l_dec_desc* d_in, const i2l_dec_params* p, void* packed, size_t packed_bytes,
                             void* stream) {
+  const DescN dn_(d_in);
+  const i2l_dec_desc* d = d_in ? &dn_.d : nullptr;
   I2L_TRY(check_common(d, packed));
   I2L_REQUIRE(p != nullptr, "i2l_dec_pack: null params");
   cudaStream_t s = (cudaStream_t)stream;
@@ -804,16 +827,20 @@ extern "C" int i2l_dec_pack(const i2l_dec_desc* d, const i2l_dec_params* p, void
   return I2L_OK;
 }
 
-extern "C" size_t i2l_dec_workspace_bytes(const i2l_dec_desc* d, int32_t rows, int32_t max_length) {
+extern "C" size_t i2l_dec_workspace_bytes(const i2l_dec_desc* d_in, int32_t rows, int32_t max_length) {
+  const DescN dn_(d_in);
+  const i2l_dec_desc* d = d_in ? &dn_.d : nullptr;
   if (!d || rows <= 0) return 0;
   size_t b = carve(*d, rows, max_length, nullptr).bytes;
   if (d->precision == I2L_BF16 && persistent_supported(*d)) b += persistent_workspace_bytes(*d, rows, max_length);
   return b;
 }
 
-extern "C" int i2l_decode_step(const i2l_dec_desc* d, const void* packed, const float* enc, const int64_t* tok,
+extern "C" int i2l_decode_step(const i2l_dec_desc* d_in, const void* packed, const float* enc, const int64_t* tok,
                                int32_t batch, const float* h_in, const float* c_in, float* logits, float* h_out,
-                               float* c_out, void* workspace, size_t workspace_bytes, void* stream) {
+                               float* c_out, int32_t* bad_token_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  const DescN dn_(d_in);
+  const i2l_dec_desc* d = d_in ? &dn_.d : nullptr;
   I2L_TRY(check_common(d, packed));
   I2L_REQUIRE(batch >= 0 && enc && tok && logits && h_out && c_out, "i2l_decode_step: null argument");
   I2L_REQUIRE((h_in == nullptr) == (c_in == nullptr), "i2l_decode_step: h_in and c_in must both be given or both NULL");
@@ -831,7 +858,9 @@ extern "C" int i2l_decode_step(const i2l_dec_desc* d, const void* packed, const 
     I2L_CUDA_OK(cudaMemsetAsync(h_out, 0, n, s));
     I2L_CUDA_OK(cudaMemsetAsync(c_out, 0, n, s));
   }
-  I2L_CUDA_OK(cudaMemcpyAsync(w.tok_cur, tok, (size_t)batch * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  // ids outside [0, V) never reach the gate-table gather: read as 0, reported through the flag (nn.Embedding: IndexError)
+  transpose_tokens_kernel<<<cdiv(batch, 256), 256, 0, s>>>(tok, w.tok_cur, batch, 1, d->vocab_size, bad_token_flag);
+  I2L_LAUNCH_OK();
   I2L_TRY(make_gctx(*d, pk, lay, enc, batch, w.gctx, s));
   DecWs w2 = w; w2.logits = logits;
   return step_rows(*d, pk, lay, w2, h_out, c_out, batch, nullptr, s);
@@ -846,6 +875,8 @@ static int run_loop(const i2l_dec_desc* d, const void* packed, const float* enc,
   I2L_REQUIRE(batch >= 0 && max_length >= 0 && tokens != nullptr, "decode loop: invalid arguments");
   I2L_REQUIRE(batch == 0 || enc != nullptr, "decode loop: null encoder output");
   I2L_REQUIRE(stop_rule >= 0 && stop_rule <= 2, "decode loop: invalid stop rule");
+  I2L_REQUIRE(start_id >= 0 && start_id < d->vocab_size, "decode loop: start token %d outside [0, %d) (nn.Embedding raises IndexError)",
+              start_id, d->vocab_size);
   if (batch == 0) return I2L_OK;
   PackedDec lay = dec_layout(*d);
   DecWs w = carve(*d, batch, max_length, workspace);
@@ -896,13 +927,15 @@ static int run_loop(const i2l_dec_desc* d, const void* packed, const float* enc,
   return I2L_OK;
 }
 
-extern "C" int i2l_decode_greedy(const i2l_dec_desc* d, const void* packed, const float* enc, int32_t batch,
+extern "C" int i2l_decode_greedy(const i2l_dec_desc* d_in, const void* packed, const float* enc, int32_t batch,
                                  int32_t start_id, int32_t end_id, int32_t max_length, float temperature,
                                  int32_t stop_rule, int64_t* tokens, int32_t* lengths, int32_t* steps_run,
                                  void* workspace, size_t workspace_bytes, void* stream) {
+  const DescN dn_(d_in);
+  const i2l_dec_desc* d = d_in ? &dn_.d : nullptr;
   I2L_TRY(check_common(d, packed));
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->precision == I2L_BF16 && persistent_supported(*d) && batch > 0 && temperature > 0.f) {
+  if (!dn_.streamed && d->precision == I2L_BF16 && persistent_supported(*d) && batch > 0 && temperature > 0.f) {
     PackedDec lay = dec_layout(*d);
     size_t gen = carve(*d, batch, max_length, nullptr).bytes;
     I2L_REQUIRE(workspace_bytes >= gen + persistent_workspace_bytes(*d, batch, max_length),
@@ -916,16 +949,18 @@ extern "C" int i2l_decode_greedy(const i2l_dec_desc* d, const void* packed, cons
                   0, nullptr, tokens, lengths, steps_run, nullptr, workspace, workspace_bytes, s);
 }
 
-extern "C" int i2l_decode_sample(const i2l_dec_desc* d, const void* packed, const float* enc, int32_t batch,
+extern "C" int i2l_decode_sample(const i2l_dec_desc* d_in, const void* packed, const float* enc, int32_t batch,
                                  int32_t start_id, int32_t end_id, int32_t max_length, float temperature,
                                  int32_t top_k, float top_p, uint64_t seed, uint64_t offset,
                                  const float* uniforms, int64_t* tokens, int32_t* lengths, int32_t* steps_run,
                                  float* probs_trace, void* workspace, size_t workspace_bytes, void* stream) {
+  const DescN dn_(d_in);
+  const i2l_dec_desc* d = d_in ? &dn_.d : nullptr;
   I2L_TRY(check_common(d, packed));
   // predictor.py:295 divides the logits by the temperature: 0 gives +-inf / NaN "probabilities" in the reference; refused here
   I2L_REQUIRE(temperature != 0.f, "i2l_decode_sample: temperature must be non-zero (the logits are divided by it)");
   cudaStream_t s = (cudaStream_t)stream;
-  const bool no_persistent = getenv("I2L_NO_PERSISTENT_SAMPLE") != nullptr;          // A/B switch (tests, tools)
+  const bool no_persistent = dn_.streamed;
   if (!no_persistent && d->precision == I2L_BF16 && persistent_supported(*d) && batch > 0 && max_length > 0 &&
       end_id >= 0 && end_id < d->vocab_size && tokens != nullptr) {
     // headline decoder shape in bf16: the whole sampling loop runs inside the persistent cluster kernel
@@ -947,15 +982,19 @@ extern "C" int i2l_decode_sample(const i2l_dec_desc* d, const void* packed, cons
                   steps_run, probs_trace, workspace, workspace_bytes, s);
 }
 
-extern "C" int i2l_decode_beam(const i2l_dec_desc* d, const void* packed, const float* enc, int32_t batch,
+extern "C" int i2l_decode_beam(const i2l_dec_desc* d_in, const void* packed, const float* enc, int32_t batch,
                                int32_t beam_size, int32_t start_id, int32_t end_id, int32_t max_length,
                                int64_t* out_tokens, int32_t* out_len, double* out_score, int32_t* trace_parent,
-                               int32_t* trace_token, double* trace_score, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               int32_t* trace_token, double* trace_score, int32_t* cand_token, float* cand_logp,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  const DescN dn_(d_in);
+  const i2l_dec_desc* d = d_in ? &dn_.d : nullptr;
   I2L_TRY(check_common(d, packed));
   I2L_REQUIRE(beam_size >= 1 && beam_size <= I2L_MAX_BEAM, "i2l_decode_beam: beam_size must be in [1,%d]", I2L_MAX_BEAM);
   I2L_REQUIRE(beam_size <= d->vocab_size, "i2l_decode_beam: beam_size exceeds the vocabulary (torch.topk would raise)");
   I2L_REQUIRE(batch >= 0 && max_length >= 1 && out_tokens && out_len && out_score, "i2l_decode_beam: invalid arguments");
+  I2L_REQUIRE(start_id >= 0 && start_id < d->vocab_size, "i2l_decode_beam: start token %d outside [0, %d) (nn.Embedding raises IndexError)",
+              start_id, d->vocab_size);
   if (batch == 0) return I2L_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int K = beam_size, R = batch * K, H = d->hidden_dim, V = d->vocab_size;
@@ -966,12 +1005,18 @@ extern "C" int i2l_decode_beam(const i2l_dec_desc* d, const void* packed, const 
   int* trp = trace_parent ? trace_parent : w.tr_parent;
   int* trt = trace_token ? trace_token : w.tr_token;
   double* trs = trace_score ? trace_score : w.tr_score;
-  if (d->precision == I2L_BF16 && persistent_beam_supported(*d, K) && end_id >= 0 && end_id < V && start_id >= 0 &&
-      start_id < V) {
+  I2L_REQUIRE((cand_token == nullptr) == (cand_logp == nullptr), "i2l_decode_beam: cand_token and cand_logp go together");
+  const bool persistent = !dn_.streamed && d->precision == I2L_BF16 && persistent_beam_supported(*d, K) && end_id >= 0 &&
+                          end_id < V;
+  if (cand_token != nullptr && !persistent) {
+    set_error("i2l_decode_beam: the candidate audit trail needs the persistent kernel (bf16 headline decoder, beam <= 8)");
+    return I2L_ERR_UNSUPPORTED;
+  }
+  if (persistent) {
     // headline shape in bf16: the whole search runs inside one persistent cluster kernel
     I2L_TRY(make_gctx(*d, pk, lay, enc, batch, w.gates, s));
     I2L_TRY(persistent_beam(*d, reinterpret_cast<const char*>(packed) + lay.bf16_section, w.gates, batch, K, start_id,
-                            end_id, max_length, w.bstate, w.score, trp, trt, trace_score, s));
+                            end_id, max_length, w.bstate, w.score, trp, trt, trace_score, cand_token, cand_logp, s));
     beam_finalize_kernel<<<cdiv(batch, 128), 128, 0, s>>>(w.bstate, w.score, trp, trt, batch, K, max_length, end_id,
                                                           out_tokens, out_len, out_score);
     I2L_LAUNCH_OK();
@@ -1034,27 +1079,22 @@ FwdWs carve_fwd(const i2l_dec_desc& d, int batch, int seq_len, void* ws) {
   return f;
 }
 // (B,T) -> (T,B); ids outside [0,V) raise the device flag (nn.Embedding would raise IndexError) and read row 0
-__global__ void transpose_tokens_kernel(const int64_t* __restrict__ src, int64_t* __restrict__ dst, int B, int T, int V,
-                                        int* bad) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * T) return;
-  int t = (int)(i / B), b = (int)(i % B);
-  int64_t v = src[(size_t)b * T + t];
-  if (v < 0 || v >= V) { if (bad) atomicExch(bad, 1); v = 0; }
-  dst[i] = v;
-}
 }  // namespace
 }  // namespace i2l
 
-extern "C" size_t i2l_dec_forward_workspace_bytes(const i2l_dec_desc* d, int32_t batch, int32_t seq_len) {
+extern "C" size_t i2l_dec_forward_workspace_bytes(const i2l_dec_desc* d_in, int32_t batch, int32_t seq_len) {
+  const DescN dn_(d_in);
+  const i2l_dec_desc* d = d_in ? &dn_.d : nullptr;
   if (!d || batch <= 0 || seq_len <= 0) return 0;
   return carve_fwd(*d, batch, seq_len, nullptr).bytes;
 }
 
-extern "C" int i2l_decoder_forward(const i2l_dec_desc* d, const void* packed, const float* enc,
+extern "C" int i2l_decoder_forward(const i2l_dec_desc* d_in, const void* packed, const float* enc,
                                    const int64_t* target, int32_t batch, int32_t seq_len, const float* h_in,
                                    const float* c_in, float* logits, float* h_out, float* c_out,
                                    int32_t* bad_token_flag, void* workspace, size_t workspace_bytes, void* stream) {
+  const DescN dn_(d_in);
+  const i2l_dec_desc* d = d_in ? &dn_.d : nullptr;
   I2L_TRY(check_common(d, packed));
   I2L_REQUIRE(batch >= 0 && seq_len >= 0, "i2l_decoder_forward: negative sizes");
   I2L_REQUIRE((h_in == nullptr) == (c_in == nullptr), "i2l_decoder_forward: h_in and c_in must both be given or both NULL");
@@ -1084,7 +1124,7 @@ extern "C" int i2l_decoder_forward(const i2l_dec_desc* d, const void* packed, co
     I2L_LAUNCH_OK();
   }
   const bool tc = lay.g16 != 0;
-  if (f.pws_bytes != 0 && h_in == nullptr && getenv("I2L_NO_PERSISTENT_FORWARD") == nullptr) {
+  if (f.pws_bytes != 0 && h_in == nullptr && !dn_.streamed) {
     // headline decoder shape in bf16, zero initial state: all T steps inside the persistent cluster kernel
     float* ho = h_out ? h_out : nullptr;
     return persistent_forward(*d, reinterpret_cast<const char*>(packed) + lay.bf16_section, pk, lay, enc, f.tok_t, B, T,
@@ -1189,13 +1229,12 @@ extern "C" int i2l_attention_fwd(int32_t H, int32_t E, const float* attn_w, cons
   return I2L_OK;
 }
 
+#ifdef I2L_DIAG   // diagnostics library only (make diag -> libi2l_b200_diag.so); the production library carries none of this
 // debug aid (tools/debug_persistent.py): dump intermediates of one step of the persistent kernel
 namespace i2l { int persistent_set_debug(float* buf); }
 extern "C" int i2l_debug_set_buffer(float* buf) { return i2l::persistent_set_debug(buf); }
 // test aid: (T,B,K,K) device buffers that receive every live beam's top-K (token, log-prob) of the
 // next persistent beam calls (NULL, NULL switches the dump off)
-namespace i2l { int persistent_beam_set_debug(int* cand_tok, float* cand_logp); int persistent_beam_set_ts(long long* ts, int step); }
+namespace i2l { int persistent_beam_set_ts(long long* ts, int step); }
 extern "C" int i2l_debug_set_beam_ts(long long* ts, int32_t step) { return i2l::persistent_beam_set_ts(ts, step); }
-extern "C" int i2l_debug_set_beam_trace(int32_t* cand_tok, float* cand_logp) {
-  return i2l::persistent_beam_set_debug(cand_tok, cand_logp);
-}
+#endif

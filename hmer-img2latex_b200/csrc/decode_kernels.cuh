@@ -81,6 +81,6 @@ int persistent_forward(const i2l_dec_desc& d, const void* section, const float* 
 bool persistent_beam_supported(const i2l_dec_desc& d, int beam_size);
 int persistent_beam(const i2l_dec_desc& d, const void* section, const float* gctx_img, int batch, int beam_size,
                     int start_id, int end_id, int max_length, BeamState* bstate, double* score, int* tr_parent,
-                    int* tr_token, double* tr_score, cudaStream_t s);
+                    int* tr_token, double* tr_score, int* cand_tok, float* cand_logp, cudaStream_t s);
 
 }  // namespace i2l

@@ -627,11 +627,13 @@ PWs pcarve(int rows, int T, void* ws) {
 
 }  // namespace
 
+#ifdef I2L_DIAG   // diagnostics library only: the DBG instantiations (clock stamps / value dumps of one step) and their host sync
 static float* g_dbg_buf = nullptr;   // host-side: when set, the DBG instantiation of the kernel is launched
 int persistent_set_debug(float* buf) {
   g_dbg_buf = buf;
   return I2L_OK;
 }
+#endif
 
 bool persistent_supported(const i2l_dec_desc& d) {
   return d.hidden_dim == H && d.embedding_dim == E && d.lstm_layers == 1 && d.vocab_size <= VMAX && d.vocab_size >= 1;
@@ -696,6 +698,7 @@ int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* p
     if (sample) {
       I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SAMPLE));
       persistent_greedy_kernel<0, 1><<<ncl * CL, THREADS, SMEM_BYTES_SAMPLE, s>>>(P);
+#ifdef I2L_DIAG
     } else if (g_dbg_buf != nullptr) {
       float hdr[2];
       I2L_CUDA_OK(cudaMemcpyAsync(hdr, g_dbg_buf, sizeof(hdr), cudaMemcpyDeviceToHost, s));
@@ -708,6 +711,7 @@ int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* p
         I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         persistent_greedy_kernel<1, 0><<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);
       }
+#endif
     } else {
       I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       persistent_greedy_kernel<0, 0><<<ncl * CL, THREADS, SMEM_BYTES, s>>>(P);

@@ -101,16 +101,20 @@ struct BeamParams {
   BeamState* bstate;             // [B]
   double* score;                 // [B*K] final beam scores
   int B, T, start_id, end_id;
-  int* dbg_ctok; float* dbg_clogp;   // optional (T,B,K,K) dump of every live beam's top-K (token, log-prob)
-  long long* dbg_ts; int dbg_step;   // optional clock64() stamps of one step of cluster 0 / rank 0 / thread 0
+  int* cand_tok; float* cand_logp;   // optional (T,B,K,K) audit trail of every live beam's top-K (token, log-prob)
+  long long* dbg_ts; int dbg_step;   // diagnostics build: clock64() stamps of one step of cluster 0 / rank 0 / thread 0
 };
 
+#ifdef I2L_DIAG
 #define BEAM_TS(slot)                                              \
   do {                                                             \
     asm volatile("" ::: "memory");                                 \
     if (ts_on && tid == 0) P.dbg_ts[slot] = clock64();             \
     asm volatile("" ::: "memory");                                 \
   } while (0)
+#else
+#define BEAM_TS(slot) do { } while (0)
+#endif
 
 template <int K>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_beam_kernel(BeamParams P) {
@@ -245,7 +249,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
     int s = 0;
     for (; s < P.T; ++s) {
       // ---------------- Epi-G(s): gates (read from the parent's column) -> c_{s+1}, h_{s+1} ----------------
+#ifdef I2L_DIAG
       const bool ts_on = P.dbg_ts != nullptr && cluster == 0 && rank == 0 && s == P.dbg_step;
+#endif
       BEAM_TS(0);
       float gt0[16], gt1[16];
 #pragma unroll
@@ -536,13 +542,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
               cand_tk[(row * K + rk[k]) * 4 + 2] = li[k];
             }
           }
-          if (P.dbg_ctok != nullptr && rank == 0 && rlive) {
+          if (P.cand_tok != nullptr && rank == 0 && rlive) {
             const int w16 = row & 15, img = cluster * G::IPC + (row >> 4) * G::IPG + w16 / K;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
               if (rk[k] < K) {
                 const size_t o = ((((size_t)s * P.B + img) * K + w16 % K) * K) + rk[k];
-                P.dbg_ctok[o] = li[k]; P.dbg_clogp[o] = clp[k];
+                P.cand_tok[o] = li[k]; P.cand_logp[o] = clp[k];
               }
             }
           }
@@ -678,15 +684,11 @@ int launch_beam(const BeamParams& P, int batch, cudaStream_t s) {
 
 }  // namespace
 
-static int* g_dbg_ctok = nullptr;     // tests only: see i2l_debug_set_beam_trace
-static float* g_dbg_clogp = nullptr;
+#ifdef I2L_DIAG
 static long long* g_dbg_ts = nullptr;
 static int g_dbg_step = 0;
 int persistent_beam_set_ts(long long* ts, int step) { g_dbg_ts = ts; g_dbg_step = step; return I2L_OK; }
-int persistent_beam_set_debug(int* cand_tok, float* cand_logp) {
-  g_dbg_ctok = cand_tok; g_dbg_clogp = cand_logp;
-  return I2L_OK;
-}
+#endif
 
 bool persistent_beam_supported(const i2l_dec_desc& d, int beam_size) {
   if (!persistent_supported(d)) return false;
@@ -695,7 +697,7 @@ bool persistent_beam_supported(const i2l_dec_desc& d, int beam_size) {
 
 int persistent_beam(const i2l_dec_desc& d, const void* section, const float* gctx_img, int batch, int beam_size,
                     int start_id, int end_id, int max_length, BeamState* bstate, double* score, int* tr_parent,
-                    int* tr_token, double* tr_score, cudaStream_t s) {
+                    int* tr_token, double* tr_score, int* cand_tok, float* cand_logp, cudaStream_t s) {
   I2L_REQUIRE(start_id >= 0 && start_id < d.vocab_size, "decode_beam: start token out of range");
   PSection ps = psection(d.vocab_size);
   const unsigned char* sec = reinterpret_cast<const unsigned char*>(section);
@@ -705,7 +707,10 @@ int persistent_beam(const i2l_dec_desc& d, const void* section, const float* gct
   P.gctx = gctx_img; P.tr_parent = tr_parent; P.tr_token = tr_token; P.tr_score = tr_score;
   P.bstate = bstate; P.score = score;
   P.B = batch; P.T = max_length; P.start_id = start_id; P.end_id = end_id;
-  P.dbg_ctok = g_dbg_ctok; P.dbg_clogp = g_dbg_clogp; P.dbg_ts = g_dbg_ts; P.dbg_step = g_dbg_step;
+  P.cand_tok = cand_tok; P.cand_logp = cand_logp;
+#ifdef I2L_DIAG
+  P.dbg_ts = g_dbg_ts; P.dbg_step = g_dbg_step;
+#endif
   // traces default to "empty slot" (-1 / NaN): the kernel writes only the steps an image is alive in
   const size_t n = (size_t)max_length * batch * beam_size;
   I2L_CUDA_OK(cudaMemsetAsync(tr_parent, 0xff, n * sizeof(int), s));

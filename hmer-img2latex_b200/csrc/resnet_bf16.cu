@@ -569,7 +569,12 @@ int resnet_bf16_fwd(const RNet& n, const i2l_resnet_desc& d, const float* folded
     a.P = B * h * wd; a.HoWo = h * wd; a.Wo = wd; a.Co = 64; a.KH = 7; a.KW = 1; a.cblocks = 1;
     a.stride_w = 1; a.stride_h = 2; a.pad_w = 0; a.pad_h = 3; a.relu = 1; a.n_mt = cdiv(a.P, BM); a.n_nt = 1;
     KernelTimer kt("rn.stem_conv7x7", s);
-    if ((h % 2) == 0 && getenv("I2L_STEM_IM2COL") == nullptr) {
+#ifdef I2L_DIAG
+    const bool stem_rows = (h % 2) == 0 && getenv("I2L_STEM_IM2COL") == nullptr;   // A/B switch of the diagnostics build
+#else
+    const bool stem_rows = (h % 2) == 0;
+#endif
+    if (stem_rows) {
       // row-window stem (stem_rows_kernel): needs an even number of output rows
       I2L_CUDA_OK(cudaMemsetAsync(w.zero_row, 0, 2048, s));
       StemArgs sa{};

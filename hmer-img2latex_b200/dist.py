@@ -5,10 +5,13 @@ replica and NO per-step communication.  The one exchange is an all-gather of the
 composes as max over ranks.  Works with NCCL (GPU) and gloo (CPU tests)."""
 from __future__ import annotations
 
-from typing import List, Tuple
+import ctypes as C
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+from . import _native as N
 
 
 def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -47,6 +50,91 @@ def gather_tokens(tokens: torch.Tensor, lengths: torch.Tensor, steps: torch.Tens
             rows.append(out[r, : hi - lo])
         full = torch.cat(rows, dim=0)
     return full[:, :T1], full[:, T1].to(torch.int32), gsteps        # tokens: a view of the gathered buffer
+
+
+class TokenExchange:
+    """The token all-gather as direct peer stores (csrc/token_exchange.cu, `i2l_token_exchange_*`): every rank owns a
+    receive buffer in symmetric memory (`torch.distributed._symmetric_memory`: cudaMalloc'd, peer-mapped over NVLink);
+    `write()` stores the rank's shard into its slot of EVERY peer's buffer and publishes a sequence flag, `read()`
+    acquires the flags of the local buffer and returns the global (n_total, T1) matrix -- no library collective, no
+    host synchronisation, nothing on the compute stream but two small kernels per step.
+
+    Pipelined use (what `bench.py --gpus N` and a serving loop do): per step `prev = xchg.step(tokens, lengths, steps)`
+    = read(previous step) then write(this step); the result of step i is returned by the call of step i + 1 (or by
+    `flush()`), a whole step after the peers produced it, so a slow rank does not stall the others' compute.
+    `peers=None` builds a single-process exchange over explicitly given buffers (tests: several "ranks" on one GPU).
+    `gather_tokens` (NCCL / gloo `all_gather_into_tensor`) stays as the checked reference of this path."""
+
+    def __init__(self, n_total: int, T1: int, device: torch.device, group=None, rank: Optional[int] = None,
+                 world: Optional[int] = None, buffers: Optional[List[torch.Tensor]] = None):
+        self.n_total, self.T1, self.device = int(n_total), int(T1), torch.device(device)
+        lib = N.lib()
+        if buffers is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = group or dist.group.WORLD
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+            nbytes = lib.i2l_token_exchange_buffer_bytes(self.world, self.n_total, self.T1)
+            self.local = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.local.zero_()
+            torch.cuda.synchronize(self.device)
+            self._hdl = symm_mem.rendezvous(self.local, group)
+            ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+            self._hdl.barrier()                                   # every buffer is zeroed before anyone writes
+        else:
+            self.rank, self.world = int(rank), int(world)
+            nbytes = lib.i2l_token_exchange_buffer_bytes(self.world, self.n_total, self.T1)
+            assert len(buffers) == self.world and all(b.numel() >= nbytes for b in buffers)
+            self.local, self._hdl = buffers[self.rank], None
+            ptrs = [b.data_ptr() for b in buffers]
+        if nbytes == 0:
+            raise RuntimeError("i2l_token_exchange_buffer_bytes rejected the configuration")
+        self._ptrs = (C.c_void_p * self.world)(*ptrs)
+        self.seq = 0                                              # sequence number of the last write
+        self.read_seq = 0
+        self._timeout = torch.zeros((), dtype=torch.int32, device=self.device)
+        lo, hi = shard_bounds(self.n_total, self.world, self.rank)
+        self.shard = hi - lo
+
+    def write(self, tokens: torch.Tensor, lengths: torch.Tensor, steps: torch.Tensor) -> None:
+        if tuple(tokens.shape) != (self.shard, self.T1) or tokens.dtype != torch.int64 or not tokens.is_contiguous():
+            raise RuntimeError(f"TokenExchange.write expects contiguous int64 ({self.shard},{self.T1}) tokens, got "
+                               f"{tokens.dtype} {tuple(tokens.shape)}")
+        if self.seq != self.read_seq:
+            raise RuntimeError("TokenExchange: read() the previous step before writing the next (two parities)")
+        self.seq += 1
+        with torch.cuda.device(self.device):
+            N.check(N.lib().i2l_token_exchange_write(N.ptr(tokens), N.ptr(lengths.to(torch.int32)),
+                                                     N.ptr(steps.to(torch.int32)), self.shard, self.T1, self.n_total,
+                                                     self.rank, self.world, self._ptrs, self.seq,
+                                                     N.stream_ptr(self.device)), "i2l_token_exchange_write")
+
+    def read(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Global (tokens (n_total,T1) int64, lengths (n_total) int32, steps) of the last written step."""
+        if self.read_seq == self.seq:
+            raise RuntimeError("TokenExchange.read: nothing pending")
+        self.read_seq = self.seq
+        tokens = torch.empty(self.n_total, self.T1, dtype=torch.int64, device=self.device)
+        lengths = torch.empty(self.n_total, dtype=torch.int32, device=self.device)
+        steps = torch.empty((), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().i2l_token_exchange_read(N.ptr(self.local), self.world, self.n_total, self.T1, self.seq,
+                                                    N.ptr(tokens), N.ptr(lengths), N.ptr(steps), N.ptr(self._timeout),
+                                                    N.stream_ptr(self.device)), "i2l_token_exchange_read")
+        return tokens, lengths, steps
+
+    def step(self, tokens, lengths, steps):
+        """read(previous step) then write(this step); returns the previous step's global result (None at first)."""
+        prev = self.read() if self.read_seq != self.seq else None
+        self.write(tokens, lengths, steps)
+        return prev
+
+    def flush(self):
+        return self.read() if self.read_seq != self.seq else None
+
+    def check(self) -> None:
+        """Host-side check (synchronises): raises if a read kernel gave up waiting for a peer."""
+        if int(self._timeout.item()):
+            raise RuntimeError("TokenExchange: a peer's shard did not arrive within the spin bound")
 
 
 def gather_counts(counts: torch.Tensor, n_total: int) -> torch.Tensor:

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import _native as N
+from .. import ops as _ops  # noqa: F401  (registers torch.ops.i2l.*)
 from ._common import Workspace, default_precision, f32c, params_key, require_cuda
 
 
@@ -36,12 +37,9 @@ class Attention(nn.Module):
             lib = N.lib()
             hid, enc = f32c(hidden.reshape(B, self.hidden_dim)), f32c(encoder_outputs)
             w, b, v = f32c(self.attn.weight), f32c(self.attn.bias), f32c(self.v.weight)
-            out = torch.empty(B, E, dtype=torch.float32, device=hidden.device)
             wsb = lib.i2l_attention_workspace_bytes(self.hidden_dim, E, B, L)
             ws = self._ws.get(wsb, hidden.device)
-            N.check(lib.i2l_attention_fwd(self.hidden_dim, E, N.ptr(w), N.ptr(b), N.ptr(v), N.ptr(hid), N.ptr(enc),
-                                          B, L, N.ptr(out), N.ptr(ws), ws.numel(), N.stream_ptr(hidden.device)),
-                    "i2l_attention_fwd")
+            out = torch.ops.i2l.attention_fwd(hid, enc, w, b, v, ws)
         return out.unsqueeze(1)
 
 
@@ -64,6 +62,9 @@ class LSTMDecoder(nn.Module):
         self.max_seq_length, self.lstm_layers, self.dropout = max_seq_length, lstm_layers, dropout
         self.use_attention = attention
         self.precision = precision or default_precision()
+        # bf16 only: run the stream-ordered path (one group of launches per step) even where a persistent cluster
+        # kernel exists (I2L_BF16_STREAMED) -- the A/B reference for the persistent kernels, same packed weights
+        self.streamed = False
         self.embedding = nn.Embedding(vocab_size, embedding_dim)
         self.lstm = nn.LSTM(input_size=2 * embedding_dim, hidden_size=hidden_dim, num_layers=lstm_layers,
                             batch_first=True, dropout=dropout if lstm_layers > 1 else 0)
@@ -81,7 +82,14 @@ class LSTMDecoder(nn.Module):
         d.vocab_size, d.embedding_dim, d.hidden_dim = self.vocab_size, self.embedding_dim, self.hidden_dim
         d.lstm_layers, d.attention = self.lstm_layers, int(self.use_attention)
         d.precision = N.PRECISIONS[self.precision]
+        if self.streamed and self.precision == "bf16":
+            d.precision = N.BF16_STREAMED
         return d
+
+    def _desc_list(self):
+        """the descriptor as the int list the custom ops take (ops.py)."""
+        d = self._desc()
+        return [d.vocab_size, d.embedding_dim, d.hidden_dim, d.lstm_layers, d.attention, d.precision]
 
     def _weights(self):
         ts = [self.embedding.weight]
@@ -135,16 +143,10 @@ class LSTMDecoder(nn.Module):
             h_in = c_in = None
             if hidden is not None:
                 h_in, c_in = f32c(hidden[0]), f32c(hidden[1])
-            logits = torch.empty(B, T, self.vocab_size, dtype=torch.float32, device=dev)
-            h_out = torch.empty(self.lstm_layers, B, self.hidden_dim, dtype=torch.float32, device=dev)
-            c_out = torch.empty_like(h_out)
-            bad = torch.zeros((), dtype=torch.int32, device=dev)
-            wsb = lib.i2l_dec_forward_workspace_bytes(C.byref(d), B, T)
+            wsb = lib.i2l_dec_forward_workspace_bytes(C.byref(d), max(B, 1), max(T, 1))
             ws = self._ws.get(wsb, dev)
-            N.check(lib.i2l_decoder_forward(C.byref(d), N.ptr(self._packed), N.ptr(enc), N.ptr(tgt), B, T,
-                                            N.ptr(h_in), N.ptr(c_in), N.ptr(logits), N.ptr(h_out), N.ptr(c_out),
-                                            N.ptr(bad), N.ptr(ws), ws.numel(), N.stream_ptr(dev)),
-                    "i2l_decoder_forward")
+            logits, h_out, c_out, bad = torch.ops.i2l.decoder_forward(enc, tgt, h_in, c_in, self._packed, ws,
+                                                                      self._desc_list())
             if int(bad.item()):                                      # nn.Embedding: IndexError
                 raise IndexError("index out of range in self (token id outside [0, vocab_size))")
         if return_hidden:
@@ -169,13 +171,11 @@ class LSTMDecoder(nn.Module):
             h_in = c_in = None
             if hidden is not None:
                 h_in, c_in = f32c(hidden[0]), f32c(hidden[1])
-            logits = torch.empty(B, self.vocab_size, dtype=torch.float32, device=dev)
-            h_out = torch.empty(self.lstm_layers, B, self.hidden_dim, dtype=torch.float32, device=dev)
-            c_out = torch.empty_like(h_out)
             ws = self._workspace(max(B, 1), 1, dev)
-            N.check(lib.i2l_decode_step(C.byref(d), N.ptr(self._packed), N.ptr(enc), N.ptr(tok), B, N.ptr(h_in),
-                                        N.ptr(c_in), N.ptr(logits), N.ptr(h_out), N.ptr(c_out), N.ptr(ws),
-                                        ws.numel(), N.stream_ptr(dev)), "i2l_decode_step")
+            logits, h_out, c_out, bad = torch.ops.i2l.decode_step(enc, tok, h_in, c_in, self._packed, ws,
+                                                                  self._desc_list())
+            if int(bad.item()):                                      # nn.Embedding: IndexError (decoder.py:232)
+                raise IndexError("index out of range in self (token id outside [0, vocab_size))")
         return logits.unsqueeze(1), (h_out, c_out)
 
     # -- device-resident loops (no host sync per token) ------------------
@@ -190,15 +190,9 @@ class LSTMDecoder(nn.Module):
             lib, d = N.lib(), self._desc()
             enc = f32c(encoder_output)
             B = enc.shape[0]
-            tokens = torch.empty(B, max_length + 1, dtype=torch.int64, device=dev)
-            lengths = torch.empty(B, dtype=torch.int32, device=dev)
-            steps = torch.zeros((), dtype=torch.int32, device=dev)
             ws = self._workspace(max(B, 1), max_length, dev)
-            N.check(lib.i2l_decode_greedy(C.byref(d), N.ptr(self._packed), N.ptr(enc), B, start_token_id,
-                                          end_token_id, max_length, float(temperature), stop_rule, N.ptr(tokens),
-                                          N.ptr(lengths), N.ptr(steps), N.ptr(ws), ws.numel(), N.stream_ptr(dev)),
-                    "i2l_decode_greedy")
-        return tokens, lengths, steps
+            return torch.ops.i2l.decode_greedy(enc, self._packed, ws, self._desc_list(), int(start_token_id),
+                                               int(end_token_id), int(max_length), float(temperature), int(stop_rule))
 
     def sample(self, encoder_output: torch.Tensor, start_token_id: int, end_token_id: int, max_length: int,
                temperature: float = 1.0, top_k: int = 0, top_p: float = 0.0, seed: int = 0, offset: int = 0,
@@ -211,28 +205,23 @@ class LSTMDecoder(nn.Module):
             lib, d = N.lib(), self._desc()
             enc = f32c(encoder_output)
             B = enc.shape[0]
-            tokens = torch.empty(B, max_length + 1, dtype=torch.int64, device=dev)
-            lengths = torch.empty(B, dtype=torch.int32, device=dev)
-            steps = torch.zeros((), dtype=torch.int32, device=dev)
-            probs = torch.zeros(max_length, B, self.vocab_size, dtype=torch.float32, device=dev) if return_probs else None
             if uniforms is not None:
                 uniforms = f32c(uniforms.to(dev))
                 if tuple(uniforms.shape) != (max_length, B):
                     raise RuntimeError(f"uniforms must be (max_length, B) = ({max_length}, {B})")
             ws = self._workspace(max(B, 1), max_length, dev)
-            N.check(lib.i2l_decode_sample(C.byref(d), N.ptr(self._packed), N.ptr(enc), B, start_token_id,
-                                          end_token_id, max_length, float(temperature), int(top_k), float(top_p),
-                                          int(seed), int(offset), N.ptr(uniforms), N.ptr(tokens), N.ptr(lengths),
-                                          N.ptr(steps), N.ptr(probs), N.ptr(ws), ws.numel(), N.stream_ptr(dev)),
-                    "i2l_decode_sample")
+            tokens, lengths, steps, probs = torch.ops.i2l.decode_sample(
+                enc, self._packed, ws, self._desc_list(), int(start_token_id), int(end_token_id), int(max_length),
+                float(temperature), int(top_k), float(top_p), int(seed), int(offset), uniforms, bool(return_probs))
         if return_probs:
             return tokens, lengths, steps, probs
         return tokens, lengths, steps
 
     def beam(self, encoder_output: torch.Tensor, start_token_id: int, end_token_id: int, max_length: int,
-             beam_size: int, return_trace: bool = False):
+             beam_size: int, return_trace: bool = False, return_candidates: bool = False):
         """Seq2SeqModel._beam_search (seq2seq.py:234-298) run independently per image, on the
-        device.  Returns out_tokens (B,max_length) int64 padded with -1, out_len (B), score (B) f64."""
+        device.  Returns out_tokens (B,max_length) int64 padded with -1, out_len (B), score (B) f64
+        [, (parent, token, score) traces (T,B,K)] [, (token, log-prob) candidate audit trail (T,B,K,K)]."""
         require_cuda(encoder_output, "LSTMDecoder.beam")
         dev = encoder_output.device
         with torch.cuda.device(dev):
@@ -240,19 +229,13 @@ class LSTMDecoder(nn.Module):
             lib, d = N.lib(), self._desc()
             enc = f32c(encoder_output)
             B, K = enc.shape[0], beam_size
-            out = torch.empty(B, max_length, dtype=torch.int64, device=dev)
-            olen = torch.empty(B, dtype=torch.int32, device=dev)
-            score = torch.empty(B, dtype=torch.float64, device=dev)
-            trp = trt = trs = None
-            if return_trace:
-                trp = torch.empty(max_length, B, K, dtype=torch.int32, device=dev)
-                trt = torch.empty(max_length, B, K, dtype=torch.int32, device=dev)
-                trs = torch.empty(max_length, B, K, dtype=torch.float64, device=dev)
             ws = self._workspace(max(B * K, 1), max_length, dev)
-            N.check(lib.i2l_decode_beam(C.byref(d), N.ptr(self._packed), N.ptr(enc), B, K, start_token_id,
-                                        end_token_id, max_length, N.ptr(out), N.ptr(olen), N.ptr(score), N.ptr(trp),
-                                        N.ptr(trt), N.ptr(trs), N.ptr(ws), ws.numel(), N.stream_ptr(dev)),
-                    "i2l_decode_beam")
+            out, olen, score, trp, trt, trs, ctok, clogp = torch.ops.i2l.decode_beam(
+                enc, self._packed, ws, self._desc_list(), int(K), int(start_token_id), int(end_token_id), int(max_length),
+                bool(return_trace), bool(return_candidates))
+        res = (out, olen, score)
         if return_trace:
-            return out, olen, score, (trp, trt, trs)
-        return out, olen, score
+            res += ((trp, trt, trs),)
+        if return_candidates:      # (T,B,K,K) audit trail: every live beam's top-K (token, log-prob), see i2l_decode_beam
+            res += ((ctok, clogp),)
+        return res

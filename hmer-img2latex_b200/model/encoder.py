@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import _native as N
+from .. import ops as _ops  # noqa: F401  (registers torch.ops.i2l.*)
 from ._common import Workspace, default_precision, f32c, params_key, require_cuda
 
 _RESNET_DEPTH = {"resnet18": 18, "resnet34": 34, "resnet50": 50, "resnet101": 101, "resnet152": 152}
@@ -101,6 +102,11 @@ class CNNEncoder(nn.Module):
         d.precision = N.PRECISIONS[self.precision]
         return d
 
+    def _desc_list(self) -> List[int]:
+        """the descriptor as the int list the custom ops take (ops.py)."""
+        return [self.img_height, self.img_width, self.channels, self.kernel_size, self.pool_size, self.embedding_dim,
+                N.PRECISIONS[self.precision]] + list(self.conv_filters)
+
     def _weights(self):
         convs = [m for m in self.cnn_layers if isinstance(m, nn.Conv2d)]
         ts = []
@@ -133,6 +139,9 @@ class CNNEncoder(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """(B, C, H, W) -> (B, embedding_dim); reference encoder.py:111-129."""
         require_cuda(x, "CNNEncoder.forward")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("CNNEncoder.forward: the native path builds no autograd graph (inference only); call "
+                               ".eval() or wrap the call in torch.no_grad()")
         if x.dim() != 4 or tuple(x.shape[1:]) != (self.channels, self.img_height, self.img_width):
             raise RuntimeError(f"CNNEncoder expected (B,{self.channels},{self.img_height},{self.img_width}), "
                                f"got {tuple(x.shape)}")
@@ -143,18 +152,11 @@ class CNNEncoder(nn.Module):
             # bf16 images are consumed as they are by the tcgen05 conv1 (precision "bf16", headline
             # shape); every other dtype goes through fp32 like the reference's tensors
             if x.dtype == torch.bfloat16 and self.precision == "bf16" and self._bf16_shape():
-                x, in_dtype = x.detach().contiguous(), N.IN_BF16
+                x = x.detach().contiguous()
             else:
-                x, in_dtype = f32c(x), N.IN_F32
-            B = x.shape[0]
-            out = torch.empty(B, self.embedding_dim, dtype=torch.float32, device=x.device)
-            if B == 0:
-                return out
-            wsb = lib.i2l_cnn_workspace_bytes(C.byref(d), B)
-            ws = self._ws.get(wsb, x.device)
-            N.check(lib.i2l_cnn_encoder_fwd_in(C.byref(d), N.ptr(self._packed), N.ptr(x), in_dtype, B, N.ptr(out),
-                                               N.ptr(ws), ws.numel(), N.stream_ptr(x.device)), "i2l_cnn_encoder_fwd")
-        return out
+                x = f32c(x)
+            ws = self._ws.get(lib.i2l_cnn_workspace_bytes(C.byref(d), max(x.shape[0], 1)), x.device)
+            return torch.ops.i2l.cnn_encoder_fwd(x, self._packed, ws, self._desc_list())
 
     def fused_u8_supported(self) -> bool:
         """True when raw uint8 pixels can be fed straight to the first convolution (``forward_u8``)."""
@@ -180,17 +182,10 @@ class CNNEncoder(nn.Module):
             self._ensure_packed(pixels.device)
             lib, d = N.lib(), self._desc()
             x = pixels.contiguous()
-            B = x.shape[0]
-            out = torch.empty(B, self.embedding_dim, dtype=torch.float32, device=x.device)
-            if B == 0:
-                return out
-            m = (C.c_float * 4)(*([float(v) for v in mean[:3]] + [0.0]))
-            sd = (C.c_float * 4)(*([float(v) for v in std[:3]] + [1.0]))
-            ws = self._ws.get(lib.i2l_cnn_workspace_bytes(C.byref(d), B), x.device)
-            N.check(lib.i2l_cnn_encoder_fwd_u8(C.byref(d), N.ptr(self._packed), N.ptr(x),
-                                               N.NORM_PM1 if normalize == "pm1" else N.NORM_MEANSTD, m, sd, B, N.ptr(out),
-                                               N.ptr(ws), ws.numel(), N.stream_ptr(x.device)), "i2l_cnn_encoder_fwd_u8")
-        return out
+            ws = self._ws.get(lib.i2l_cnn_workspace_bytes(C.byref(d), max(x.shape[0], 1)), x.device)
+            return torch.ops.i2l.cnn_encoder_fwd_u8(x, self._packed, ws, self._desc_list(),
+                                                    N.NORM_PM1 if normalize == "pm1" else N.NORM_MEANSTD,
+                                                    [float(v) for v in mean[:3]], [float(v) for v in std[:3]])
 
     def _bf16_shape(self) -> bool:
         return ((self.channels, self.img_height, self.img_width) == (3, 64, 320) and self.conv_filters == [32, 64, 128]
@@ -358,6 +353,10 @@ class ResNetEncoder(nn.Module):
         """(B, 3, H, W) -> (B, embedding_dim); any W (the trunk ends in adaptive average
         pooling), which is what width bucketing relies on.  reference encoder.py:231-249."""
         require_cuda(x, "ResNetEncoder.forward")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("ResNetEncoder.forward: only eval-mode inference runs on the native path (BatchNorm is "
+                               "folded from the running statistics and no autograd graph is built); call .eval() or "
+                               "wrap the call in torch.no_grad()")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.img_height:
             raise RuntimeError(f"ResNetEncoder expected (B,3,{self.img_height},W), got {tuple(x.shape)}")
         with torch.cuda.device(x.device):
@@ -366,12 +365,7 @@ class ResNetEncoder(nn.Module):
             d = self._desc()
             x = f32c(x)
             B, W = x.shape[0], x.shape[3]
-            out = torch.empty(B, self.embedding_dim, dtype=torch.float32, device=x.device)
-            if B == 0:
-                return out
-            wsb = lib.i2l_resnet_workspace_bytes(C.byref(d), B, W)
+            wsb = lib.i2l_resnet_workspace_bytes(C.byref(d), max(B, 1), W)
             ws = (_ws or self._ws).get(wsb, x.device)
-            N.check(lib.i2l_resnet_encoder_fwd(C.byref(d), N.ptr(self._packed), N.ptr(x), B, W, N.ptr(out),
-                                               N.ptr(ws), ws.numel(), N.stream_ptr(x.device)),
-                    "i2l_resnet_encoder_fwd")
-        return out
+            return torch.ops.i2l.resnet_encoder_fwd(x, self._packed, ws, [d.depth, d.img_height, d.embedding_dim,
+                                                                           d.precision])

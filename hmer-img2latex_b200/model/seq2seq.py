@@ -108,7 +108,7 @@ class Seq2SeqModel(nn.Module):
     @torch.no_grad()
     def greedy_stream(self, host_batches: Iterable[torch.Tensor], start_token_id: int, end_token_id: int,
                       max_length: int = 150, temperature: float = 1.0, stop_rule: int = N.STOP_ALL_END_SAME_STEP,
-                      device: Optional[torch.device] = None, normalize: str = "pm1",
+                      device: Optional[torch.device] = None, normalize: str = "pm1", exchange=None,
                       ) -> Iterator[Tuple[torch.Tensor, torch.Tensor, int]]:
         """Serving loop over HOST batches (ideally pinned (B,C,H,W) tensors: fp32 like the
         reference's, bf16, or raw uint8 pixels that are normalised on the device with
@@ -117,7 +117,12 @@ class Seq2SeqModel(nn.Module):
         token ids come back through a pinned buffer.  Yields (tokens (B,max_length+1) int64 on the
         host, lengths (B) int32 on the host, steps_run) per batch -- same content as
         encoder + LSTMDecoder.greedy.  Not in the reference (its Predictor copies and computes
-        serially, training/predictor.py:245-262)."""
+        serially, training/predictor.py:245-262).
+
+        ``exchange`` (a ``dist.TokenExchange``, batch-sharded multi-GPU serving): every rank streams ITS shard of each
+        global batch; the ids are exchanged on the device by direct peer stores and the yielded triple is the GLOBAL
+        (n_total, max_length+1) result -- one batch later than without (read of step i runs behind the compute of
+        step i + 1), all global batches having the same size."""
         dev = device or next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("greedy_stream needs the model on a CUDA device")
@@ -133,9 +138,14 @@ class Seq2SeqModel(nn.Module):
         out_steps: List[Optional[torch.Tensor]] = [None, None]
 
         def stage(slot: int, xb: torch.Tensor) -> None:
-            if bufs[slot] is None or bufs[slot].shape != xb.shape or bufs[slot].dtype != xb.dtype:
-                bufs[slot] = torch.empty(xb.shape, dtype=xb.dtype, device=dev)
             with torch.cuda.stream(copy_stream):
+                if bufs[slot] is None or bufs[slot].shape != xb.shape or bufs[slot].dtype != xb.dtype:
+                    # (re)allocate ON the copy stream, ordered after everything queued on the compute stream: the
+                    # caching allocator may hand back a block whose last kernels (an encoder temporary, the caller's
+                    # own work) are still in flight there; record_stream keeps the block alive for the reader
+                    copy_stream.wait_stream(compute)
+                    bufs[slot] = torch.empty(xb.shape, dtype=xb.dtype, device=dev)
+                    bufs[slot].record_stream(compute)
                 if used[slot]:
                     copy_stream.wait_event(consumed[slot])        # the batch that used this buffer has been encoded
                 bufs[slot].copy_(xb, non_blocking=True)
@@ -173,6 +183,13 @@ class Seq2SeqModel(nn.Module):
             used[slot] = True
             tokens, lengths, steps = self.decoder.greedy(enc, start_token_id, end_token_id, max_length, temperature,
                                                          stop_rule)
+            if exchange is not None:
+                res = exchange.step(tokens, lengths, steps)       # global result of the PREVIOUS batch (None at first)
+                if res is None:
+                    cur = nxt
+                    i += 1
+                    continue
+                tokens, lengths, steps = res
             if out_tok[slot] is None or out_tok[slot].shape != tokens.shape:
                 out_tok[slot] = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
                 out_len[slot] = torch.empty(lengths.shape, dtype=lengths.dtype).pin_memory()
@@ -186,5 +203,21 @@ class Seq2SeqModel(nn.Module):
             prev = slot
             cur = nxt
             i += 1
+        if exchange is not None:
+            res = exchange.flush()
+            if res is not None:                                   # the last batch's global result
+                slot = i & 1
+                tokens, lengths, steps = res
+                if out_tok[slot] is None or out_tok[slot].shape != tokens.shape:
+                    out_tok[slot] = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
+                    out_len[slot] = torch.empty(lengths.shape, dtype=lengths.dtype).pin_memory()
+                    out_steps[slot] = torch.empty((), dtype=steps.dtype).pin_memory()
+                out_tok[slot].copy_(tokens, non_blocking=True)
+                out_len[slot].copy_(lengths, non_blocking=True)
+                out_steps[slot].copy_(steps, non_blocking=True)
+                done[slot].record(compute)
+                if prev >= 0:
+                    yield collect(prev)
+                prev = slot
         if prev >= 0:
             yield collect(prev)

@@ -45,7 +45,10 @@ typedef enum {
   I2L_ERR_WORKSPACE = -5    /* workspace / packed buffer too small                 */
 } i2l_status;
 
-typedef enum { I2L_FP32 = 0, I2L_BF16 = 1 } i2l_precision;
+/* I2L_BF16_STREAMED (decoder descriptors only): bf16 tensor-core arithmetic on the stream-ordered path (one group
+ * of launches per step) even where a persistent cluster kernel exists -- same packed layout and workspace sizes
+ * as I2L_BF16, so one packed model serves both; the A/B reference for the persistent kernels. */
+typedef enum { I2L_FP32 = 0, I2L_BF16 = 1, I2L_BF16_STREAMED = 2 } i2l_precision;
 
 /* Loop-exit rules of the reference's three decode loops. */
 typedef enum {
@@ -223,10 +226,12 @@ size_t i2l_dec_workspace_bytes(const i2l_dec_desc* d, int32_t rows, int32_t max_
 
 /* replaces LSTMDecoder.decode_step, model/decoder.py:197-284.
  * enc (B,E) fp32; tok (B) int64; h_in/c_in (L,B,H) fp32 or NULL (= zeros, decoder.py:253-266);
- * logits (B,V) fp32; h_out/c_out (L,B,H) fp32 (may not alias h_in/c_in). */
+ * logits (B,V) fp32; h_out/c_out (L,B,H) fp32 (may not alias h_in/c_in).
+ * bad_token_flag: optional device int32 set to 1 when an id lies outside [0, vocab_size) (such
+ * ids are read as 0 by the table gather, never out of bounds; nn.Embedding raises IndexError). */
 int i2l_decode_step(const i2l_dec_desc* d, const void* packed, const float* enc, const int64_t* tok,
                     int32_t batch, const float* h_in, const float* c_in, float* logits, float* h_out,
-                    float* c_out, void* workspace, size_t workspace_bytes, void* stream);
+                    float* c_out, int32_t* bad_token_flag, void* workspace, size_t workspace_bytes, void* stream);
 
 /* replaces LSTMDecoder.forward in eval mode (dropout = identity), model/decoder.py:100-195:
  * the teacher-forced pass over a known token sequence (validation loss / accuracy path,
@@ -267,12 +272,42 @@ int i2l_decode_sample(const i2l_dec_desc* d, const void* packed, const float* en
  * per image (the reference handles B==1 only).  out_tokens (B,max_length) int64:
  * best sequence, START stripped, cut at END, padded with -1; out_len (B) int32;
  * out_score (B) fp64.  Optional traces (max_length,B,K): parent slot / token /
- * score of every kept beam per step (-1 / NaN where a slot is empty). */
+ * score of every kept beam per step (-1 / NaN where a slot is empty).
+ * cand_token / cand_logp: optional (max_length,B,K,K) int32 / fp32 audit trail -- for every live
+ * beam of every step the K (token, fp32 log-prob) pairs of torch.topk(log_softmax(logits), K)
+ * (seq2seq.py:266-267) the bookkeeping was fed; entries of dead beams are left untouched.  Both
+ * or neither; supported where the search runs inside the persistent kernel (bf16 headline
+ * decoder), I2L_ERR_UNSUPPORTED otherwise. */
 int i2l_decode_beam(const i2l_dec_desc* d, const void* packed, const float* enc, int32_t batch,
                     int32_t beam_size, int32_t start_id, int32_t end_id, int32_t max_length,
                     int64_t* out_tokens, int32_t* out_len, double* out_score, int32_t* trace_parent,
-                    int32_t* trace_token, double* trace_score, void* workspace, size_t workspace_bytes,
-                    void* stream);
+                    int32_t* trace_token, double* trace_score, int32_t* cand_token, float* cand_logp,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Multi-GPU token exchange: the one collective of the batch-sharded */
+/* path -- every rank ends with the (n_total, T1) id matrix -- as direct peer     */
+/* stores over NVLink.  The reference has no distributed code; this replaces the  */
+/* `torch.distributed.all_gather_into_tensor` a data-parallel port would call     */
+/* after Seq2SeqModel._greedy_search (model/seq2seq.py:192-232) and is checked    */
+/* against that collective (hmer-img2latex_b200/dist.py: gather_tokens).          */
+/* ------------------------------------------------------------------------- */
+/* Bytes of one rank's receive buffer (symmetric across ranks; must start zeroed):
+ * [2 parities][world][cap = ceil(n_total/world)][T1 + 1] int32 + flags. */
+size_t i2l_token_exchange_buffer_bytes(int32_t world, int32_t n_total, int32_t T1);
+/* Stores this rank's shard -- tokens (b,T1) int64, lengths (b) int32, steps (device scalar) --
+ * into slot `rank`, parity seq & 1, of EVERY buffer in peer_buffers[world] (device pointers
+ * valid on this device: the local buffer and the peer-mapped ones), then publishes sequence
+ * number `seq` (non-zero, +1 per step) with a system-scope release.  Rows beyond b are -1. */
+int i2l_token_exchange_write(const int64_t* tokens, const int32_t* lengths, const int32_t* steps, int32_t b,
+                             int32_t T1, int32_t n_total, int32_t rank, int32_t world, void* const* peer_buffers,
+                             uint32_t seq, void* stream);
+/* Waits (on the device, bounded spin: *timeout_flag = 1 on expiry) until all `world` slots of
+ * parity seq & 1 carry `seq`, then widens them into tokens (n_total,T1) int64 in global image
+ * order (contiguous balanced shards), lengths (n_total) and steps = max over ranks.  Call
+ * read(seq - 1) before write(seq) on the same stream: two parities are then race-free. */
+int i2l_token_exchange_read(const void* local_buffer, int32_t world, int32_t n_total, int32_t T1, uint32_t seq,
+                            int64_t* tokens, int32_t* lengths, int32_t* steps, int32_t* timeout_flag, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Evaluation metrics -- the integer work of levenshtein_distance / bleu_n_score  */

@@ -14,7 +14,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("I2L_REFERENCE_ROOT", "/root/reference")
+_TRAVELLING = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/make_ref.py
+
+
+def _default_root() -> str:
+    """/root/reference in the build container, else the copy oracle/make_ref.py left under oracle/_ref/."""
+    if os.path.isdir("/root/reference/img2latex/model"):
+        return "/root/reference"
+    return _TRAVELLING
+
+
+REFERENCE_ROOT = os.environ.get("I2L_REFERENCE_ROOT") or _default_root()
 
 
 def available() -> bool:

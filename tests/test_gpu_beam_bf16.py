@@ -10,8 +10,6 @@ Three layers of checks, all through the C-ABI (`i2l_decode_beam`, precision bf16
     (oracle scores of the two candidates within BF16_GAP).
  3. beam 1 == the persistent greedy kernel (same MMAs, same logits) cut at the first END.
 """
-import ctypes as C
-
 import pytest
 import torch
 
@@ -52,33 +50,18 @@ def replay_reference_beam(ctok, clogp, start, end, T, K):
 
 
 def run_beam_with_dump(pkg, m, enc, T, K):
-    B = enc.shape[0]
-    lib = pkg._native.lib()
-    lib.i2l_debug_set_beam_trace.restype = C.c_int
-    lib.i2l_debug_set_beam_trace.argtypes = [C.c_void_p, C.c_void_p]
-    ctok = torch.full((T, B, K, K), -1, dtype=torch.int32, device="cuda")
-    clogp = torch.full((T, B, K, K), float("nan"), dtype=torch.float32, device="cuda")
-    lib.i2l_debug_set_beam_trace(ctok.data_ptr(), clogp.data_ptr())
-    try:
-        out, olen, score, (trp, trt, trs) = m.decoder.beam(enc, H.START, H.END, T, K, return_trace=True)
-        torch.cuda.synchronize()
-    finally:
-        lib.i2l_debug_set_beam_trace(None, None)
+    """decoder.beam with the (T,B,K,K) candidate audit trail of `i2l_decode_beam` (cand_token / cand_logp)."""
+    out, olen, score, (trp, trt, trs), (ctok, clogp) = m.decoder.beam(enc, H.START, H.END, T, K, return_trace=True,
+                                                                      return_candidates=True)
+    torch.cuda.synchronize()
     return [t.cpu() for t in (out, olen, score, trp, trt, trs, ctok, clogp)]
 
 
-@pytest.mark.parametrize("B,K,T,seed,end_boost", [(7, 5, 30, 2, 1.0), (40, 5, 25, 1, 0.5), (13, 3, 40, 2, 2.0),
-                                                  (9, 8, 16, 3, 1.0), (5, 1, 30, 1, 1.0), (6, 2, 20, 2, 0.0),
-                                                  (11, 4, 20, 1, 1.5), (3, 7, 12, 2, 1.0), (4, 6, 12, 3, 3.0)])
-def test_beam_bookkeeping_bit_exact_given_scores(pkg, B, K, T, seed, end_boost):
-    cfg = H.HEADLINE
-    p = oracle.make_params(cfg, seed, sharp=True)
-    p["decoder.output_layer.bias"][H.END] += end_boost
-    m16 = H.build_model(pkg, cfg, p, precision="bf16")
-    enc = torch.relu(torch.randn(B, 256, generator=torch.Generator().manual_seed(seed))).cuda()
-    out, olen, score, trp, trt, trs, ctok, clogp = run_beam_with_dump(pkg, m16, enc, T, K)
+def check_bookkeeping(rows, T, K, out, olen, score, trp, trt, trs, ctok, clogp):
+    """Replay seq2seq.py:254-290 on the kernel's own candidates: parents / tokens / fp64 scores of every step, the
+    final sequence and the final score must be reproduced bit for bit.  Returns how many images finished early."""
     n_completed_early = 0
-    for b in range(B):
+    for b in rows:
         seq, sc, trace = replay_reference_beam(ctok[:, b].tolist(), clogp[:, b].tolist(), H.START, H.END, T, K)
         for t, beams in enumerate(trace):
             nb = len(beams)
@@ -92,28 +75,28 @@ def test_beam_bookkeeping_bit_exact_given_scores(pkg, B, K, T, seed, end_boost):
         assert out[b, int(olen[b]):].tolist() == [-1] * (T - int(olen[b]))
         assert float(score[b]) == sc
         n_completed_early += len(trace) < T
+    return n_completed_early
+
+
+@pytest.mark.parametrize("B,K,T,seed,end_boost", [(7, 5, 30, 2, 1.0), (40, 5, 25, 1, 0.5), (13, 3, 40, 2, 2.0),
+                                                  (9, 8, 16, 3, 1.0), (5, 1, 30, 1, 1.0), (6, 2, 20, 2, 0.0),
+                                                  (11, 4, 20, 1, 1.5), (3, 7, 12, 2, 1.0), (4, 6, 12, 3, 3.0)])
+def test_beam_bookkeeping_bit_exact_given_scores(pkg, B, K, T, seed, end_boost):
+    cfg = H.HEADLINE
+    p = oracle.make_params(cfg, seed, sharp=True)
+    p["decoder.output_layer.bias"][H.END] += end_boost
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    enc = torch.relu(torch.randn(B, 256, generator=torch.Generator().manual_seed(seed))).cuda()
+    out, olen, score, trp, trt, trs, ctok, clogp = run_beam_with_dump(pkg, m16, enc, T, K)
+    n_completed_early = check_bookkeeping(range(B), T, K, out, olen, score, trp, trt, trs, ctok, clogp)
     print(f"beam K={K} B={B}: {n_completed_early}/{B} images finished before max_length")
 
 
-@pytest.mark.parametrize("B,K,T", [(12, 5, 20), (6, 3, 25)])
-def test_beam_bf16_vs_fp32_oracle(pkg, B, K, T):
-    """Walk every image step by step against the fp32 oracle.  While the kept beams (parents and
-    tokens, in order) are identical the fp64 scores must agree within the accumulated bf16 error;
-    the first step where they differ must be a near tie -- the oracle's own score of the candidate
-    the kernel kept is within BF16_GAP of the candidate the oracle kept at that rank -- after which
-    the image is no longer comparable (the beam states differ)."""
-    cfg = H.HEADLINE
-    p = oracle.make_params(cfg, 2, sharp=True)
-    p["decoder.output_layer.bias"][H.END] += 1.0
-    m16 = H.build_model(pkg, cfg, p, precision="bf16")
-    m32 = H.build_model(pkg, cfg, p, precision="fp32")
-    x = H.make_images(cfg, B)
-    enc_ref = oracle.encoder(p, x, cfg)
-    enc = m32.encoder(x.cuda())                              # isolate the decoder
-    out, olen, score, (trp, trt, trs) = m16.decoder.beam(enc, H.START, H.END, T, K, return_trace=True)
-    out, olen, score, trp, trt, trs = (t.cpu() for t in (out, olen, score, trp, trt, trs))
+def walk_against_oracle(p, cfg, enc_ref, rows, T, K, out, olen, score, trp, trt, trs):
+    """Step-by-step comparison of the kernel's kept beams with `oracle.beam_search` for the images in `rows`
+    (see test_beam_bf16_vs_fp32_oracle).  Returns (#identical images, #compared steps, near ties, bad)."""
     full, steps_cmp, near, bad = 0, 0, [], []
-    for b in range(B):
+    for b in rows:
         seq, sc, trace, cands = oracle.beam_search(p, enc_ref[b:b + 1], H.START, H.END, T, K, cfg, return_cands=True)
         same = True
         for t, beams in enumerate(trace):
@@ -138,6 +121,27 @@ def test_beam_bf16_vs_fp32_oracle(pkg, B, K, T):
             full += 1
             assert out[b, : int(olen[b])].tolist() == seq, b
             assert abs(float(score[b]) - sc) < 0.03 * (len(trace) + 1)
+    return full, steps_cmp, near, bad
+
+
+@pytest.mark.parametrize("B,K,T", [(12, 5, 20), (6, 3, 25)])
+def test_beam_bf16_vs_fp32_oracle(pkg, B, K, T):
+    """Walk every image step by step against the fp32 oracle.  While the kept beams (parents and
+    tokens, in order) are identical the fp64 scores must agree within the accumulated bf16 error;
+    the first step where they differ must be a near tie -- the oracle's own score of the candidate
+    the kernel kept is within BF16_GAP of the candidate the oracle kept at that rank -- after which
+    the image is no longer comparable (the beam states differ)."""
+    cfg = H.HEADLINE
+    p = oracle.make_params(cfg, 2, sharp=True)
+    p["decoder.output_layer.bias"][H.END] += 1.0
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    m32 = H.build_model(pkg, cfg, p, precision="fp32")
+    x = H.make_images(cfg, B)
+    enc_ref = oracle.encoder(p, x, cfg)
+    enc = m32.encoder(x.cuda())                              # isolate the decoder
+    out, olen, score, (trp, trt, trs) = m16.decoder.beam(enc, H.START, H.END, T, K, return_trace=True)
+    out, olen, score, trp, trt, trs = (t.cpu() for t in (out, olen, score, trp, trt, trs))
+    full, steps_cmp, near, bad = walk_against_oracle(p, cfg, enc_ref, range(B), T, K, out, olen, score, trp, trt, trs)
     print(f"bf16 beam vs fp32 oracle: {full}/{B} images identical end to end, {steps_cmp} steps compared, "
           f"near-tie divergences {near}")
     assert not bad, f"divergence away from a near tie: {bad}"
@@ -172,3 +176,30 @@ def test_beam_bf16_model_api_and_general_fallback(pkg):
     assert one == batch[0]
     big = m16.beam_search_batch(m16.encoder(x.cuda()), H.START, H.END, 6, 10)
     assert len(big) == 2 and all(len(r) <= 6 for r in big)
+
+
+def test_beam_at_the_benchmarked_config(pkg):
+    """BASELINE configs[2] exactly as bench.py runs it: B = 512 images, K = 5, T = 150 (86 clusters; more CTAs than
+    the 148 SMs hold at once, so the launch runs in several waves -- a regime the small cases above never enter).
+    (1) bookkeeping replay bit-exact for ALL 512 images; (2) fp32-oracle walk on a strided sample of 32 images;
+    (3) the same images decoded in a small batch give bit-identical results (an image's search does not depend on
+    which cluster / wave it ran in)."""
+    cfg = H.HEADLINE
+    B, K, T = 512, 5, 150
+    p = oracle.make_params(cfg, 2, sharp=True)
+    p["decoder.output_layer.bias"][H.END] += 0.5
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    g = torch.Generator().manual_seed(21)
+    enc_ref = torch.relu(torch.randn(B, 256, generator=g)) * (0.5 + torch.rand(B, 1, generator=g))
+    enc = enc_ref.cuda()
+    out, olen, score, trp, trt, trs, ctok, clogp = run_beam_with_dump(pkg, m16, enc, T, K)
+    early = check_bookkeeping(range(B), T, K, out, olen, score, trp, trt, trs, ctok, clogp)
+    sample = list(range(5, B, 16))
+    full, steps_cmp, near, bad = walk_against_oracle(p, cfg, enc_ref, sample, T, K, out, olen, score, trp, trt, trs)
+    print(f"beam-5 B=512 T=150: bookkeeping bit-exact for {B} images ({early} finished early); oracle walk on "
+          f"{len(sample)} images: {full} identical end to end, {steps_cmp} steps compared, near ties {near}")
+    assert not bad, f"divergence away from a near tie: {bad}"
+    assert steps_cmp >= 4 * len(sample)
+    sub = torch.tensor(sample[:7])
+    o2, l2, s2 = m16.decoder.beam(enc[sub.cuda()].contiguous(), H.START, H.END, T, K)
+    assert torch.equal(o2.cpu(), out[sub]) and torch.equal(l2.cpu(), olen[sub]) and torch.equal(s2.cpu(), score[sub])

@@ -46,7 +46,7 @@ def test_persistent_greedy_vs_oracle(pkg, B, T, seed, sharp):
     exact, near, bad = divergence_report(toks, ref, trace)
     print(f"bf16 persistent greedy B={B} T={T}: exact rows {exact}/{B}, near-tie divergences {near}")
     assert not bad, f"rows diverging at a step with a clear margin: {bad}"
-    assert exact >= 0.6 * B
+    assert exact >= 0.9 * B
     if not near:
         assert int(steps) == steps_ref
         for b in range(B):
@@ -71,7 +71,7 @@ def test_persistent_sticky_stop_and_lengths(pkg):
     for b in range(B):
         a, r = t16[b, : int(l16[b])].tolist(), t32[b, : int(l32[b])].tolist()
         agree += a == r
-    assert agree >= 0.8 * B
+    assert agree >= 0.9 * B
     if agree == B:
         assert int(s16) == int(s32)
 
@@ -258,13 +258,14 @@ def test_general_bf16_sampling_and_greedy(pkg, cfg, B, T):
             assert both.any()
             d = (probs[t, b] - ptrace[t][b]).abs()[both].max() / ptrace[t][b].max()
             assert float(d) < 6e-2, (b, t, float(d))
-    assert same_rows >= 0.7 * B, f"only {same_rows}/{B} sampled rows follow the oracle"
+    print(f"general bf16 sampling {cfg.get('model_name', 'cnn')} B={B}: {same_rows}/{B} rows follow the oracle")
+    assert same_rows >= 0.9 * B, f"only {same_rows}/{B} sampled rows follow the oracle"
     if not pkg._native.lib().i2l_device_check() and cfg is not H.HEADLINE:     # greedy takes the general path too
         ref, steps_ref, trace = oracle.greedy_search(p, enc_ref, H.START, H.END, T, 1.0, cfg, return_logits=True)
         tok, _, _ = m16.decoder.greedy(enc, H.START, H.END, T)
         exact, near, bad = divergence_report(tok.cpu()[:, : steps_ref + 1].tolist(), ref, trace)
         assert not bad, f"rows diverging at a step with a clear margin: {bad}"
-        assert exact >= 0.6 * B
+        assert exact >= 0.9 * B
 
 
 @pytest.mark.parametrize("B,T,temperature,top_k,top_p", [(40, 30, 0.9, 20, 0.9), (64, 40, 0.8, 50, 0.9), (33, 25, 1.0, 0, 0.7),
@@ -286,9 +287,9 @@ def test_persistent_sampling_vs_general_and_oracle(pkg, monkeypatch, B, T, tempe
     tokens, lengths, steps, probs = m16.decoder.sample(enc, H.START, H.END, T, temperature, top_k, top_p, uniforms=u,
                                                        return_probs=True)
     prof = pkg._native
-    monkeypatch.setenv("I2L_NO_PERSISTENT_SAMPLE", "1")
+    m16.decoder.streamed = True                        # I2L_BF16_STREAMED: same weights, stream-ordered launches
     tok_g, len_g, steps_g = m16.decoder.sample(enc, H.START, H.END, T, temperature, top_k, top_p, uniforms=u)
-    monkeypatch.delenv("I2L_NO_PERSISTENT_SAMPLE")
+    m16.decoder.streamed = False
     tokens, probs, tok_g = tokens.cpu(), probs.cpu(), tok_g.cpu()
     same_oracle = same_general = 0
     sampling = temperature > 0 and (top_k > 0 or top_p > 0.0)                     # predictor.py:330
@@ -383,3 +384,114 @@ def test_persistent_sampling_philox_reproducible(pkg):
     n = min(full.shape[1], half.shape[1])
     live = (half[:, :n] >= 0) & (full[32:64, :n] >= 0)
     assert torch.equal(half[:, :n][live], full[32:64, :n][live])
+
+
+# ---- the configurations bench.py measures (BASELINE configs[1] / configs[4]) at their full sizes ----------------------
+def test_greedy_at_the_benchmarked_config(pkg):
+    """BASELINE configs[1] as bench.py runs it: B = 1024 sequences, T = 150 steps, V = 512, bf16 persistent kernel
+    (32 clusters of 4 CTAs), against `oracle.greedy_search` on the SAME encodings (decoder isolated).  Rows may leave
+    the oracle only at a near tie of the oracle's own top-2 logits (BF16_MARGIN); at least 90 % of the 1024 rows must
+    be identical over all 150 steps.  Lengths / steps_run must be consistent with the kernel's own tokens."""
+    cfg = H.HEADLINE
+    B, T = 1024, 150
+    p = oracle.make_params(cfg, 3, sharp=True)
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    g = torch.Generator().manual_seed(17)
+    enc_ref = torch.relu(torch.randn(B, 256, generator=g)) * (0.5 + torch.rand(B, 1, generator=g))
+    ref, steps_ref, trace = oracle.greedy_search(p, enc_ref, H.START, H.END, T, 1.0, cfg, return_logits=True)
+    tokens, lengths, steps = m16.decoder.greedy(enc_ref.cuda(), H.START, H.END, T)
+    torch.cuda.synchronize()
+    tokens, lengths, n = tokens.cpu(), lengths.cpu(), int(steps)
+    exact, near, bad = divergence_report(tokens[:, : steps_ref + 1].tolist(), ref, trace)
+    print(f"bf16 persistent greedy B=1024 T=150: exact rows {exact}/{B}, {len(near)} near-tie divergences, steps {n} "
+          f"(oracle {steps_ref})")
+    assert not bad, f"rows diverging at a step with a clear margin: {bad[:10]}"
+    assert exact >= 0.9 * B
+    for b in range(0, B, 7):                          # bookkeeping against the kernel's own tokens
+        row = tokens[b, 1: n + 1].tolist()
+        assert int(lengths[b]) == (row.index(H.END) + 1 if H.END in row else n + 1)
+    assert n == T or all(int(tokens[b, n]) == H.END for b in range(B))          # seq2seq.py:220
+    assert (tokens[:, n + 1:] == -1).all()
+
+
+def test_cnn_greedy_full_pipeline_at_the_benchmarked_config(pkg):
+    """The whole bf16 step bench.py times -- raw uint8 pixels -> fused conv1 -> conv2/3 -> FC -> 150-step persistent
+    greedy decode -- at B = 1024 against the fp32 oracle on the same pixels: every one of the 1024 encodings within
+    the stated 3e-2 of max|enc|; tokens compared on a 128-row oracle sample (the encoder's bf16 error moves the
+    logits, so a row may leave the oracle where the oracle's margin is below BF16_MARGIN)."""
+    cfg = H.HEADLINE
+    B, T, S = 1024, 150, 128
+    p = oracle.make_params(cfg, 1, sharp=True)
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    g = torch.Generator().manual_seed(5)
+    px = torch.randint(0, 256, (B, 3, 64, 320), dtype=torch.uint8, generator=g)
+    enc = m16.encoder.forward_u8(px.cuda(), "pm1")
+    tokens, lengths, steps = m16.decoder.greedy(enc, H.START, H.END, T)
+    torch.cuda.synchronize()
+    rows = list(range(0, B, B // S))
+    enc_ref = oracle.encoder(p, oracle.normalize_u8(px[rows], "pm1"), cfg)
+    err = H.rel_err(enc[rows], enc_ref)
+    assert err < 3e-2, err
+    # rows outside the sample: the same image must give the same encoding wherever it sits in the batch
+    enc2 = m16.encoder.forward_u8(px[rows].cuda().contiguous(), "pm1")
+    assert torch.equal(enc2, enc[rows])
+    ref, steps_ref, trace = oracle.greedy_search(p, enc_ref, H.START, H.END, T, 1.0, cfg, return_logits=True)
+    n = min(steps_ref, int(steps))
+    got = tokens.cpu()[rows][:, : n + 1].tolist()
+    exact, near, bad = divergence_report(got, [r[: n + 1] for r in ref], trace)
+    print(f"bf16 full pipeline B=1024: encoder rel err {err:.2e}; sample of {S}: exact rows {exact}, near ties {len(near)}, "
+          f"clear-margin divergences {bad}")
+    assert exact + len(near) >= 0.97 * S and exact >= 0.85 * S
+
+
+def test_resnet50_sampling_at_the_benchmarked_config(pkg):
+    """BASELINE configs[4] as bench.py runs it on one GPU: ResNet50 trunk (bf16 tcgen05) + sampling loop (temperature
+    0.8, top_k 50, top_p 0.9) inside the persistent kernel, B = 1024, 3x64x320, T = 150, E = H = 256, V = 512.
+    A strided sample of 64 rows is checked against the fp32 oracle (ResNet50 encoder + `sample_loop` on the same
+    uniforms): encodings within 3e-2; filtered distributions within 6e-2 of the row maximum up to the row's first
+    divergence; every draw of ALL 1024 rows is the inverse CDF of the kernel's own distribution."""
+    cfg = dict(H.R50, vocab_size=512, embedding_dim=256, hidden_dim=256, img_width=320)
+    B, T, S = 1024, 150, 64
+    p = oracle.make_params(cfg, 2, sharp=True)
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    x = H.make_images(cfg, B, seed=3)
+    u = torch.rand(T, B, generator=torch.Generator().manual_seed(9))
+    enc = m16.encoder(x.cuda())
+    tokens, lengths, steps, probs = m16.decoder.sample(enc, H.START, H.END, T, 0.8, 50, 0.9, uniforms=u, return_probs=True)
+    torch.cuda.synchronize()
+    tokens, n = tokens.cpu(), int(steps)
+    rows = list(range(3, B, B // S))
+    enc_ref = oracle.encoder(p, x[rows], cfg)
+    err = H.rel_err(enc[rows], enc_ref)
+    assert err < RESNET_BF16_TOL, err
+    seqs, trimmed, steps_ref, ptrace = oracle.sample_loop(p, enc_ref, H.START, H.END, T, 0.8, 50, 0.9, cfg,
+                                                          uniforms=u[:, rows].contiguous(), return_probs=True)
+    probs_s = probs[:, rows].cpu()
+    same = 0
+    for i, b in enumerate(rows):
+        ref_row = seqs[i].tolist()
+        got_row = tokens[b, : len(ref_row)].tolist()
+        t_div = next((k for k, (a, r) in enumerate(zip(got_row, ref_row)) if a != r), None)
+        same += t_div is None
+        upto = min(len(ref_row) - 1 if t_div is None else t_div, steps_ref, n)
+        for t in range(upto):
+            both = (probs_s[t, i] > 0) & (ptrace[t][i] > 0)
+            assert both.any()
+            d = (probs_s[t, i] - ptrace[t][i]).abs()[both].max() / ptrace[t][i].max()
+            assert float(d) < 6e-2, (b, t, float(d))
+    # all 1024 rows, all executed steps: the token taken is the inverse CDF of the kernel's own filtered distribution
+    bad_total = 0
+    for t0 in range(0, n, 25):                                                     # chunks: (25, 1024, 512) fp64
+        pr = probs[t0: min(n, t0 + 25)].double()
+        cdf = torch.cumsum(pr, dim=2)
+        tgt = u[t0: t0 + pr.shape[0]].double().cuda() * cdf[:, :, -1]
+        drawn = (cdf > tgt.unsqueeze(2)).int().argmax(dim=2)
+        taken = tokens[:, 1 + t0: 1 + t0 + pr.shape[0]].t().cuda()
+        for t, b in (drawn != taken).nonzero().tolist():                           # only at a cdf boundary (fp64 sum order)
+            gap = (cdf[t, b] - tgt[t, b]).abs().min()
+            assert float(gap) < 1e-6, (t0 + t, b)
+            bad_total += 1
+        assert (pr.sum(dim=2) - 1.0).abs().max() < 1e-4
+    print(f"resnet50 + persistent sampling B=1024: encoder rel err {err:.2e}; {same}/{S} sampled rows follow the oracle "
+          f"end to end; {bad_total} draws sit on a cdf boundary; steps {n}")
+    assert same >= 0.5 * S

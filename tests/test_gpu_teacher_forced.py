@@ -98,9 +98,9 @@ def test_persistent_forward_vs_general_and_oracle(pkg, monkeypatch, B, T):
     tgt = torch.randint(0, cfg["vocab_size"], (B, T), generator=g)
     ref = oracle.decoder_forward(p, enc, tgt, cfg)
     out, (h, c) = m.decoder(enc.cuda(), tgt.cuda(), return_hidden=True)
-    monkeypatch.setenv("I2L_NO_PERSISTENT_FORWARD", "1")
+    m.decoder.streamed = True                          # I2L_BF16_STREAMED: same weights, stream-ordered launches
     out_g, (h_g, c_g) = m.decoder(enc.cuda(), tgt.cuda(), return_hidden=True)
-    monkeypatch.delenv("I2L_NO_PERSISTENT_FORWARD")
+    m.decoder.streamed = False
     assert out.shape == (B, T, cfg["vocab_size"])
     TOL, TOL_STATE = 3e-2, 8e-2
     print(f"persistent forward B={B} T={T}: vs oracle {H.rel_err(out, ref):.4f}, general vs oracle {H.rel_err(out_g, ref):.4f}, "

@@ -3,6 +3,8 @@ them with the CPU oracle.  Usage (GPU box): python tools/debug_persistent.py [st
 import ctypes as C
 import os
 import sys
+# needs the diagnostics library: make -C hmer-img2latex_b200/csrc diag
+os.environ.setdefault("I2L_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hmer-img2latex_b200", "csrc", "libi2l_b200_diag.so"))
 
 import torch
 

@@ -1,6 +1,8 @@
 """Diagnostic (GPU box): per-phase clock64 stamps of one step of the persistent beam kernel.
 Usage: python tools/time_beam.py [step] [B] [K]"""
 import ctypes as C, os, sys
+# needs the diagnostics library: make -C hmer-img2latex_b200/csrc diag
+os.environ.setdefault("I2L_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hmer-img2latex_b200", "csrc", "libi2l_b200_diag.so"))
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch

@@ -1,5 +1,5 @@
 """GPU box: time the sampling decode loop (headline decoder, B=1024, 150 steps): persistent kernel vs the
-stream-ordered general path (I2L_NO_PERSISTENT_SAMPLE=1)."""
+stream-ordered general path (decoder.streamed = True, I2L_BF16_STREAMED)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -13,8 +13,7 @@ m = pkg.Seq2SeqModel("cnn_lstm", 512, dict(img_height=64, img_width=320, channel
                      dict(hidden_dim=256, lstm_layers=1, attention=True), precision="bf16").cuda().eval()
 enc = torch.relu(torch.randn(B, 256)).cuda()
 for label, env in (("persistent", None), ("general", "1")):
-    if env: os.environ["I2L_NO_PERSISTENT_SAMPLE"] = env
-    else: os.environ.pop("I2L_NO_PERSISTENT_SAMPLE", None)
+    m.decoder.streamed = bool(env)
     for args in ((0.8, 50, 0.9), (1.0, 0, 0.9), (1.0, 200, 0.0), (0.7, 0, 0.0)):
         for _ in range(2):
             m.decoder.sample(enc, 1, 2, T, *args, seed=1)
