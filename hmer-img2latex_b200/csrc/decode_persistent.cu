@@ -39,6 +39,10 @@
 #ifndef I2L_ABL
 #define I2L_ABL 0
 #endif
+#ifndef I2L_TANH_F16X2
+#define I2L_TANH_F16X2 0     // 1 = cell-update activations as tanh.approx.f16x2.  NOT a win on sm_100a: ptxas emits TWO
+                             // MUFU.TANH.F16 (.H0 / .H1) per f16x2, so the XU-pipe op count is unchanged (cuobjdump -sass)
+#endif
 
 namespace i2l {
 
@@ -317,8 +321,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
           float* dm = P.dbg + 16 + 200000 + (size_t)((cluster * 4 + rank) * 2) * 4096;
           dm[p * 32 + col0 + j] = __uint_as_float(r0[j]); dm[4096 + p * 32 + col0 + j] = __uint_as_float(r1[j]);
         }
+#if I2L_TANH_F16X2
+        float t0, t1;
+        tanh2_f16(0.5f * x0, s1 * x1, t0, t1);                     // one MUFU for both gates of the row
+        y0[j] = fmaf(t0, 0.5f, 0.5f);                              // sigmoid(i) | sigmoid(f)
+        y1[j] = fmaf(t1, m1, b1);                                  // tanh(g)    | sigmoid(o)
+#else
         y0[j] = fmaf(TANH(0.5f * x0), 0.5f, 0.5f);                 // sigmoid(i) | sigmoid(f)
         y1[j] = fmaf(TANH(s1 * x1), m1, b1);                       // tanh(g)    | sigmoid(o)
+#endif
       }
       // phase 2: sigma(i) tanh(g) moves from lanes 0..15 to the lanes 16..31 that own c
       float pg[16];
@@ -326,6 +337,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       for (int j = 0; j < 16; ++j) pg[j] = __shfl_xor_sync(0xffffffffu, y0[j] * y1[j], 16);
       // phase 3: cell / hidden update (lanes 16..31 are the owners; 0..15 compute don't-cares)
       float hn[16];
+#if I2L_TANH_F16X2
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const float ca = fmaf(y0[j], c[j], pg[j]), cb = fmaf(y0[j + 1], c[j + 1], pg[j + 1]);
+        c[j] = ca; c[j + 1] = cb;
+        float ta, tb;
+        tanh2_f16(ca, cb, ta, tb);
+        hn[j] = y1[j] * ta; hn[j + 1] = y1[j + 1] * tb;
+        if (MODE == 2) { hlast[j] = hn[j]; hlast[j + 1] = hn[j + 1]; }
+      }
+#else
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float cn = fmaf(y0[j], c[j], pg[j]);
@@ -333,6 +355,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
         hn[j] = y1[j] * TANH(cn);
         if (MODE == 2) hlast[j] = hn[j];
       }
+#endif
       if (hi) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {

@@ -1,8 +1,13 @@
 // Persistent beam search for the headline shape (E = H = 256, one LSTM layer, V <= 512, bf16):
 // Seq2SeqModel._beam_search (model/seq2seq.py:234-298) run independently per image, all
 // max_length steps inside ONE kernel, on the same resident-weight cluster design as the greedy
-// kernel (decode_persistent.cu): a cluster of 4 CTAs owns 32 beam rows = 2 column groups of
-// floor(16/K) images x K beams; W_hh / W_out slices live in tensor memory as the MMA A operand.
+// kernel (decode_persistent.cu): a cluster of 4 CTAs owns BNB = 48 beam rows = 3 column groups of
+// floor(16/K) images x K beams (12 epilogue warps = 4 TMEM lane quadrants x 3 column groups); W_hh / W_out
+// slices live in tensor memory as the MMA A operand.  With K = 5 that is 9 images per cluster: the 512 images
+// of BASELINE configs[2] are 57 clusters = 228 CTAs = 2 waves on 148 SMs (the 32-row version needed 86
+// clusters = 3 waves).  Tensor memory: 3 x 128 weight columns + 2 x 48 accumulator columns -- the logits
+// accumulator ALIASES the second gate accumulator: the gates of step s are consumed before MMA-L(s) is issued,
+// and MMA-G1(s+1) is issued only after every warp has copied the logits of step s out of tensor memory.
 //
 //   per step:   Epi-G   gates of row j are read from the accumulator column of its PARENT beam
 //                       (tcgen05.ld of one column at a run-time address) and c follows the parent
@@ -23,33 +28,47 @@
 // only where two distinct logits round to the same log-prob (documented near tie).
 #include "decode_persistent_common.cuh"
 
+#ifndef I2L_TANH_F16X2
+#define I2L_TANH_F16X2 0     // see decode_persistent.cu: two MUFU.TANH.F16 per f16x2 on sm_100a, no gain
+#endif
+
 namespace i2l {
 namespace {
+
+constexpr int NG = 3;                          // 16-column groups per cluster
+constexpr int BNB = 16 * NG;                   // beam rows per cluster = N of every MMA
+constexpr int BHSLICE = BNB * 128;             // one K-block of the h operand (one CTA's 64 units), bytes
+constexpr int BHB = 4 * BHSLICE;               // one h buffer
+constexpr int MW = (BNB + 31) / 32;            // merge warps: lane <-> beam row 32 w + lane
+// tensor-memory columns: fp32 accumulators (the logits accumulator aliases the second gate accumulator, see above)
+constexpr int BTC_G0 = 0, BTC_G1 = BNB, BTC_L = BNB;
+static_assert(2 * BNB <= 128, "accumulators must stay below the first weight tile (column 128)");
+constexpr uint32_t BIDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNB >> 3) << 17) | ((128u >> 4) << 24);
 
 template <int K>
 struct Geo {
   static constexpr int IPG = 16 / K;                       // images per 16-column group
-  static constexpr int IPC = 2 * IPG;                      // images per cluster
+  static constexpr int IPC = NG * IPG;                     // images per cluster
   static constexpr int USED = IPG * K;                     // live columns per group
   static constexpr int XW = (2 * K + 2 + 3) / 4 * 4;       // 32-bit words per exchange record (16-byte multiple)
   // shared memory map (bytes)
   static constexpr int OFF_H = 0;                          // 2 h buffers (B operand)
-  static constexpr int OFF_LT = OFF_H + 2 * HB_BYTES;      // logits tile, transposed: [32 rows][128 vocab] fp32
-  static constexpr int OFF_XCHG = OFF_LT + NB * 128 * 4;   // [4 ctas][32 rows] records
-  static constexpr int OFF_CAND = OFF_XCHG + CL * NB * XW * 4;   // [32 rows][K] (double score, int tok, pad)
-  static constexpr int OFF_ROW = OFF_CAND + NB * K * 16;   // [32] (double score, int live, pad)
-  static constexpr int OFF_NEW = OFF_ROW + NB * 16;        // [32] (double score, int parent slot, int tok)
-  static constexpr int OFF_PUB = OFF_NEW + NB * 16;        // [32] (int parent column in group, int tok)
-  static constexpr int OFF_BAR = OFF_PUB + NB * 8;
+  static constexpr int OFF_LT = OFF_H + 2 * BHB;           // logits tile, transposed: [BNB rows][128 vocab] fp32
+  static constexpr int OFF_XCHG = OFF_LT + BNB * 128 * 4;  // [4 ctas][BNB rows] records
+  static constexpr int OFF_CAND = OFF_XCHG + CL * BNB * XW * 4;   // [BNB rows][K] (double score, int tok, pad)
+  static constexpr int OFF_ROW = OFF_CAND + BNB * K * 16;  // [BNB] (double score, int live, pad)
+  static constexpr int OFF_NEW = OFF_ROW + BNB * 16;       // [BNB] (double score, int parent slot, int tok)
+  static constexpr int OFF_PUB = OFF_NEW + BNB * 16;       // [BNB] (int parent column in group, int tok)
+  static constexpr int OFF_BAR = OFF_PUB + BNB * 8;
   static constexpr int OFF_MISC = OFF_BAR + 16 * 8;
-  static constexpr int SMEM = OFF_MISC + 16;
+  static constexpr int SMEM = OFF_MISC + 32;               // tmem base, -, -, -, per-merge-warp "all images done"
   static_assert(K >= 1 && K <= 16 && SMEM <= 232448, "beam geometry");
 };
 
-// 8 warps, no dedicated MMA warp: a 9th warp would put 3 warps on one SM sub-partition and cap the
-// kernel at 168 registers (16384 / (3 x 32)); warp 0 issues the MMAs at the point where it would
-// otherwise just wait for them.
-constexpr int BT = EPI_THREADS;
+// 4 x NG warps, no dedicated MMA warp: warp 0 issues the MMAs at the point where it would otherwise just wait for
+// them.  12 warps = 3 per SM sub-partition = at most 168 registers per thread.
+constexpr int BT = 4 * NG * 32;
+__device__ __forceinline__ void beam_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(BT) : "memory"); }
 
 // BAR_HS + 4 * buf + d: K-block of h buffer `buf` written by the CTA at cluster distance d (rank - d; d = 0: this CTA)
 enum { BAR_LDONE = 3, BAR_GDONE = 4, BAR_TOK = 5, BAR_FINAL = 6, BAR_HS = 8 };
@@ -142,13 +161,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + G::OFF_MISC) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < 2 * HB_BYTES / 16; i += BT) reinterpret_cast<uint4*>(smem + G::OFF_H)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * BHB / 16; i += BT) reinterpret_cast<uint4*>(smem + G::OFF_H)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = misc[0];
-  {   // resident weights -> tensor memory (same image as the greedy kernel)
+  if (warp < 8) {   // resident weights -> tensor memory (same image as the greedy kernel), warps 0-7
     const int p = 32 * (warp & 3) + lane;
     const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     const int half = warp >> 2;
@@ -174,7 +193,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
   tc_fence_after();
   cluster_sync_all();
 
-  const uint32_t TM_L = tmem + TC_L, TM_G0 = tmem + TC_G0, TM_G1 = tmem + TC_G1;
+  const uint32_t TM_L = tmem + BTC_L, TM_G0 = tmem + BTC_G0, TM_G1 = tmem + BTC_G1;
 
   // MMA issue (warp 0, one elected lane): D[gate/vocab row, beam row] = W (TMEM A operand) x h^T (smem B operand)
   const uint64_t dbase = DESC_HI | (uint64_t)(((sbase >> 4) & 0x3FFFu) | (1u << 16));
@@ -183,8 +202,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
     for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        uint64_t bd = dbase + (uint64_t)((h_off + kb * HSLICE_BYTES + k * 32) >> 4);
-        tc_mma_ts(d_tmem, tmem + a_col + (kb * 4 + k) * 8, bd, IDESC, (kb | k) ? 1u : 0u);
+        uint64_t bd = dbase + (uint64_t)((h_off + kb * BHSLICE + k * 32) >> 4);
+        tc_mma_ts(d_tmem, tmem + a_col + (kb * 4 + k) * 8, bd, BIDESC, (kb | k) ? 1u : 0u);
       }
     }
   };
@@ -228,12 +247,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
     // 4*part .. 4*part+3) read conflict-free float4s
     const int pw = 32 * q + ((((lane >> 2) ^ q) << 2) | (lane & 3));
 
-    // ---- row / image state of the merge warp (warp 0: lane n <-> beam row n of the cluster) ----
-    const int n = lane;                                   // meaningful in warp 0 only
+    // ---- row / image state of the merge warps (warp w < MW: lane <-> beam row n = 32 w + lane of the cluster) ----
+    const bool mw = warp < MW;
+    const int n = 32 * warp + lane;                       // meaningful in the merge warps only
     const int n_w = n & 15, n_img_l = n_w / K, n_slot = n_w - n_img_l * K;
     const int n_img = cluster * G::IPC + (n >> 4) * G::IPG + n_img_l;
-    const bool n_valid = n_w < G::USED && n_img < P.B;
-    const int n_leader = n - n_slot;                      // lane of beam slot 0 of the image
+    const bool n_valid = mw && n < BNB && n_w < G::USED && n_img < P.B;
+    const int n_leader = lane - n_slot;                   // lane of beam slot 0 of the image (same warp: groups are 16-aligned)
     const bool is_leader = n_valid && n_slot == 0;
     double base = 0.0;                                    // score of the beam in this row
     long long basekey = 0;                                // score_key(base)
@@ -242,7 +262,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
     int st_alive = n_valid ? 1 : 0, st_nbeams = 1, st_has = 0, st_best_step = -1, st_best_slot = -1, st_last = -1;
     long long st_best = 0;                                // best completed score as an order-preserving key
 
-    if (warp == 0) {   // row record of step 0: only slot 0 (the START beam) is live
+    if (mw && n < BNB) {   // row record of step 0: only slot 0 (the START beam) is live
       reinterpret_cast<double*>(smem + G::OFF_ROW)[n * 2] = 0.0;
       reinterpret_cast<int*>(smem + G::OFF_ROW)[n * 4 + 2] = (n_valid && n_slot == 0) ? 1 : 0;
     }
@@ -290,25 +310,43 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
         for (int j = 0; j < 16; ++j) c[j] = cn[j];
       }
       const int nb = (s + 1) & 1;
-      unsigned char* hdst = smem + G::OFF_H + nb * HB_BYTES + rank * HSLICE_BYTES;
+      unsigned char* hdst = smem + G::OFF_H + nb * BHB + rank * BHSLICE;
       float y0[16], y1[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float x0 = __uint_as_float(r0[j]) + gt0[j] + gctx0[j];
         float x1 = __uint_as_float(r1[j]) + gt1[j] + gctx1[j];
+#if I2L_TANH_F16X2
+        float t0, t1;
+        tanh2_f16(0.5f * x0, s1 * x1, t0, t1);
+        y0[j] = fmaf(t0, 0.5f, 0.5f);
+        y1[j] = fmaf(t1, m1, b1);
+#else
         y0[j] = fmaf(tanh_approx(0.5f * x0), 0.5f, 0.5f);
         y1[j] = fmaf(tanh_approx(s1 * x1), m1, b1);
+#endif
       }
       float pg[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) pg[j] = __shfl_xor_sync(0xffffffffu, y0[j] * y1[j], 16);
       float hn[16];
+#if I2L_TANH_F16X2
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const float ca = fmaf(y0[j], c[j], pg[j]), cb = fmaf(y0[j + 1], c[j + 1], pg[j + 1]);
+        c[j] = ca; c[j + 1] = cb;
+        float ta, tb;
+        tanh2_f16(ca, cb, ta, tb);
+        hn[j] = y1[j] * ta; hn[j + 1] = y1[j + 1] * tb;
+      }
+#else
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float cnv = fmaf(y0[j], c[j], pg[j]);
         c[j] = cnv;
         hn[j] = y1[j] * tanh_approx(cnv);
       }
+#endif
       if (hi) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -320,22 +358,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
       BEAM_TS(4);
       fence_proxy_async();
       tc_fence_before();
-      epi_bar_sync();
+      beam_bar_sync();
       if (tid == 0) {
-        const uint32_t src = sbase + G::OFF_H + nb * HB_BYTES + rank * HSLICE_BYTES;
+        const uint32_t src = sbase + G::OFF_H + nb * BHB + rank * BHSLICE;
         mbar_arrive(BAR(BAR_HS + 4 * nb));                          // own K-block is in place
 #pragma unroll
         for (uint32_t d = 1; d < CL; ++d) {
           // arm the barrier of the block that arrives from distance d, send ours to the CTA at distance d
-          mbar_arrive_expect_tx(BAR(BAR_HS + 4 * nb + d), HSLICE_BYTES);
+          mbar_arrive_expect_tx(BAR(BAR_HS + 4 * nb + d), BHSLICE);
           const uint32_t peer = (rank + d) & (CL - 1);
-          bulk_s2peer(mapa(src, peer), src, HSLICE_BYTES, mapa(BAR(BAR_HS + 4 * nb + d), peer));
+          bulk_s2peer(mapa(src, peer), src, BHSLICE, mapa(BAR(BAR_HS + 4 * nb + d), peer));
         }
       }
       if (warp == 0) {
         // MMA-L(s): the 4 MMAs of a K-block as soon as THAT block of h arrived (own block first, then the peers' in
         // the order their copies were sent; a 128x32x16 MMA costs ~45 cycles of the tensor pipe), then MMA-G(s+1)
-        const uint32_t hb = G::OFF_H + nb * HB_BYTES;
+        const uint32_t hb = G::OFF_H + nb * BHB;
 #pragma unroll
         for (uint32_t d = 0; d < CL; ++d) {
           mbar_wait(BAR(BAR_HS + 4 * nb + d), (uint32_t)((s >> 1) & 1));
@@ -344,18 +382,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t bd = dbase + (uint64_t)((hb + kb * HSLICE_BYTES + k * 32) >> 4);
-              tc_mma_ts(TM_L, tmem + TC_WO + (kb * 4 + k) * 8, bd, IDESC, (d | (uint32_t)k) ? 1u : 0u);
+              const uint64_t bd = dbase + (uint64_t)((hb + kb * BHSLICE + k * 32) >> 4);
+              tc_mma_ts(TM_L, tmem + TC_WO + (kb * 4 + k) * 8, bd, BIDESC, (d | (uint32_t)k) ? 1u : 0u);
             }
             if (d == CL - 1) tc_commit(BAR(BAR_LDONE));
           }
           __syncwarp();
         }
-        if (s + 1 < P.T && elect_one()) {
-          issue_tile(TM_G0, TC_WG0, hb);                  // gates of step s+1
-          issue_tile(TM_G1, TC_WG1, hb);
-          tc_commit(BAR(BAR_GDONE));
-        }
+        if (s + 1 < P.T && elect_one()) issue_tile(TM_G0, TC_WG0, hb);   // first gate tile of step s+1 (its accumulator is free)
         __syncwarp();
       }
       // ---------------- Epi-L(s): logits -> per-row top-K + log-sum-exp partials ----------------
@@ -371,7 +405,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
         for (int j = 0; j < 16; ++j) LT[(col0 + j) * 128 + pw] = lg[j] + bias;  // lanes -> distinct banks
       }
       BEAM_TS(7);
-      epi_bar_sync();
+      beam_bar_sync();
+      if (warp == 0) {
+        // every warp has copied the logits out of tensor memory (tcgen05.ld + fence::before_thread_sync above): the
+        // accumulator the logits shared with the second gate tile is free -> MMA-G1(s+1), hidden under the top-K work
+        tc_fence_after();
+        if (s + 1 < P.T && elect_one()) {
+          issue_tile(TM_G1, TC_WG1, G::OFF_H + ((s + 1) & 1) * BHB);
+          tc_commit(BAR(BAR_GDONE));
+        }
+        __syncwarp();
+      }
       BEAM_TS(8);
       {
         const int row = tid >> 3, part = tid & 7;           // 8 threads per beam row, vocabulary entries [16 part, 16 part + 16)
@@ -439,31 +483,31 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
 #pragma unroll
           for (int k = 0; k < K; ++k) { w[2 * k] = __float_as_uint(lv[k]); w[2 * k + 1] = (uint32_t)(li[k] + 128 * (int)rank); }
           w[2 * K] = __float_as_uint(mref); w[2 * K + 1] = __float_as_uint(se);
-          uint4* dst = reinterpret_cast<uint4*>(smem + G::OFF_XCHG + (rank * NB + row) * (G::XW * 4));
+          uint4* dst = reinterpret_cast<uint4*>(smem + G::OFF_XCHG + (rank * BNB + row) * (G::XW * 4));
 #pragma unroll
           for (int i = 0; i < G::XW / 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
           fence_proxy_async();
         }
       }
-      if (warp == 0) {                                      // slots of the new beams start empty
+      if (mw && n < BNB) {                                  // slots of the new beams start empty
         double* new_sc = reinterpret_cast<double*>(smem + G::OFF_NEW);
         int* new_i = reinterpret_cast<int*>(smem + G::OFF_NEW);
         new_sc[n * 2] = 0.0; new_i[n * 4 + 2] = -1; new_i[n * 4 + 3] = -1;
       }
       BEAM_TS(11);
-      epi_bar_sync();
+      beam_bar_sync();
       BEAM_TS(23);
       if (tid == 0) {                                       // the CTA's 32 records -> the three peers (one bulk copy each)
-        const uint32_t src = sbase + G::OFF_XCHG + rank * NB * (G::XW * 4);
-        mbar_arrive_expect_tx(BAR(BAR_TOK), (CL - 1) * NB * G::XW * 4);
+        const uint32_t src = sbase + G::OFF_XCHG + rank * BNB * (G::XW * 4);
+        mbar_arrive_expect_tx(BAR(BAR_TOK), (CL - 1) * BNB * G::XW * 4);
 #pragma unroll
         for (uint32_t d = 1; d < CL; ++d) {
           const uint32_t peer = (rank + d) & (CL - 1);
-          bulk_s2peer(mapa(src, peer), src, NB * G::XW * 4, mapa(BAR(BAR_TOK), peer));
+          bulk_s2peer(mapa(src, peer), src, BNB * G::XW * 4, mapa(BAR(BAR_TOK), peer));
         }
       }
       BEAM_TS(24);
-      if (warp == 0 && s > 0) {
+      if (mw && s > 0) {
         // finished beams retire to `completed` when next visited (258-260): depends on the previous step
         // only, so it runs while the records are in flight.  First-wins max in slot order.
         const int alive_i = __shfl_sync(0xffffffffu, st_alive, n_leader);
@@ -471,7 +515,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
         const bool ret = n_valid && alive_i && n_slot < nbeams_i && curtok == P.end_id;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          const int src = (n_leader + k) & 31;
+          const int src = (n_leader + k) & 31;              // lane of slot k of the image
           const int rk = __shfl_sync(0xffffffffu, ret ? 1 : 0, src);
           const long long sk = __shfl_sync(0xffffffffu, basekey, src);
           if (rk && (!st_has || sk > st_best)) { st_has = 1; st_best = sk; st_best_step = s - 1; st_best_slot = k; }
@@ -480,12 +524,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
       BEAM_TS(12);
       mbar_wait_cluster(BAR(BAR_TOK), s & 1);
       BEAM_TS(18);
-      if (warp < 4) {
-        // ---- torch.topk(log_softmax(logits), K) per row (seq2seq.py:266-267) on warps 0-3: 4 lanes per row take
+      if (tid < 4 * BNB) {
+        // ---- torch.topk(log_softmax(logits), K) per row (seq2seq.py:266-267) on the first 4 BNB threads: 4 lanes per row take
         // one CTA record each; 4-way merge = K rounds of best-head butterfly (lower rank = lower vocabulary
         // index wins ties); log-sum-exp combined over the 4 partials
         const int row = tid >> 2, part = tid & 3;
-        const float* X = reinterpret_cast<const float*>(smem + G::OFF_XCHG) + (part * NB + row) * G::XW;
+        const float* X = reinterpret_cast<const float*>(smem + G::OFF_XCHG) + (part * BNB + row) * G::XW;
         float lv[K]; int li[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -556,7 +600,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
         BEAM_TS(13);
       }
       BEAM_TS(14);
-      epi_bar_sync();
+      beam_bar_sync();
       BEAM_TS(19);
       {
         // stable descending order of the image's K x K candidates (sorted(..., reverse=True)[:K], 279-280) by
@@ -589,16 +633,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
         }
       }
       BEAM_TS(20);
-      epi_bar_sync();
+      beam_bar_sync();
       BEAM_TS(15);
-      if (warp == 0) {
+      if (mw) {
+        const int nn_ = n < BNB ? n : 0;                    // lanes beyond the last row read row 0 and write nothing
         const long long* new_key = reinterpret_cast<const long long*>(smem + G::OFF_NEW);
         const int* new_i = reinterpret_cast<const int*>(smem + G::OFF_NEW);
         const int alive_i = __shfl_sync(0xffffffffu, st_alive, n_leader);
-        const int ps = new_i[n * 4 + 2], tk = new_i[n * 4 + 3];
-        const long long nkey = new_key[n * 2];
+        const int ps = new_i[nn_ * 4 + 2], tk = new_i[nn_ * 4 + 3];
+        const long long nkey = new_key[nn_ * 2];
         const double nsc = key_score(nkey);
-        const uint32_t img_mask = ((1u << K) - 1u) << n_leader;
+        const uint32_t img_mask = ((1u << K) - 1u) << (n_leader & 31);
         const uint32_t kept = __ballot_sync(0xffffffffu, n_valid && ps >= 0) & img_mask;
         const uint32_t notend = __ballot_sync(0xffffffffu, n_valid && ps >= 0 && tk != P.end_id) & img_mask;
         if (is_leader && st_alive) {
@@ -615,7 +660,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
           }
         }
         int* pub = reinterpret_cast<int*>(smem + G::OFF_PUB);
-        if (n_valid && alive_i) {
+        if (n >= BNB) {
+          // no row
+        } else if (n_valid && alive_i) {
           const size_t tro = ((size_t)s * P.B + n_img) * K + n_slot;
           if (rank == 0) {
             P.tr_parent[tro] = ps; P.tr_token[tro] = tk;
@@ -635,22 +682,27 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(BT, 1) persistent_b
         // row record of the next step: (score, live) -- a beam whose last token is END is not expanded (258-260)
         double* row_sc = reinterpret_cast<double*>(smem + G::OFF_ROW);
         int* row_i = reinterpret_cast<int*>(smem + G::OFF_ROW);
-        row_sc[n * 2] = base;
-        row_i[n * 4 + 2] = (n_valid && alive_now && n_slot < nbeams_now && curtok != P.end_id) ? 1 : 0;
-        const bool cluster_done = __all_sync(0xffffffffu, !n_valid || !alive_now);
-        if (lane == 0 && cluster_done) misc[1] = 1;
+        if (n < BNB) {
+          row_sc[n * 2] = base;
+          row_i[n * 4 + 2] = (n_valid && alive_now && n_slot < nbeams_now && curtok != P.end_id) ? 1 : 0;
+        }
+        const bool warp_done = __all_sync(0xffffffffu, !n_valid || !alive_now);
+        if (lane == 0) misc[4 + warp] = warp_done ? 1u : 0u;
         BEAM_TS(16);
       }
-      epi_bar_sync();
+      beam_bar_sync();
+      bool all_done = true;                                 // uniform: flags written before the barrier
+#pragma unroll
+      for (int w = 0; w < MW; ++w) all_done = all_done && reinterpret_cast<volatile uint32_t*>(misc)[4 + w] != 0;
       BEAM_TS(17);
       {
         const int* pub = reinterpret_cast<const int*>(smem + G::OFF_PUB);
 #pragma unroll
         for (int j = 0; j < 16; ++j) { par[j] = pub[(col0 + j) * 2]; tok[j] = pub[(col0 + j) * 2 + 1]; }
       }
-      if (*reinterpret_cast<volatile uint32_t*>(&misc[1])) { ++s; break; }
+      if (all_done) { ++s; break; }
     }
-    if (warp == 0 && rank == 0 && n_valid) {
+    if (rank == 0 && n_valid) {
       P.score[(size_t)n_img * K + n_slot] = base;
       if (is_leader) {
         BeamState st;

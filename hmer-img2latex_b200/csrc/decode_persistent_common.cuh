@@ -2,6 +2,7 @@
 // decode_persistent_beam.cu): geometry, packed bf16 section layout, PTX wrappers, UMMA descriptors.
 #pragma once
 #include "decode_kernels.cuh"
+#include <cuda_fp16.h>
 
 namespace i2l {
 namespace {
@@ -167,6 +168,18 @@ __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// two tanh per MUFU op: (a, b) -> f16x2 -> tanh.approx.f16x2 -> back to fp32.  The cell update of the persistent kernels
+// is bound by the XU pipe (16 MUFU/clk/SM: 48 tanh per thread and step); packing halves that.  Absolute error of a
+// result <= 2^-11 (f16 rounding of an output in [-1, 1]) + the f16 rounding of the argument times tanh' <= 1, the same
+// order as tanh.approx.f32 (2^-10.99) and 8x below the bf16 rounding the h operand gets anyway.
+__device__ __forceinline__ void tanh2_f16(float a, float b, float& ta, float& tb) {
+  uint32_t p, t;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(b), "f"(a));      // hi = b, lo = a
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(p));
+  const __half2 h = *reinterpret_cast<const __half2*>(&t);
+  ta = __low2float(h);
+  tb = __high2float(h);
 }
 __device__ __forceinline__ float redux_max(float v) {
   float m;

@@ -119,7 +119,7 @@ extern "C" int i2l_token_exchange_write(const int64_t* tokens, const int32_t* le
                                         void* const* peer_buffers, uint32_t seq, void* stream) {
   I2L_TRY(device_check());
   I2L_REQUIRE(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world, "token exchange: invalid rank / world");
-  I2L_REQUIRE(tokens && lengths && steps && peer_buffers && b >= 0 && T1 >= 1 && n_total >= 1 && seq != 0,
+  I2L_REQUIRE(steps && peer_buffers && b >= 0 && (b == 0 || (tokens && lengths)) && T1 >= 1 && n_total >= 1 && seq != 0,
               "token exchange: invalid arguments (seq must be non-zero)");
   const int cap = (n_total + world - 1) / world;
   I2L_REQUIRE(b <= cap, "token exchange: shard of %d rows exceeds the slot capacity %d", b, cap);

@@ -252,16 +252,43 @@ def attention(attn_w, attn_b, v_w, hidden: torch.Tensor, encoder_outputs: torch.
     return torch.bmm(wts, encoder_outputs)                                     # :341
 
 
-def lstm_step(p: Params, x: torch.Tensor, h: torch.Tensor, c: torch.Tensor, L: int):
+def _r16(t: torch.Tensor) -> torch.Tensor:
+    """round to bf16 and back (round-to-nearest-even, what the kernels' operand conversion does)"""
+    return t.bfloat16().float()
+
+
+def lstm_step(p: Params, x: torch.Tensor, h: torch.Tensor, c: torch.Tensor, L: int, bf16_operands: bool = False):
     """One time step of `nn.LSTM(batch_first=True)` (decoder.py:76-82, called at
     :277) written out: gates (i,f,g,o) = x W_ih^T + b_ih + h W_hh^T + b_hh;
     c' = sig(f) c + sig(i) tanh(g); h' = sig(o) tanh(c').  x (B,In), h/c (L,B,H).
-    Inter-layer dropout is inactive in eval (decoder.py:81)."""
+    Inter-layer dropout is inactive in eval (decoder.py:81).
+
+    ``bf16_operands`` (cfg["operand_rounding"] == "bf16", NOT the reference's arithmetic): the same recurrence with
+    the operands of the tensor-core GEMMs rounded to bf16 exactly where precision="bf16" of the CUDA path rounds them
+    -- h, W_hh, the context half of layer 0's input (enc, W_ih[:, E:]), deeper layers' inputs and W_ih -- fp32
+    accumulation, fp32 token term (emb W_ih[:, :E]^T), fp32 biases, cell state and activations.  Lets the tests
+    separate "bf16 operand rounding" (inherent to the mode) from kernel error: against THIS variant the bf16 kernels
+    must agree almost everywhere, against the fp32 restatement only up to near ties."""
     hs, cs = [], []
     inp = x
     for l in range(L):
-        gates = (F.linear(inp, p[f"decoder.lstm.weight_ih_l{l}"], p[f"decoder.lstm.bias_ih_l{l}"])
-                 + F.linear(h[l], p[f"decoder.lstm.weight_hh_l{l}"], p[f"decoder.lstm.bias_hh_l{l}"]))
+        w_ih, w_hh = p[f"decoder.lstm.weight_ih_l{l}"], p[f"decoder.lstm.weight_hh_l{l}"]
+        if bf16_operands:
+            if l == 0:
+                E = w_ih.shape[1] // 2
+                gi = F.linear(inp[:, :E], w_ih[:, :E]) + F.linear(_r16(inp[:, E:]), _r16(w_ih[:, E:]))
+            else:
+                gi = F.linear(_r16(inp), _r16(w_ih))
+            gates = (gi + p[f"decoder.lstm.bias_ih_l{l}"] + p[f"decoder.lstm.bias_hh_l{l}"]
+                     + F.linear(_r16(h[l]), _r16(w_hh)))
+            i, f, g, o = gates.chunk(4, dim=1)
+            cn = torch.sigmoid(f) * c[l] + torch.sigmoid(i) * torch.tanh(g)
+            hn = torch.sigmoid(o) * torch.tanh(cn)
+            hs.append(hn); cs.append(cn)
+            inp = hn
+            continue
+        gates = (F.linear(inp, w_ih, p[f"decoder.lstm.bias_ih_l{l}"])
+                 + F.linear(h[l], w_hh, p[f"decoder.lstm.bias_hh_l{l}"]))
         i, f, g, o = gates.chunk(4, dim=1)
         cn = torch.sigmoid(f) * c[l] + torch.sigmoid(i) * torch.tanh(g)
         hn = torch.sigmoid(o) * torch.tanh(cn)
@@ -289,6 +316,10 @@ def decode_step(p: Params, encoder_output: torch.Tensor, input_token: torch.Tens
     else:
         ctx = encoder_output.unsqueeze(1)                                      # :218
     x = torch.cat([emb, ctx], dim=2).squeeze(1)                                # :228 / :274
+    if cfg.get("operand_rounding") == "bf16":        # see lstm_step; the kernels keep the bf16-rounded h as the state
+        top, hn, cn = lstm_step(p, x, h, c, L, bf16_operands=True)
+        logits = F.linear(_r16(top), _r16(p["decoder.output_layer.weight"]), p["decoder.output_layer.bias"])
+        return logits.unsqueeze(1), (hn, cn)
     top, hn, cn = lstm_step(p, x, h, c, L)                                     # :247 / :277
     logits = F.linear(top, p["decoder.output_layer.weight"], p["decoder.output_layer.bias"])  # :250/:280
     return logits.unsqueeze(1), (hn, cn)
