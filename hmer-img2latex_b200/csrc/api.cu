@@ -43,7 +43,10 @@ int num_sms() {
 
 // ---------------------------------------------------------------- launch counter + kernel timers
 static std::atomic<long long> g_launches{0};
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static thread_local bool g_counting = true;    // off while a launch sequence is being CAPTURED (nothing executes)
+void count_launch() { if (g_counting) g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }   // kernel nodes of a graph replay
+void set_launch_counting(bool on) { g_counting = on; }
 
 namespace {
 constexpr int kMaxProf = 96, kMaxEv = 4096;

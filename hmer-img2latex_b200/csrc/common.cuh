@@ -11,6 +11,8 @@ namespace i2l {
 
 void set_error(const char* fmt, ...);
 void count_launch();   // every kernel launch of the library is counted (bench.py "gpu_launches")
+void count_launches(long long n);      // kernel nodes executed by one replay of a captured launch sequence
+void set_launch_counting(bool on);     // thread-local: off while a sequence is being captured
 
 // Optional per-kernel CUDA-event timing (bench.py roofline): enabled by i2l_prof_enable(1).
 // Usage: { KernelTimer t("conv2", stream); kernel<<<...>>>(...); }

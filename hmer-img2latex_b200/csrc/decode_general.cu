@@ -8,6 +8,9 @@
 #include "gemm_bf16.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
 
 namespace i2l {
 
@@ -46,6 +49,14 @@ PackedDec dec_layout(const i2l_dec_desc& d) {
     }
     L.g16_out_w = take16(V * H);
     L.g16_w_ctx = take16(4 * H * E);
+    L.g16c = 0;
+    if ((H % 32) == 0) {
+      L.g16c = bytes;
+      for (int l = 0; l < d.lstm_layers; ++l) {
+        L.g16c_w_hh[l] = take16(4 * H * H);
+        L.g16c_w_ih[l] = l == 0 ? 0 : take16(4 * H * H);
+      }
+    }
   }
   L.total_bytes = bytes;
   return L;
@@ -76,6 +87,16 @@ __global__ void transpose_tokens_kernel(const int64_t* __restrict__ src, int64_t
   int64_t v = src[(size_t)b * T + t];
   if (v < 0 || v >= V) { if (bad) atomicExch(bad, 1); v = 0; }
   dst[i] = v;
+}
+
+// (4H, K) fp32 gate weights -> bf16 with the rows of every 128-row tile ordered [gate][32 units]:
+// dst row 128 t + 32 g + ul  <-  src row g H + 32 t + ul
+__global__ void pack_cell_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int H, int K) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)4 * H * K) return;
+  const int k = (int)(i % K), r = (int)(i / K);
+  const int t = r >> 7, gt = (r >> 5) & 3, ul = r & 31;
+  dst[i] = __float2bfloat16(src[((size_t)gt * H + 32 * t + ul) * K + k]);
 }
 
 __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
@@ -591,11 +612,15 @@ __global__ void attention_combine_kernel(const float* __restrict__ p1, const flo
 struct DecWs {
   float *gctx, *gates, *logits, *h[2], *c[2];
   __nv_bfloat16* hb;             // bf16 copy of h[0] (L,R,H): A operand of the tcgen05 GEMMs (precision bf16)
+  __nv_bfloat16* hb2;            // second copy: the fused gate-GEMM + cell kernels read one and write the other
   int64_t* tok_cur;
   int* first_end;
   LoopState* st;
   // beam only
   BeamState* bstate; double* score; int* live; int* parent; int* tr_parent; int* tr_token; double* tr_score;
+  // graph-replayed loops: the captured launch sequence reads / writes ONLY workspace and packed-weight addresses;
+  // the caller's tensors are copied in / out around the replay (see run_loop)
+  float* g_enc; int64_t* g_tokens; int32_t* g_lengths; int32_t* g_steps; float* g_uniforms;
   size_t bytes;
 };
 
@@ -608,6 +633,7 @@ DecWs carve(const i2l_dec_desc& d, int rows, int max_length, void* ws) {
   w.logits = a.take<float>(R * V);
   for (int i = 0; i < 2; ++i) { w.h[i] = a.take<float>(L * R * H); w.c[i] = a.take<float>(L * R * H); }
   w.hb = a.take<__nv_bfloat16>(L * R * H);
+  w.hb2 = a.take<__nv_bfloat16>(L * R * H);
   w.tok_cur = a.take<int64_t>(R);
   w.first_end = a.take<int>(R);
   w.st = a.take<LoopState>(1);
@@ -619,6 +645,11 @@ DecWs carve(const i2l_dec_desc& d, int rows, int max_length, void* ws) {
   w.tr_parent = a.take<int>(T * R);
   w.tr_token = a.take<int>(T * R);
   w.tr_score = a.take<double>(T * R);
+  w.g_enc = a.take<float>(R * (size_t)d.embedding_dim);
+  w.g_tokens = a.take<int64_t>(R * (T + 1));
+  w.g_lengths = a.take<int32_t>(R);
+  w.g_steps = a.take<int32_t>(1);
+  w.g_uniforms = a.take<float>(T * R);
   w.bytes = align_up(a.off, 256);
   return w;
 }
@@ -707,6 +738,68 @@ int make_step_bf16(const i2l_dec_desc& d, const void* packed, const PackedDec& l
   g.K1 = H;
   g.bias = pk + lay.out_b;
   return I2L_OK;
+}
+
+// Fused variant (H % 32 == 0): per layer ONE launch = gate GEMM + LSTM cell in the epilogue (no (rows,4H) fp32 gates
+// round trip, no cell kernel).  h is double buffered in bf16: even steps read w.hb and write w.hb2, odd steps the
+// reverse -- a launch must not overwrite the operand other CTAs are still reading.  par[k] = structures of a step
+// that READS buffer k.
+struct StepFused { GemmBf16 gates[2][I2L_MAX_LSTM_LAYERS]; GemmBf16 logits[2]; };
+
+int make_step_fused(const i2l_dec_desc& d, const void* packed, const PackedDec& lay, const DecWs& w, float* h, float* c,
+                    int rows, const int* skip, StepFused* st) {
+  const int H = d.hidden_dim, V = d.vocab_size;
+  const float* pk = reinterpret_cast<const float*>(packed);
+  const char* pb = reinterpret_cast<const char*>(packed);
+  for (int par = 0; par < 2; ++par) {
+    __nv_bfloat16* rd = par == 0 ? w.hb : w.hb2;          // h of the previous step
+    __nv_bfloat16* wr = par == 0 ? w.hb2 : w.hb;          // h of this step
+    for (int l = 0; l < d.lstm_layers; ++l) {
+      GemmBf16& g = st->gates[par][l];
+      g = GemmBf16{};
+      g.M = rows; g.N = 4 * H; g.skip_flag = skip;
+      g.cell_c = c + (size_t)l * rows * H; g.cell_h = h + (size_t)l * rows * H; g.cell_hb = wr + (size_t)l * rows * H;
+      g.cell_H = H;
+      if (l == 0) {
+        I2L_TRY(gemm_bf16_a_map(&g.tmA1, rd, rows, H, H));
+        I2L_TRY(gemm_bf16_w_map(&g.tmW1, pb + lay.g16c_w_hh[0], 4 * H, H, H));
+        g.K1 = H;
+        g.add_rows = w.gctx; g.ld_add = 4 * H;
+        g.add_table = pk + lay.gtok; g.ld_tab = 4 * H; g.tab_idx = w.tok_cur;
+      } else {
+        I2L_TRY(gemm_bf16_a_map(&g.tmA1, wr + (size_t)(l - 1) * rows * H, rows, H, H));     // this step's h of the layer below
+        I2L_TRY(gemm_bf16_w_map(&g.tmW1, pb + lay.g16c_w_ih[l], 4 * H, H, H));
+        I2L_TRY(gemm_bf16_a_map(&g.tmA2, rd + (size_t)l * rows * H, rows, H, H));
+        I2L_TRY(gemm_bf16_w_map(&g.tmW2, pb + lay.g16c_w_hh[l], 4 * H, H, H));
+        g.K1 = H; g.K2 = H;
+        g.bias = pk + lay.bsum[l];
+      }
+    }
+    GemmBf16& g = st->logits[par];
+    g = GemmBf16{};
+    g.M = rows; g.N = V; g.C = w.logits; g.ldc = V; g.skip_flag = skip;
+    I2L_TRY(gemm_bf16_a_map(&g.tmA1, wr + (size_t)(d.lstm_layers - 1) * rows * H, rows, H, H));
+    I2L_TRY(gemm_bf16_w_map(&g.tmW1, pb + lay.g16_out_w, V, H, H));
+    g.K1 = H;
+    g.bias = pk + lay.out_b;
+  }
+  return I2L_OK;
+}
+
+#ifdef I2L_DIAG   // diagnostics build: per-kernel CUDA-event timers (recorded as event nodes when the loop is captured)
+#define I2L_DIAG_TIMER(name) KernelTimer kt_diag_(name, s)
+#else
+#define I2L_DIAG_TIMER(name) do { } while (0)
+#endif
+
+int step_rows_fused(const i2l_dec_desc& d, const StepFused& st, int step, cudaStream_t s) {
+  const int par = step & 1;
+  for (int l = 0; l < d.lstm_layers; ++l) {
+    I2L_DIAG_TIMER(l == 0 ? "gen.gate_cell_l0" : "gen.gate_cell_l1plus");
+    I2L_TRY(gemm_bf16(st.gates[par][l], s));
+  }
+  I2L_DIAG_TIMER("gen.logits_gemm");
+  return gemm_bf16(st.logits[par], s);
 }
 
 int step_rows_bf16(const i2l_dec_desc& d, const StepBf16& st, const DecWs& w, float* h, float* c, int rows,
@@ -818,6 +911,18 @@ extern "C" int i2l_dec_pack(const i2l_dec_desc* d_in, const i2l_dec_params* p, v
       if (l > 0) I2L_TRY(conv(p->w_ih[l], lay.g16_w_ih[l], 4 * H * H));
     }
     I2L_TRY(conv(p->out_w, lay.g16_out_w, V * H));
+    if (lay.g16c) {
+      auto convc = [&](const float* src, size_t off) -> int {
+        const size_t n = 4 * H * H;
+        pack_cell_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(pb + off), (int)H, (int)H);
+        I2L_LAUNCH_OK();
+        return I2L_OK;
+      };
+      for (int l = 0; l < d->lstm_layers; ++l) {
+        I2L_TRY(convc(p->w_hh[l], lay.g16c_w_hh[l]));
+        if (l > 0) I2L_TRY(convc(p->w_ih[l], lay.g16c_w_ih[l]));
+      }
+    }
     {
       const size_t n = 4 * H * E;
       f32_to_bf16_ld_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->w_ih[0] + E, 2 * (int)E, reinterpret_cast<__nv_bfloat16*>(pb + lay.g16_w_ctx), (int)E, n);
@@ -866,21 +971,33 @@ extern "C" int i2l_decode_step(const i2l_dec_desc* d_in, const void* packed, con
   return step_rows(*d, pk, lay, w2, h_out, c_out, batch, nullptr, s);
 }
 
-static int run_loop(const i2l_dec_desc* d, const void* packed, const float* enc, int batch, int start_id,
-                    int end_id, int max_length, float temperature, int stop_rule, bool sampling_path,
-                    int top_k, float top_p, uint64_t seed, uint64_t offset, const float* uniforms,
-                    int64_t* tokens, int32_t* lengths, int32_t* steps_run, float* probs_trace, void* workspace,
-                    size_t workspace_bytes, cudaStream_t s) {
-  I2L_TRY(check_common(d, packed));
-  I2L_REQUIRE(batch >= 0 && max_length >= 0 && tokens != nullptr, "decode loop: invalid arguments");
-  I2L_REQUIRE(batch == 0 || enc != nullptr, "decode loop: null encoder output");
-  I2L_REQUIRE(stop_rule >= 0 && stop_rule <= 2, "decode loop: invalid stop rule");
-  I2L_REQUIRE(start_id >= 0 && start_id < d->vocab_size, "decode loop: start token %d outside [0, %d) (nn.Embedding raises IndexError)",
-              start_id, d->vocab_size);
-  if (batch == 0) return I2L_OK;
-  PackedDec lay = dec_layout(*d);
-  DecWs w = carve(*d, batch, max_length, workspace);
-  if (workspace_bytes < w.bytes) { set_error("decode loop: workspace too small (%zu < %zu)", workspace_bytes, w.bytes); return I2L_ERR_WORKSPACE; }
+// ---------------------------------------------------------------------------------------------
+// The stream-ordered decode loops as ONE CUDA graph.  A step of the general path is 2 L + 2 small launches (gate GEMM
+// + cell per layer, logits GEMM, selection) whose kernels run 1-4 us each: issued one by one the loop is bound by
+// the host's launch rate (~5-7 us per launch through the C-ABI, 40-50 us per step for L = 2).  All loop bookkeeping
+// already lives on the device (token append, EOS masks, both stop rules, the `done` flag every kernel checks), so the
+// whole max_length-step sequence is captured once per (weights, workspace, shape, loop arguments) and replayed with a
+// single cudaGraphLaunch.  The captured kernels read and write only workspace / packed-weight addresses; the caller's
+// enc / uniforms are copied in before the replay and tokens / lengths / steps are copied out after it, so fresh
+// output tensors per call do not invalidate the graph.  Capture runs on a private non-blocking stream (the caller's
+// may be the legacy default stream, which cannot be captured); nothing executes during capture.
+struct LoopKey {
+  const void* packed; const void* ws; i2l_dec_desc d;
+  int batch, start_id, end_id, max_length, stop_rule, sampling, top_k, has_uniforms, dev;
+  float temperature, top_p; unsigned long long seed, offset;
+  bool operator==(const LoopKey& o) const { return memcmp(this, &o, sizeof(LoopKey)) == 0; }
+};
+struct LoopGraph { LoopKey key; cudaGraphExec_t exec; long long kernels; unsigned long long last_use; };
+constexpr int kLoopGraphs = 16;
+static std::mutex g_graph_mu;
+static LoopGraph g_graphs[kLoopGraphs];
+static int g_n_graphs = 0;
+static unsigned long long g_graph_tick = 0;
+
+static int enqueue_loop(const i2l_dec_desc* d, const void* packed, const PackedDec& lay, const DecWs& w, const float* enc,
+                        int batch, int start_id, int end_id, int max_length, float temperature, int stop_rule,
+                        bool sampling_path, int top_k, float top_p, uint64_t seed, uint64_t offset, const float* uniforms,
+                        int64_t* tokens, int32_t* lengths, int32_t* steps_run, float* probs_trace, cudaStream_t s) {
   const float* pk = reinterpret_cast<const float*>(packed);
   const int T1 = max_length + 1, V = d->vocab_size;
   size_t tot = (size_t)batch * T1;
@@ -899,14 +1016,17 @@ static int run_loop(const i2l_dec_desc* d, const void* packed, const float* enc,
   }
   const int do_sample = temperature > 0.f && (top_k > 0 || top_p > 0.0f);   // predictor.py:330
   const bool tc = lay.g16 != 0;                       // precision bf16: the per-step GEMMs run on tcgen05
+  const bool fused = tc && lay.g16c != 0;             // ... with the LSTM cell fused into the gate GEMM's epilogue
   StepBf16 st16;
+  static thread_local StepFused stf;                  // ~10 KB of tensor maps: not on the stack
   if (tc) {
     I2L_CUDA_OK(cudaMemsetAsync(w.hb, 0, (size_t)d->lstm_layers * batch * d->hidden_dim * 2, s));
-    I2L_TRY(make_step_bf16(*d, packed, lay, w, batch, skip, &st16));
+    if (fused) I2L_TRY(make_step_fused(*d, packed, lay, w, w.h[0], w.c[0], batch, skip, &stf));
+    else I2L_TRY(make_step_bf16(*d, packed, lay, w, batch, skip, &st16));
   }
-  KernelTimer kt(sampling_path ? "dec.sample_loop_general" : "dec.greedy_loop_general", s);
   for (int step = 0; step < max_length; ++step) {
-    if (tc) I2L_TRY(step_rows_bf16(*d, st16, w, w.h[0], w.c[0], batch, skip, s));
+    if (fused) I2L_TRY(step_rows_fused(*d, stf, step, s));
+    else if (tc) I2L_TRY(step_rows_bf16(*d, st16, w, w.h[0], w.c[0], batch, skip, s));
     else I2L_TRY(step_rows(*d, pk, lay, w, w.h[0], w.c[0], batch, skip, s));
     if (sampling_path && V <= 512) {
       sample_select_warp_kernel<<<cdiv(batch, 8), 256, 0, s>>>(w.logits, V, batch, temperature, top_k, top_p, do_sample,
@@ -917,6 +1037,7 @@ static int run_loop(const i2l_dec_desc* d, const void* packed, const float* enc,
                                                    seed, offset, uniforms, probs_trace, step, T1, end_id,
                                                    stop_rule, tokens, w.tok_cur, w.first_end, w.st);
     } else {
+      I2L_DIAG_TIMER("gen.greedy_select");
       greedy_select_kernel<<<cdiv(batch, 8), 256, 0, s>>>(w.logits, V, batch, temperature, step, T1, end_id,
                                                           stop_rule, tokens, w.tok_cur, w.first_end, w.st);
     }
@@ -924,6 +1045,93 @@ static int run_loop(const i2l_dec_desc* d, const void* packed, const float* enc,
   }
   loop_finalize_kernel<<<cdiv(batch, 256), 256, 0, s>>>(w.first_end, batch, max_length, lengths, steps_run, w.st);
   I2L_LAUNCH_OK();
+  return I2L_OK;
+}
+
+static int run_loop(const i2l_dec_desc* d, const void* packed, const float* enc, int batch, int start_id,
+                    int end_id, int max_length, float temperature, int stop_rule, bool sampling_path,
+                    int top_k, float top_p, uint64_t seed, uint64_t offset, const float* uniforms,
+                    int64_t* tokens, int32_t* lengths, int32_t* steps_run, float* probs_trace, void* workspace,
+                    size_t workspace_bytes, cudaStream_t s) {
+  I2L_TRY(check_common(d, packed));
+  I2L_REQUIRE(batch >= 0 && max_length >= 0 && tokens != nullptr, "decode loop: invalid arguments");
+  I2L_REQUIRE(batch == 0 || enc != nullptr, "decode loop: null encoder output");
+  I2L_REQUIRE(stop_rule >= 0 && stop_rule <= 2, "decode loop: invalid stop rule");
+  I2L_REQUIRE(start_id >= 0 && start_id < d->vocab_size, "decode loop: start token %d outside [0, %d) (nn.Embedding raises IndexError)",
+              start_id, d->vocab_size);
+  if (batch == 0) return I2L_OK;
+  PackedDec lay = dec_layout(*d);
+  DecWs w = carve(*d, batch, max_length, workspace);
+  if (workspace_bytes < w.bytes) { set_error("decode loop: workspace too small (%zu < %zu)", workspace_bytes, w.bytes); return I2L_ERR_WORKSPACE; }
+  const char* timer_name = sampling_path ? "dec.sample_loop_general" : "dec.greedy_loop_general";
+  // graph replay: loops long enough to amortise a capture, no per-step trace requested, caller not capturing itself
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
+  const bool use_graph = max_length >= 8 && probs_trace == nullptr && cap == cudaStreamCaptureStatusNone &&
+                         lengths != nullptr && steps_run != nullptr;
+  if (!use_graph) {
+    KernelTimer kt(timer_name, s);
+    return enqueue_loop(d, packed, lay, w, enc, batch, start_id, end_id, max_length, temperature, stop_rule, sampling_path,
+                        top_k, top_p, seed, offset, uniforms, tokens, lengths, steps_run, probs_trace, s);
+  }
+  LoopKey key;
+  memset(&key, 0, sizeof(key));
+  key.packed = packed; key.ws = workspace; key.d = *d; key.batch = batch; key.start_id = start_id; key.end_id = end_id;
+  key.max_length = max_length; key.stop_rule = stop_rule; key.sampling = sampling_path ? 1 : 0; key.top_k = top_k;
+  key.has_uniforms = uniforms != nullptr; key.temperature = temperature; key.top_p = top_p;
+  key.seed = sampling_path && !uniforms ? seed : 0; key.offset = sampling_path && !uniforms ? offset : 0;
+  I2L_CUDA_OK(cudaGetDevice(&key.dev));
+  cudaGraphExec_t exec = nullptr;
+  long long kernels = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    for (int i = 0; i < g_n_graphs; ++i)
+      if (g_graphs[i].key == key) { exec = g_graphs[i].exec; kernels = g_graphs[i].kernels; g_graphs[i].last_use = ++g_graph_tick; break; }
+    if (exec == nullptr) {
+      static thread_local cudaStream_t cs = nullptr;          // capture stream (never executes anything)
+      if (cs == nullptr) I2L_CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      I2L_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      set_launch_counting(false);
+      const int rc = enqueue_loop(d, packed, lay, w, w.g_enc, batch, start_id, end_id, max_length, temperature, stop_rule,
+                                  sampling_path, top_k, top_p, seed, offset, uniforms ? w.g_uniforms : nullptr, w.g_tokens,
+                                  w.g_lengths, w.g_steps, nullptr, cs);
+      set_launch_counting(true);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      if (rc != I2L_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+      if (ce != cudaSuccess) { set_error("decode loop: graph capture failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return I2L_ERR_CUDA; }
+      size_t n_nodes = 0;
+      cudaGraphGetNodes(graph, nullptr, &n_nodes);
+      std::vector<cudaGraphNode_t> nodes(n_nodes);
+      if (n_nodes) cudaGraphGetNodes(graph, nodes.data(), &n_nodes);
+      for (size_t i = 0; i < n_nodes; ++i) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++kernels;
+      }
+      const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) { set_error("decode loop: graph instantiation failed: %s", cudaGetErrorString(ie)); cudaGetLastError(); return I2L_ERR_CUDA; }
+      int slot = g_n_graphs;
+      if (g_n_graphs < kLoopGraphs) ++g_n_graphs;
+      else {                                                    // evict the least recently used graph
+        slot = 0;
+        for (int i = 1; i < kLoopGraphs; ++i) if (g_graphs[i].last_use < g_graphs[slot].last_use) slot = i;
+        cudaGraphExecDestroy(g_graphs[slot].exec);
+      }
+      g_graphs[slot] = LoopGraph{key, exec, kernels, ++g_graph_tick};
+    }
+  }
+  I2L_CUDA_OK(cudaMemcpyAsync(w.g_enc, enc, (size_t)batch * d->embedding_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (uniforms)
+    I2L_CUDA_OK(cudaMemcpyAsync(w.g_uniforms, uniforms, (size_t)max_length * batch * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  {
+    KernelTimer kt(timer_name, s);
+    I2L_CUDA_OK(cudaGraphLaunch(exec, s));
+  }
+  count_launches(kernels);
+  I2L_CUDA_OK(cudaMemcpyAsync(tokens, w.g_tokens, (size_t)batch * (max_length + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  I2L_CUDA_OK(cudaMemcpyAsync(lengths, w.g_lengths, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+  I2L_CUDA_OK(cudaMemcpyAsync(steps_run, w.g_steps, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
   return I2L_OK;
 }
 

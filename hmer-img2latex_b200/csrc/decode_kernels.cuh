@@ -35,6 +35,9 @@ struct PackedDec {     // offsets (in floats) into the packed decoder buffer, fp
   // W_hh[l] (4H,H), W_ih[l >= 1] (4H,H), W_out (V,H) -- operands of gemm_bf16.cu
   size_t g16, g16_w_hh[I2L_MAX_LSTM_LAYERS], g16_w_ih[I2L_MAX_LSTM_LAYERS], g16_out_w;
   size_t g16_w_ctx;     // W_ih0[:, E:2E] (4H,E): the per-sequence constant gate term gctx = enc W_ctx^T + b_ih0 + b_hh0
+  // H % 32 == 0: the same gate weights with the rows of every 128-row tile ordered [i | f | g | o] x 32 units, for the
+  // gate GEMM with the LSTM cell fused into its epilogue (gemm_bf16.cu, GemmBf16::cell_*); g16c == 0 if absent
+  size_t g16c, g16c_w_hh[I2L_MAX_LSTM_LAYERS], g16c_w_ih[I2L_MAX_LSTM_LAYERS];
   size_t total_bytes;
 };
 // precision == I2L_BF16 and TMA-addressable rows (H % 8 == 0, E % 8 == 0): the general loops run their GEMMs on tcgen05

@@ -12,6 +12,12 @@ namespace {
 
 using namespace tc;
 
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int GB_BM = 128, GB_BN = 128, GB_BK = 64, GB_STAGES = 4;
 constexpr int GB_A_BYTES = GB_BM * GB_BK * 2, GB_B_BYTES = GB_BN * GB_BK * 2;
 constexpr int GB_STAGE = GB_A_BYTES + GB_B_BYTES;
@@ -85,6 +91,68 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant
     const float* trow = (g.add_table != nullptr && mv) ? g.add_table + (size_t)g.tab_idx[m] * g.ld_tab : nullptr;
     mbar_wait(TFULL, 0);
     tc_fence_after();
+    if (g.cell_c != nullptr) {
+      // ---- fused LSTM cell: tile columns [32 gate + ul] = gate (i,f,g,o) of hidden unit u0 + ul; 16 units per pass
+      const int Hh = g.cell_H, u0 = blockIdx.y * 32;
+      const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[4][16];
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) tc_ld16_nowait(ta + gt * 32 + half * 16, r[gt]);
+        tc_wait_ld();
+        if (mv) {
+        const int ub = u0 + half * 16;                      // first of the 16 units of this pass
+        float x[4][16];
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) {
+          const int col = gt * Hh + ub;                     // PyTorch gate-major column of the epilogue terms
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g.bias != nullptr) { const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + col + 4 * i)); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+            if (arow != nullptr) { const float4 t = *reinterpret_cast<const float4*>(arow + col + 4 * i); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+            if (trow != nullptr) { const float4 t = __ldg(reinterpret_cast<const float4*>(trow + col + 4 * i)); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+            x[gt][4 * i] = __uint_as_float(r[gt][4 * i]) + a.x;
+            x[gt][4 * i + 1] = __uint_as_float(r[gt][4 * i + 1]) + a.y;
+            x[gt][4 * i + 2] = __uint_as_float(r[gt][4 * i + 2]) + a.z;
+            x[gt][4 * i + 3] = __uint_as_float(r[gt][4 * i + 3]) + a.w;
+          }
+        }
+        float* cp = g.cell_c + (size_t)m * Hh + ub;
+        float* hp = g.cell_h + (size_t)m * Hh + ub;
+        float hn[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 cv = *reinterpret_cast<const float4*>(cp + 4 * i);
+          float cc[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = 4 * i + e;
+            // MUFU.TANH activations (sigmoid(x) = 0.5 tanh(x / 2) + 0.5), as in the persistent kernels: the precise
+            // expf / tanhf / division sequences cost ~140 instructions per unit on the 4 epilogue warps of a CTA
+            const float ig = fmaf(tanh_fast(0.5f * x[0][k]), 0.5f, 0.5f), fg = fmaf(tanh_fast(0.5f * x[1][k]), 0.5f, 0.5f);
+            const float gg = tanh_fast(x[2][k]), og = fmaf(tanh_fast(0.5f * x[3][k]), 0.5f, 0.5f);
+            const float cn = fmaf(fg, cc[e], ig * gg);
+            cc[e] = cn;
+            hn[k] = og * tanh_fast(cn);
+          }
+          *reinterpret_cast<float4*>(cp + 4 * i) = make_float4(cc[0], cc[1], cc[2], cc[3]);
+          *reinterpret_cast<float4*>(hp + 4 * i) = make_float4(hn[4 * i], hn[4 * i + 1], hn[4 * i + 2], hn[4 * i + 3]);
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(hn[2 * i], hn[2 * i + 1]);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        uint4* hb = reinterpret_cast<uint4*>(g.cell_hb + (size_t)m * Hh + ub);
+        hb[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        hb[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        __syncwarp();
+      }
+    } else {
     // 16 consecutive columns per tcgen05.ld: 64-byte row segments of C / add_rows / the token's table row, moved as
     // float4 when the segment is complete and 16-byte aligned (always, for N % 16 == 0 and 4-float-aligned rows)
     const bool vec_ok = (g.ldc % 4) == 0 && (g.ld_add % 4) == 0 && (g.ld_tab % 4) == 0 && (reinterpret_cast<uintptr_t>(g.C) % 16) == 0 &&
@@ -132,6 +200,7 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_kernel(const __grid_constant
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -153,7 +222,10 @@ int gemm_bf16_w_map(CUtensorMap* out, const void* w, int N, int K, int ldw) { re
 
 int gemm_bf16(const GemmBf16& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0) return I2L_OK;
-  I2L_REQUIRE(g.K1 > 0 && g.C != nullptr, "gemm_bf16: invalid arguments");
+  I2L_REQUIRE(g.K1 > 0 && (g.C != nullptr || g.cell_c != nullptr), "gemm_bf16: invalid arguments");
+  if (g.cell_c != nullptr)
+    I2L_REQUIRE(g.cell_h && g.cell_hb && g.cell_H > 0 && g.N == 4 * g.cell_H && (g.cell_H % 32) == 0 &&
+                (g.ld_add % 4) == 0 && (g.ld_tab % 4) == 0, "gemm_bf16: invalid fused-cell arguments");
   static thread_local int attr_dev = -1;
   int dev = 0;
   I2L_CUDA_OK(cudaGetDevice(&dev));

@@ -127,7 +127,23 @@ class Seq2SeqModel(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("greedy_stream needs the model on a CUDA device")
         copy_stream = torch.cuda.Stream(dev)
+        out_stream = torch.cuda.Stream(dev)                       # device->host copies of the results: off the compute stream
         compute = torch.cuda.current_stream(dev)
+        computed = [torch.cuda.Event(), torch.cuda.Event()]       # results of the slot exist on the device
+
+        def read_back(slot: int, tokens, lengths, steps) -> None:
+            if out_tok[slot] is None or out_tok[slot].shape != tokens.shape:
+                out_tok[slot] = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
+                out_len[slot] = torch.empty(lengths.shape, dtype=lengths.dtype).pin_memory()
+                out_steps[slot] = torch.empty((), dtype=steps.dtype).pin_memory()
+            computed[slot].record(compute)
+            with torch.cuda.stream(out_stream):
+                out_stream.wait_event(computed[slot])
+                for dst, src in ((out_tok[slot], tokens), (out_len[slot], lengths), (out_steps[slot], steps)):
+                    dst.copy_(src, non_blocking=True)
+                    src.record_stream(out_stream)                 # the caching allocator must not recycle it under the copy
+                done[slot].record(out_stream)
+
         bufs: List[Optional[torch.Tensor]] = [None, None]
         ready = [torch.cuda.Event(), torch.cuda.Event()]          # H2D copy of the slot has landed
         consumed = [torch.cuda.Event(), torch.cuda.Event()]       # the encoder has read the slot
@@ -190,14 +206,7 @@ class Seq2SeqModel(nn.Module):
                     i += 1
                     continue
                 tokens, lengths, steps = res
-            if out_tok[slot] is None or out_tok[slot].shape != tokens.shape:
-                out_tok[slot] = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
-                out_len[slot] = torch.empty(lengths.shape, dtype=lengths.dtype).pin_memory()
-                out_steps[slot] = torch.empty((), dtype=steps.dtype).pin_memory()
-            out_tok[slot].copy_(tokens, non_blocking=True)
-            out_len[slot].copy_(lengths, non_blocking=True)
-            out_steps[slot].copy_(steps, non_blocking=True)
-            done[slot].record(compute)
+            read_back(slot, tokens, lengths, steps)
             if prev >= 0:
                 yield collect(prev)
             prev = slot
@@ -207,15 +216,7 @@ class Seq2SeqModel(nn.Module):
             res = exchange.flush()
             if res is not None:                                   # the last batch's global result
                 slot = i & 1
-                tokens, lengths, steps = res
-                if out_tok[slot] is None or out_tok[slot].shape != tokens.shape:
-                    out_tok[slot] = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
-                    out_len[slot] = torch.empty(lengths.shape, dtype=lengths.dtype).pin_memory()
-                    out_steps[slot] = torch.empty((), dtype=steps.dtype).pin_memory()
-                out_tok[slot].copy_(tokens, non_blocking=True)
-                out_len[slot].copy_(lengths, non_blocking=True)
-                out_steps[slot].copy_(steps, non_blocking=True)
-                done[slot].record(compute)
+                read_back(slot, *res)
                 if prev >= 0:
                     yield collect(prev)
                 prev = slot

@@ -16,6 +16,9 @@ HEADLINE = dict(model_type="cnn_lstm", vocab_size=512, embedding_dim=256, hidden
                 attention=True, img_height=64, img_width=320, channels=3)
 SMALL = dict(model_type="cnn_lstm", vocab_size=46, embedding_dim=32, hidden_dim=48, lstm_layers=2,
              attention=True, img_height=16, img_width=40, channels=1, conv_filters=[8, 16])
+# the reference's shipped decoder (img2latex/configs/config.yaml:45-50): E = H = 512, two LSTM layers
+SHIPPED = dict(model_type="cnn_lstm", vocab_size=512, embedding_dim=512, hidden_dim=512, lstm_layers=2, attention=True,
+               img_height=16, img_width=32, channels=1, conv_filters=[8])
 R18 = dict(model_type="resnet_lstm", model_name="resnet18", vocab_size=46, embedding_dim=64, hidden_dim=64,
            lstm_layers=1, attention=True, img_height=64, img_width=128, channels=3)
 R50 = dict(model_type="resnet_lstm", model_name="resnet50", vocab_size=46, embedding_dim=64, hidden_dim=64,

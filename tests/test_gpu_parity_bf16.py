@@ -537,3 +537,55 @@ def test_resnet50_sampling_at_the_benchmarked_config(pkg):
           f"oracle end to end, {same16}/{S} the bf16-operand oracle on the same encodings; {bad_total} draws sit on a cdf "
           f"boundary; steps {n}")
     assert same16 >= 0.5 * S
+
+
+@pytest.mark.parametrize("cfg,B,T", [(H.SHIPPED, 200, 60), (dict(H.SHIPPED, embedding_dim=128, hidden_dim=96, lstm_layers=3), 70, 30)])
+def test_wide_decoder_fused_graph_loop(pkg, cfg, B, T):
+    """Decoders outside the persistent kernel's shape -- here the reference's SHIPPED one, E = H = 512 / 2 layers
+    (configs/config.yaml:45-50) -- run the stream-ordered loop as ONE replayed CUDA graph whose per-layer launch is
+    the gate GEMM with the LSTM cell fused into its epilogue (gemm_bf16.cu, H % 32 == 0).  Greedy rows against the
+    fp32 oracle (near ties only) and the bf16-operand oracle (>= 90 % identical); a second call replays the cached
+    graph with different encodings and must give that call's own result; the sampling loop draws the inverse CDF."""
+    wide = cfg["hidden_dim"] >= 256
+    p = oracle.make_params(cfg, 4, sharp=not wide)       # (the END-bias recipe of `sharp` ends every 512-wide row at step 1)
+    if wide:
+        p["decoder.output_layer.weight"] *= 4.0
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    g = torch.Generator().manual_seed(23)
+    E = cfg["embedding_dim"]
+    enc_a = torch.relu(torch.randn(B, E, generator=g))
+    enc_b = torch.relu(torch.randn(B, E, generator=g)) * 0.7
+    lib = pkg._native.lib()
+    res = {}
+    for name, enc_ref in (("a", enc_a), ("b", enc_b), ("a2", enc_a)):
+        l0 = lib.i2l_launch_count()
+        tokens, lengths, steps = m16.decoder.greedy(enc_ref.cuda(), H.START, H.END, T)
+        torch.cuda.synchronize()
+        res[name] = (tokens.cpu(), lengths.cpu(), int(steps), lib.i2l_launch_count() - l0)
+    assert torch.equal(res["a"][0], res["a2"][0]) and torch.equal(res["a"][1], res["a2"][1])
+    assert not torch.equal(res["a"][0], res["b"][0])
+    L = cfg["lstm_layers"]
+    assert res["b"][3] >= T * (L + 2), "the replay's kernel nodes are counted as launches"
+    for name, enc_ref in (("a", enc_a), ("b", enc_b)):
+        tokens, lengths, n, _ = res[name]
+        ref, steps_ref, trace = oracle.greedy_search(p, enc_ref, H.START, H.END, T, 1.0, cfg, return_logits=True)
+        exact, near, bad = divergence_report(tokens[:, : steps_ref + 1].tolist(), ref, trace)
+        ref16, steps16 = oracle.greedy_search(p, enc_ref, H.START, H.END, T, 1.0, bf16_cfg(cfg))
+        same16 = rows_identical(tokens[:, : steps16 + 1].tolist(), ref16)
+        print(f"wide decoder E={E} H={cfg['hidden_dim']} L={L} B={B} T={T} [{name}]: rows on the fp32 oracle {exact}/{B} "
+              f"({len(near)} near ties), on the bf16-operand oracle {same16}/{B}")
+        assert not bad, f"rows diverging at a step with a clear margin: {bad[:10]}"
+        # the tiny 3-layer case is all near ties (measured 52 / 51 of 70 on the two oracles): near-tie accounting only
+        assert same16 >= 0.9 * B if wide else max(exact, same16) >= 0.7 * B
+    # sampling loop through the same graph machinery: every draw is the inverse CDF of the kernel's own distribution
+    u = torch.rand(T, B, generator=g)
+    tok_s, len_s, st_s = m16.decoder.sample(enc_a.cuda(), H.START, H.END, T, 0.9, 30, 0.9, uniforms=u)
+    tok_p, _, st_p, probs = m16.decoder.sample(enc_a.cuda(), H.START, H.END, T, 0.9, 30, 0.9, uniforms=u, return_probs=True)
+    assert torch.equal(tok_s, tok_p) and int(st_s) == int(st_p)           # graph replay == launch-by-launch (trace requested)
+    n = int(st_p)
+    cdf = torch.cumsum(probs[:n].double(), dim=2)
+    tgt = u[:n].double().cuda() * cdf[:, :, -1]
+    drawn = (cdf > tgt.unsqueeze(2)).int().argmax(dim=2)
+    taken = tok_p[:, 1: n + 1].t()
+    for t, b in (drawn != taken).nonzero().tolist():
+        assert float((cdf[t, b] - tgt[t, b]).abs().min()) < 1e-6, (t, b)
