@@ -230,13 +230,14 @@ def run_ours(args):
         def host_batches(k):
             for i in range(k):
                 yield hosts[i % len(hosts)]
-        for _ in model.greedy_stream(host_batches(2), START, END, MAX_LEN, exchange=xchg):
+        rb = "global" if rank == 0 else "shard"      # rank 0 hands the job's (global) result to the host; the others their rows
+        for _ in model.greedy_stream(host_batches(2), START, END, MAX_LEN, exchange=xchg, exchange_readback=rb):
             pass
         barrier()
         t0 = time.perf_counter()
         last = None
-        for last in model.greedy_stream(host_batches(n), START, END, MAX_LEN, exchange=xchg):
-            pass   # N > 1: the yielded triples are the GLOBAL id matrices (exchange + D2H inside the timed region)
+        for last in model.greedy_stream(host_batches(n), START, END, MAX_LEN, exchange=xchg, exchange_readback=rb):
+            pass   # N > 1: exchange on the device + D2H (rank 0: the GLOBAL id matrix) inside the timed region
         barrier()
         return time.perf_counter() - t0, last
 
@@ -560,6 +561,44 @@ def resnet_lines(pkg, dev, B, reps=3, world=1):
         "encoder_ms": round(enc_ms, 3), "encoder_tflops": round(fl / enc_ms / 1e9, 1),
         "encoder_frac_of_bf16_peak": round(fl / enc_ms / 1e9 / peaks()["tf_sust"], 3),
         "decode_ms": round(ms - enc_ms, 3)}
+    del m, x
+    # ---- the reference's SHIPPED configuration (img2latex/configs/config.yaml:45-50: embedding_dim 512, hidden_dim 512,
+    # lstm_layers 2; encoder.py:50-64: grey 1x64x800 images) -> two extra lines:
+    #   (a) CNN encoder at 1x64x800 (tcgen05 path, cnn_bf16.cu) + the headline decoder: the serving shape of Predictor
+    #   (b) the 512 / 512 / 2 decoder alone (graph-replayed stream-ordered loop with the fused gate-GEMM + cell launch)
+    m = pkg.Seq2SeqModel("cnn_lstm", CFG["vocab_size"], dict(img_height=64, img_width=800, channels=1, embedding_dim=256),
+                         dict(hidden_dim=256, lstm_layers=1, attention=True), precision="bf16").to(dev).eval()
+    px = torch.randint(0, 256, (B, 1, 64, 800), dtype=torch.uint8, device=dev)
+
+    def step800():
+        return gathered(m.decoder.greedy(m.encoder.forward_u8(px), START, END, MAX_LEN, 1.0, N.STOP_ALL_END_SAME_STEP))
+
+    ms, prof = timed(step800)
+    enc_ms = sum(v for k, v in prof.items() if k.startswith("cnn."))
+    fl = B * 2.0 * (32 * 9 * 1 * 64 * 800 + 64 * 9 * 32 * 32 * 400 + 128 * 9 * 64 * 16 * 200 + 256 * 128 * 8 * 100)
+    out["cnn_1x64x800_greedy"] = {
+        "workload": "reference default / serving shape (encoder.py:50-64, predictor.py:409-414): CNN-LSTM greedy decode, "
+                    "%d grey 1x64x800 uint8 images per GPU on %d GPU(s), max_len 150" % (B, world),
+        "value": round(world * B / ms * 1e3, 1), "unit": "images/s", "n_gpus": world, "ms_per_step": round(ms, 3),
+        "encoder_ms": round(enc_ms, 3), "encoder_tflops": round(fl / enc_ms / 1e9, 1),
+        "encoder_frac_of_bf16_peak": round(fl / enc_ms / 1e9 / peaks()["tf_sust"], 3),
+        "kernels_ms": {k: v for k, v in prof.items() if k.startswith("cnn.") or k.startswith("dec.")}}
+    del m, px
+    dec = pkg.LSTMDecoder(CFG["vocab_size"], 512, 512, MAX_LEN, 2, 0.0, True, precision="bf16").to(dev).eval()
+    enc = torch.relu(torch.randn(B, 512, device=dev))
+    ms, prof = timed(lambda: gathered(dec.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_NONE)))
+    fl_step = B * 11.01e6                                       # live FLOPs per sequence and step @512/512/2
+    out["decoder_512_512_2_greedy"] = {
+        "workload": "the reference's shipped decoder (configs/config.yaml:45-50: E = H = 512, 2 LSTM layers), greedy, "
+                    "%d sequences per GPU on %d GPU(s), 150 steps, V = 512" % (B, world),
+        "value": round(world * B / ms * 1e3, 1), "unit": "sequences/s", "n_gpus": world, "ms_per_step": round(ms, 3),
+        "us_per_decode_step": round(ms / MAX_LEN * 1e3, 2),
+        "roofline": {"bound": "tensor", "achieved": round(fl_step / (ms / MAX_LEN * 1e-3) / 1e12, 1),
+                     "peak": peaks()["tf_sust"], "unit": "TFLOP/s",
+                     "frac": round(fl_step / (ms / MAX_LEN * 1e-3) / 1e12 / peaks()["tf_sust"], 3)},
+        "note": "stream-ordered loop replayed as ONE CUDA graph, L + 2 launches per step (gate GEMM with the LSTM cell "
+                "fused into its epilogue per layer, logits GEMM, selection); no persistent kernel for this shape yet: "
+                "6.5 MB of bf16 weights do not fit the tensor + shared memory of a 4..16-CTA cluster"}
     return out
 
 

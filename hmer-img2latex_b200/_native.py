@@ -70,6 +70,7 @@ SIGNATURES = {
     "i2l_version": (C.c_char_p, []),
     "i2l_last_error": (C.c_char_p, []),
     "i2l_device_check": (C.c_int, []),
+    "i2l_cnn_tensor_core_path": (C.c_int, [C.POINTER(CnnDesc)]),
     "i2l_cnn_packed_bytes": (C.c_size_t, [C.POINTER(CnnDesc)]),
     "i2l_cnn_pack": (C.c_int, [C.POINTER(CnnDesc), C.POINTER(CnnParams), _fp, C.c_size_t, _fp]),
     "i2l_cnn_workspace_bytes": (C.c_size_t, [C.POINTER(CnnDesc), C.c_int32]),

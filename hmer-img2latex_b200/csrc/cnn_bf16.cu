@@ -1,5 +1,7 @@
-// bf16 CNN encoder for the headline shape (3x64x320 -> conv 32/64/128 -> FC 40960->256),
-// CNNEncoder.forward (model/encoder.py:111-129), as tcgen05 implicit-GEMM kernels:
+// bf16 CNN encoder, CNNEncoder.forward (model/encoder.py:111-129), as tcgen05 implicit-GEMM kernels for the
+// reference's conv stack (conv 32/64/128, 3x3 "same", 2x2 max-pool, FC -> 256) on C x H x W images with C in {1, 3},
+// H % 64 == 0, W % 32 == 0: the headline 3x64x320 (BASELINE configs 1-3) and the reference's default / serving shape
+// 1x64x800 (encoder.py:50-64, training/predictor.py:409-414) among them.  Comments quote the headline sizes.
 //
 //   conv1  fp32 NCHW input -> bf16.  K = 27 (padded to 32): the im2col rows are built in shared
 //          memory by the CTA (K-major SWIZZLE_64B UMMA operand), 4 accumulators = the 4 pixels
@@ -22,14 +24,37 @@ namespace {
 
 using namespace tc;
 
-constexpr int IMG_H = 64, IMG_W = 320, C0 = 3, C1 = 32, C2 = 64, C3 = 128, EMB = 256;
-constexpr int FLAT = C3 * 8 * 40;   // 40960
+constexpr int C1 = 32, C2 = 64, C3 = 128, EMB = 256;
+
+// run-time geometry of one encoder configuration
+struct Geom {
+  int H, W, C0;                 // input image
+  int TW, TH;                   // conv1 tiles (16 x 32 conv pixels = 8 x 16 pooled pixels) per image
+  int PH1, PW1, PH2, PW2, PH3, PW3;   // pooled map sizes after conv1 / conv2 / conv3
+  int WW2, WW3;                 // pooled columns per conv2 / conv3 tile (x 16 / WW images x 8 rows = 128 pixels)
+  int FLAT;                     // FC input features
+  int splits;                   // FC split-K factor
+};
+Geom make_geom(const i2l_cnn_desc& d) {
+  Geom g{};
+  g.H = d.img_height; g.W = d.img_width; g.C0 = d.channels;
+  g.TW = g.W / 32; g.TH = g.H / 16;
+  g.PH1 = g.H / 2; g.PW1 = g.W / 2; g.PH2 = g.H / 4; g.PW2 = g.W / 4; g.PH3 = g.H / 8; g.PW3 = g.W / 8;
+  g.WW2 = (g.PW2 % 16) == 0 ? 16 : 8;                                 // W % 32 == 0  =>  PW2 % 8 == 0
+  g.WW3 = (g.PW3 % 16) == 0 ? 16 : ((g.PW3 % 8) == 0 ? 8 : 4);        //              =>  PW3 % 4 == 0
+  g.FLAT = C3 * g.PH3 * g.PW3;
+  const int kblocks = g.FLAT / 64;
+  g.splits = 1;
+  for (int sp = 16; sp >= 1; --sp) if (kblocks % sp == 0) { g.splits = sp; break; }
+  return g;
+}
+constexpr int BPAD = 4;       // the batch is padded to a multiple of the largest images-per-tile count (16 / 4)
 
 // ------------------------------------------------------------------ packed section layout
 struct Sec {
   size_t w1, b1, w2, b2, w3, b3, wfc, bfc, total;
 };
-Sec sec_layout() {
+Sec sec_layout(const Geom& G) {
   Sec s{};
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o = align_up(o + n, 1024); return r; };
@@ -39,7 +64,7 @@ Sec sec_layout() {
   s.b2 = take(C2 * 4);
   s.w3 = take(9 * C3 * C2 * 2);         // 9 taps x [128][64] SW128
   s.b3 = take(C3 * 4);
-  s.wfc = take((size_t)EMB * FLAT * 2); // [256][40960] bf16, NHWC column order
+  s.wfc = take((size_t)EMB * G.FLAT * 2); // [256][40960] bf16, NHWC column order
   s.bfc = take(EMB * 4);
   s.total = o;
   return s;
@@ -51,7 +76,7 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, int co_n, int ci
   if (layer == 1) {
     if (i >= 32 * 32) return;
     int co = i / 32, k = i % 32;
-    float v = k < 27 ? w[co * 27 + k] : 0.f;
+    float v = k < 9 * ci_n ? w[co * 9 * ci_n + k] : 0.f;
     *reinterpret_cast<__nv_bfloat16*>(dst + swz_off(co, k / 8, 64) + (k % 8) * 2) = __float2bfloat16(v);
   } else {
     if (i >= 9 * co_n * ci_n) return;
@@ -62,13 +87,13 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, int co_n, int ci
   }
 }
 
-__global__ void pack_fc_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst) {
-  // dst[e][(h*40+w)*128 + c] = w[e][c*320 + h*40 + w]    (nn.Flatten on NCHW, encoder.py:125)
+__global__ void pack_fc_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int FLAT, int HW) {
+  // dst[e][(h*40+w)*128 + c] = w[e][c*320 + h*40 + w]    (nn.Flatten on NCHW, encoder.py:125); HW = 8 * 40
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)EMB * FLAT) return;
   int kk = (int)(i % FLAT), e = (int)(i / FLAT);
   int c = kk % C3, hw = kk / C3;
-  dst[i] = __float2bfloat16(w[(size_t)e * FLAT + (size_t)c * 320 + hw]);
+  dst[i] = __float2bfloat16(w[(size_t)e * FLAT + (size_t)c * HW + hw]);
 }
 
 // ------------------------------------------------------------------ conv1
@@ -103,12 +128,15 @@ constexpr int C1_OFF_PATCH = C1_OFF_W + 2048;
 constexpr int C1_OFF_BAR = C1_OFF_PATCH + C1_PS * C1_PATCH_STRIDE;
 constexpr int C1_SMEM = C1_OFF_BAR + 256;
 
-template <typename InT>
+template <typename InT, int CIN0>
 __global__ void __launch_bounds__(C1_THREADS, 1)
 conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __restrict__ w1img,
-             const float* __restrict__ bias1, __nv_bfloat16* __restrict__ act1, int B, int n_tiles, int dbg, const C1Norm nrm) {
+             const float* __restrict__ bias1, __nv_bfloat16* __restrict__ act1, int B, int n_tiles, int dbg, const C1Norm nrm,
+             int TW, int TH) {
   constexpr int PATCH_W = C1In<InT>::PATCH_W, PATCH_X0 = C1In<InT>::X0;
-  constexpr int C1_PATCH_BYTES = 3 * PATCH_H * PATCH_W * C1In<InT>::ELT;
+  constexpr int C1_PATCH_BYTES = CIN0 * PATCH_H * PATCH_W * C1In<InT>::ELT;
+  const int TPI = TW * TH;                      // tiles per image
+  const int QH = 4 * TH, QW = 8 * TW;           // act1 plane rows / columns (H / 4, W / 4)
   static_assert(C1_PATCH_BYTES <= C1_PATCH_STRIDE, "patch ring slot too small");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -144,7 +172,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
     if (elect_one()) {
       int it = 0;
       for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
-        const int tw = tile % 10, th = (tile / 10) % 4, b = tile / 40;
+        const int tw = tile % TW, th = (tile / TW) % TH, b = tile / TPI;
         const int s = it % C1_PS;
         mbar_wait(PEMPTY(s), ((it / C1_PS) & 1) ^ 1);
         if (dbg & 1) { mbar_arrive(PFULL(s)); continue; }
@@ -185,11 +213,11 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
     for (int i = 0; i < 8; ++i) { float4 v = reinterpret_cast<const float4*>(bias1)[i]; bias[4 * i] = v.x; bias[4 * i + 1] = v.y; bias[4 * i + 2] = v.z; bias[4 * i + 3] = v.w; }
     int it = 0;
     for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
-      const int tw = tile % 10, th = (tile / 10) % 4, b = tile / 40;
+      const int tw = tile % TW, th = (tile / TW) % TH, b = tile / TPI;
       const int g = it & 1; const uint32_t par = (it >> 1) & 1;
       const int ph = th * 8 + (m >> 4), pw = tw * 16 + (m & 15);
       // act1 layout [plane = (ph&1)*2 + (pw&1)][16][B][80][32]
-      const size_t pix = ((((size_t)((ph & 1) * 2 + (pw & 1)) * 16 + (ph >> 1)) * B + b) * 80 + (pw >> 1));
+      const size_t pix = ((((size_t)((ph & 1) * 2 + (pw & 1)) * QH + (ph >> 1)) * B + b) * QW + (pw >> 1));
       uint4* dst = reinterpret_cast<uint4*>(act1 + pix * C1);
       mbar_wait(TFULL(g), par);
       tc_fence_after();
@@ -233,17 +261,17 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
       const unsigned char* patch = smem + C1_OFF_PATCH + s * C1_PATCH_STRIDE;
       // raw[ci][kh][j]: 32-bit words holding the 4 needed columns (qw + kw = 0..3) of patch row
       // (ci, 2*pl + qh + kh); fp32: one value per word, bf16: column e of the pair in half (e & 1)
-      uint32_t raw[3][3][4];
+      uint32_t raw[CIN0][3][4];
       if constexpr (sizeof(InT) == 1) {
         // needed patch bytes 15 + 2*pwl + j (j = 0..3): an unaligned 4-byte window over two words
-        const int tw = tile % 10, th = (tile / 10) % 4;
-        const bool top = th == 0 && pl == 0 && qh == 0, bot = th == 3 && pl == 7 && qh == 1;      // kh = 0 / kh = 2 outside
-        const bool left = tw == 0 && pwl == 0, right = tw == 9 && pwl == 15;                      // j = 0 / j = 3 outside
+        const int tw = tile % TW, th = (tile / TW) % TH;
+        const bool top = th == 0 && pl == 0 && qh == 0, bot = th == TH - 1 && pl == 7 && qh == 1;  // kh = 0 / kh = 2 outside
+        const bool left = tw == 0 && pwl == 0, right = tw == TW - 1 && pwl == 15;                  // j = 0 / j = 3 outside
         const int b0 = C1In<uint8_t>::X0 + 2 * pwl;
         const uint32_t* p0 = reinterpret_cast<const uint32_t*>(patch) + (2 * pl + qh) * (PATCH_W / 4) + (b0 >> 2);
         const uint32_t sh = (uint32_t)(b0 & 3) * 8;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
+        for (int ci = 0; ci < CIN0; ++ci)
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             const uint32_t* pp = p0 + (ci * PATCH_H + kh) * (PATCH_W / 4);
@@ -261,7 +289,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
       } else if constexpr (sizeof(InT) == 4) {
         const float* p0 = reinterpret_cast<const float*>(patch) + (2 * pl + qh) * PATCH_W + 2 * pwl;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
+        for (int ci = 0; ci < CIN0; ++ci)
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             // needed columns 2*pwl + 3 .. + 6 of the patch row: three aligned LDS.64 (cols 2*pwl + 2 .. + 7)
@@ -274,7 +302,7 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
         // needed columns 2*pwl + 7 .. + 10: words pwl + 3 (hi), pwl + 4 (lo, hi), pwl + 5 (lo)
         const uint32_t* p0 = reinterpret_cast<const uint32_t*>(patch) + (2 * pl + qh) * (PATCH_W / 2) + pwl + 3;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
+        for (int ci = 0; ci < CIN0; ++ci)
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             const uint32_t* pp = p0 + (ci * PATCH_H + kh) * (PATCH_W / 2);
@@ -292,15 +320,16 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
         for (int k2 = 0; k2 < 16; ++k2) {
           const int ka = 2 * k2, kb = 2 * k2 + 1;
           const int ja = qw + ka % 3, jb = qw + kb % 3;       // column index 0..3 within raw[][][]
+          constexpr int KREAL = 9 * CIN0;                     // 27 (RGB) or 9 (grey) real K entries, zero beyond
           if constexpr (sizeof(InT) != 2) {
-            float va = ka < 27 ? __uint_as_float(raw[ka / 9 % 3][(ka % 9) / 3][ja]) : 0.f;
-            float vb = kb < 27 ? __uint_as_float(raw[kb / 9 % 3][(kb % 9) / 3][jb]) : 0.f;
+            float va = ka < KREAL ? __uint_as_float(raw[ka / 9 % CIN0][(ka % 9) / 3][ja]) : 0.f;
+            float vb = kb < KREAL ? __uint_as_float(raw[kb / 9 % CIN0][(kb % 9) / 3][jb]) : 0.f;
             __nv_bfloat162 h2 = __floats2bfloat162_rn(va, vb);
             pk[k2] = *reinterpret_cast<uint32_t*>(&h2);
           } else {
             // columns j = 0, 2 sit in the high half of their word, j = 1, 3 in the low half
-            const uint32_t wa = ka < 27 ? raw[ka / 9 % 3][(ka % 9) / 3][ja] : 0u;
-            const uint32_t wb = kb < 27 ? raw[kb / 9 % 3][(kb % 9) / 3][jb] : 0u;
+            const uint32_t wa = ka < KREAL ? raw[ka / 9 % CIN0][(ka % 9) / 3][ja] : 0u;
+            const uint32_t wb = kb < KREAL ? raw[kb / 9 % CIN0][(kb % 9) / 3][jb] : 0u;
             const uint32_t sel = ((ja & 1) ? 0x10u : 0x32u) | (((jb & 1) ? 0x54u : 0x76u) << 8);
             pk[k2] = __byte_perm(wa, wb, sel);
           }
@@ -594,35 +623,54 @@ __global__ void fc_reduce_kernel(const float* __restrict__ partial, const float*
 
 // ------------------------------------------------------------------ workspace
 struct Ws { __nv_bfloat16 *act1, *act2, *act3; float* partial; size_t bytes; int splits; };
-constexpr int FC_SPLITS = 16;
-Ws carve(int B, void* ws) {
+Ws carve(const Geom& G, int B, void* ws) {
   Arena a(ws, (size_t)-1);
   Ws w{};
-  int Bp = (B + 1) & ~1;   // conv3 tiles cover image pairs
-  w.act1 = a.take<__nv_bfloat16>((size_t)Bp * 32 * 160 * C1);
-  w.act2 = a.take<__nv_bfloat16>((size_t)Bp * 16 * 80 * C2);
-  w.act3 = a.take<__nv_bfloat16>((size_t)Bp * 8 * 40 * C3);
-  w.splits = FC_SPLITS;
+  int Bp = (B + BPAD - 1) / BPAD * BPAD;   // conv2 / conv3 tiles cover groups of up to 4 images
+  w.act1 = a.take<__nv_bfloat16>((size_t)Bp * G.PH1 * G.PW1 * C1);
+  w.act2 = a.take<__nv_bfloat16>((size_t)Bp * G.PH2 * G.PW2 * C2);
+  w.act3 = a.take<__nv_bfloat16>((size_t)Bp * G.PH3 * G.PW3 * C3);
+  w.splits = G.splits;
   w.partial = a.take<float>((size_t)w.splits * B * EMB);
   w.bytes = align_up(a.off, 256);
   return w;
 }
 
-using Cfg2 = ConvCfg<C1, C2, 16, 1, 8, 2>;
-using Cfg3 = ConvCfg<C2, C3, 8, 2, 4, 1>;
+// conv2 / conv3 launch for one (pooled columns per tile) instantiation: WW x (16 / WW) images x 8 pooled rows
+template <int CIN, int COUT, int WW, int STAGES, int NACC, bool OUT_PARITY>
+int launch_conv_pool(const __nv_bfloat16* in, const unsigned char* wimg, const float* bias, __nv_bfloat16* out, int Bp,
+                     int B_store, int PH, int PW, int sms, const char* name, cudaStream_t s) {
+  constexpr int NIMG = 16 / WW;
+  using Cfg = ConvCfg<CIN, COUT, WW, NIMG, STAGES, NACC>;
+  // input planes [4][PH][Bp][PW][CIN] (PH x PW = this layer's POOLED output size = half the input map)
+  CUtensorMap tm;
+  uint64_t dims[5] = {(uint64_t)CIN, (uint64_t)PW, (uint64_t)Bp, (uint64_t)PH, 4};
+  uint64_t str[4] = {(uint64_t)CIN * 2, (uint64_t)PW * CIN * 2, (uint64_t)Bp * PW * CIN * 2, (uint64_t)PH * Bp * PW * CIN * 2};
+  uint32_t box[5] = {(uint32_t)CIN, (uint32_t)WW, (uint32_t)NIMG, 9, 1};
+  I2L_TRY(make_tensor_map(&tm, in, 5, dims, str, box, CIN * 2, 2));
+  auto kern = conv_pool_kernel<Cfg, CIN, COUT, WW, NIMG, STAGES, NACC, OUT_PARITY>;
+  I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  const int n_tiles = (Bp / NIMG) * (PH / 8) * (PW / WW);
+  KernelTimer kt(name, s);
+  kern<<<min(n_tiles, sms), 192, Cfg::SMEM, s>>>(tm, wimg, bias, out, B_store, PH, PW, n_tiles);
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
 
 }  // namespace
 
 bool cnn_bf16_supported(const i2l_cnn_desc& d) {
-  return d.img_height == IMG_H && d.img_width == IMG_W && d.channels == C0 && d.n_conv == 3 && d.filters[0] == C1 &&
+  return (d.channels == 1 || d.channels == 3) && d.img_height >= 64 && (d.img_height % 64) == 0 && d.img_width >= 32 &&
+         (d.img_width % 32) == 0 && d.img_height <= 1024 && d.img_width <= 8192 && d.n_conv == 3 && d.filters[0] == C1 &&
          d.filters[1] == C2 && d.filters[2] == C3 && d.kernel_size == 3 && d.pool_size == 2 && d.embedding_dim == EMB;
 }
-size_t cnn_bf16_packed_bytes(const i2l_cnn_desc&) { return sec_layout().total; }
+size_t cnn_bf16_packed_bytes(const i2l_cnn_desc& d) { return sec_layout(make_geom(d)).total; }
 
-int cnn_bf16_pack(const i2l_cnn_desc&, const i2l_cnn_params& p, void* section, cudaStream_t s) {
-  Sec L = sec_layout();
+int cnn_bf16_pack(const i2l_cnn_desc& d, const i2l_cnn_params& p, void* section, cudaStream_t s) {
+  const Geom G = make_geom(d);
+  Sec L = sec_layout(G);
   unsigned char* sec = reinterpret_cast<unsigned char*>(section);
-  pack_conv_w_kernel<<<4, 256, 0, s>>>(p.conv_w[0], C1, C0, 1, sec + L.w1);
+  pack_conv_w_kernel<<<4, 256, 0, s>>>(p.conv_w[0], C1, G.C0, 1, sec + L.w1);
   I2L_LAUNCH_OK();
   pack_conv_w_kernel<<<cdiv(9 * C2 * C1, 256), 256, 0, s>>>(p.conv_w[1], C2, C1, 2, sec + L.w2);
   I2L_LAUNCH_OK();
@@ -632,15 +680,16 @@ int cnn_bf16_pack(const i2l_cnn_desc&, const i2l_cnn_params& p, void* section, c
   I2L_CUDA_OK(cudaMemcpyAsync(sec + L.b2, p.conv_b[1], C2 * 4, cudaMemcpyDeviceToDevice, s));
   I2L_CUDA_OK(cudaMemcpyAsync(sec + L.b3, p.conv_b[2], C3 * 4, cudaMemcpyDeviceToDevice, s));
   I2L_CUDA_OK(cudaMemcpyAsync(sec + L.bfc, p.fc_b, EMB * 4, cudaMemcpyDeviceToDevice, s));
-  size_t n = (size_t)EMB * FLAT;
-  pack_fc_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p.fc_w, reinterpret_cast<__nv_bfloat16*>(sec + L.wfc));
+  size_t n = (size_t)EMB * G.FLAT;
+  pack_fc_w_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p.fc_w, reinterpret_cast<__nv_bfloat16*>(sec + L.wfc), G.FLAT,
+                                                               G.PH3 * G.PW3);
   I2L_LAUNCH_OK();
   return I2L_OK;
 }
 
-size_t cnn_bf16_workspace_bytes(const i2l_cnn_desc&, int batch) { return carve(batch, nullptr).bytes; }
+size_t cnn_bf16_workspace_bytes(const i2l_cnn_desc& d, int batch) { return carve(make_geom(d), batch, nullptr).bytes; }
 
-// I2L_DEBUG_SYNC=1: synchronise after every encoder kernel so that a device fault is attributed
+// I2L_DEBUG_SYNC=1 (diagnostics build): synchronise after every encoder kernel so that a device fault is attributed
 static int dbg_sync(const char* what, cudaStream_t s) {
 #ifdef I2L_DIAG
   static const bool on = getenv("I2L_DEBUG_SYNC") != nullptr;
@@ -653,90 +702,85 @@ static int dbg_sync(const char* what, cudaStream_t s) {
   return I2L_OK;
 }
 
-int cnn_bf16_fwd(const i2l_cnn_desc&, const void* section, const void* x, int in_dtype, int B, float* out, void* ws,
+template <typename InT, int CIN0>
+static int launch_conv1(const CUtensorMap& tm, const unsigned char* w1, const float* b1, __nv_bfloat16* act1, int Bp, int n_tiles,
+                        int dbg, const C1Norm& nrm, const Geom& G, int sms, cudaStream_t s) {
+  auto kern = conv1_kernel<InT, CIN0>;
+  I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
+  kern<<<min(n_tiles, sms), C1_THREADS, C1_SMEM, s>>>(tm, w1, b1, act1, Bp, n_tiles, dbg, nrm, G.TW, G.TH);
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
+
+int cnn_bf16_fwd(const i2l_cnn_desc& d, const void* section, const void* x, int in_dtype, int B, float* out, void* ws,
                  size_t ws_bytes, cudaStream_t s, const float* norm_a, const float* norm_b) {
-  Ws w = carve(B, ws);
+  const Geom G = make_geom(d);
+  Ws w = carve(G, B, ws);
   if (ws_bytes < w.bytes) { set_error("cnn_bf16_fwd: workspace too small (%zu < %zu)", ws_bytes, w.bytes); return I2L_ERR_WORKSPACE; }
-  Sec L = sec_layout();
+  Sec L = sec_layout(G);
   const unsigned char* sec = reinterpret_cast<const unsigned char*>(section);
   const int sms = num_sms();
-  const int Bp = (B + 1) & ~1;
-  if (Bp != B) {   // the odd tail image of conv3's pair tiles reads zeros
-    I2L_CUDA_OK(cudaMemsetAsync(w.act2, 0, (size_t)Bp * 16 * 80 * C2 * 2, s));
+  const int Bp = (B + BPAD - 1) / BPAD * BPAD;
+  if (Bp != B) {   // the padding images of the multi-image conv3 tiles read zeros (their outputs are never stored)
+    I2L_CUDA_OK(cudaMemsetAsync(w.act2, 0, (size_t)Bp * G.PH2 * G.PW2 * C2 * 2, s));
   }
-  // ---- conv1: input x (B,3,64,320) fp32 / bf16 NCHW read through a 4-D tensor map
+  // ---- conv1: input x (B,C,H,W) fp32 / bf16 / uint8 NCHW read through a 4-D tensor map
   {
     const bool in_bf16 = in_dtype == I2L_IN_BF16, in_u8 = in_dtype == I2L_IN_U8;
     const uint64_t el = in_u8 ? 1 : (in_bf16 ? 2 : 4);
     C1Norm nrm{};
-    if (in_u8) for (int c = 0; c < 3; ++c) { nrm.a[c] = norm_a[c]; nrm.b[c] = norm_b[c]; }
+    if (in_u8) for (int c = 0; c < G.C0; ++c) { nrm.a[c] = norm_a[c]; nrm.b[c] = norm_b[c]; }
     CUtensorMap tm;
-    uint64_t dims[4] = {IMG_W, IMG_H, C0, (uint64_t)B};
-    uint64_t str[3] = {IMG_W * el, (uint64_t)IMG_W * IMG_H * el, (uint64_t)IMG_W * IMG_H * C0 * el};
-    uint32_t box[4] = {(uint32_t)(in_u8 ? C1In<uint8_t>::PATCH_W : in_bf16 ? C1In<__nv_bfloat16>::PATCH_W : C1In<float>::PATCH_W), PATCH_H, C0, 1};
+    uint64_t dims[4] = {(uint64_t)G.W, (uint64_t)G.H, (uint64_t)G.C0, (uint64_t)B};
+    uint64_t str[3] = {G.W * el, (uint64_t)G.W * G.H * el, (uint64_t)G.W * G.H * G.C0 * el};
+    uint32_t box[4] = {(uint32_t)(in_u8 ? C1In<uint8_t>::PATCH_W : in_bf16 ? C1In<__nv_bfloat16>::PATCH_W : C1In<float>::PATCH_W), PATCH_H,
+                       (uint32_t)G.C0, 1};
     I2L_TRY(make_tensor_map(&tm, x, 4, dims, str, box, 0, (int)el));
-    const int n_tiles = B * 40;
+    const int n_tiles = B * G.TW * G.TH;
 #ifdef I2L_DIAG
     const int dbg = getenv("I2L_CONV1_DBG") ? atoi(getenv("I2L_CONV1_DBG")) : 0;
 #else
     const int dbg = 0;
 #endif
+    const unsigned char* w1 = sec + L.w1;
+    const float* b1 = reinterpret_cast<const float*>(sec + L.b1);
     KernelTimer kt(in_u8 ? "cnn.conv1_u8in" : in_bf16 ? "cnn.conv1_bf16in" : "cnn.conv1_bf16", s);
-    if (in_u8) {
-      I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
-      conv1_kernel<uint8_t><<<min(n_tiles, sms), C1_THREADS, C1_SMEM, s>>>(
-          tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1), w.act1, Bp, n_tiles, dbg, nrm);
-    } else if (in_bf16) {
-      I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
-      conv1_kernel<__nv_bfloat16><<<min(n_tiles, sms), C1_THREADS, C1_SMEM, s>>>(
-          tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1), w.act1, Bp, n_tiles, dbg, nrm);
+    if (G.C0 == 3) {
+      if (in_u8) I2L_TRY((launch_conv1<uint8_t, 3>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
+      else if (in_bf16) I2L_TRY((launch_conv1<__nv_bfloat16, 3>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
+      else I2L_TRY((launch_conv1<float, 3>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
     } else {
-      I2L_CUDA_OK(cudaFuncSetAttribute(conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
-      conv1_kernel<float><<<min(n_tiles, sms), C1_THREADS, C1_SMEM, s>>>(
-          tm, sec + L.w1, reinterpret_cast<const float*>(sec + L.b1), w.act1, Bp, n_tiles, dbg, nrm);
+      if (in_u8) I2L_TRY((launch_conv1<uint8_t, 1>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
+      else if (in_bf16) I2L_TRY((launch_conv1<__nv_bfloat16, 1>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
+      else I2L_TRY((launch_conv1<float, 1>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
     }
-    I2L_LAUNCH_OK();
   }
   I2L_TRY(dbg_sync("conv1", s));
-  // ---- conv2: input planes [4][16][Bp][80][32]
+  // ---- conv2: input planes [4][16][Bp][80][32] -> act2 planes [4][8][Bp][40][64]
   {
-    CUtensorMap tm;
-    uint64_t dims[5] = {C1, 80, (uint64_t)Bp, 16, 4};
-    uint64_t str[4] = {C1 * 2, 80ull * C1 * 2, (uint64_t)Bp * 80 * C1 * 2, 16ull * Bp * 80 * C1 * 2};
-    uint32_t box[5] = {C1, 16, 1, 9, 1};
-    I2L_TRY(make_tensor_map(&tm, w.act1, 5, dims, str, box, 64, 2));
-    auto kern = conv_pool_kernel<Cfg2, C1, C2, 16, 1, 8, 2, true>;
-    I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM));
-    const int n_tiles = B * 2 * 5;
-    KernelTimer kt("cnn.conv2_bf16", s);
-    kern<<<min(n_tiles, sms), 192, Cfg2::SMEM, s>>>(tm, sec + L.w2, reinterpret_cast<const float*>(sec + L.b2), w.act2, Bp, 16, 80, n_tiles);
-    I2L_LAUNCH_OK();
+    const float* b2 = reinterpret_cast<const float*>(sec + L.b2);
+    if (G.WW2 == 16) I2L_TRY((launch_conv_pool<C1, C2, 16, 8, 2, true>(w.act1, sec + L.w2, b2, w.act2, Bp, Bp, G.PH2, G.PW2, sms, "cnn.conv2_bf16", s)));
+    else I2L_TRY((launch_conv_pool<C1, C2, 8, 8, 2, true>(w.act1, sec + L.w2, b2, w.act2, Bp, Bp, G.PH2, G.PW2, sms, "cnn.conv2_bf16", s)));
   }
   I2L_TRY(dbg_sync("conv2", s));
-  // ---- conv3: input planes [4][8][Bp][40][64]
+  // ---- conv3: input planes [4][8][Bp][40][64] -> act3 [B][8][40][128]
   {
-    CUtensorMap tm;
-    uint64_t dims[5] = {C2, 40, (uint64_t)Bp, 8, 4};
-    uint64_t str[4] = {C2 * 2, 40ull * C2 * 2, (uint64_t)Bp * 40 * C2 * 2, 8ull * Bp * 40 * C2 * 2};
-    uint32_t box[5] = {C2, 8, 2, 9, 1};
-    I2L_TRY(make_tensor_map(&tm, w.act2, 5, dims, str, box, 128, 2));
-    auto kern = conv_pool_kernel<Cfg3, C2, C3, 8, 2, 4, 1, false>;
-    I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::SMEM));
-    const int n_tiles = (Bp / 2) * 1 * 5;
-    KernelTimer kt("cnn.conv3_bf16", s);
-    kern<<<min(n_tiles, sms), 192, Cfg3::SMEM, s>>>(tm, sec + L.w3, reinterpret_cast<const float*>(sec + L.b3), w.act3, B, 8, 40, n_tiles);
-    I2L_LAUNCH_OK();
+    const float* b3 = reinterpret_cast<const float*>(sec + L.b3);
+    if (G.WW3 == 16) I2L_TRY((launch_conv_pool<C2, C3, 16, 4, 1, false>(w.act2, sec + L.w3, b3, w.act3, Bp, B, G.PH3, G.PW3, sms, "cnn.conv3_bf16", s)));
+    else if (G.WW3 == 8) I2L_TRY((launch_conv_pool<C2, C3, 8, 4, 1, false>(w.act2, sec + L.w3, b3, w.act3, Bp, B, G.PH3, G.PW3, sms, "cnn.conv3_bf16", s)));
+    else I2L_TRY((launch_conv_pool<C2, C3, 4, 4, 1, false>(w.act2, sec + L.w3, b3, w.act3, Bp, B, G.PH3, G.PW3, sms, "cnn.conv3_bf16", s)));
   }
   I2L_TRY(dbg_sync("conv3", s));
   // ---- fc
   {
     CUtensorMap tmA, tmW;
+    const uint64_t FLAT = (uint64_t)G.FLAT;
     uint64_t dA[2] = {FLAT, (uint64_t)B}; uint64_t sA[1] = {FLAT * 2ull}; uint32_t bA[2] = {FC_BK, FC_BM};
     uint64_t dW[2] = {FLAT, EMB}; uint32_t bW[2] = {FC_BK, FC_BN};
     I2L_TRY(make_tensor_map(&tmA, w.act3, 2, dA, sA, bA, 128, 2));
     I2L_TRY(make_tensor_map(&tmW, sec + L.wfc, 2, dW, sA, bW, 128, 2));
     I2L_CUDA_OK(cudaFuncSetAttribute(fc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
-    const int kbs = FLAT / FC_BK / w.splits;
+    const int kbs = G.FLAT / FC_BK / w.splits;
     KernelTimer kt("cnn.fc_bf16", s);
     fc_splitk_kernel<<<dim3(cdiv(B, FC_BM), w.splits), 192, FC_SMEM, s>>>(tmA, tmW, w.partial, B, kbs);
     I2L_LAUNCH_OK();

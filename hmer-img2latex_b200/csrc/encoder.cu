@@ -101,6 +101,10 @@ __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restr
 using namespace i2l;
 
 // ====================================================================== CNN C ABI
+extern "C" int i2l_cnn_tensor_core_path(const i2l_cnn_desc* d) {
+  return (d != nullptr && d->precision == I2L_BF16 && i2l::cnn_bf16_supported(*d)) ? 1 : 0;
+}
+
 extern "C" size_t i2l_cnn_packed_bytes(const i2l_cnn_desc* d) {
   if (cnn_check(d) != I2L_OK) return 0;
   return cnn_layout(*d).total_bytes;
@@ -236,7 +240,7 @@ extern "C" int i2l_cnn_encoder_fwd_in(const i2l_cnn_desc* d, const void* packed,
     return cnn_bf16_fwd(*d, reinterpret_cast<const char*>(packed) + L.bf16_section, xin, x_dtype, batch, out, workspace,
                         workspace_bytes, s);
   if (x_dtype != I2L_IN_F32) {
-    set_error("i2l_cnn_encoder_fwd: bf16 input needs precision == I2L_BF16 and the tcgen05 shape (3x64x320, 32/64/128, E=256)");
+    set_error("i2l_cnn_encoder_fwd: bf16 input needs precision == I2L_BF16 and a tcgen05 configuration (i2l_cnn_tensor_core_path)");
     return I2L_ERR_UNSUPPORTED;
   }
   const float* x = reinterpret_cast<const float*>(xin);
@@ -274,7 +278,7 @@ extern "C" int i2l_cnn_encoder_fwd_u8(const i2l_cnn_desc* d, const void* packed,
   I2L_REQUIRE(x && out && workspace, "i2l_cnn_encoder_fwd_u8: null buffer");
   CnnLayout L = cnn_layout(*d);
   if (!L.bf16_section) {
-    set_error("i2l_cnn_encoder_fwd_u8: fused uint8 input needs precision == I2L_BF16 and the tcgen05 shape (3x64x320, 32/64/128, "
+    set_error("i2l_cnn_encoder_fwd_u8: fused uint8 input needs precision == I2L_BF16 and a tcgen05 configuration (i2l_cnn_tensor_core_path: 32/64/128, "
               "E=256); use i2l_normalize_u8 + i2l_cnn_encoder_fwd otherwise");
     return I2L_ERR_UNSUPPORTED;
   }

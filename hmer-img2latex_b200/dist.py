@@ -93,7 +93,7 @@ class TokenExchange:
         self.read_seq = 0
         self._timeout = torch.zeros((), dtype=torch.int32, device=self.device)
         lo, hi = shard_bounds(self.n_total, self.world, self.rank)
-        self.shard = hi - lo
+        self.shard, self.shard_lo = hi - lo, lo
 
     def write(self, tokens: torch.Tensor, lengths: torch.Tensor, steps: torch.Tensor) -> None:
         if tuple(tokens.shape) != (self.shard, self.T1) or tokens.dtype != torch.int64 or not tokens.is_contiguous():

@@ -188,8 +188,11 @@ class CNNEncoder(nn.Module):
                                                     [float(v) for v in mean[:3]], [float(v) for v in std[:3]])
 
     def _bf16_shape(self) -> bool:
-        return ((self.channels, self.img_height, self.img_width) == (3, 64, 320) and self.conv_filters == [32, 64, 128]
-                and self.kernel_size == 3 and self.pool_size == 2 and self.embedding_dim == 256)
+        """the shape runs on the tcgen05 kernels in precision "bf16" (`i2l_cnn_tensor_core_path`: filters 32/64/128,
+        3x3, pool 2, E = 256, 1 or 3 channels, H % 64 == 0, W % 32 == 0)"""
+        d = self._desc()
+        d.precision = N.BF16
+        return bool(N.lib().i2l_cnn_tensor_core_path(C.byref(d)))
 
 
 class ResNetEncoder(nn.Module):

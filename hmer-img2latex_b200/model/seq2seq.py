@@ -109,7 +109,7 @@ class Seq2SeqModel(nn.Module):
     def greedy_stream(self, host_batches: Iterable[torch.Tensor], start_token_id: int, end_token_id: int,
                       max_length: int = 150, temperature: float = 1.0, stop_rule: int = N.STOP_ALL_END_SAME_STEP,
                       device: Optional[torch.device] = None, normalize: str = "pm1", exchange=None,
-                      ) -> Iterator[Tuple[torch.Tensor, torch.Tensor, int]]:
+                      exchange_readback: str = "global") -> Iterator[Tuple[torch.Tensor, torch.Tensor, int]]:
         """Serving loop over HOST batches (ideally pinned (B,C,H,W) tensors: fp32 like the
         reference's, bf16, or raw uint8 pixels that are normalised on the device with
         ``normalize`` = "pm1" | "meanstd", see ``normalize_u8``): the host->device
@@ -122,7 +122,9 @@ class Seq2SeqModel(nn.Module):
         ``exchange`` (a ``dist.TokenExchange``, batch-sharded multi-GPU serving): every rank streams ITS shard of each
         global batch; the ids are exchanged on the device by direct peer stores and the yielded triple is the GLOBAL
         (n_total, max_length+1) result -- one batch later than without (read of step i runs behind the compute of
-        step i + 1), all global batches having the same size."""
+        step i + 1), all global batches having the same size.  ``exchange_readback="shard"``: every rank still holds the
+        global ids in HBM after the exchange, but copies only its OWN rows to the host (the rank that hands the job's
+        result to the consumer uses "global"; N host copies of the same matrix are N - 1 too many)."""
         dev = device or next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("greedy_stream needs the model on a CUDA device")
@@ -206,6 +208,9 @@ class Seq2SeqModel(nn.Module):
                     i += 1
                     continue
                 tokens, lengths, steps = res
+                if exchange_readback == "shard":
+                    lo = exchange.shard_lo
+                    tokens, lengths = tokens[lo: lo + exchange.shard], lengths[lo: lo + exchange.shard]
             read_back(slot, tokens, lengths, steps)
             if prev >= 0:
                 yield collect(prev)
@@ -216,7 +221,11 @@ class Seq2SeqModel(nn.Module):
             res = exchange.flush()
             if res is not None:                                   # the last batch's global result
                 slot = i & 1
-                read_back(slot, *res)
+                tokens, lengths, steps = res
+                if exchange_readback == "shard":
+                    lo = exchange.shard_lo
+                    tokens, lengths = tokens[lo: lo + exchange.shard], lengths[lo: lo + exchange.shard]
+                read_back(slot, tokens, lengths, steps)
                 if prev >= 0:
                     yield collect(prev)
                 prev = slot

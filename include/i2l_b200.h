@@ -83,6 +83,11 @@ typedef struct {                         /* state_dict tensors, fp32, device    
   const float* fc_b;                     /* embedding_layer.bias                   */
 } i2l_cnn_params;
 
+/* 1 when this configuration runs on the tcgen05 implicit-GEMM kernels (precision == I2L_BF16, conv filters
+ * 32/64/128, 3x3, pool 2, embedding 256, channels 1 or 3, height % 64 == 0, width % 32 == 0 -- the reference's
+ * default 1x64x800, model/encoder.py:50-64, and the 3x64x320 benchmark shape among them), 0 when it runs on the
+ * fp32 CUDA-core kernels.  bf16 / uint8 image tensors are accepted on the tensor-core path only. */
+int i2l_cnn_tensor_core_path(const i2l_cnn_desc* d);
 size_t i2l_cnn_packed_bytes(const i2l_cnn_desc* d);
 int i2l_cnn_pack(const i2l_cnn_desc* d, const i2l_cnn_params* p, void* packed, size_t packed_bytes,
                  void* stream);

@@ -257,7 +257,7 @@ def _r16(t: torch.Tensor) -> torch.Tensor:
     return t.bfloat16().float()
 
 
-def lstm_step(p: Params, x: torch.Tensor, h: torch.Tensor, c: torch.Tensor, L: int, bf16_operands: bool = False):
+def lstm_step(p: Params, x: torch.Tensor, h: torch.Tensor, c: torch.Tensor, L: int, bf16_operands=False):
     """One time step of `nn.LSTM(batch_first=True)` (decoder.py:76-82, called at
     :277) written out: gates (i,f,g,o) = x W_ih^T + b_ih + h W_hh^T + b_hh;
     c' = sig(f) c + sig(i) tanh(g); h' = sig(o) tanh(c').  x (B,In), h/c (L,B,H).
@@ -268,13 +268,18 @@ def lstm_step(p: Params, x: torch.Tensor, h: torch.Tensor, c: torch.Tensor, L: i
     -- h, W_hh, the context half of layer 0's input (enc, W_ih[:, E:]), deeper layers' inputs and W_ih -- fp32
     accumulation, fp32 token term (emb W_ih[:, :E]^T), fp32 biases, cell state and activations.  Lets the tests
     separate "bf16 operand rounding" (inherent to the mode) from kernel error: against THIS variant the bf16 kernels
-    must agree almost everywhere, against the fp32 restatement only up to near ties."""
+    must agree almost everywhere, against the fp32 restatement only up to near ties.
+    ``bf16_operands="recurrent"`` (cfg["operand_rounding"] == "bf16_recurrent"): the stream-ordered path's variant --
+    it computes the whole layer-0 input term (token AND context half) in fp32 and rounds only the recurrent / deeper
+    products."""
     hs, cs = [], []
     inp = x
     for l in range(L):
         w_ih, w_hh = p[f"decoder.lstm.weight_ih_l{l}"], p[f"decoder.lstm.weight_hh_l{l}"]
         if bf16_operands:
-            if l == 0:
+            if l == 0 and bf16_operands == "recurrent":
+                gi = F.linear(inp, w_ih)
+            elif l == 0:
                 E = w_ih.shape[1] // 2
                 gi = F.linear(inp[:, :E], w_ih[:, :E]) + F.linear(_r16(inp[:, E:]), _r16(w_ih[:, E:]))
             else:
@@ -316,8 +321,8 @@ def decode_step(p: Params, encoder_output: torch.Tensor, input_token: torch.Tens
     else:
         ctx = encoder_output.unsqueeze(1)                                      # :218
     x = torch.cat([emb, ctx], dim=2).squeeze(1)                                # :228 / :274
-    if cfg.get("operand_rounding") == "bf16":        # see lstm_step; the kernels keep the bf16-rounded h as the state
-        top, hn, cn = lstm_step(p, x, h, c, L, bf16_operands=True)
+    if cfg.get("operand_rounding") in ("bf16", "bf16_recurrent"):   # see lstm_step
+        top, hn, cn = lstm_step(p, x, h, c, L, bf16_operands="recurrent" if cfg["operand_rounding"] == "bf16_recurrent" else True)
         logits = F.linear(_r16(top), _r16(p["decoder.output_layer.weight"]), p["decoder.output_layer.bias"])
         return logits.unsqueeze(1), (hn, cn)
     top, hn, cn = lstm_step(p, x, h, c, L)                                     # :247 / :277
