@@ -17,6 +17,7 @@
 //          permuted to NHWC order at pack time), fp32 partials + bias/ReLU reduction.
 #include "encoder_bf16.cuh"
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace i2l {
@@ -52,7 +53,7 @@ constexpr int BPAD = 4;       // the batch is padded to a multiple of the larges
 
 // ------------------------------------------------------------------ packed section layout
 struct Sec {
-  size_t w1, b1, w2, b2, w3, b3, wfc, bfc, total;
+  size_t w1, b1, w2, b2, w3, b3, wfc, bfc, w1h, total;
 };
 Sec sec_layout(const Geom& G) {
   Sec s{};
@@ -66,6 +67,7 @@ Sec sec_layout(const Geom& G) {
   s.b3 = take(C3 * 4);
   s.wfc = take((size_t)EMB * G.FLAT * 2); // [256][40960] bf16, NHWC column order
   s.bfc = take(EMB * 4);
+  s.w1h = take(32 * 64);                // conv1 weights once more as fp16 (conv1_u8_kernel), same SW64 image
   s.total = o;
   return s;
 }
@@ -85,6 +87,14 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, int co_n, int ci
     uint32_t rb = ci_n * 2;
     *reinterpret_cast<__nv_bfloat16*>(dst + (size_t)tap * co_n * rb + swz_off(co, ci / 8, rb) + (ci % 8) * 2) = __float2bfloat16(v);
   }
+}
+
+__global__ void pack_conv1_w_f16_kernel(const float* __restrict__ w, int ci_n, unsigned char* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * 32) return;
+  int co = i / 32, k = i % 32;
+  float v = k < 9 * ci_n ? w[co * 9 * ci_n + k] : 0.f;
+  *reinterpret_cast<__half*>(dst + swz_off(co, k / 8, 64) + (k % 8) * 2) = __float2half_rn(v);
 }
 
 __global__ void pack_fc_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int FLAT, int HW) {
@@ -340,6 +350,227 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(AFULL(g));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------ conv1, raw uint8 pixels (the bench / serving input)
+// Same tile, patch ring, TMEM A operand and accumulators as conv1_kernel, restructured around the two costs ncu showed
+// for the uint8 instantiation of that kernel (3100 warp-instructions per tile, half of them byte -> fp32 -> affine ->
+// bf16 conversions repeated for every filter row a pixel takes part in):
+//   * the im2col operand is FP16, not bf16: 0x6400 | byte IS the fp16 number 1024 + byte, so one PRMT places two pixels
+//     in a half2, one HADD2 removes the offset exactly and one HFMA2 applies x * a[c] + b[c] (load_image / _prepare_image)
+//     to both -- 3 instructions per pixel PAIR instead of 4 per pixel; fp16 carries 11 significant bits, so the operand
+//     is closer to the reference's fp32 pixels than the bf16 one.  conv1's weights are packed as fp16 for this kernel.
+//   * a builder thread owns a whole 2x2 pooling window (4 patch rows x 4 columns, every pixel converted once per thread
+//     instead of once per filter row) and writes the four im2col rows of its pooled pixel; 4 warps build a tile, and
+//     C1U_NG such groups work on consecutive tiles (one TMEM A buffer each) so that their LDS / STTM latencies overlap
+//   * 8 epilogue warps (16 channels each), max-pool + bias + ReLU as two 3-input maxima and one add per channel
+//   * tile coordinates advance incrementally (the generalised geometry made % TW, / TH run-time divisions)
+constexpr int C1U_NG = 3;                                   // builder groups = TMEM A buffers
+constexpr int C1U_EPI = 8;                                  // epilogue warps
+constexpr int C1U_B0 = 2 + C1U_EPI;                         // first builder warp
+constexpr int C1U_THREADS = 32 * (C1U_B0 + 4 * C1U_NG);     // 22 warps
+constexpr int C1U_PATCH_W = 64, C1U_X0 = 15;                // box starts 16 bytes left of image column 32 tw
+constexpr int C1U_PATCH_STRIDE = 3584;                      // 3 x 18 x 64 = 3456 bytes per patch
+constexpr int C1U_OFF_W = 0;
+constexpr int C1U_OFF_PATCH = 2048;
+constexpr int C1U_OFF_BAR = C1U_OFF_PATCH + C1_PS * C1U_PATCH_STRIDE;
+constexpr int C1U_SMEM = C1U_OFF_BAR + 256;
+constexpr int C1U_TC_A = 256;                               // TMEM: 2 x 128 accumulator columns, then C1U_NG x 64 A columns
+static_assert(C1U_TC_A + 64 * C1U_NG <= 512, "TMEM columns");
+
+struct TileIt {   // (tw, th) of a tile index that advances by a fixed step; the image index is not needed by every role
+  int tw, th, b, TW, TH;
+  __device__ TileIt(int tile, int TW_, int TH_) : TW(TW_), TH(TH_) { tw = tile % TW; th = (tile / TW) % TH; b = tile / (TW * TH); }
+  __device__ void advance(int n) {
+    tw += n;
+    while (tw >= TW) { tw -= TW; if (++th == TH) { th = 0; ++b; } }
+  }
+};
+
+template <int CIN0>
+__global__ void __launch_bounds__(C1U_THREADS, 1)
+conv1_u8_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __restrict__ w1img_f16,
+                const float* __restrict__ bias1, __nv_bfloat16* __restrict__ act1, int B, int n_tiles, const C1Norm nrm,
+                int TW, int TH) {
+  constexpr int PATCH_BYTES = CIN0 * PATCH_H * C1U_PATCH_W;
+  constexpr int PW4 = C1U_PATCH_W / 4;
+  static_assert(PATCH_BYTES <= C1U_PATCH_STRIDE, "patch ring slot too small");
+  const int QH = 4 * TH, QW = 8 * TW;           // act1 plane rows / columns (H / 4, W / 4)
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar = sbase + C1U_OFF_BAR;
+  auto PFULL = [&](int s) { return bar + 8u * s; };
+  auto PEMPTY = [&](int s) { return bar + 8u * (C1_PS + s); };
+  auto AFULL = [&](int a) { return bar + 8u * (2 * C1_PS + a); };
+  auto AEMPTY = [&](int a) { return bar + 8u * (2 * C1_PS + 4 + a); };
+  auto TFULL = [&](int g) { return bar + 8u * (2 * C1_PS + 8 + g); };
+  auto TEMPTY = [&](int g) { return bar + 8u * (2 * C1_PS + 10 + g); };
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + C1U_OFF_BAR + 8 * (2 * C1_PS + 12));
+  if ((sbase & 1023u) != 0) __trap();
+  if (tid == 0) {
+    for (int i = 0; i < C1_PS; ++i) { mbar_init(PFULL(i), 1); mbar_init(PEMPTY(i), 4); }
+    for (int a = 0; a < C1U_NG; ++a) { mbar_init(AFULL(a), 4); mbar_init(AEMPTY(a), 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(TFULL(g), 1); mbar_init(TEMPTY(g), C1U_EPI); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmx);
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(misc));
+  for (int i = tid; i < 2048 / 16; i += C1U_THREADS) reinterpret_cast<uint4*>(smem + C1U_OFF_W)[i] = reinterpret_cast<const uint4*>(w1img_f16)[i];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc[0];
+  const int per = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile_beg = blockIdx.x * per, tile_end = min(n_tiles, tile_beg + per);
+  const int nt = max(tile_end - tile_beg, 0);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one() && nt > 0) {
+      TileIt t(tile_beg, TW, TH);
+      for (int it = 0; it < nt; ++it, t.advance(1)) {
+        const int s = it % C1_PS;
+        mbar_wait(PEMPTY(s), ((it / C1_PS) & 1) ^ 1);
+        mbar_arrive_expect_tx(PFULL(s), PATCH_BYTES);
+        tma_load_4d(sbase + C1U_OFF_PATCH + s * C1U_PATCH_STRIDE, &tmx, 32 * t.tw - 1 - C1U_X0, 16 * t.th - 1, 0, t.b, PFULL(s));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint64_t dW = desc_base(sbase + C1U_OFF_W, 64);
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f16 x f16 -> f32
+    int a = 0; uint32_t apar = 0;
+    for (int it = 0; it < nt; ++it) {
+      const int g = it & 1; const uint32_t par = (it >> 1) & 1;
+      mbar_wait(TEMPTY(g), par ^ 1);
+      mbar_wait(AFULL(a), apar);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            tc_mma_ts(tmem + g * 128 + qd * 32, tmem + C1U_TC_A + a * 64 + qd * 16 + ks * 8, dW + (uint64_t)((ks * 32) >> 4), IDESC, ks);
+        tc_commit(AEMPTY(a));
+        tc_commit(TFULL(g));
+      }
+      __syncwarp();
+      if (++a == C1U_NG) { a = 0; apar ^= 1; }
+    }
+  } else if (warp < C1U_B0) {
+    // ===================== epilogue (8 warps: TMEM lane quadrant x channel half) =====================
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int m = 32 * q + lane;
+    float bias[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float4 v = reinterpret_cast<const float4*>(bias1)[half * 4 + i]; bias[4 * i] = v.x; bias[4 * i + 1] = v.y; bias[4 * i + 2] = v.z; bias[4 * i + 3] = v.w; }
+    TileIt t(tile_beg, TW, TH);
+    for (int it = 0; it < nt; ++it, t.advance(1)) {
+      const int g = it & 1; const uint32_t par = (it >> 1) & 1;
+      const int ph = t.th * 8 + (m >> 4), pw = t.tw * 16 + (m & 15);
+      // act1 layout [plane = (ph&1)*2 + (pw&1)][H/4][B][W/4][32]
+      const size_t pix = ((((size_t)((ph & 1) * 2 + (pw & 1)) * QH + (ph >> 1)) * B + t.b) * QW + (pw >> 1));
+      uint4* dst = reinterpret_cast<uint4*>(act1 + pix * C1 + half * 16);
+      mbar_wait(TFULL(g), par);
+      tc_fence_after();
+      const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + g * 128 + half * 16;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        uint32_t r0[8], r1[8], r2[8], r3[8];
+        tc_ld8_nowait(ta + pass * 8, r0); tc_ld8_nowait(ta + 32 + pass * 8, r1);
+        tc_ld8_nowait(ta + 64 + pass * 8, r2); tc_ld8_nowait(ta + 96 + pass * 8, r3);
+        tc_wait_ld();
+        if (pass == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(TEMPTY(g));     // the accumulator values are in registers
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          // relu(max4 + b) = max(max4, -b) + b: two 3-input maxima and one add per channel
+          const float b0 = bias[pass * 8 + 2 * i], b1 = bias[pass * 8 + 2 * i + 1];
+          const float x0 = fmaxf(fmaxf(__uint_as_float(r0[2 * i]), __uint_as_float(r1[2 * i])), __uint_as_float(r2[2 * i]));
+          const float x1 = fmaxf(fmaxf(__uint_as_float(r0[2 * i + 1]), __uint_as_float(r1[2 * i + 1])), __uint_as_float(r2[2 * i + 1]));
+          const float y0 = fmaxf(fmaxf(x0, __uint_as_float(r3[2 * i])), -b0) + b0;
+          const float y1 = fmaxf(fmaxf(x1, __uint_as_float(r3[2 * i + 1])), -b1) + b1;
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+          o[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        dst[pass] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  } else {
+    // ===================== im2col builders: group gi takes tiles it = gi, gi + NG, ... =====================
+    const int q = warp & 3, gi = (warp - C1U_B0) >> 2;
+    const int m = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const int pl = m >> 4, pwl = m & 15;
+    const int b0 = C1U_X0 + 2 * pwl;                               // patch byte of image column 2 pw - 1
+    const uint32_t sh = (uint32_t)(b0 & 3) * 8;
+    const int word0 = (2 * pl) * PW4 + (b0 >> 2);
+    __half2 na[CIN0], nb[CIN0];
+#pragma unroll
+    for (int ci = 0; ci < CIN0; ++ci) { na[ci] = __float2half2_rn(nrm.a[ci]); nb[ci] = __float2half2_rn(nrm.b[ci]); }
+    const __half2 k1024 = __float2half2_rn(1024.f);
+    TileIt t(tile_beg + gi, TW, TH);
+    uint32_t apar = 0;
+    for (int it = gi; it < nt; it += C1U_NG, t.advance(C1U_NG), apar ^= 1) {
+      const int s = it % C1_PS;
+      // out-of-image taps are zero in NORMALISED space (the conv's padding): masks per patch row / column pair
+      const uint32_t mtop = (t.th == 0 && pl == 0) ? 0u : 0xFFFFFFFFu, mbot = (t.th == TH - 1 && pl == 7) ? 0u : 0xFFFFFFFFu;
+      const uint32_t m01 = (t.tw == 0 && pwl == 0) ? 0xFFFF0000u : 0xFFFFFFFFu, m23 = (t.tw == TW - 1 && pwl == 15) ? 0x0000FFFFu : 0xFFFFFFFFu;
+      mbar_wait(PFULL(s), (it / C1_PS) & 1);
+      const uint32_t* p0 = reinterpret_cast<const uint32_t*>(smem + C1U_OFF_PATCH + s * C1U_PATCH_STRIDE) + word0;
+      uint32_t v01[CIN0][4], v23[CIN0][4];     // normalised fp16 pixel pairs (columns 0,1 / 2,3 of the 4 x 4 window)
+#pragma unroll
+      for (int ci = 0; ci < CIN0; ++ci)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint32_t* pp = p0 + (ci * PATCH_H + r) * PW4;
+          const uint32_t win = __funnelshift_r(pp[0], pp[1], sh);
+          uint32_t u01 = __byte_perm(win, 0x64006400u, 0x5150), u23 = __byte_perm(win, 0x64006400u, 0x5352);
+          __half2 h01 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&u01), k1024), na[ci], nb[ci]);
+          __half2 h23 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&u23), k1024), na[ci], nb[ci]);
+          const uint32_t mr = r == 0 ? mtop : (r == 3 ? mbot : 0xFFFFFFFFu);
+          v01[ci][r] = *reinterpret_cast<uint32_t*>(&h01) & (m01 & mr);
+          v23[ci][r] = *reinterpret_cast<uint32_t*>(&h23) & (m23 & mr);
+        }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(PEMPTY(s));       // patch values are in registers
+      mbar_wait(AEMPTY(gi), apar ^ 1);
+      constexpr int KREAL = 9 * CIN0;
+#pragma unroll
+      for (int qh = 0; qh < 2; ++qh)
+#pragma unroll
+        for (int qw = 0; qw < 2; ++qw) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int k2 = 0; k2 < 16; ++k2) {
+            const int ka = 2 * k2, kb = 2 * k2 + 1;
+            // K index k = (ci, kh, kw): window element (row qh + kh, column qw + kw); columns 0,2 = low halves
+            const int ja = qw + ka % 3, jb = qw + kb % 3;
+            const uint32_t wa = ka < KREAL ? (ja < 2 ? v01[ka / 9 % CIN0][qh + (ka % 9) / 3] : v23[ka / 9 % CIN0][qh + (ka % 9) / 3]) : 0u;
+            const uint32_t wb = kb < KREAL ? (jb < 2 ? v01[kb / 9 % CIN0][qh + (kb % 9) / 3] : v23[kb / 9 % CIN0][qh + (kb % 9) / 3]) : 0u;
+            if (ka >= KREAL) pk[k2] = 0u;
+            else if (kb >= KREAL) pk[k2] = (ja & 1) ? (wa >> 16) : (wa & 0xFFFFu);
+            else if (!(ja & 1) && (jb & 1) && ka / 3 == kb / 3) pk[k2] = wa;             // an aligned pair of one word
+            else pk[k2] = __byte_perm(wa, wb, ((ja & 1) ? 0x32u : 0x10u) | (((jb & 1) ? 0x76u : 0x54u) << 8));
+          }
+          tc_st16(tmem + lane_addr + C1U_TC_A + gi * 64 + (qh * 2 + qw) * 16, pk);
+        }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(AFULL(gi));
     }
   }
   tc_fence_before();
@@ -672,6 +903,8 @@ int cnn_bf16_pack(const i2l_cnn_desc& d, const i2l_cnn_params& p, void* section,
   unsigned char* sec = reinterpret_cast<unsigned char*>(section);
   pack_conv_w_kernel<<<4, 256, 0, s>>>(p.conv_w[0], C1, G.C0, 1, sec + L.w1);
   I2L_LAUNCH_OK();
+  pack_conv1_w_f16_kernel<<<4, 256, 0, s>>>(p.conv_w[0], G.C0, sec + L.w1h);
+  I2L_LAUNCH_OK();
   pack_conv_w_kernel<<<cdiv(9 * C2 * C1, 256), 256, 0, s>>>(p.conv_w[1], C2, C1, 2, sec + L.w2);
   I2L_LAUNCH_OK();
   pack_conv_w_kernel<<<cdiv(9 * C3 * C2, 256), 256, 0, s>>>(p.conv_w[2], C3, C2, 3, sec + L.w3);
@@ -712,6 +945,16 @@ static int launch_conv1(const CUtensorMap& tm, const unsigned char* w1, const fl
   return I2L_OK;
 }
 
+template <int CIN0>
+static int launch_conv1_u8(const CUtensorMap& tm, const unsigned char* w1h, const float* b1, __nv_bfloat16* act1, int Bp, int n_tiles,
+                           const C1Norm& nrm, const Geom& G, int sms, cudaStream_t s) {
+  auto kern = conv1_u8_kernel<CIN0>;
+  I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C1U_SMEM));
+  kern<<<min(n_tiles, sms), C1U_THREADS, C1U_SMEM, s>>>(tm, w1h, b1, act1, Bp, n_tiles, nrm, G.TW, G.TH);
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
+
 int cnn_bf16_fwd(const i2l_cnn_desc& d, const void* section, const void* x, int in_dtype, int B, float* out, void* ws,
                  size_t ws_bytes, cudaStream_t s, const float* norm_a, const float* norm_b) {
   const Geom G = make_geom(d);
@@ -739,18 +982,22 @@ int cnn_bf16_fwd(const i2l_cnn_desc& d, const void* section, const void* x, int 
     const int n_tiles = B * G.TW * G.TH;
 #ifdef I2L_DIAG
     const int dbg = getenv("I2L_CONV1_DBG") ? atoi(getenv("I2L_CONV1_DBG")) : 0;
+    const bool u8_legacy = getenv("I2L_CONV1_U8_LEGACY") != nullptr;   // A-B: the bf16-operand builder kernel
 #else
     const int dbg = 0;
+    constexpr bool u8_legacy = false;
 #endif
     const unsigned char* w1 = sec + L.w1;
     const float* b1 = reinterpret_cast<const float*>(sec + L.b1);
     KernelTimer kt(in_u8 ? "cnn.conv1_u8in" : in_bf16 ? "cnn.conv1_bf16in" : "cnn.conv1_bf16", s);
     if (G.C0 == 3) {
-      if (in_u8) I2L_TRY((launch_conv1<uint8_t, 3>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
+      if (in_u8 && !u8_legacy) I2L_TRY((launch_conv1_u8<3>(tm, sec + L.w1h, b1, w.act1, Bp, n_tiles, nrm, G, sms, s)));
+      else if (in_u8) I2L_TRY((launch_conv1<uint8_t, 3>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
       else if (in_bf16) I2L_TRY((launch_conv1<__nv_bfloat16, 3>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
       else I2L_TRY((launch_conv1<float, 3>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
     } else {
-      if (in_u8) I2L_TRY((launch_conv1<uint8_t, 1>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
+      if (in_u8 && !u8_legacy) I2L_TRY((launch_conv1_u8<1>(tm, sec + L.w1h, b1, w.act1, Bp, n_tiles, nrm, G, sms, s)));
+      else if (in_u8) I2L_TRY((launch_conv1<uint8_t, 1>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
       else if (in_bf16) I2L_TRY((launch_conv1<__nv_bfloat16, 1>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
       else I2L_TRY((launch_conv1<float, 1>(tm, w1, b1, w.act1, Bp, n_tiles, dbg, nrm, G, sms, s)));
     }

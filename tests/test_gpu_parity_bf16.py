@@ -146,23 +146,42 @@ def test_normalize_u8(pkg, shape, mode, nhwc):
     assert torch.equal(out16.cpu(), ref.bfloat16())
 
 
-@pytest.mark.parametrize("B,mode", [(5, "pm1"), (4, "meanstd"), (1, "pm1")])
-def test_cnn_fused_uint8_conv1(pkg, B, mode):
-    """CNNEncoder.forward_u8 (normalisation fused into the tcgen05 conv1, i2l_cnn_encoder_fwd_u8) is bit-identical
-    to normalize_u8 -> bf16 -> forward (tests/test_oracle_golden.py::test_fused_affine_equals_reference_after_bf16
-    shows why: the affine form rounds to the same bf16 for all 256 pixel values), including the zero padding in
-    normalised space at the image border, and within the bf16 tolerance of the fp32 oracle."""
-    cfg = H.HEADLINE
-    p = oracle.make_params(cfg, 1)
+def _check_fused_u8(pkg, cfg, p, px, mode):
+    """forward_u8 runs conv1 with an FP16 operand built from the raw bytes (cnn_bf16.cu: conv1_u8_kernel), the two-step
+    path with the bf16 tensor.  (1) Both within the stated bf16 tolerance (3e-2 of max|out|) of the fp32 oracle, the
+    fused one no worse than the two-step one; (2) the two differ by operand rounding only (measured ~3e-3), a
+    border / padding bug moves whole output rows; (3) with a normalisation and conv1 weights that are exact in bf16
+    AND fp16 (x / 128, weights on a 2^-8 grid) the two paths multiply identical numbers and must agree bit for bit,
+    including the zero padding in NORMALISED space at the image border (raw 0 is not padding)."""
     m16 = H.build_model(pkg, cfg, p, precision="bf16")
-    g = torch.Generator().manual_seed(11 + B)
-    px = torch.randint(0, 256, (B, 3, 64, 320), dtype=torch.uint8, generator=g)
-    px[:, :, 0, :] = 0; px[:, :, -1, :] = 255; px[:, :, :, 0] = 0; px[:, :, :, -1] = 7      # borders: raw 0 is not padding
+    ref = oracle.cnn_encoder(p, oracle.normalize_u8(px, mode))
     fused = m16.encoder.forward_u8(px.cuda(), mode)
     two_step = m16.encoder(pkg.normalize_u8(px.cuda(), mode, out_dtype=torch.bfloat16))
     torch.cuda.synchronize()
+    e_f, e_t, d = H.rel_err(fused, ref), H.rel_err(two_step, ref), H.rel_err(fused, two_step)
+    print(f"fused-u8 vs oracle {e_f:.2e}, two-step bf16 vs oracle {e_t:.2e}, fused vs two-step {d:.2e}")
+    assert e_f < 3e-2 and e_f < 1.5 * e_t + 1e-3 and d < 1e-2
+    # exact-operand case
+    q = {k: v.clone() for k, v in p.items()}
+    wkey = "encoder.cnn_layers.0.weight"
+    q[wkey] = (q[wkey].clamp(-0.99, 0.99) * 256).round() / 256
+    mq = H.build_model(pkg, cfg, q, precision="bf16")
+    mean, std = (0.0, 0.0, 0.0), (128.0 / 255.0,) * 3
+    fused = mq.encoder.forward_u8(px.cuda(), "meanstd", mean, std)
+    two_step = mq.encoder(pkg.normalize_u8(px.cuda(), "meanstd", mean, std, out_dtype=torch.bfloat16))
+    torch.cuda.synchronize()
     assert torch.equal(fused, two_step)
-    assert H.rel_err(fused, oracle.cnn_encoder(p, oracle.normalize_u8(px, mode))) < 3e-2
+
+
+@pytest.mark.parametrize("B,mode", [(5, "pm1"), (4, "meanstd"), (1, "pm1")])
+def test_cnn_fused_uint8_conv1(pkg, B, mode):
+    """CNNEncoder.forward_u8 (normalisation fused into the tcgen05 conv1, i2l_cnn_encoder_fwd_u8) at the headline shape."""
+    cfg = H.HEADLINE
+    p = oracle.make_params(cfg, 1)
+    g = torch.Generator().manual_seed(11 + B)
+    px = torch.randint(0, 256, (B, 3, 64, 320), dtype=torch.uint8, generator=g)
+    px[:, :, 0, :] = 0; px[:, :, -1, :] = 255; px[:, :, :, 0] = 0; px[:, :, :, -1] = 7      # borders: raw 0 is not padding
+    _check_fused_u8(pkg, cfg, p, px, mode)
 
 
 def test_greedy_stream_uint8_and_bf16_hosts(pkg):
@@ -627,16 +646,10 @@ def test_cnn_encoder_bf16_other_shapes(pkg, c, h, w, B):
 
 @pytest.mark.parametrize("c,h,w,B,mode", [(1, 64, 800, 6, "pm1"), (1, 64, 96, 3, "meanstd"), (3, 128, 64, 2, "pm1")])
 def test_cnn_fused_uint8_other_shapes(pkg, c, h, w, B, mode):
-    """forward_u8 (normalisation fused into conv1) on the other tcgen05 shapes: bit-identical to normalize_u8 -> bf16 ->
-    forward, including the zero padding in normalised space at the borders, and within the bf16 tolerance of the oracle."""
+    """forward_u8 (normalisation fused into conv1) on the other tcgen05 shapes: same criteria as the headline shape."""
     cfg = _cnn_cfg(c, h, w)
     p = oracle.make_params(cfg, 2)
-    m16 = H.build_model(pkg, cfg, p, precision="bf16")
     g = torch.Generator().manual_seed(13 + w)
     px = torch.randint(0, 256, (B, c, h, w), dtype=torch.uint8, generator=g)
     px[:, :, 0, :] = 0; px[:, :, -1, :] = 255; px[:, :, :, 0] = 0; px[:, :, :, -1] = 9
-    fused = m16.encoder.forward_u8(px.cuda(), mode)
-    two_step = m16.encoder(pkg.normalize_u8(px.cuda(), mode, out_dtype=torch.bfloat16))
-    torch.cuda.synchronize()
-    assert torch.equal(fused, two_step)
-    assert H.rel_err(fused, oracle.cnn_encoder(p, oracle.normalize_u8(px, mode))) < 3e-2
+    _check_fused_u8(pkg, cfg, p, px, mode)
