@@ -200,22 +200,25 @@ def run_ours(args):
     if world > 1 and not args.nccl_gather:
         try:
             xchg = TokenExchange(B * world, MAX_LEN + 1, dev)
-            exchange_kind = "p2p stores into symmetric memory + flags (i2l_token_exchange_*), read one step behind"
+            exchange_kind = ("p2p stores into symmetric memory + flags (i2l_token_exchange_*) on a side stream, released beside "
+                             "the next batch's decode kernel (which leaves 20 SMs idle), results one step behind")
         except Exception as e:
             print("TokenExchange unavailable (%r): NCCL all-gather instead" % (e,), file=sys.stderr)
     if world > 1 and xchg is None:
         exchange_kind = "NCCL all_gather_into_tensor on the compute stream"
 
     def step(inp, xc=None, rows=None):
-        """one pass of the hot path over one batch; N > 1 returns the global result of the PREVIOUS step (p2p path)"""
+        """one pass of the hot path over one batch; N > 1: the shard result is staged for the p2p exchange, which is
+        released (TokenExchange.kick) between the NEXT batch's encoder and decode and runs beside that decode"""
         xc = xchg if xc is None else xc
         if rows is not None:
             inp = inp[:rows]
         enc = model.encoder.forward_u8(inp) if inp.dtype == torch.uint8 else model.encoder(inp)
+        prev = xc.kick() if (world > 1 and xc is not None) else None
         tokens, lengths, steps = model.decoder.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_ALL_END_SAME_STEP)
         if world > 1:
             if xc is not None:
-                prev = xc.step(tokens, lengths, steps)
+                xc.stage(tokens, lengths, steps)
                 return prev if prev is not None else (tokens, lengths, steps)
             tokens, lengths, steps = gather_tokens(tokens, lengths, steps, inp.shape[0] * world)
         return tokens, lengths, steps
@@ -280,7 +283,7 @@ def run_ours(args):
         for i in range(args.steps):
             out = step(x_dev[i % NB])
         if xchg is not None:
-            out = xchg.flush()                                # the last step's global result: inside the timed region
+            out = xchg.flush()[-1]                            # the last steps' global results: inside the timed region
         e1.record()
         barrier()
         launches = lib.i2l_launch_count() - l0

@@ -370,10 +370,9 @@ conv1_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __res
 //     C1U_NG such groups work on consecutive tiles (one TMEM A buffer each) so that their LDS / STTM latencies overlap
 //   * 8 epilogue warps (16 channels each), max-pool + bias + ReLU as two 3-input maxima and one add per channel
 //   * tile coordinates advance incrementally (the generalised geometry made % TW, / TH run-time divisions)
-constexpr int C1U_NG = 3;                                   // builder groups = TMEM A buffers
 constexpr int C1U_EPI = 8;                                  // epilogue warps
 constexpr int C1U_B0 = 2 + C1U_EPI;                         // first builder warp
-constexpr int C1U_THREADS = 32 * (C1U_B0 + 4 * C1U_NG);     // 22 warps
+__host__ __device__ constexpr int c1u_threads(int ng) { return 32 * (C1U_B0 + 4 * ng); }   // ng builder groups = TMEM A buffers: 22 warps for 3
 constexpr int C1U_PATCH_W = 64, C1U_X0 = 15;                // box starts 16 bytes left of image column 32 tw
 constexpr int C1U_PATCH_STRIDE = 3584;                      // 3 x 18 x 64 = 3456 bytes per patch
 constexpr int C1U_OFF_W = 0;
@@ -381,7 +380,7 @@ constexpr int C1U_OFF_PATCH = 2048;
 constexpr int C1U_OFF_BAR = C1U_OFF_PATCH + C1_PS * C1U_PATCH_STRIDE;
 constexpr int C1U_SMEM = C1U_OFF_BAR + 256;
 constexpr int C1U_TC_A = 256;                               // TMEM: 2 x 128 accumulator columns, then C1U_NG x 64 A columns
-static_assert(C1U_TC_A + 64 * C1U_NG <= 512, "TMEM columns");
+
 
 struct TileIt {   // (tw, th) of a tile index that advances by a fixed step; the image index is not needed by every role
   int tw, th, b, TW, TH;
@@ -392,13 +391,15 @@ struct TileIt {   // (tw, th) of a tile index that advances by a fixed step; the
   }
 };
 
-template <int CIN0>
-__global__ void __launch_bounds__(C1U_THREADS, 1)
+template <int CIN0, int C1U_NG>
+__global__ void __launch_bounds__(c1u_threads(C1U_NG), 1)
 conv1_u8_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __restrict__ w1img_f16,
                 const float* __restrict__ bias1, __nv_bfloat16* __restrict__ act1, int B, int n_tiles, const C1Norm nrm,
                 int TW, int TH) {
   constexpr int PATCH_BYTES = CIN0 * PATCH_H * C1U_PATCH_W;
   constexpr int PW4 = C1U_PATCH_W / 4;
+  constexpr int C1U_THREADS = c1u_threads(C1U_NG);
+  static_assert(C1U_TC_A + 64 * C1U_NG <= 512, "TMEM columns");
   static_assert(PATCH_BYTES <= C1U_PATCH_STRIDE, "patch ring slot too small");
   const int QH = 4 * TH, QW = 8 * TW;           // act1 plane rows / columns (H / 4, W / 4)
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -945,14 +946,24 @@ static int launch_conv1(const CUtensorMap& tm, const unsigned char* w1, const fl
   return I2L_OK;
 }
 
+template <int CIN0, int NG>
+static int launch_conv1_u8_ng(const CUtensorMap& tm, const unsigned char* w1h, const float* b1, __nv_bfloat16* act1, int Bp, int n_tiles,
+                              const C1Norm& nrm, const Geom& G, int sms, cudaStream_t s) {
+  auto kern = conv1_u8_kernel<CIN0, NG>;
+  I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C1U_SMEM));
+  kern<<<min(n_tiles, sms), c1u_threads(NG), C1U_SMEM, s>>>(tm, w1h, b1, act1, Bp, n_tiles, nrm, G.TW, G.TH);
+  I2L_LAUNCH_OK();
+  return I2L_OK;
+}
 template <int CIN0>
 static int launch_conv1_u8(const CUtensorMap& tm, const unsigned char* w1h, const float* b1, __nv_bfloat16* act1, int Bp, int n_tiles,
                            const C1Norm& nrm, const Geom& G, int sms, cudaStream_t s) {
-  auto kern = conv1_u8_kernel<CIN0>;
-  I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C1U_SMEM));
-  kern<<<min(n_tiles, sms), C1U_THREADS, C1U_SMEM, s>>>(tm, w1h, b1, act1, Bp, n_tiles, nrm, G.TW, G.TH);
-  I2L_LAUNCH_OK();
-  return I2L_OK;
+#ifdef I2L_DIAG
+  const int ng = getenv("I2L_CONV1_NG") ? atoi(getenv("I2L_CONV1_NG")) : 3;     // A-B: builder groups
+  if (ng == 2) return launch_conv1_u8_ng<CIN0, 2>(tm, w1h, b1, act1, Bp, n_tiles, nrm, G, sms, s);
+  if (ng == 4) return launch_conv1_u8_ng<CIN0, 4>(tm, w1h, b1, act1, Bp, n_tiles, nrm, G, sms, s);
+#endif
+  return launch_conv1_u8_ng<CIN0, 3>(tm, w1h, b1, act1, Bp, n_tiles, nrm, G, sms, s);
 }
 
 int cnn_bf16_fwd(const i2l_cnn_desc& d, const void* section, const void* x, int in_dtype, int B, float* out, void* ws,

@@ -131,9 +131,11 @@ extern "C" int i2l_token_exchange_write(const int64_t* tokens, const int32_t* le
     P.flags[p] = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(peer_buffers[p]) + fo);
   }
   unsigned int* counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(peer_buffers[rank]) + fo + 256);
-  const int grid = min(cdiv(cap, 8), 2 * num_sms());
+  // small footprint (<= 40 blocks of 16 warps): the pipelined exchange runs beside the persistent decode kernel, which
+  // leaves 20 SMs idle; 5 MB of peer stores need a few us either way
+  const int grid = min(cdiv(cap, 16), 40);
   KernelTimer kt("xchg.write_p2p", (cudaStream_t)stream);
-  xchg_write_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tokens, lengths, steps, b, T1, cap, rank, world, (int)(seq & 1),
+  xchg_write_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(tokens, lengths, steps, b, T1, cap, rank, world, (int)(seq & 1),
                                                             seq, P, counter);
   I2L_LAUNCH_OK();
   return I2L_OK;
@@ -148,9 +150,9 @@ extern "C" int i2l_token_exchange_read(const void* local_buffer, int32_t world, 
   const int cap = (n_total + world - 1) / world;
   const char* base = reinterpret_cast<const char*>(local_buffer);
   const size_t fo = flags_offset(world, n_total, T1);
-  const int grid = min(cdiv(n_total, 8), 2 * num_sms());
+  const int grid = min(cdiv(n_total, 16), 40);
   KernelTimer kt("xchg.read_wait", (cudaStream_t)stream);
-  xchg_read_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int32_t*>(base),
+  xchg_read_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int32_t*>(base),
                                                            reinterpret_cast<const uint32_t*>(base + fo), world, cap, T1,
                                                            n_total, (int)(seq & 1), seq, tokens, lengths, steps, timeout_flag);
   I2L_LAUNCH_OK();

@@ -92,6 +92,9 @@ class TokenExchange:
         self.seq = 0                                              # sequence number of the last write
         self.read_seq = 0
         self._timeout = torch.zeros((), dtype=torch.int32, device=self.device)
+        self._stream = None                                       # side stream of kick() / flush(), created on first use
+        self._staged = None
+        self.result_event = None
         lo, hi = shard_bounds(self.n_total, self.world, self.rank)
         self.shard, self.shard_lo = hi - lo, lo
 
@@ -108,28 +111,113 @@ class TokenExchange:
                                                      self.rank, self.world, self._ptrs, self.seq,
                                                      N.stream_ptr(self.device)), "i2l_token_exchange_write")
 
-    def read(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """Global (tokens (n_total,T1) int64, lengths (n_total) int32, steps) of the last written step."""
+    def read(self, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None
+             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Global (tokens (n_total,T1) int64, lengths (n_total) int32, steps) of the last written step, on the current
+        stream; `out` = caller-owned result tensors (otherwise fresh ones)."""
         if self.read_seq == self.seq:
             raise RuntimeError("TokenExchange.read: nothing pending")
         self.read_seq = self.seq
-        tokens = torch.empty(self.n_total, self.T1, dtype=torch.int64, device=self.device)
-        lengths = torch.empty(self.n_total, dtype=torch.int32, device=self.device)
-        steps = torch.empty((), dtype=torch.int32, device=self.device)
+        if out is None:
+            out = (torch.empty(self.n_total, self.T1, dtype=torch.int64, device=self.device),
+                   torch.empty(self.n_total, dtype=torch.int32, device=self.device),
+                   torch.empty((), dtype=torch.int32, device=self.device))
+        tokens, lengths, steps = out
         with torch.cuda.device(self.device):
             N.check(N.lib().i2l_token_exchange_read(N.ptr(self.local), self.world, self.n_total, self.T1, self.seq,
                                                     N.ptr(tokens), N.ptr(lengths), N.ptr(steps), N.ptr(self._timeout),
                                                     N.stream_ptr(self.device)), "i2l_token_exchange_read")
         return tokens, lengths, steps
 
-    def step(self, tokens, lengths, steps):
-        """read(previous step) then write(this step); returns the previous step's global result (None at first)."""
-        prev = self.read() if self.read_seq != self.seq else None
-        self.write(tokens, lengths, steps)
+    # ---- pipelined use: the exchange runs on its OWN stream, next to the decode kernel of the following batch ----------
+    # The encoder kernels are persistent with one CTA per SM, so anything that shares the GPU with them delays whole
+    # tile ranges (measured: conv2 0.16 -> 0.27 ms with the exchange beside it); the persistent decode kernel leaves 20
+    # of the 148 SMs idle and is latency-bound.  `stage()` therefore only remembers a step's result; `kick()`, called
+    # by the serving loop between the NEXT batch's encoder and decode, releases it on the side stream.
+    def _side(self):
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(self.device)
+            self._produced = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()]
+            self.result_event = torch.cuda.Event()
+            # three rotating result sets: a result handed out by kick() stays valid for two more kicks
+            self._ring = [(torch.empty(self.n_total, self.T1, dtype=torch.int64, device=self.device),
+                           torch.empty(self.n_total, dtype=torch.int32, device=self.device),
+                           torch.empty((), dtype=torch.int32, device=self.device)) for _ in range(3)]
+            self._turn = 0
+            self._kicks = 0
+        return self._stream
+
+    def stage(self, tokens, lengths, steps) -> None:
+        """remember this step's shard result (produced on the current stream) for the next kick()"""
+        if self._staged is not None:
+            raise RuntimeError("TokenExchange.stage: kick() the previous step first")
+        side = self._side()
+        ev = self._produced[self.seq & 1]
+        ev.record(torch.cuda.current_stream(self.device))
+        for t in (tokens, lengths, steps):
+            t.record_stream(side)                                 # the caller may drop them before the stores have run
+        self._staged = (tokens, lengths, steps, ev)
+
+    def kick(self):
+        """read(previous step) then write(staged step) on the side stream, ordered after the work queued on the current
+        stream so far (the serving loop calls it right before the decode launch of the next batch).  Returns the
+        previous step's global result or None: device tensors of a 3-deep ring, complete once `result_event` has fired
+        -- `wait_result()` / `flush()` make the current stream wait for it.  The current stream is held back only when
+        it runs more than two exchanges ahead of the side stream (a peer that far behind)."""
+        if self._staged is None:
+            return None
+        side = self._side()
+        cur = torch.cuda.current_stream(self.device)
+        tokens, lengths, steps, produced = self._staged
+        self._staged = None
+        here = torch.cuda.Event()
+        here.record(cur)
+        if self._kicks >= 3:
+            cur.wait_event(self._consumed[self._kicks % 3])      # bounded run-ahead: the kick of three steps ago is done
+        prev = None
+        with torch.cuda.stream(side):
+            side.wait_event(produced)
+            side.wait_event(here)
+            if self.read_seq != self.seq:
+                prev = self.read(self._ring[self._turn])
+                self._turn = (self._turn + 1) % 3
+                self.result_event.record(side)
+            self.write(tokens, lengths, steps)
+            self._consumed[self._kicks % 3].record(side)
+        self._kicks += 1
         return prev
 
+    def step(self, tokens, lengths, steps):
+        """stage() + kick() at once: the exchange starts as soon as the step's result exists (beside whatever the
+        current stream runs next).  Returns the previous step's global result (None at first), see kick()."""
+        self.stage(tokens, lengths, steps)
+        return self.kick()
+
+    def wait_result(self) -> None:
+        """make the current stream wait for the last result handed out by kick() / step()"""
+        if self._stream is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.result_event)
+
     def flush(self):
-        return self.read() if self.read_seq != self.seq else None
+        """Drain the pipeline: the results not handed out yet, oldest first (0, 1 or 2 triples); the current stream
+        waits for them."""
+        out = []
+        if self._staged is not None:
+            prev = self.kick()
+            if prev is not None:
+                out.append(prev)
+        if self.read_seq != self.seq:
+            if self._stream is None:
+                out.append(self.read())
+            else:
+                side = self._side()
+                with torch.cuda.stream(side):
+                    out.append(self.read(self._ring[self._turn]))
+                    self._turn = (self._turn + 1) % 3
+                    self.result_event.record(side)
+        self.wait_result()
+        return out
 
     def check(self) -> None:
         """Host-side check (synchronises): raises if a read kernel gave up waiting for a peer."""

@@ -121,8 +121,9 @@ class Seq2SeqModel(nn.Module):
 
         ``exchange`` (a ``dist.TokenExchange``, batch-sharded multi-GPU serving): every rank streams ITS shard of each
         global batch; the ids are exchanged on the device by direct peer stores and the yielded triple is the GLOBAL
-        (n_total, max_length+1) result -- one batch later than without (read of step i runs behind the compute of
-        step i + 1), all global batches having the same size.  ``exchange_readback="shard"``: every rank still holds the
+        (n_total, max_length+1) result -- two batches later than without (the exchange of batch i runs on a side
+        stream beside the decode kernel of batch i + 1 and is handed out during batch i + 2), all global batches having
+        the same size.  ``exchange_readback="shard"``: every rank still holds the
         global ids in HBM after the exchange, but copies only its OWN rows to the host (the rank that hands the job's
         result to the consumer uses "global"; N host copies of the same matrix are N - 1 too many)."""
         dev = device or next(self.parameters()).device
@@ -133,14 +134,15 @@ class Seq2SeqModel(nn.Module):
         compute = torch.cuda.current_stream(dev)
         computed = [torch.cuda.Event(), torch.cuda.Event()]       # results of the slot exist on the device
 
-        def read_back(slot: int, tokens, lengths, steps) -> None:
+        def read_back(slot: int, tokens, lengths, steps, after=None) -> None:
             if out_tok[slot] is None or out_tok[slot].shape != tokens.shape:
                 out_tok[slot] = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
                 out_len[slot] = torch.empty(lengths.shape, dtype=lengths.dtype).pin_memory()
                 out_steps[slot] = torch.empty((), dtype=steps.dtype).pin_memory()
-            computed[slot].record(compute)
+            if after is None:
+                computed[slot].record(compute)
             with torch.cuda.stream(out_stream):
-                out_stream.wait_event(computed[slot])
+                out_stream.wait_event(computed[slot] if after is None else after)
                 for dst, src in ((out_tok[slot], tokens), (out_len[slot], lengths), (out_steps[slot], steps)):
                     dst.copy_(src, non_blocking=True)
                     src.record_stream(out_stream)                 # the caching allocator must not recycle it under the copy
@@ -183,6 +185,15 @@ class Seq2SeqModel(nn.Module):
         stage(0, cur)
         i = 0
         prev = -1
+        nres = 0
+
+        def shard_view(res):
+            tokens, lengths, steps = res
+            if exchange is not None and exchange_readback == "shard":
+                lo = exchange.shard_lo
+                tokens, lengths = tokens[lo: lo + exchange.shard], lengths[lo: lo + exchange.shard]
+            return tokens, lengths, steps
+
         while cur is not None:
             nxt = next(it, None)
             slot = i & 1
@@ -199,35 +210,34 @@ class Seq2SeqModel(nn.Module):
                 enc = self.encoder(xin)
             consumed[slot].record(compute)
             used[slot] = True
+            res, ev = None, None
+            if exchange is not None:
+                # release the exchange of the PREVIOUS batch's shard result here, between this batch's encoder and its
+                # decode (it then runs beside the decode kernel); hands out the global result of the batch before that
+                res, ev = exchange.kick(), exchange.result_event
             tokens, lengths, steps = self.decoder.greedy(enc, start_token_id, end_token_id, max_length, temperature,
                                                          stop_rule)
             if exchange is not None:
-                res = exchange.step(tokens, lengths, steps)       # global result of the PREVIOUS batch (None at first)
-                if res is None:
-                    cur = nxt
-                    i += 1
-                    continue
-                tokens, lengths, steps = res
-                if exchange_readback == "shard":
-                    lo = exchange.shard_lo
-                    tokens, lengths = tokens[lo: lo + exchange.shard], lengths[lo: lo + exchange.shard]
-            read_back(slot, tokens, lengths, steps)
-            if prev >= 0:
-                yield collect(prev)
-            prev = slot
+                exchange.stage(tokens, lengths, steps)
+            else:
+                res = (tokens, lengths, steps)
+            if res is not None:
+                oslot = nres & 1
+                nres += 1
+                # exchanged results are produced on the exchange's side stream: the copy waits for THAT event
+                read_back(oslot, *shard_view(res), after=ev)
+                if prev >= 0:
+                    yield collect(prev)
+                prev = oslot
             cur = nxt
             i += 1
         if exchange is not None:
-            res = exchange.flush()
-            if res is not None:                                   # the last batch's global result
-                slot = i & 1
-                tokens, lengths, steps = res
-                if exchange_readback == "shard":
-                    lo = exchange.shard_lo
-                    tokens, lengths = tokens[lo: lo + exchange.shard], lengths[lo: lo + exchange.shard]
-                read_back(slot, tokens, lengths, steps)
+            for res in exchange.flush():                          # the last two batches' global results
+                oslot = nres & 1
+                nres += 1
+                read_back(oslot, *shard_view(res))
                 if prev >= 0:
                     yield collect(prev)
-                prev = slot
+                prev = oslot
         if prev >= 0:
             yield collect(prev)
