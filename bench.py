@@ -590,6 +590,9 @@ def resnet_lines(pkg, dev, B, reps=3, world=1):
     dec = pkg.LSTMDecoder(CFG["vocab_size"], 512, 512, MAX_LEN, 2, 0.0, True, precision="bf16").to(dev).eval()
     enc = torch.relu(torch.randn(B, 512, device=dev))
     ms, prof = timed(lambda: gathered(dec.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_NONE)))
+    dec.streamed = True                                         # I2L_BF16_STREAMED: the stream-ordered loop, same weights
+    ms_streamed, _ = timed(lambda: gathered(dec.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_NONE)))
+    dec.streamed = False
     fl_step = B * 11.01e6                                       # live FLOPs per sequence and step @512/512/2
     out["decoder_512_512_2_greedy"] = {
         "workload": "the reference's shipped decoder (configs/config.yaml:45-50: E = H = 512, 2 LSTM layers), greedy, "
@@ -599,9 +602,12 @@ def resnet_lines(pkg, dev, B, reps=3, world=1):
         "roofline": {"bound": "tensor", "achieved": round(fl_step / (ms / MAX_LEN * 1e-3) / 1e12, 1),
                      "peak": peaks()["tf_sust"], "unit": "TFLOP/s",
                      "frac": round(fl_step / (ms / MAX_LEN * 1e-3) / 1e12 / peaks()["tf_sust"], 3)},
-        "note": "stream-ordered loop replayed as ONE CUDA graph, L + 2 launches per step (gate GEMM with the LSTM cell "
-                "fused into its epilogue per layer, logits GEMM, selection); no persistent kernel for this shape yet: "
-                "6.5 MB of bf16 weights do not fit the tensor + shared memory of a 4..16-CTA cluster"}
+        "kernels_ms": {k: v for k, v in prof.items() if k.startswith("dec.")},
+        "stream_ordered_us_per_decode_step": round(ms_streamed / MAX_LEN * 1e3, 2),
+        "note": "decode_wide.cu: ONE cooperative kernel runs all 150 steps on the whole GPU (128-sequence x 128-gate-column "
+                "tiles with static ownership, one counter per 128-sequence block instead of launches, weights streamed "
+                "from L2 -- 6.5 MB of bf16 weights do not fit a cluster); stream_ordered_* = the CUDA-graph loop of "
+                "L + 2 launches per step it replaces (I2L_BF16_STREAMED)"}
     return out
 
 

@@ -613,6 +613,7 @@ struct DecWs {
   float *gctx, *gates, *logits, *h[2], *c[2];
   __nv_bfloat16* hb;             // bf16 copy of h[0] (L,R,H): A operand of the tcgen05 GEMMs (precision bf16)
   __nv_bfloat16* hb2;            // second copy: the fused gate-GEMM + cell kernels read one and write the other
+  __nv_bfloat16* encb;           // bf16 copy of the encoder output: A operand of the context-term GEMM (precision bf16)
   int64_t* tok_cur;
   int* first_end;
   LoopState* st;
@@ -634,6 +635,7 @@ DecWs carve(const i2l_dec_desc& d, int rows, int max_length, void* ws) {
   for (int i = 0; i < 2; ++i) { w.h[i] = a.take<float>(L * R * H); w.c[i] = a.take<float>(L * R * H); }
   w.hb = a.take<__nv_bfloat16>(L * R * H);
   w.hb2 = a.take<__nv_bfloat16>(L * R * H);
+  w.encb = a.take<__nv_bfloat16>(R * (size_t)d.embedding_dim);
   w.tok_cur = a.take<int64_t>(R);
   w.first_end = a.take<int>(R);
   w.st = a.take<LoopState>(1);
@@ -767,10 +769,12 @@ int make_step_fused(const i2l_dec_desc& d, const void* packed, const PackedDec& 
         g.add_rows = w.gctx; g.ld_add = 4 * H;
         g.add_table = pk + lay.gtok; g.ld_tab = 4 * H; g.tab_idx = w.tok_cur;
       } else {
-        I2L_TRY(gemm_bf16_a_map(&g.tmA1, wr + (size_t)(l - 1) * rows * H, rows, H, H));     // this step's h of the layer below
-        I2L_TRY(gemm_bf16_w_map(&g.tmW1, pb + lay.g16c_w_ih[l], 4 * H, H, H));
-        I2L_TRY(gemm_bf16_a_map(&g.tmA2, rd + (size_t)l * rows * H, rows, H, H));
-        I2L_TRY(gemm_bf16_w_map(&g.tmW2, pb + lay.g16c_w_hh[l], 4 * H, H, H));
+        // recurrent product first, then this step's h of the layer below: the accumulation order of decode_wide.cu,
+        // so that the two paths agree bit for bit
+        I2L_TRY(gemm_bf16_a_map(&g.tmA1, rd + (size_t)l * rows * H, rows, H, H));
+        I2L_TRY(gemm_bf16_w_map(&g.tmW1, pb + lay.g16c_w_hh[l], 4 * H, H, H));
+        I2L_TRY(gemm_bf16_a_map(&g.tmA2, wr + (size_t)(l - 1) * rows * H, rows, H, H));
+        I2L_TRY(gemm_bf16_w_map(&g.tmW2, pb + lay.g16c_w_ih[l], 4 * H, H, H));
         g.K1 = H; g.K2 = H;
         g.bias = pk + lay.bsum[l];
       }
@@ -938,6 +942,7 @@ extern "C" size_t i2l_dec_workspace_bytes(const i2l_dec_desc* d_in, int32_t rows
   if (!d || rows <= 0) return 0;
   size_t b = carve(*d, rows, max_length, nullptr).bytes;
   if (d->precision == I2L_BF16 && persistent_supported(*d)) b += persistent_workspace_bytes(*d, rows, max_length);
+  if (wide_supported(*d)) b += wide_workspace_bytes(*d, rows, max_length);
   return b;
 }
 
@@ -1006,7 +1011,9 @@ static int enqueue_loop(const i2l_dec_desc* d, const void* packed, const PackedD
   size_t n = (size_t)d->lstm_layers * batch * d->hidden_dim * sizeof(float);
   I2L_CUDA_OK(cudaMemsetAsync(w.h[0], 0, n, s));
   I2L_CUDA_OK(cudaMemsetAsync(w.c[0], 0, n, s));
-  I2L_TRY(make_gctx(*d, pk, lay, enc, batch, w.gctx, s));
+  // precision bf16: the context term on the tensor cores too (bf16 operands, like decode_persistent.cu / decode_wide.cu)
+  if (lay.g16 != 0) I2L_TRY(make_gctx_bf16(*d, packed, lay, enc, batch, w.gctx, w.encb, s));
+  else I2L_TRY(make_gctx(*d, pk, lay, enc, batch, w.gctx, s));
   const int* skip = &w.st->done;
   int n2 = 1; while (n2 < V) n2 <<= 1;
   size_t smem = (size_t)V * 8 + (size_t)V * 4 + (size_t)n2 * 8;
@@ -1152,6 +1159,15 @@ extern "C" int i2l_decode_greedy(const i2l_dec_desc* d_in, const void* packed, c
                              reinterpret_cast<const float*>(packed), lay, enc, batch, start_id, end_id,
                              max_length, temperature, stop_rule, tokens, lengths, steps_run,
                              reinterpret_cast<char*>(workspace) + gen, workspace_bytes - gen, s);
+  }
+  if (!dn_.streamed && wide_batch_supported(*d, batch) && temperature > 0.f && max_length > 0 && lengths && steps_run) {
+    // decoders beyond the cluster kernel (the reference's shipped 512 / 512 / 2, 1024 / 1024 / 3): one cooperative
+    // kernel runs the whole loop on the whole GPU (decode_wide.cu)
+    PackedDec lay = dec_layout(*d);
+    size_t gen = carve(*d, batch, max_length, nullptr).bytes;
+    I2L_REQUIRE(workspace_bytes >= gen + wide_workspace_bytes(*d, batch, max_length), "i2l_decode_greedy: workspace too small");
+    return wide_greedy(*d, packed, lay, enc, batch, start_id, end_id, max_length, temperature, stop_rule, tokens, lengths,
+                       steps_run, reinterpret_cast<char*>(workspace) + gen, workspace_bytes - gen, s);
   }
   return run_loop(d, packed, enc, batch, start_id, end_id, max_length, temperature, stop_rule, false, 0, 0.f, 0,
                   0, nullptr, tokens, lengths, steps_run, nullptr, workspace, workspace_bytes, s);

@@ -86,4 +86,14 @@ int persistent_beam(const i2l_dec_desc& d, const void* section, const float* gct
                     int start_id, int end_id, int max_length, BeamState* bstate, double* score, int* tr_parent,
                     int* tr_token, double* tr_score, int* cand_tok, float* cand_logp, cudaStream_t s);
 
+// persistent whole-GPU greedy loop for the decoders the cluster kernel does not cover (decode_wide.cu): bf16, any
+// L <= 4, H % 64 == 0 -- the reference's shipped 512 / 512 / 2 and 1024 / 1024 / 3 decoders
+bool wide_supported(const i2l_dec_desc& d);
+bool wide_batch_supported(const i2l_dec_desc& d, int rows);
+size_t wide_workspace_bytes(const i2l_dec_desc& d, int rows, int max_length);
+int wide_greedy(const i2l_dec_desc& d, const void* packed, const PackedDec& lay, const float* enc, int batch, int start_id,
+                int end_id, int max_length, float temperature, int stop_rule, int64_t* tokens, int32_t* lengths,
+                int32_t* steps_run, void* ws, size_t ws_bytes, cudaStream_t s);
+int wide_aborted(const void* ws, const i2l_dec_desc& d, int rows, int max_length, int* out);
+
 }  // namespace i2l

@@ -195,7 +195,7 @@ def decode_greedy(enc: Tensor, packed: Tensor, workspace: Tensor, dec_desc: List
     B, dev = enc.shape[0], enc.device
     tokens = torch.empty(B, max_length + 1, dtype=torch.int64, device=dev)
     lengths = torch.empty(B, dtype=torch.int32, device=dev)
-    steps = torch.zeros((), dtype=torch.int32, device=dev)
+    steps = torch.empty((), dtype=torch.int32, device=dev)      # written by every loop's finalize kernel
     with torch.cuda.device(dev):
         N.check(N.lib().i2l_decode_greedy(C.byref(d), N.ptr(packed), N.ptr(enc), B, start_id, end_id, max_length,
                                           float(temperature), stop_rule, N.ptr(tokens), N.ptr(lengths), N.ptr(steps),
@@ -219,7 +219,7 @@ def decode_sample(enc: Tensor, packed: Tensor, workspace: Tensor, dec_desc: List
     B, dev = enc.shape[0], enc.device
     tokens = torch.empty(B, max_length + 1, dtype=torch.int64, device=dev)
     lengths = torch.empty(B, dtype=torch.int32, device=dev)
-    steps = torch.zeros((), dtype=torch.int32, device=dev)
+    steps = torch.empty((), dtype=torch.int32, device=dev)      # written by every loop's finalize kernel
     probs = (torch.zeros(max_length, B, d.vocab_size, dtype=torch.float32, device=dev) if return_probs
              else torch.empty(0, dtype=torch.float32, device=dev))
     with torch.cuda.device(dev):

@@ -570,6 +570,7 @@ def test_wide_decoder_fused_graph_loop(pkg, cfg, B, T):
     if wide:
         p["decoder.output_layer.weight"] *= 4.0
     m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    m16.decoder.streamed = True      # I2L_BF16_STREAMED: the stream-ordered loop (greedy would take decode_wide.cu otherwise)
     g = torch.Generator().manual_seed(23)
     E = cfg["embedding_dim"]
     enc_a = torch.relu(torch.randn(B, E, generator=g))
@@ -609,6 +610,59 @@ def test_wide_decoder_fused_graph_loop(pkg, cfg, B, T):
     taken = tok_p[:, 1: n + 1].t()
     for t, b in (drawn != taken).nonzero().tolist():
         assert float((cdf[t, b] - tgt[t, b]).abs().min()) < 1e-6, (t, b)
+
+
+WIDE_1024 = dict(H.SHIPPED, embedding_dim=1024, hidden_dim=1024, lstm_layers=3)     # configs/resnet_lstm.yaml:45-50
+
+
+@pytest.mark.parametrize("cfg,B,T,rule", [(H.SHIPPED, 200, 40, "same_step"), (H.SHIPPED, 1024, 150, "same_step"),
+                                          (H.SHIPPED, 300, 40, "sticky"), (WIDE_1024, 257, 20, "same_step"),
+                                          (dict(H.SHIPPED, hidden_dim=192, embedding_dim=64, lstm_layers=1, vocab_size=77), 130, 25, "sticky")])
+def test_wide_persistent_loop(pkg, cfg, B, T, rule):
+    """decode_wide.cu: the whole greedy loop of a wide / multi-layer decoder as ONE cooperative kernel (tiles of 128
+    sequences, per-block counters instead of launches).  It runs the same tcgen05 products in the same accumulation
+    order and the same epilogue arithmetic as the stream-ordered fused loop (gemm_bf16.cu), so the two must agree BIT
+    FOR BIT (tokens up to the stop step, lengths, steps); the stream-ordered loop is the one the oracle criteria are
+    checked on (test_wide_decoder_fused_graph_loop), and the fp32 / bf16-operand oracles are applied here directly too."""
+    N = pkg._native
+    stop = N.STOP_ALL_END_SAME_STEP if rule == "same_step" else N.STOP_ALL_FINISHED_STICKY
+    p = oracle.make_params(cfg, 5)
+    p["decoder.output_layer.weight"] *= 4.0
+    if rule == "sticky":
+        p["decoder.output_layer.bias"][H.END] += 1.5                  # rows end at different steps, whole blocks stop early
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    g = torch.Generator().manual_seed(31 + B)
+    enc = torch.relu(torch.randn(B, cfg["embedding_dim"], generator=g))
+    lib = N.lib()
+    m16.decoder.greedy(enc[:2].cuda(), H.START, H.END, 2, 1.0, stop)          # packs the weights (counted launches)
+    l0 = lib.i2l_launch_count()
+    tok_w, len_w, st_w = m16.decoder.greedy(enc.cuda(), H.START, H.END, T, 1.0, stop)
+    torch.cuda.synchronize()
+    launches = lib.i2l_launch_count() - l0
+    assert launches <= 8, f"{launches} launches: the loop did not take the persistent kernel"
+    m16.decoder.streamed = True
+    tok_s, len_s, st_s = m16.decoder.greedy(enc.cuda(), H.START, H.END, T, 1.0, stop)
+    m16.decoder.streamed = False
+    n = int(st_s)
+    assert int(st_w) == n
+    assert torch.equal(len_w, len_s)
+    tw, ts = tok_w.cpu()[:, : n + 1], tok_s.cpu()[:, : n + 1]
+    if rule == "sticky":
+        # a 128-sequence block stops once ITS rows have finished (the stream-ordered loop runs every row to the global
+        # stop): compare every row up to its own END
+        for b in range(B):
+            k = int(len_s[b])
+            assert tw[b, : k + 1].tolist() == ts[b, : k + 1].tolist(), b
+    else:
+        assert torch.equal(tw, ts)
+    if B <= 300:
+        ocfg = dict(cfg)
+        if rule == "same_step":
+            ref, steps_ref, trace = oracle.greedy_search(p, enc, H.START, H.END, T, 1.0, ocfg, return_logits=True)
+            exact, near, bad = divergence_report(tok_w.cpu()[:, : steps_ref + 1].tolist(), ref, trace)
+            print(f"wide persistent loop H={cfg['hidden_dim']} L={cfg['lstm_layers']} B={B} T={T}: rows on the fp32 oracle "
+                  f"{exact}/{B} ({len(near)} near ties), steps {n} (oracle {steps_ref})")
+            assert not bad, f"rows diverging at a step with a clear margin: {bad[:10]}"
 
 
 # ---- the tcgen05 CNN encoder beyond the benchmark shape (cnn_bf16.cu: C in {1,3}, H % 64 == 0, W % 32 == 0) -----------
