@@ -32,6 +32,7 @@
 #include "decode_kernels.cuh"
 #include "tc_common.cuh"
 #include <limits.h>
+#include <stdlib.h>
 
 namespace i2l {
 
@@ -51,7 +52,7 @@ constexpr int WD_OFF_STATE = WD_OFF_BAR + 256;              // [WD_MAXT][128] fi
 constexpr int WD_OFF_MISC = WD_OFF_STATE + WD_MAXT * 128;   // epilogue scratch
 constexpr int WD_SMEM = WD_OFF_MISC + 64;
 constexpr int WD_MAXL = 4;
-constexpr int WD_THREADS = 192;
+constexpr int WD_THREADS = 320;                             // producer + MMA issuer + 8 epilogue warps
 constexpr long long WD_SPIN_CYCLES = 4000000000LL;          // ~2 s at 1.9 GHz
 
 struct WideParams {
@@ -64,7 +65,7 @@ struct WideParams {
   const float* out_b;               // [V]
   __nv_bfloat16* hbuf;
   float* c;                         // [L][Bp][H]
-  float2* partial;                  // [MB][NV][128] (max logit, index) of a step's logits tiles
+  unsigned long long* best;         // [2 step parities][MB][128]: max over a step's logits tiles of (ordered logit, ~index)
   unsigned* cnt;                    // [MB] finished tiles
   int* stop_at;                     // [MB] step at which the block stopped (INT_MAX-ish: running)
   int* abort_flag;
@@ -75,7 +76,14 @@ struct WideParams {
   int B, Bp, H, L, V, T, NT, NV, MB, KB;
   int start_id, end_id, stop_rule;
   float temperature;
+  long long* dbg_ts;                // diagnostics build: clock64 stamps of CTA 0, [step][8]
 };
+
+#ifdef I2L_DIAG
+#define WD_TS(step, slot) do { if (P.dbg_ts != nullptr && blockIdx.x == 0) P.dbg_ts[(size_t)(step) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define WD_TS(step, slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -102,7 +110,7 @@ __device__ __noinline__ bool wait_count(const WideParams& P, int mb, unsigned ta
 __device__ __forceinline__ bool block_dead(const WideParams& P, int mb, int s) {
   return ld_volatile_s32(P.stop_at + mb) <= s || ld_volatile_s32(P.abort_flag) != 0;
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_constant__ WideParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
               for (int kb = 0; kb < KB; ++kb) {
                 const uint32_t dst = slot(WD_STAGE);
                 tma_load_2d(dst + WD_A_BYTES, &P.tmW[2 * l + 1], kb * WD_BK, n0, FULL(stage));
-                if (!ok) { wait_count(P, mb, (unsigned)s * PS + (unsigned)l * NT, s); asm volatile("fence.proxy.async;" ::: "memory"); ok = true; }
+                if (!ok) { wait_count(P, mb, (unsigned)s * PS + (unsigned)l * NT, s); asm volatile("fence.proxy.async;" ::: "memory"); ok = true; if (l == 1) WD_TS(s, 2); }
                 tma_load_2d(dst, &P.tmH, kb * WD_BK, (par * L + l - 1) * P.Bp + m0, FULL(stage));
                 next();
               }
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
           for (int kb = 0; kb < KB; ++kb) {
             const uint32_t dst = slot(WD_A_BYTES + WD_WL_BYTES);
             tma_load_2d(dst + WD_A_BYTES, &P.tmO, kb * WD_BK, n0, FULL(stage));
-            if (!ok) { wait_count(P, mb, (unsigned)s * PS + (unsigned)L * NT, s); asm volatile("fence.proxy.async;" ::: "memory"); ok = true; }
+            if (!ok) { wait_count(P, mb, (unsigned)s * PS + (unsigned)L * NT, s); asm volatile("fence.proxy.async;" ::: "memory"); ok = true; WD_TS(s, 5); }
             tma_load_2d(dst, &P.tmH, kb * WD_BK, (par * L + L - 1) * P.Bp + m0, FULL(stage));
             next();
           }
@@ -222,24 +230,21 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
       for (int t = cta; t < n_vt; t += G) run_tile(KB, IDESC_L);
     }
   } else {
-    // ===================== epilogue (warps 2..5: TMEM lane quadrant = warp & 3) =====================
-    const int q = warp & 3;
+    // ===================== epilogue (warps 2..9: TMEM lane quadrant = warp & 3, column half = (warp - 2) / 4) =========
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = 32 * q + lane;                               // row of the tile
-    const int et = tid - 64;                                   // 0..127
+    const int et = tid - 64;                                   // 0..255
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
     const int H = P.H, T1 = P.T + 1;
+    const bool sticky = P.stop_rule == I2L_STOP_ALL_FINISHED_STICKY;
     uint32_t it = 0;
-    // token of a row from the NV argmax partials of the previous step (ascending column order, strict >: first maximum)
-    auto reduce_token = [&](int mb) {
-      const float2* pp = P.partial + ((size_t)mb * NV) * 128 + r;
-      float best = 0.f; int bi = 0;
-      for (int nv = 0; nv < NV; ++nv) {
-        const float2 e = __ldcg(pp + (size_t)nv * 128);
-        if (nv == 0 || e.x > best) { best = e.x; bi = __float_as_int(e.y); }
-      }
-      return bi;
+    // token of a row = low word of the block's 64-bit (logit, ~index) maximum of the previous step
+    auto token_of = [&](int mb, int step) {
+      const unsigned long long k = __ldcg(P.best + ((size_t)(step & 1) * P.MB + mb) * 128 + r);
+      return (int)(0xFFFFFFFFu - (uint32_t)k);
     };
-    // EOS bookkeeping of token `tok` = the output of step s - 1 (position s); returns true when the block stops here
+    // EOS bookkeeping of token `tok` = the output of step s - 1 (position s), by the 128 threads of column half 0; the
+    // warp votes land in misc[0..3] (bit 0: every row emitted END at this step, bit 1: every row has finished)
     auto account = [&](int mb, int slot_i, bool owner, int s, int tok) {
       const int row = mb * WD_BM + r;
       const bool valid = row < P.B;
@@ -253,11 +258,15 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
       fin[slot_i * 128 + r] = f;
       const bool w_end = __all_sync(0xffffffffu, !valid || is_end), w_fin = __all_sync(0xffffffffu, !valid || f);
       if (lane == 0) misc[q] = (w_end ? 1 : 0) | (w_fin ? 2 : 0);
+    };
+    // publish the tile: the CTA barrier orders every thread's global writes before the one release increment
+    auto publish = [&](uint32_t a, int mb, bool dead) {
+      tc_fence_before();
       epi_bar();
-      const int m = misc[0] & misc[1] & misc[2] & misc[3];
-      epi_bar();
-      if (owner && et == 0) P.allend[(size_t)mb * P.T + s - 1] = (unsigned char)(m & 1);
-      return P.stop_rule == I2L_STOP_ALL_FINISHED_STICKY && (m & 2) != 0;
+      if (et == 0) {
+        mbar_arrive(TEMPTY(a));
+        if (!dead) { __threadfence(); atomicAdd(P.cnt + mb, 1u); }
+      }
     };
     for (int s = 0; s < P.T; ++s) {
       const int par = s & 1;
@@ -269,6 +278,19 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
           const bool valid = row < P.B;
           const uint32_t a = it & 1, apar = (it >> 1) & 1;
           ++it;
+          const int ub = nt * 32 + half * 16;                  // first of this thread's 16 hidden units
+          // ---- operands that depend on neither the token nor the accumulator: requested first
+          float4 cv[4], ev[4][4];
+          float* cp = P.c + ((size_t)l * P.Bp + (valid ? row : 0)) * H + ub;
+          {
+            const float* erow = l == 0 ? P.gctx + (size_t)(valid ? row : 0) * 4 * H : P.bsum[l];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cv[i] = __ldcg(reinterpret_cast<const float4*>(cp + 4 * i));
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) ev[gt][i] = __ldg(reinterpret_cast<const float4*>(erow + gt * H + ub + 4 * i));
+          }
           bool dead = false;
           int tok = P.start_id;
           if (l == 0 && s > 0) {
@@ -276,11 +298,17 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
             if (et == 0) misc[4] = wait_count(P, mb, (unsigned)s * PS, s) ? 0 : 1;
             epi_bar();
             dead = misc[4] != 0;
+            if (et == 0) WD_TS(s, 0);
+            if (!dead) {
+              tok = token_of(mb, s - 1);
+              if (half == 0) account(mb, slot_i, nt == 0, s, tok);
+            }
             epi_bar();
             if (!dead) {
-              tok = reduce_token(mb);
-              if (account(mb, slot_i, nt == 0, s, tok)) {
-                dead = true;
+              const int m = misc[0] & misc[1] & misc[2] & misc[3];
+              if (nt == 0 && et == 0) P.allend[(size_t)mb * P.T + s - 1] = (unsigned char)(m & 1);
+              if (sticky && (m & 2) != 0) {
+                dead = true;                                   // every row of the block has finished: it stops here
                 if (nt == 0 && et == 0) {
                   P.block_steps[mb] = s;
                   __threadfence();
@@ -289,113 +317,101 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
               }
             }
           }
-          // Gtok / Gctx / bias terms do not depend on the accumulator: issue their loads before waiting for it
+          if (l == 0 && !dead && valid) {
+            const float* trow = P.gtok + (size_t)tok * 4 * H + ub;
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(trow + gt * H + 4 * i));
+                ev[gt][i].x += v.x; ev[gt][i].y += v.y; ev[gt][i].z += v.z; ev[gt][i].w += v.w;
+              }
+          }
           mbar_wait(TFULL(a), apar);
           tc_fence_after();
-          if (l > 0) dead = block_dead(P, mb, s);
-          if (!dead) {
-            const float* arow = (l == 0 && valid) ? P.gctx + (size_t)row * 4 * H : nullptr;
-            const float* trow = (l == 0 && valid) ? P.gtok + (size_t)tok * 4 * H : nullptr;
-            const float* brow = l > 0 ? P.bsum[l] : nullptr;
-            const uint32_t ta = tmem + lane_addr + a * 128;
-            const int u0 = nt * 32;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-              uint32_t acc[4][16];
+          if (et == 0 && l == 1) WD_TS(s, 3);
+          if (l > 0 && sticky) dead = ld_volatile_s32(P.stop_at + mb) <= s;
+          uint32_t acc[4][16];
 #pragma unroll
-              for (int gt = 0; gt < 4; ++gt) tc_ld16_nowait(ta + gt * 32 + half * 16, acc[gt]);
-              tc_wait_ld();
-              if (valid) {
-                const int ub = u0 + half * 16;
-                float x[4][16];
+          for (int gt = 0; gt < 4; ++gt) tc_ld16_nowait(tmem + lane_addr + a * 128 + gt * 32 + half * 16, acc[gt]);
+          tc_wait_ld();
+          if (!dead && valid) {
+            float hn[16];
 #pragma unroll
-                for (int gt = 0; gt < 4; ++gt) {
-                  const int col = gt * H + ub;                 // PyTorch gate-major column of the epilogue terms
+            for (int i = 0; i < 4; ++i) {
+              float cc[4] = {cv[i].x, cv[i].y, cv[i].z, cv[i].w};
+              const float e0[4] = {ev[0][i].x, ev[0][i].y, ev[0][i].z, ev[0][i].w}, e1[4] = {ev[1][i].x, ev[1][i].y, ev[1][i].z, ev[1][i].w};
+              const float e2[4] = {ev[2][i].x, ev[2][i].y, ev[2][i].z, ev[2][i].w}, e3[4] = {ev[3][i].x, ev[3][i].y, ev[3][i].z, ev[3][i].w};
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (brow != nullptr) { const float4 v = __ldg(reinterpret_cast<const float4*>(brow + col + 4 * i)); e.x += v.x; e.y += v.y; e.z += v.z; e.w += v.w; }
-                    if (arow != nullptr) { const float4 v = __ldg(reinterpret_cast<const float4*>(arow + col + 4 * i)); e.x += v.x; e.y += v.y; e.z += v.z; e.w += v.w; }
-                    if (trow != nullptr) { const float4 v = __ldg(reinterpret_cast<const float4*>(trow + col + 4 * i)); e.x += v.x; e.y += v.y; e.z += v.z; e.w += v.w; }
-                    x[gt][4 * i] = __uint_as_float(acc[gt][4 * i]) + e.x;
-                    x[gt][4 * i + 1] = __uint_as_float(acc[gt][4 * i + 1]) + e.y;
-                    x[gt][4 * i + 2] = __uint_as_float(acc[gt][4 * i + 2]) + e.z;
-                    x[gt][4 * i + 3] = __uint_as_float(acc[gt][4 * i + 3]) + e.w;
-                  }
-                }
-                float* cp = P.c + ((size_t)l * P.Bp + row) * H + ub;
-                float hn[16];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 cv = __ldcg(reinterpret_cast<const float4*>(cp + 4 * i));
-                  float cc[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const int k = 4 * i + e;
-                    const float ig = fmaf(tanh_fast(0.5f * x[0][k]), 0.5f, 0.5f), fg = fmaf(tanh_fast(0.5f * x[1][k]), 0.5f, 0.5f);
-                    const float gg = tanh_fast(x[2][k]), og = fmaf(tanh_fast(0.5f * x[3][k]), 0.5f, 0.5f);
-                    const float cn = fmaf(fg, cc[e], ig * gg);
-                    cc[e] = cn;
-                    hn[k] = og * tanh_fast(cn);
-                  }
-                  __stcg(reinterpret_cast<float4*>(cp + 4 * i), make_float4(cc[0], cc[1], cc[2], cc[3]));
-                }
-                uint32_t pk[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  __nv_bfloat162 h2 = __floats2bfloat162_rn(hn[2 * i], hn[2 * i + 1]);
-                  pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-                }
-                uint4* hb = reinterpret_cast<uint4*>(P.hbuf + (((size_t)par * L + l) * P.Bp + row) * H + ub);
-                __stcg(hb, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-                __stcg(hb + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+              for (int e = 0; e < 4; ++e) {
+                const int k = 4 * i + e;
+                // gate pre-activations: accumulator + (bias | Gctx row + Gtok row); MUFU.TANH activations
+                const float xi = __uint_as_float(acc[0][k]) + e0[e], xf = __uint_as_float(acc[1][k]) + e1[e];
+                const float xg = __uint_as_float(acc[2][k]) + e2[e], xo = __uint_as_float(acc[3][k]) + e3[e];
+                const float ig = fmaf(tanh_fast(0.5f * xi), 0.5f, 0.5f), fg = fmaf(tanh_fast(0.5f * xf), 0.5f, 0.5f);
+                const float gg = tanh_fast(xg), og = fmaf(tanh_fast(0.5f * xo), 0.5f, 0.5f);
+                const float cn = fmaf(fg, cc[e], ig * gg);
+                cc[e] = cn;
+                hn[k] = og * tanh_fast(cn);
               }
+              __stcg(reinterpret_cast<float4*>(cp + 4 * i), make_float4(cc[0], cc[1], cc[2], cc[3]));
             }
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(hn[2 * i], hn[2 * i + 1]);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            uint4* hb = reinterpret_cast<uint4*>(P.hbuf + (((size_t)par * L + l) * P.Bp + row) * H + ub);
+            __stcg(hb, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            __stcg(hb + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
           }
-          // the accumulator slot is free; h / c of this tile are published with one counter increment
-          tc_fence_before();
-          __threadfence();
-          epi_bar();
-          if (et == 0) {
-            mbar_arrive(TEMPTY(a));
-            if (!dead) atomicAdd(P.cnt + mb, 1u);
-          }
+          publish(a, mb, dead);
+          if (et == 0 && l == 0) WD_TS(s, 1);
+          if (et == 0 && l == 1) WD_TS(s, 4);
         }
       }
       for (int t = cta; t < n_vt; t += G) {
         const int mb = t / NV, nv = t - mb * NV;
-        const int row = mb * WD_BM + r;
         const uint32_t a = it & 1, apar = (it >> 1) & 1;
         ++it;
+        float bv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int v = nv * WD_LN + half * 16 + i;
+          bv[i] = v < P.V ? __ldg(P.out_b + v) : 0.f;
+        }
         mbar_wait(TFULL(a), apar);
         tc_fence_after();
-        const bool dead = block_dead(P, mb, s);
-        uint32_t acc[2][16];
-        tc_ld16_nowait(tmem + lane_addr + a * 128, acc[0]);
-        tc_ld16_nowait(tmem + lane_addr + a * 128 + 16, acc[1]);
+        if (et == 0) WD_TS(s, 6);
+        const bool dead = sticky && ld_volatile_s32(P.stop_at + mb) <= s;
+        uint32_t acc[16];
+        tc_ld16_nowait(tmem + lane_addr + a * 128 + half * 16, acc);
         tc_wait_ld();
         if (!dead) {
-          float best = -INFINITY; int bi = 0x7fffffff;
+          float best = 0.f; int bi = -1;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int v = nv * WD_LN + hh * 16 + i;
-              if (v < P.V) {
-                float x = __uint_as_float(acc[hh][i]) + __ldg(P.out_b + v);
-                if (P.temperature != 1.0f) x = x / P.temperature;        // seq2seq.py:213-214
-                if (x > best || bi == 0x7fffffff) { best = x; bi = v; }   // ascending v, strict >: first maximum
-              }
+          for (int i = 0; i < 16; ++i) {
+            const int v = nv * WD_LN + half * 16 + i;
+            if (v < P.V) {
+              float x = __uint_as_float(acc[i]) + bv[i];
+              if (P.temperature != 1.0f) x = x / P.temperature;          // seq2seq.py:213-214
+              if (bi < 0 || x > best) { best = x; bi = v; }              // ascending v, strict >: first maximum
             }
-          if (row < P.Bp) __stcg(P.partial + ((size_t)mb * NV + nv) * 128 + r, make_float2(best, __int_as_float(bi)));
+          }
+          unsigned long long* slot_p = P.best + ((size_t)par * P.MB + mb) * 128 + r;
+          if (bi >= 0) {
+            // order-preserving key (-0 -> +0: equal under torch's compare); ties between tiles: the lower index wins
+            uint32_t u = __float_as_uint(best + 0.0f);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            atomicMax(slot_p, ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)bi));
+          }
+          // the other parity was read by the layer-0 epilogues of this step (all finished: this tile's flag) and is
+          // written again by the logits tiles of step s + 1, which start after this tile has been published
+          if (nv == 0 && half == 0 && s > 0) __stcg(P.best + ((size_t)(par ^ 1) * P.MB + mb) * 128 + r, 0ull);
         }
-        tc_fence_before();
-        __threadfence();
-        epi_bar();
-        if (et == 0) {
-          mbar_arrive(TEMPTY(a));
-          if (!dead) atomicAdd(P.cnt + mb, 1u);
-        }
+        publish(a, mb, dead);
+        if (et == 0) WD_TS(s, 7);
       }
     }
     // ---- the token of the last step: appended by the owner tile of every block that is still running
@@ -407,12 +423,13 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
         if (et == 0) misc[4] = wait_count(P, mb, (unsigned)P.T * PS, P.T) ? 0 : 1;
         epi_bar();
         const bool dead = misc[4] != 0;
+        if (!dead && half == 0) account(mb, slot_i, true, P.T, token_of(mb, P.T - 1));
         epi_bar();
-        if (!dead) {
-          const int tok = reduce_token(mb);
-          account(mb, slot_i, true, P.T, tok);
-          if (et == 0) P.block_steps[mb] = P.T;
+        if (!dead && et == 0) {
+          P.allend[(size_t)mb * P.T + P.T - 1] = (unsigned char)(misc[0] & misc[1] & misc[2] & misc[3] & 1);
+          P.block_steps[mb] = P.T;
         }
+        epi_bar();
       }
     }
   }
@@ -461,19 +478,19 @@ __global__ void wide_finalize_kernel(const int* first_end, const unsigned char* 
 }
 
 struct WWs {
-  float* gctx; __nv_bfloat16* encb; __nv_bfloat16* hbuf; float* c; float2* partial; unsigned* cnt; int* stop_at;
+  float* gctx; __nv_bfloat16* encb; __nv_bfloat16* hbuf; float* c; unsigned long long* best; unsigned* cnt; int* stop_at;
   int* block_steps; int* abort_flag; int* first_end; unsigned char* allend; size_t bytes;
 };
 WWs wcarve(const i2l_dec_desc& d, int rows, int T, void* ws) {
   Arena a(ws, (size_t)-1);
   WWs w{};
   const size_t H = d.hidden_dim, L = d.lstm_layers, E = d.embedding_dim;
-  const size_t MB = cdiv(rows, WD_BM), Bp = MB * WD_BM, NV = cdiv(d.vocab_size, WD_LN);
+  const size_t MB = cdiv(rows, WD_BM), Bp = MB * WD_BM;
   w.gctx = a.take<float>(Bp * 4 * H);
   w.encb = a.take<__nv_bfloat16>(Bp * E);
   w.hbuf = a.take<__nv_bfloat16>(2 * L * Bp * H);
   w.c = a.take<float>(L * Bp * H);
-  w.partial = a.take<float2>(MB * NV * 128);
+  w.best = a.take<unsigned long long>(2 * MB * 128);
   w.cnt = a.take<unsigned>(MB);
   w.stop_at = a.take<int>(MB);
   w.block_steps = a.take<int>(MB);
@@ -523,6 +540,7 @@ int wide_greedy(const i2l_dec_desc& d, const void* packed, const PackedDec& lay,
   }
   I2L_CUDA_OK(cudaMemsetAsync(w.hbuf, 0, (size_t)2 * L * Bp * H * 2, s));
   I2L_CUDA_OK(cudaMemsetAsync(w.c, 0, (size_t)L * Bp * H * 4, s));
+  I2L_CUDA_OK(cudaMemsetAsync(w.best, 0, (size_t)2 * MB * 128 * 8, s));
   {
     KernelTimer kt("dec.gctx_gemm", s);
     I2L_TRY(make_gctx_bf16(d, packed, lay, enc, batch, w.gctx, w.encb, s));
@@ -538,7 +556,7 @@ int wide_greedy(const i2l_dec_desc& d, const void* packed, const PackedDec& lay,
     }
     I2L_TRY(gemm_bf16_operand_map(&P.tmO, pb + lay.g16_out_w, V, H, H, WD_LN));
     P.gctx = w.gctx; P.gtok = pk + lay.gtok; P.out_b = pk + lay.out_b;
-    P.hbuf = w.hbuf; P.c = w.c; P.partial = w.partial; P.cnt = w.cnt; P.stop_at = w.stop_at; P.abort_flag = w.abort_flag;
+    P.hbuf = w.hbuf; P.c = w.c; P.best = w.best; P.cnt = w.cnt; P.stop_at = w.stop_at; P.abort_flag = w.abort_flag;
     P.tokens = tokens; P.first_end = w.first_end; P.allend = w.allend; P.block_steps = w.block_steps;
     P.B = batch; P.Bp = Bp; P.H = H; P.L = L; P.V = V; P.T = max_length; P.NT = H / 32; P.NV = cdiv(V, WD_LN); P.MB = MB;
     P.KB = H / WD_BK;
@@ -549,10 +567,32 @@ int wide_greedy(const i2l_dec_desc& d, const void* packed, const PackedDec& lay,
     int per_sm = 0;
     I2L_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_loop_kernel, WD_THREADS, WD_SMEM));
     I2L_REQUIRE(per_sm >= 1 && grid <= per_sm * num_sms(), "wide_greedy: the cooperative grid (%d CTAs) is not co-resident", grid);
+#ifdef I2L_DIAG
+    static long long* ts_dev = nullptr;                        // I2L_WIDE_TS=1: per-phase clock stamps of CTA 0, printed after a sync
+    const bool want_ts = getenv("I2L_WIDE_TS") != nullptr && max_length <= 256;
+    if (want_ts && ts_dev == nullptr) I2L_CUDA_OK(cudaMalloc(&ts_dev, 256 * 8 * sizeof(long long)));
+    if (want_ts) { I2L_CUDA_OK(cudaMemsetAsync(ts_dev, 0, 256 * 8 * sizeof(long long), s)); P.dbg_ts = ts_dev; }
+#endif
     void* args[] = {(void*)&P};
-    KernelTimer kt("dec.greedy_wide", s);
-    I2L_CUDA_OK(cudaLaunchCooperativeKernel((const void*)wide_loop_kernel, dim3(grid), dim3(WD_THREADS), args, WD_SMEM, s));
-    count_launch();
+    {
+      KernelTimer kt("dec.greedy_wide", s);
+      I2L_CUDA_OK(cudaLaunchCooperativeKernel((const void*)wide_loop_kernel, dim3(grid), dim3(WD_THREADS), args, WD_SMEM, s));
+      count_launch();
+    }
+#ifdef I2L_DIAG
+    if (want_ts) {
+      static long long ts[256 * 8];
+      I2L_CUDA_OK(cudaStreamSynchronize(s));
+      I2L_CUDA_OK(cudaMemcpy(ts, ts_dev, sizeof(ts), cudaMemcpyDeviceToHost));
+      const int s0 = max_length / 2;
+      for (int st = s0; st < s0 + 3 && st + 1 < max_length; ++st) {
+        const long long* t = ts + st * 8;
+        fprintf(stderr, "wide step %d (cycles since tokens known): L0 epi done %lld | L1 flag %lld  acc ready %lld  epi done %lld | "
+                        "LG flag %lld  acc ready %lld  epi done %lld | next tokens known %lld\n", st, t[1] - t[0], t[2] - t[0],
+                t[3] - t[0], t[4] - t[0], t[5] - t[0], t[6] - t[0], t[7] - t[0], ts[(st + 1) * 8] - t[0]);
+      }
+    }
+#endif
   } else {
     I2L_CUDA_OK(cudaMemsetAsync(w.block_steps, 0, (size_t)MB * 4, s));
   }
