@@ -214,12 +214,17 @@ def run_ours(args):
         if rows is not None:
             inp = inp[:rows]
         enc = model.encoder.forward_u8(inp) if inp.dtype == torch.uint8 else model.encoder(inp)
-        prev = xc.kick() if (world > 1 and xc is not None) else None
+        side = args.xchg_mode == "side"
+        prev = xc.kick() if (world > 1 and xc is not None and side) else None
         tokens, lengths, steps = model.decoder.greedy(enc, START, END, MAX_LEN, 1.0, N.STOP_ALL_END_SAME_STEP)
-        if world > 1:
-            if xc is not None:
+        if world > 1 and args.xchg_mode != "none":
+            if xc is not None and side:
                 xc.stage(tokens, lengths, steps)
                 return prev if prev is not None else (tokens, lengths, steps)
+            if xc is not None:
+                got = xc.read() if xc.read_seq != xc.seq else None
+                xc.write(tokens, lengths, steps)
+                return got if got is not None else (tokens, lengths, steps)
             tokens, lengths, steps = gather_tokens(tokens, lengths, steps, inp.shape[0] * world)
         return tokens, lengths, steps
 
@@ -234,7 +239,7 @@ def run_ours(args):
             for i in range(k):
                 yield hosts[i % len(hosts)]
         rb = "global" if rank == 0 else "shard"      # rank 0 hands the job's (global) result to the host; the others their rows
-        for _ in model.greedy_stream(host_batches(2), START, END, MAX_LEN, exchange=xchg, exchange_readback=rb):
+        for _ in model.greedy_stream(host_batches(2 if world == 1 else 12), START, END, MAX_LEN, exchange=xchg, exchange_readback=rb):
             pass
         barrier()
         t0 = time.perf_counter()
@@ -261,7 +266,9 @@ def run_ours(args):
         # clocks / throttle reasons are sampled by one `nvidia-smi -lms 50` child from the warm-up on (the tool needs
         # ~0.1-0.3 s before its first line, longer when 8 ranks start one each) through both timed regions
         sampler = ClockSampler(local); sampler.start()
-        for i in range(max(args.warmup, 3)):
+        # N > 1: the exchange pipeline (side stream, result ring, allocator pool) reaches its steady state after a few
+        # dozen steps; they are run untimed on top of the requested warm-up
+        for i in range(max(args.warmup, 3) + (32 if world > 1 else 0)):
             step(x_dev[i % NB])
         if xchg is not None:
             # parity of the p2p exchange with the library collective on the same shard results (every rank checks)
@@ -283,7 +290,8 @@ def run_ours(args):
         for i in range(args.steps):
             out = step(x_dev[i % NB])
         if xchg is not None:
-            out = xchg.flush()[-1]                            # the last steps' global results: inside the timed region
+            fl = xchg.flush()                                 # the last steps' global results: inside the timed region
+            out = fl[-1] if fl else out
         e1.record()
         barrier()
         launches = lib.i2l_launch_count() - l0
@@ -372,6 +380,9 @@ def run_ours(args):
                 nxt = next_row_lines(pkg, dev, B) if world == 1 else None
             except Exception as e:
                 nxt = {"error": repr(e)[:300]}
+    if world > 1 and os.environ.get("I2L_BENCH_RANK_DEBUG"):
+        print("rank %d: timed region %.3f ms, e2e %.3f ms, kernels %s" % (rank, ms, e2e_s * 1e3, {k: (v[0], round(v[1] / max(v[0], 1), 4)) for k, v in sorted(prof.items())}),
+              file=sys.stderr, flush=True)
     tms = torch.tensor([ms, e2e_s * 1e3, beam[0] if beam else 0.0, h2d_s * 1e3, strong or 0.0], device=dev,
                        dtype=torch.float64)
     if world > 1:
@@ -836,6 +847,10 @@ def main():
                     help="element type of the image tensors (HBM-resident for `value`, pinned host for `e2e`)")
     ap.add_argument("--beam-batch", type=int, default=512, help="images per GPU for the beam-5 line")
     ap.add_argument("--no-extras", action="store_true", help="skip the beam-5 and other-host-dtype measurements")
+    ap.add_argument("--xchg-mode", default="side", choices=["side", "inline", "none"],
+                    help="diagnostic (N > 1): side = the p2p exchange on its own stream beside the next decode (default); "
+                         "inline = read + write on the compute stream right after the decode; none = no exchange at all "
+                         "(what 8 independent replicas cost on this box)")
     ap.add_argument("--nccl-gather", action="store_true",
                     help="N > 1: token all-gather through NCCL on the compute stream (the checked reference of the p2p exchange)")
     args = ap.parse_args()

@@ -139,6 +139,8 @@ class TokenExchange:
             self._stream = torch.cuda.Stream(self.device)
             self._produced = [torch.cuda.Event(), torch.cuda.Event()]
             self._consumed = [torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()]
+            self._here = [torch.cuda.Event() for _ in range(4)]
+            self._held = [None] * 4
             self.result_event = torch.cuda.Event()
             # three rotating result sets: a result handed out by kick() stays valid for two more kicks
             self._ring = [(torch.empty(self.n_total, self.T1, dtype=torch.int64, device=self.device),
@@ -155,8 +157,6 @@ class TokenExchange:
         side = self._side()
         ev = self._produced[self.seq & 1]
         ev.record(torch.cuda.current_stream(self.device))
-        for t in (tokens, lengths, steps):
-            t.record_stream(side)                                 # the caller may drop them before the stores have run
         self._staged = (tokens, lengths, steps, ev)
 
     def kick(self):
@@ -171,7 +171,7 @@ class TokenExchange:
         cur = torch.cuda.current_stream(self.device)
         tokens, lengths, steps, produced = self._staged
         self._staged = None
-        here = torch.cuda.Event()
+        here = self._here[self._kicks % 4]
         here.record(cur)
         if self._kicks >= 3:
             cur.wait_event(self._consumed[self._kicks % 3])      # bounded run-ahead: the kick of three steps ago is done
@@ -185,6 +185,11 @@ class TokenExchange:
                 self.result_event.record(side)
             self.write(tokens, lengths, steps)
             self._consumed[self._kicks % 3].record(side)
+        # The inputs stay referenced for four more kicks instead of record_stream(): by then the current stream has
+        # waited for this kick's `_consumed` event, so whatever reuses their memory is ordered after the peer stores.
+        # (record_stream defers the reuse to the caching allocator's event polling; its pool then grows by cudaMalloc --
+        # slow and device-synchronising with peer mappings in place -- for the first dozens of steps of every run.)
+        self._held[self._kicks % 4] = (tokens, lengths, steps)
         self._kicks += 1
         return prev
 
