@@ -617,7 +617,8 @@ WIDE_1024 = dict(H.SHIPPED, embedding_dim=1024, hidden_dim=1024, lstm_layers=3) 
 
 @pytest.mark.parametrize("cfg,B,T,rule", [(H.SHIPPED, 200, 40, "same_step"), (H.SHIPPED, 1024, 150, "same_step"),
                                           (H.SHIPPED, 300, 40, "sticky"), (WIDE_1024, 257, 20, "same_step"),
-                                          (dict(H.SHIPPED, hidden_dim=192, embedding_dim=64, lstm_layers=1, vocab_size=77), 130, 25, "sticky")])
+                                          (dict(H.SHIPPED, hidden_dim=192, embedding_dim=64, lstm_layers=1, vocab_size=77), 130, 25, "sticky"),
+                                          (dict(H.HEADLINE, vocab_size=700), 150, 25, "same_step")])   # V > 512: beyond the cluster kernel
 def test_wide_persistent_loop(pkg, cfg, B, T, rule):
     """decode_wide.cu: the whole greedy loop of a wide / multi-layer decoder as ONE cooperative kernel (tiles of 128
     sequences, per-block counters instead of launches).  It runs the same tcgen05 products in the same accumulation
