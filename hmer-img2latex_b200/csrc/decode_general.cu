@@ -1201,6 +1201,19 @@ extern "C" int i2l_decode_sample(const i2l_dec_desc* d_in, const void* packed, c
                              temperature, I2L_STOP_ALL_FINISHED_STICKY, tokens, lengths, steps_run,
                              reinterpret_cast<char*>(workspace) + gen, workspace_bytes - gen, s, &sa);
   }
+  if (!no_persistent && wide_batch_supported(*d, batch) && d->vocab_size <= 512 && max_length > 0 && end_id >= 0 &&
+      end_id < d->vocab_size && tokens != nullptr && lengths != nullptr && steps_run != nullptr) {
+    // wide / multi-layer decoders (the reference's shipped 512 / 512 / 2): the sampling loop inside decode_wide.cu
+    PackedDec lay = dec_layout(*d);
+    size_t gen = carve(*d, batch, max_length, nullptr).bytes;
+    I2L_REQUIRE(workspace_bytes >= gen + wide_workspace_bytes(*d, batch, max_length), "i2l_decode_sample: workspace too small");
+    PersistentSampleArgs sa{};
+    sa.top_k = top_k; sa.top_p = top_p;
+    sa.do_sample = temperature > 0.f && (top_k > 0 || top_p > 0.0f);               // predictor.py:330
+    sa.seed = seed; sa.offset = offset; sa.uniforms = uniforms; sa.probs_trace = probs_trace;
+    return wide_greedy(*d, packed, lay, enc, batch, start_id, end_id, max_length, temperature, I2L_STOP_ALL_FINISHED_STICKY,
+                       tokens, lengths, steps_run, reinterpret_cast<char*>(workspace) + gen, workspace_bytes - gen, s, &sa);
+  }
   return run_loop(d, packed, enc, batch, start_id, end_id, max_length, temperature,
                   I2L_STOP_ALL_FINISHED_STICKY, true, top_k, top_p, seed, offset, uniforms, tokens, lengths,
                   steps_run, probs_trace, workspace, workspace_bytes, s);

@@ -93,7 +93,7 @@ bool wide_batch_supported(const i2l_dec_desc& d, int rows);
 size_t wide_workspace_bytes(const i2l_dec_desc& d, int rows, int max_length);
 int wide_greedy(const i2l_dec_desc& d, const void* packed, const PackedDec& lay, const float* enc, int batch, int start_id,
                 int end_id, int max_length, float temperature, int stop_rule, int64_t* tokens, int32_t* lengths,
-                int32_t* steps_run, void* ws, size_t ws_bytes, cudaStream_t s);
+                int32_t* steps_run, void* ws, size_t ws_bytes, cudaStream_t s, const PersistentSampleArgs* sample = nullptr);
 int wide_aborted(const void* ws, const i2l_dec_desc& d, int rows, int max_length, int* out);
 
 }  // namespace i2l

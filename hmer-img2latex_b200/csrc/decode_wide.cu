@@ -31,6 +31,7 @@
 //             all remaining tiles dead, the kernel ends and the host call reports the failure instead of hanging.
 #include "decode_kernels.cuh"
 #include "tc_common.cuh"
+#include "sample_select.cuh"
 #include <limits.h>
 #include <stdlib.h>
 
@@ -77,6 +78,15 @@ struct WideParams {
   int start_id, end_id, stop_rule;
   float temperature;
   long long* dbg_ts;                // diagnostics build: clock64 stamps of CTA 0, [step][8]
+  // sampling mode (Predictor.predict_batch, training/predictor.py:295-335): the logits tiles write whole rows, a
+  // selection phase (one epilogue warp per row, sample_select.cuh: the routine of the other sampling paths) draws
+  float* logits;                    // [Bp][VP] fp32, VP = 32 NV
+  int* tokbuf;                      // [2 step parities][Bp]
+  int VP, top_k, do_sample;
+  float top_p;
+  unsigned long long seed, offset;
+  const float* uniforms;            // [T][B] or null (Philox)
+  float* probs_trace;               // [T][B][V] or null
 };
 
 #ifdef I2L_DIAG
@@ -112,6 +122,8 @@ __device__ __forceinline__ bool block_dead(const WideParams& P, int mb, int s) {
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// MODE 0: greedy argmax (64-bit atomicMax keys); MODE 1: temperature / top-k / top-p sampling (V <= 512)
+template <int MODE>
 __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_constant__ WideParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
   const uint32_t tmem = *tmem_slot;
   const int G = gridDim.x, cta = blockIdx.x;
   const int L = P.L, NT = P.NT, NV = P.NV, KB = P.KB;
-  const unsigned PS = (unsigned)(L * NT + NV);                 // tiles of one block per step
+  const unsigned PS = (unsigned)(L * NT + NV + (MODE == 1 ? NT : 0));   // tiles (+ selection slices) of one block per step
   const int n_lt = P.MB * NT, n_vt = P.MB * NV;                // tiles per layer phase / logits phase
 
   if (warp == 0) {
@@ -240,6 +252,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
     uint32_t it = 0;
     // token of a row = low word of the block's 64-bit (logit, ~index) maximum of the previous step
     auto token_of = [&](int mb, int step) {
+      if (MODE == 1) return __ldcg(P.tokbuf + (size_t)(step & 1) * P.Bp + mb * WD_BM + r);
       const unsigned long long k = __ldcg(P.best + ((size_t)(step & 1) * P.MB + mb) * 128 + r);
       return (int)(0xFFFFFFFFu - (uint32_t)k);
     };
@@ -388,7 +401,14 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
         uint32_t acc[16];
         tc_ld16_nowait(tmem + lane_addr + a * 128 + half * 16, acc);
         tc_wait_ld();
-        if (!dead) {
+        if (!dead && MODE == 1) {
+          // sampling: the raw logits (+ bias) of this thread's 16 columns, whole rows for the selection phase
+          float4* dst = reinterpret_cast<float4*>(P.logits + ((size_t)mb * WD_BM + r) * P.VP + nv * WD_LN + half * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            __stcg(dst + i, make_float4(__uint_as_float(acc[4 * i]) + bv[4 * i], __uint_as_float(acc[4 * i + 1]) + bv[4 * i + 1],
+                                        __uint_as_float(acc[4 * i + 2]) + bv[4 * i + 2], __uint_as_float(acc[4 * i + 3]) + bv[4 * i + 3]));
+        } else if (!dead) {
           float best = 0.f; int bi = -1;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -412,6 +432,34 @@ __global__ void __launch_bounds__(WD_THREADS, 1) wide_loop_kernel(const __grid_c
         }
         publish(a, mb, dead);
         if (et == 0) WD_TS(s, 7);
+      }
+      if (MODE == 1) {
+        // ---- selection: the 128 rows of a block are spread over its NT layer-tile owners, one epilogue warp per row
+        const int rp = (WD_BM + NT - 1) / NT;
+        for (int t = cta; t < n_lt; t += G) {
+          const int mb = t / NT, nt = t - mb * NT;
+          if (et == 0) misc[4] = wait_count(P, mb, (unsigned)s * PS + (unsigned)(L * NT + NV), s) ? 0 : 1;
+          epi_bar();
+          const bool dead = misc[4] != 0;
+          if (!dead) {
+            const int r_end = min(WD_BM, (nt + 1) * rp);
+            for (int rr = nt * rp + (warp - 2); rr < r_end; rr += 8) {
+              const int row = mb * WD_BM + rr;
+              if (row >= P.B) continue;
+              const float* x = P.logits + (size_t)row * P.VP;
+              float lg[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) lg[i] = (16 * lane + i) < P.V ? __ldcg(x + 16 * lane + i) : 0.f;
+              float u = 0.f;
+              if (P.do_sample) u = P.uniforms ? P.uniforms[(size_t)s * P.B + row] : philox_uniform(P.seed, P.offset + (uint64_t)s * P.B + row);
+              const int chosen = warp_sample_select(lg, P.V, lane, P.temperature, P.top_k, P.top_p, P.do_sample, u,
+                                                    P.probs_trace ? P.probs_trace + ((size_t)s * P.B + row) * P.V : nullptr);
+              if (lane == 0) __stcg(P.tokbuf + (size_t)par * P.Bp + row, chosen);
+            }
+          }
+          epi_bar();
+          if (et == 0 && !dead) { __threadfence(); atomicAdd(P.cnt + mb, 1u); }
+        }
       }
     }
     // ---- the token of the last step: appended by the owner tile of every block that is still running
@@ -479,7 +527,7 @@ __global__ void wide_finalize_kernel(const int* first_end, const unsigned char* 
 
 struct WWs {
   float* gctx; __nv_bfloat16* encb; __nv_bfloat16* hbuf; float* c; unsigned long long* best; unsigned* cnt; int* stop_at;
-  int* block_steps; int* abort_flag; int* first_end; unsigned char* allend; size_t bytes;
+  int* block_steps; int* abort_flag; int* first_end; unsigned char* allend; float* logits; int* tokbuf; size_t bytes;
 };
 WWs wcarve(const i2l_dec_desc& d, int rows, int T, void* ws) {
   Arena a(ws, (size_t)-1);
@@ -497,6 +545,8 @@ WWs wcarve(const i2l_dec_desc& d, int rows, int T, void* ws) {
   w.abort_flag = a.take<int>(1);
   w.first_end = a.take<int>(rows);
   w.allend = a.take<unsigned char>(MB * (size_t)(T > 0 ? T : 1));
+  w.logits = a.take<float>(Bp * (size_t)cdiv(d.vocab_size, WD_LN) * WD_LN);   // sampling mode only
+  w.tokbuf = a.take<int>(2 * Bp);
   w.bytes = align_up(a.off, 256);
   return w;
 }
@@ -522,7 +572,8 @@ bool wide_batch_supported(const i2l_dec_desc& d, int rows) { return wide_support
 
 int wide_greedy(const i2l_dec_desc& d, const void* packed, const PackedDec& lay, const float* enc, int batch, int start_id,
                 int end_id, int max_length, float temperature, int stop_rule, int64_t* tokens, int32_t* lengths,
-                int32_t* steps_run, void* ws, size_t ws_bytes, cudaStream_t s) {
+                int32_t* steps_run, void* ws, size_t ws_bytes, cudaStream_t s, const PersistentSampleArgs* sample) {
+  I2L_REQUIRE(sample == nullptr || d.vocab_size <= 512, "wide_greedy: the in-kernel selection covers V <= 512");
   I2L_REQUIRE(start_id >= 0 && start_id < d.vocab_size, "decode loop: start token %d outside [0, %d) (nn.Embedding raises IndexError)",
               start_id, d.vocab_size);
   I2L_REQUIRE(lay.g16c != 0, "wide_greedy: packed weights lack the cell-ordered bf16 section");
@@ -563,9 +614,16 @@ int wide_greedy(const i2l_dec_desc& d, const void* packed, const PackedDec& lay,
     P.start_id = start_id; P.end_id = end_id; P.stop_rule = stop_rule; P.temperature = temperature;
     const int grid = wide_grid(d, batch);
     I2L_REQUIRE(grid > 0, "wide_greedy: %d sequences need more tiles per CTA than the loop covers", batch);
-    I2L_CUDA_OK(cudaFuncSetAttribute(wide_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM));
+    P.logits = w.logits; P.tokbuf = w.tokbuf; P.VP = P.NV * WD_LN;
+    if (sample) {
+      P.top_k = sample->top_k; P.top_p = sample->top_p; P.do_sample = sample->do_sample;
+      P.seed = sample->seed; P.offset = sample->offset; P.uniforms = sample->uniforms; P.probs_trace = sample->probs_trace;
+    }
+    const void* kern = sample ? (const void*)wide_loop_kernel<1> : (const void*)wide_loop_kernel<0>;
+    I2L_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WD_SMEM));
     int per_sm = 0;
-    I2L_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_loop_kernel, WD_THREADS, WD_SMEM));
+    if (sample) I2L_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_loop_kernel<1>, WD_THREADS, WD_SMEM));
+    else I2L_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_loop_kernel<0>, WD_THREADS, WD_SMEM));
     I2L_REQUIRE(per_sm >= 1 && grid <= per_sm * num_sms(), "wide_greedy: the cooperative grid (%d CTAs) is not co-resident", grid);
 #ifdef I2L_DIAG
     static long long* ts_dev = nullptr;                        // I2L_WIDE_TS=1: per-phase clock stamps of CTA 0, printed after a sync
@@ -575,8 +633,8 @@ int wide_greedy(const i2l_dec_desc& d, const void* packed, const PackedDec& lay,
 #endif
     void* args[] = {(void*)&P};
     {
-      KernelTimer kt("dec.greedy_wide", s);
-      I2L_CUDA_OK(cudaLaunchCooperativeKernel((const void*)wide_loop_kernel, dim3(grid), dim3(WD_THREADS), args, WD_SMEM, s));
+      KernelTimer kt(sample ? "dec.sample_wide" : "dec.greedy_wide", s);
+      I2L_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(WD_THREADS), args, WD_SMEM, s));
       count_launch();
     }
 #ifdef I2L_DIAG

@@ -98,7 +98,6 @@ __device__ __forceinline__ int warp_sample_select(const float (&logit)[16], int 
 #pragma unroll
   for (int i = 0; i < 16; ++i) { const float e = (16 * lane + i) < V ? __expf(po[i] - lm) : 0.f; po[i] = e; ls += e; }
   const float s = warp_sum(ls);
-#pragma unroll
   const RowDiv ds = row_div(s);
 #pragma unroll
   for (int i = 0; i < 16; ++i) po[i] = div_by(po[i], ds);

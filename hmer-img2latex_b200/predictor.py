@@ -36,12 +36,21 @@ class Predictor:
         self.tokenizer = tokenizer
 
     @classmethod
-    def from_checkpoint(cls, checkpoint_path: str, device=None, precision: Optional[str] = None) -> "Predictor":
+    def from_checkpoint(cls, checkpoint_path: str, device=None, precision: Optional[str] = None,
+                        allow_unsafe_pickle: bool = False) -> "Predictor":
         """Reference checkpoints (layout written by training/trainer.py:207-221) consumed exactly as
         training/predictor.py:61-137 does: tokenizer from ``tokenizer_config``, encoder parameters from
         ``config.model.encoder.{cnn|resnet}``, ``config.model.embedding_dim`` (default 256) for both halves,
         ``model_state_dict`` loaded strictly."""
-        ck = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+        # The trainer's checkpoints are plain dicts / lists / tensors (training/trainer.py:207-221): the safe unpickler is
+        # enough.  Files that need arbitrary objects are loaded only on explicit request (allow_unsafe_pickle=True).
+        try:
+            ck = torch.load(checkpoint_path, map_location="cpu", weights_only=True)
+        except Exception as e:
+            if not allow_unsafe_pickle:
+                raise RuntimeError(f"{checkpoint_path}: not loadable with weights_only=True ({e}); pass "
+                                   "allow_unsafe_pickle=True if the file is trusted") from e
+            ck = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
         config = ck.get("config", {})
         model_config = config.get("model", {})
         model_type = model_config.get("name", "cnn_lstm")

@@ -62,27 +62,51 @@ class _ImagePlan(C.Structure):        # mirrors ImagePlan in csrc/preprocess.cu
 
 class _PinnedPool:
     """Two reusable pinned staging buffers (cudaHostAlloc of tens of MB per batch would cost more than the
-    copy).  A buffer is handed out again only after the H2D copy that last read it has completed."""
+    copy).  A slot belongs to the plan that took it until that plan's `run()` has queued its H2D copy (`mark`); it is
+    handed out again only after that copy has completed.  A plan created while both slots are still held by un-run
+    plans (or by other threads: loader threads, two Predictors) gets a private, unpooled pinned buffer instead of
+    overwriting pixels somebody still needs.  All state changes happen under one lock."""
 
     def __init__(self):
+        import threading
+        self._lock = threading.Lock()
         self._bufs = [None, None]
         self._events = [None, None]
+        self._held = [False, False]
         self._turn = 0
 
     def get(self, nbytes: int):
-        i = self._turn
-        self._turn ^= 1
-        if self._events[i] is not None:
-            self._events[i].synchronize()
-            self._events[i] = None
+        with self._lock:
+            order = (self._turn, self._turn ^ 1)
+            i = next((k for k in order if not self._held[k]), -1)
+            if i >= 0:
+                self._held[i] = True
+                self._turn = i ^ 1
+                ev, self._events[i] = self._events[i], None
+        if i < 0:                                                 # both slots belong to plans that have not run yet
+            return -1, torch.empty(max(int(nbytes), 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        if ev is not None:
+            ev.synchronize()                                      # the copy that last read this slot (outside the lock)
         b = self._bufs[i]
         if b is None or b.numel() < nbytes:
             b = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
-            self._bufs[i] = b
+            self._bufs[i] = b                                     # only the holder of slot i touches _bufs[i]
         return i, b[:nbytes]
 
     def mark(self, i: int, event) -> None:
-        self._events[i] = event
+        """the plan's H2D copy has been queued: the slot is free for the next taker once `event` has fired"""
+        if i < 0:
+            return
+        with self._lock:
+            self._events[i] = event
+            self._held[i] = False
+
+    def release(self, i: int) -> None:
+        """a plan that is dropped without having run gives its slot back"""
+        if i < 0:
+            return
+        with self._lock:
+            self._held[i] = False
 
 
 _POOL = _PinnedPool()
@@ -158,6 +182,12 @@ class ResizePlan:
             out.append(d)
         return out
 
+    def __del__(self):
+        try:
+            _POOL.release(getattr(self, "_slot", -1))
+        except Exception:
+            pass
+
     def run(self, device, workspace: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One H2D copy (pixels + plan) and two launches -> uint8 (n, C_out, Ht, Wt) on `device`."""
         device = torch.device(device)
@@ -168,6 +198,8 @@ class ResizePlan:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(device))
             _POOL.mark(self._slot, ev)
+            self._slot = -1                                       # a second run() re-reads the host slice it no longer owns:
+            # allowed while no other plan has taken the slot since (as before); the pool no longer tracks this plan
             if out is None:
                 out = torch.empty(self.n, self.out_channels, self.target_height, self.target_width, dtype=torch.uint8,
                                   device=device)

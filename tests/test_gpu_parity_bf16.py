@@ -666,6 +666,47 @@ def test_wide_persistent_loop(pkg, cfg, B, T, rule):
             assert not bad, f"rows diverging at a step with a clear margin: {bad[:10]}"
 
 
+@pytest.mark.parametrize("cfg,B,T,args", [(H.SHIPPED, 300, 40, (0.8, 50, 0.9)), (H.SHIPPED, 130, 30, (1.0, 0, 0.0)),
+                                          (WIDE_1024, 140, 16, (0.9, 20, 0.0)),
+                                          (dict(H.SHIPPED, hidden_dim=192, embedding_dim=64, lstm_layers=1, vocab_size=77), 200, 25, (0.7, 0, 0.8))])
+def test_wide_persistent_sampling(pkg, cfg, B, T, args):
+    """Predictor.predict_batch's loop (predictor.py:283-347) on a wide decoder inside decode_wide.cu: the logits tiles
+    write whole rows, one epilogue warp per row runs the selection routine of the other sampling paths
+    (sample_select.cuh).  Same products, same routine, same uniforms as the stream-ordered loop => identical tokens (every
+    row up to its own END: a 128-sequence block stops once ITS rows have finished), lengths, steps and filtered
+    distributions; every draw is the inverse CDF of the kernel's own distribution."""
+    temperature, top_k, top_p = args
+    N = pkg._native
+    p = oracle.make_params(cfg, 6)
+    p["decoder.output_layer.weight"] *= 4.0
+    p["decoder.output_layer.bias"][H.END] += 2.0
+    m16 = H.build_model(pkg, cfg, p, precision="bf16")
+    g = torch.Generator().manual_seed(41 + B)
+    enc = torch.relu(torch.randn(B, cfg["embedding_dim"], generator=g)).cuda()
+    u = torch.rand(T, B, generator=g)
+    lib = N.lib()
+    m16.decoder.sample(enc[:2], H.START, H.END, 2, temperature, top_k, top_p, uniforms=u[:2, :2].contiguous())   # packs the weights
+    l0 = lib.i2l_launch_count()
+    tok_w, len_w, st_w, pr_w = m16.decoder.sample(enc, H.START, H.END, T, temperature, top_k, top_p, uniforms=u, return_probs=True)
+    torch.cuda.synchronize()
+    assert lib.i2l_launch_count() - l0 <= 8, "the sampling loop did not take the persistent kernel"
+    m16.decoder.streamed = True
+    tok_s, len_s, st_s, pr_s = m16.decoder.sample(enc, H.START, H.END, T, temperature, top_k, top_p, uniforms=u, return_probs=True)
+    m16.decoder.streamed = False
+    n = int(st_s)
+    assert int(st_w) == n and torch.equal(len_w, len_s)
+    tw, ts, ln = tok_w.cpu(), tok_s.cpu(), len_s.cpu()
+    pw, ps = pr_w.cpu(), pr_s.cpu()
+    for b in range(B):
+        k = min(int(ln[b]), n)
+        assert tw[b, : k + 1].tolist() == ts[b, : k + 1].tolist(), b
+        assert torch.equal(pw[:k, b], ps[:k, b]), b
+    # Philox draws: reproducible, and the same as the stream-ordered loop's
+    a1 = m16.decoder.sample(enc, H.START, H.END, T, temperature, top_k, top_p, seed=7, offset=3)
+    a2 = m16.decoder.sample(enc, H.START, H.END, T, temperature, top_k, top_p, seed=7, offset=3)
+    assert torch.equal(a1[0], a2[0]) and torch.equal(a1[1], a2[1])
+
+
 # ---- the tcgen05 CNN encoder beyond the benchmark shape (cnn_bf16.cu: C in {1,3}, H % 64 == 0, W % 32 == 0) -----------
 def _cnn_cfg(c, h, w):
     return dict(H.HEADLINE, channels=c, img_height=h, img_width=w)

@@ -134,3 +134,17 @@ def test_resize_errors(pkg):
     with pytest.raises(TypeError):
         P.ResizePlan([np.zeros((4, 4), np.float32)], 16, 100)
     assert P.ResizePlan([], 16, 100).run("cuda").shape == (0, 1, 16, 100)
+
+
+def test_staging_pool_never_overwrites_an_unrun_plan(pkg):
+    """three plans created before any of them runs must each keep their own pixels (the third one gets a
+    private pinned buffer instead of recycling a slot an un-run plan still points into), in any run order."""
+    import numpy as np
+    P = pkg.preprocess
+    g = np.random.default_rng(5)
+    batches = [[g.integers(0, 256, (40 + 3 * k, 200 + 11 * k), dtype=np.uint8) for _ in range(3)] for k in range(4)]
+    ref = [P.ResizePlan(b, 64, 320).run("cuda").cpu() for b in batches]
+    plans = [P.ResizePlan(b, 64, 320) for b in batches]           # four un-run plans alive at once
+    assert len({p.host.data_ptr() for p in plans}) == 4
+    for k in (2, 0, 3, 1):
+        assert torch.equal(plans[k].run("cuda").cpu(), ref[k])

@@ -31,3 +31,21 @@ for streamed in (False, True):
         keep = out[0].clone()
     else:
         print("identical tokens:", bool(torch.equal(keep, out[0])))
+
+# sampling loop (Predictor.predict_batch): temperature 0.8, top-k 50, top-p 0.9, fixed uniforms
+if len(sys.argv) <= 6 or sys.argv[6] != "nosample":
+    u = torch.rand(T, B, device="cuda")
+    for streamed in (False, True):
+        dec.streamed = streamed
+        for _ in range(2):
+            out = dec.sample(enc, 1, 2, T, 0.8, 50, 0.9, uniforms=u)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            out = dec.sample(enc, 1, 2, T, 0.8, 50, 0.9, uniforms=u)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        n = max(int(out[2]), 1)
+        print(f"sampling {'stream-ordered graph loop' if streamed else 'persistent wide kernel'}: {ms:.3f} ms, "
+              f"{ms / n * 1e3:.2f} us/step over {n} steps", flush=True)
