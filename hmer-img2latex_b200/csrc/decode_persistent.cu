@@ -64,7 +64,7 @@ constexpr int SMEM_BYTES_SAMPLE = OFF_RX + CL * LG_BLOCK_BYTES;
 static_assert(SMEM_BYTES_SAMPLE <= 232448, "shared memory budget exceeded");
 
 // BAR_HS + 4 * buf + d: K-block of h buffer `buf` written by the CTA at cluster distance d (rank - d; d = 0: this CTA)
-enum { BAR_W = 0, BAR_LDONE = 3, BAR_GDONE = 4, BAR_TOK = 5, BAR_FINAL = 6, BAR_LG = 7, BAR_HS = 8 };
+enum { BAR_W = 0, BAR_CTX = 1, BAR_LDONE = 3, BAR_GDONE = 4, BAR_TOK = 5, BAR_FINAL = 6, BAR_LG = 7, BAR_HS = 8 };
 
 // debug build of the kernel only (tools/debug_persistent.py): per-phase clock64() stamps of one
 // step of cluster 0 / rank 0, and optional dumps of gates / h / logits of that step
@@ -83,7 +83,9 @@ struct Params {
   const unsigned char* wimg;     // per-rank weight images
   const float* gtok;             // [V][4][128][2]
   const float* bias;             // [512]
-  const float* gctx;             // [B][1024] fp32 (PyTorch gate order)
+  const unsigned char* wctx;     // per-rank W_ctx images (2 tiles, the gate tiles' row order)
+  const float* enc;              // [B][E] fp32 encoder output
+  const float* bsum0;            // [1024] b_ih0 + b_hh0 (PyTorch gate order)
   int64_t* tokens;               // [B][T+1]
   int* first_end;                // [B]
   unsigned char* allend;         // [n_clusters][T]
@@ -131,6 +133,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
     mbar_init(BAR(BAR_TOK), 1);
     mbar_init(BAR(BAR_FINAL), 1);
     mbar_init(BAR(BAR_LG), 1);
+    mbar_init(BAR(BAR_CTX), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     misc[1] = 0;
   }
@@ -145,50 +148,116 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = misc[0];
-  if (warp < 8) {
-    // resident weights -> tensor memory: thread (quadrant q, lane) owns row p = 32q + lane of each
-    // tile; warps 0-3 write K columns [0,64), warps 4-7 columns [64,128) (two bf16 per column)
-    const int p = 32 * (warp & 3) + lane;
-    const uint32_t lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
-    const int half = warp >> 2;
-#pragma unroll 1
-    for (int t = 0; t < 3; ++t) {
-      const uint4* src = reinterpret_cast<const uint4*>(P.wimg + (size_t)rank * WROW_BYTES + ((size_t)t * 128 + p) * (H * 2)) + half * 16;
-      const uint32_t tcol = t == 0 ? TC_WG0 : (t == 1 ? TC_WG1 : TC_WO);
+  const uint32_t TM_L = tmem + TC_L, TM_G0 = tmem + TC_G0, TM_G1 = tmem + TC_G1;
+  const uint64_t dbase = DESC_HI | (uint64_t)(((sbase >> 4) & 0x3FFFu) | (1u << 16));
+  // one 128-row tile of gates / logits: D[row, sequence] += W (TMEM A operand, 16 K-elements = 8 columns per MMA) h^T
+  auto issue_tile = [&](uint32_t d_tmem, uint32_t a_col, uint32_t h_off) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[16];
+    for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 v = __ldg(src + c * 4 + i);
-          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
-        }
-        tc_st16(tmem + lane_addr + tcol + half * 64 + c * 16, r);
+      for (int k = 0; k < 4; ++k) {
+        uint64_t bd = dbase + (uint64_t)((h_off + kb * HSLICE_BYTES + k * 32) >> 4);
+        tc_mma_ts(d_tmem, tmem + a_col + (kb * 4 + k) * 8, bd, IDESC, (kb | k) ? 1u : 0u);
       }
     }
+  };
+  // 128 x 256 bf16 weight tile -> tensor memory: thread (quadrant q, lane) owns row 32q + lane; warps 0-3 write K
+  // columns [0,64), warps 4-7 columns [64,128) (two bf16 per column)
+  auto tile_to_tmem = [&](const unsigned char* tile, uint32_t tcol) {
+    const int prow = 32 * (warp & 3) + lane;
+    const int halfk = warp >> 2;
+    const uint4* src = reinterpret_cast<const uint4*>(tile + (size_t)prow * (H * 2)) + halfk * 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 v = __ldg(src + c * 4 + i);
+        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+      }
+      tc_st16(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + tcol + halfk * 64 + c * 16, r);
+    }
+  };
+  // ---- context term of the gates, once per sequence (attention over src_len == 1 is the identity):
+  // Gctx = W_ih0[:, E:2E] enc^T + b_ih0 + b_hh0 as the kernel's first two MMA tiles.  The W_ctx tiles borrow the tensor-
+  // memory columns of the W_hh tiles, the bf16 copy of the cluster's 32 encoder rows borrows h buffer 0; every epilogue
+  // thread ends up with exactly the 2 x 16 values it adds every step (the separate f32->bf16 + GEMM launches and the
+  // 4 MB round trip through HBM of round 1 are gone).
+  float gctx0[16], gctx1[16];
+  {
+    if (warp < 8) {
+      tile_to_tmem(P.wctx + ((size_t)rank * 2 + 0) * 128 * (H * 2), TC_WG0);
+      tile_to_tmem(P.wctx + ((size_t)rank * 2 + 1) * 128 * (H * 2), TC_WG1);
+      tile_to_tmem(P.wimg + (size_t)rank * WROW_BYTES + (size_t)2 * 128 * (H * 2), TC_WO);     // W_out is not borrowed
+    }
+    // enc rows -> bf16 B operand (K-major SWIZZLE_128B, the layout the cell update writes h in)
+    for (int i = tid; i < NB * (E / 8); i += THREADS) {
+      const int n = i / (E / 8), ch = i % (E / 8);          // sequence, 8-element chunk
+      const int row = row0 + n;
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (row < P.B) {
+        const float4* src = reinterpret_cast<const float4*>(P.enc + (size_t)row * E + ch * 8);
+        const float4 a = __ldg(src), b = __ldg(src + 1);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+        o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                       *reinterpret_cast<uint32_t*>(&h3));
+      }
+      const int kb = ch >> 3, c8 = ch & 7;
+      *reinterpret_cast<uint4*>(smem + OFF_H + kb * HSLICE_BYTES + n * 128 + ((c8 ^ (n & 7)) << 4)) = o;
+    }
+    if (warp < 8) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 8) {
+      if (elect_one()) {
+        issue_tile(TM_G0, TC_WG0, OFF_H);
+        issue_tile(TM_G1, TC_WG1, OFF_H);
+        tc_commit(BAR(BAR_CTX));
+      }
+      __syncwarp();
+    }
+    mbar_wait(BAR(BAR_CTX), 0);
+    tc_fence_after();
+    if (warp < 8) {
+      const int q_ = warp & 3, cg_ = warp >> 2;
+      const int u_ = 16 * q_ + (lane & 15);
+      const bool hi_ = lane >= 16;
+      uint32_t r0[16], r1[16];
+      tc_ld16_nowait(TM_G0 + ((uint32_t)(32 * q_) << 16) + 16 * cg_, r0);
+      tc_ld16_nowait(TM_G1 + ((uint32_t)(32 * q_) << 16) + 16 * cg_, r1);
+      tc_wait_ld();
+      const float b0 = P.bsum0[(hi_ ? 1 : 0) * 256 + 64 * rank + u_], b1 = P.bsum0[(hi_ ? 3 : 2) * 256 + 64 * rank + u_];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const bool live = row0 + 16 * cg_ + j < P.B;
+        gctx0[j] = live ? __uint_as_float(r0[j]) + b0 : 0.f;
+        gctx1[j] = live ? __uint_as_float(r1[j]) + b1 : 0.f;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                 // the context MMAs have completed and been read: their operands can be replaced
+    tc_fence_after();
+  }
+  if (warp < 8) {
+    // resident W_hh tiles -> tensor memory; h_0 = 0 back in buffer 0 (decoder.py:253-266)
+    tile_to_tmem(P.wimg + (size_t)rank * WROW_BYTES + (size_t)0 * 128 * (H * 2), TC_WG0);
+    tile_to_tmem(P.wimg + (size_t)rank * WROW_BYTES + (size_t)1 * 128 * (H * 2), TC_WG1);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
   }
+  for (int i = tid; i < HB_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem + OFF_H)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
   __syncthreads();
   tc_fence_after();
   cluster_sync_all();   // every CTA's barriers are initialised before any remote traffic
 
-  const uint32_t TM_L = tmem + TC_L, TM_G0 = tmem + TC_G0, TM_G1 = tmem + TC_G1;
 
   if (warp == 8) {
     // =========================== MMA issuer warp ===========================
     // the whole warp stays converged (waits are executed by all lanes); one elected lane issues
-    const uint64_t dbase = DESC_HI | (uint64_t)(((sbase >> 4) & 0x3FFFu) | (1u << 16));
-    auto issue_tile = [&](uint32_t d_tmem, uint32_t a_col, uint32_t h_off) {
-#pragma unroll
-      for (int kb = 0; kb < 4; ++kb) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint64_t bd = dbase + (uint64_t)((h_off + kb * HSLICE_BYTES + k * 32) >> 4);
-          tc_mma_ts(d_tmem, tmem + a_col + (kb * 4 + k) * 8, bd, IDESC, (kb | k) ? 1u : 0u);   // 16 K-elements = 8 columns
-        }
-      }
-    };
     tc_fence_after();
     if (elect_one()) {   // gates of step 0 from h_0 = 0 (buffer 0)
       issue_tile(TM_G0, TC_WG0, OFF_H);
@@ -243,19 +312,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
     const bool hi = lane >= 16;                           // lanes 16-31 hold f / o and the cell state
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
     const int col0 = 16 * cg;
-    float gctx0[16], gctx1[16], c[16];
+    float c[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      int row = row0 + col0 + j;
-      c[j] = 0.f;
-      if (row < P.B) {
-        const float* g = P.gctx + (size_t)row * 1024 + 64 * rank + u;
-        gctx0[j] = g[(hi ? 1 : 0) * 256];
-        gctx1[j] = g[(hi ? 3 : 2) * 256];
-      } else {
-        gctx0[j] = 0.f; gctx1[j] = 0.f;
-      }
-    }
+    for (int j = 0; j < 16; ++j) c[j] = 0.f;
     const float bias = P.bias[128 * rank + p];
     const float s1 = hi ? 0.5f : 1.0f, m1 = hi ? 0.5f : 1.0f, b1 = hi ? 0.5f : 0.0f;
     int tok[16];
@@ -269,6 +328,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
     int* tok_s = reinterpret_cast<int*>(smem + OFF_TOK);
     const float2* gt_base = reinterpret_cast<const float2*>(P.gtok + (size_t)rank * 256) + p;   // [V][rank][128 rows][tile 0,1]
     int s = 0;
+    if (MODE != 2 && rank == 0 && xt >= 0 && xt < NB && row0 + xt < P.B) P.tokens[(size_t)(row0 + xt) * (P.T + 1)] = P.start_id;
     float hlast[16];                                      // MODE 2: h of the last step (fp32, before the bf16 rounding)
     if (MODE == 2) {
 #pragma unroll
@@ -542,7 +602,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) persist
       }
     } else if (rank == 0 && xt >= 0 && xt < NB) {
       const int row = row0 + xt;
-      if (row < P.B) P.first_end[row] = fe;
+      if (row < P.B) {
+        P.first_end[row] = fe;
+        // positions past the cluster's last step keep the general path's "never written" value (the separate init
+        // kernel of round 1 wrote -1 everywhere first)
+        for (int t = s + 1; t <= P.T; ++t) P.tokens[(size_t)row * (P.T + 1) + t] = -1;
+      }
       if (xt == 0) P.cluster_steps[cluster] = s;
     }
     if (*reinterpret_cast<volatile uint32_t*>(&misc[1]) && tid == 0) {
@@ -580,6 +645,20 @@ __global__ void pack_weights_kernel(const float* __restrict__ w_hh, const float*
   }
   size_t off = (size_t)r * WROW_BYTES + (((size_t)t * 128 + p) * H + k) * 2;
   *reinterpret_cast<__nv_bfloat16*>(wimg + off) = __float2bfloat16(v);
+}
+
+__global__ void pack_wctx_kernel(const float* __restrict__ w_ih0, unsigned char* __restrict__ img) {
+  // one thread per (rank, tile(0..1), row p, k): W_ih0[:, E:2E] in the row order of the gate tiles (pack_weights_kernel)
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)CL * 2 * 128 * E) return;
+  int k = (int)(i % E);
+  int p = (int)((i / E) % 128);
+  int t = (int)((i / (E * 128)) % 2);
+  int r = (int)(i / ((size_t)E * 128 * 2));
+  int qd = p >> 5, l = p & 31;
+  int unit = 64 * r + 16 * qd + (l & 15);
+  int gate = 2 * t + (l >= 16 ? 1 : 0);
+  reinterpret_cast<__nv_bfloat16*>(img)[i] = __float2bfloat16(w_ih0[(size_t)(gate * H + unit) * (2 * E) + E + k]);
 }
 
 __global__ void pack_gtok_kernel(const float* __restrict__ gtok, int V, float* __restrict__ out) {
@@ -679,6 +758,9 @@ int persistent_pack(const i2l_dec_desc& d, const i2l_dec_params& p, const float*
   I2L_LAUNCH_OK();
   pack_bias_kernel<<<2, 256, 0, s>>>(p.out_b, d.vocab_size, reinterpret_cast<float*>(sec + ps.bias));
   I2L_LAUNCH_OK();
+  n = (size_t)CL * 2 * 128 * E;
+  pack_wctx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p.w_ih[0], sec + ps.wctx);
+  I2L_LAUNCH_OK();
   return I2L_OK;
 }
 
@@ -694,22 +776,19 @@ int persistent_greedy(const i2l_dec_desc& d, const void* section, const float* p
   PSection ps = psection(d.vocab_size);
   const unsigned char* sec = reinterpret_cast<const unsigned char*>(section);
   const int T1 = max_length + 1;
-  {
-    size_t tot = (size_t)batch * T1;
-    persistent_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(tokens, T1, batch, start_id);
+  if (max_length <= 0) {            // no kernel: the START column alone
+    persistent_init_kernel<<<(unsigned)((batch * (size_t)T1 + 255) / 256), 256, 0, s>>>(tokens, T1, batch, start_id);
     I2L_LAUNCH_OK();
   }
-  // per-sequence constant gates: enc W_ih[:, E:2E]^T + b_ih + b_hh  (tcgen05 GEMM, bf16 operands)
-  {
-    KernelTimer kt("dec.gctx_gemm", s);
-    I2L_TRY(make_gctx_bf16(d, packed_f32, lay, enc, batch, w.gctx, w.encb, s));
-  }
+  // (round 1 launched a token-init kernel, an f32 -> bf16 copy of enc and the context-term GEMM here; all three are now
+  // part of the persistent kernel's prologue / tail)
   const int ncl = cdiv(batch, NB);
   if (max_length > 0) {
     Params P{};
     P.wimg = sec + ps.wimg; P.gtok = reinterpret_cast<const float*>(sec + ps.gtok);
     P.bias = reinterpret_cast<const float*>(sec + ps.bias);
-    P.gctx = w.gctx; P.tokens = tokens; P.first_end = w.first_end; P.allend = w.allend; P.cluster_steps = w.cluster_steps;
+    P.wctx = sec + ps.wctx; P.enc = enc; P.bsum0 = packed_f32 + lay.bsum[0];
+    P.tokens = tokens; P.first_end = w.first_end; P.allend = w.allend; P.cluster_steps = w.cluster_steps;
     P.B = batch; P.T = max_length; P.start_id = start_id; P.end_id = end_id; P.stop_rule = stop_rule;
     P.temperature = temperature;
     P.V = d.vocab_size;
@@ -758,11 +837,11 @@ int persistent_forward(const i2l_dec_desc& d, const void* section, const float* 
   if (ws_bytes < w.bytes) { set_error("persistent_forward: workspace too small"); return I2L_ERR_WORKSPACE; }
   PSection ps = psection(d.vocab_size);
   const unsigned char* sec = reinterpret_cast<const unsigned char*>(section);
-  I2L_TRY(make_gctx_bf16(d, packed_f32, lay, enc, batch, w.gctx, w.encb, s));
   Params P{};
   P.wimg = sec + ps.wimg; P.gtok = reinterpret_cast<const float*>(sec + ps.gtok);
   P.bias = reinterpret_cast<const float*>(sec + ps.bias);
-  P.gctx = w.gctx; P.B = batch; P.T = seq_len; P.V = d.vocab_size; P.temperature = 1.0f;
+  P.wctx = sec + ps.wctx; P.enc = enc; P.bsum0 = packed_f32 + lay.bsum[0];
+  P.B = batch; P.T = seq_len; P.V = d.vocab_size; P.temperature = 1.0f;
   P.tok_t = tok_t; P.logits_out = logits; P.h_out = h_out; P.c_out = c_out;
   KernelTimer kt("dec.forward_persistent", s);
   I2L_CUDA_OK(cudaFuncSetAttribute(persistent_greedy_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -24,6 +24,7 @@ struct PSection {
   size_t wimg;      // [4 ranks][3 tiles][128 rows][256] bf16
   size_t gtok;      // fp32 [V][4 ranks][128 rows][2 tiles]
   size_t bias;      // fp32 [512]  (-inf beyond V)
+  size_t wctx;      // [4 ranks][2 tiles][128 rows][256] bf16: W_ih0[:, E:2E] in the row order of the gate tiles
   size_t total;
 };
 PSection psection(int V) {
@@ -32,6 +33,7 @@ PSection psection(int V) {
   s.wimg = o; o += (size_t)CL * WROW_BYTES;
   s.gtok = o; o += (size_t)V * 1024 * 4;
   s.bias = o; o += VMAX * 4;
+  s.wctx = o; o += (size_t)CL * 2 * 128 * E * 2;
   s.total = align_up(o, 1024);
   return s;
 }
