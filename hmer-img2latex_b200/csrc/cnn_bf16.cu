@@ -473,13 +473,15 @@ conv1_u8_kernel(const __grid_constant__ CUtensorMap tmx, const unsigned char* __
     float bias[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { float4 v = reinterpret_cast<const float4*>(bias1)[half * 4 + i]; bias[4 * i] = v.x; bias[4 * i + 1] = v.y; bias[4 * i + 2] = v.z; bias[4 * i + 3] = v.w; }
+    // act1 layout [plane = (ph&1)*2 + (pw&1)][H/4][B][W/4][32] with ph = 8 th + (m >> 4), pw = 16 tw + (m & 15): the pixel
+    // index splits into a per-thread constant and a per-tile part (32-bit: B H W / 4 pixels)
+    const int rowpix = B * QW;                                  // pixels of one plane row
+    const int pix_thread = ((((m >> 4) & 1) * 2 + (m & 1)) * QH + (m >> 5)) * rowpix + ((m & 15) >> 1);
     TileIt t(tile_beg, TW, TH);
     for (int it = 0; it < nt; ++it, t.advance(1)) {
       const int g = it & 1; const uint32_t par = (it >> 1) & 1;
-      const int ph = t.th * 8 + (m >> 4), pw = t.tw * 16 + (m & 15);
-      // act1 layout [plane = (ph&1)*2 + (pw&1)][H/4][B][W/4][32]
-      const size_t pix = ((((size_t)((ph & 1) * 2 + (pw & 1)) * QH + (ph >> 1)) * B + t.b) * QW + (pw >> 1));
-      uint4* dst = reinterpret_cast<uint4*>(act1 + pix * C1 + half * 16);
+      const int pix = pix_thread + (t.th * 4) * rowpix + t.b * QW + t.tw * 8;
+      uint4* dst = reinterpret_cast<uint4*>(act1 + (size_t)pix * C1 + half * 16);
       mbar_wait(TFULL(g), par);
       tc_fence_after();
       const uint32_t ta = tmem + ((uint32_t)(32 * q) << 16) + g * 128 + half * 16;
