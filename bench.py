@@ -410,10 +410,11 @@ def run_ours(args):
                     "launch_ms": round(tot / cnt, 4), "share_of_step": round(tot / ms, 4)}
     # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
+        tr_file = "r2_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r2_traffic.json")) else "r1_traffic.json"
+        tr = json.load(open(os.path.join(ROOT, "profiles", tr_file)))["kernels"]
         if roof and roof["kernel"] in tr and B == 1024:
             roof["traffic"] = tr[roof["kernel"]]["dram_bytes_per_launch"]
-            roof["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json)"
+            roof["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/%s)" % tr_file
     except Exception:
         pass
     rooflines = {}
