@@ -116,7 +116,8 @@ class Seq2SeqModel(nn.Module):
         copy of batch i+1 runs on a copy stream while batch i is encoded and decoded, and the
         token ids come back through a pinned buffer.  Yields (tokens (B,max_length+1) int64 on the
         host, lengths (B) int32 on the host, steps_run) per batch -- same content as
-        encoder + LSTMDecoder.greedy.  Not in the reference (its Predictor copies and computes
+        encoder + LSTMDecoder.greedy.  The yielded tensors are pinned buffers owned by the model (two slots, reused by
+        later batches AND later calls): copy what must outlive the next iteration.  Not in the reference (its Predictor copies and computes
         serially, training/predictor.py:245-262).
 
         ``exchange`` (a ``dist.TokenExchange``, batch-sharded multi-GPU serving): every rank streams ITS shard of each
@@ -136,9 +137,17 @@ class Seq2SeqModel(nn.Module):
 
         def read_back(slot: int, tokens, lengths, steps, after=None) -> None:
             if out_tok[slot] is None or out_tok[slot].shape != tokens.shape:
-                out_tok[slot] = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
-                out_len[slot] = torch.empty(lengths.shape, dtype=lengths.dtype).pin_memory()
-                out_steps[slot] = torch.empty((), dtype=steps.dtype).pin_memory()
+                # pinned result buffers are kept on the model across calls: cudaHostAlloc costs milliseconds, and a
+                # short stream would pay it for every slot inside its own run
+                key = (slot, tuple(tokens.shape), tuple(lengths.shape), tokens.dtype, lengths.dtype, steps.dtype)
+                cache = self.__dict__.setdefault("_pinned_results", {})
+                if key not in cache:
+                    if len(cache) >= 8:
+                        cache.clear()
+                    cache[key] = (torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory(),
+                                  torch.empty(lengths.shape, dtype=lengths.dtype).pin_memory(),
+                                  torch.empty((), dtype=steps.dtype).pin_memory())
+                out_tok[slot], out_len[slot], out_steps[slot] = cache[key]
             if after is None:
                 computed[slot].record(compute)
             with torch.cuda.stream(out_stream):
