@@ -13,6 +13,9 @@
 //   weights are the (resident) A operand with M = 128 and the 32 sequences are the N = 32
 //   B operand (h as bf16, 16 KB, double buffered).  Accumulators live in TMEM (3 x 32 cols).
 //
+//   prologue:   Gctx = W_ih0[:, E:2E] enc^T + b_ih0 + b_hh0 as the kernel's first two MMA tiles (the W_ctx tiles borrow
+//               the tensor-memory columns of W_hh, the bf16 copy of the cluster's encoder rows borrows h buffer 0):
+//               every epilogue thread ends up with the 2 x 16 per-sequence constants it adds each step
 //   per step:   MMA-G  gates  = W_hh h_s            (tcgen05, issued by one thread)
 //               Epi-G  + Gtok[tok_s] + Gctx, sigmoid/tanh (MUFU.TANH), c/h update in
 //                      registers; i/g and f/o of a unit sit in lanes l and l+16 of one warp

@@ -20,11 +20,15 @@
 //   warp 0    TMA producer: weight tiles are requested BEFORE the flag wait (they do not depend on it), the h tiles
 //             after it; layer l >= 1 runs its h_l(s-1) W_hh half first, which is a whole step old
 //   warp 1    MMA issuer (tcgen05, fp32 accumulators in TMEM, two accumulator slots)
-//   warps 2-5 epilogue: LSTM cell (MUFU.TANH activations as in the other decode kernels) -> c (fp32) and h (bf16,
-//             double buffered by step parity) in L2-resident global memory; or per-row argmax partials of the tile.
-//             The layer-0 epilogue of step s first reduces the NV argmax partials of step s-1 to the token (every tile
-//             of the block does so redundantly; tile column 0 appends it and keeps the EOS bookkeeping), then gathers
-//             that token's Gtok row.  Its MMAs do not wait for the token, only its epilogue does.
+//   warps 2-9 epilogue (TMEM lane quadrant x 16 of the tile's 32 units): LSTM cell (MUFU.TANH activations as in the other
+//             decode kernels) -> c (fp32) and h (bf16, double buffered by step parity) in L2-resident global memory.
+//             A logits tile folds its columns of a row into a 64-bit atomicMax key (order-preserving logit bits, then
+//             ~index: the lowest index wins ties like torch.argmax); the layer-0 epilogue of step s reads ONE key per
+//             row = the token of step s-1 (every tile of the block does so redundantly; tile column 0 appends it and
+//             keeps the EOS bookkeeping), then gathers that token's Gtok row.  Its MMAs do not wait for the token, only
+//             its epilogue does.  A tile is published by ONE release (CTA barrier, then fence + atomic of one thread).
+//   sampling  MODE 1 (Predictor.predict_batch, V <= 512): the logits tiles store whole rows, a fourth phase spreads the
+//             128 rows of a block over its layer-tile owners, one epilogue warp per row runs sample_select.cuh
 //   stop      STICKY: a block whose sequences have all finished publishes stop_at[block]; its later tiles are "dead"
 //             (processed without waiting, nothing written).  ALL_END_SAME_STEP: per-step flags, resolved by the
 //             finalize kernel, as in decode_persistent.cu.  Every spin is bounded (~2 s): on expiry an abort flag makes
