@@ -32,7 +32,7 @@
 //   stop      STICKY: a block whose sequences have all finished publishes stop_at[block]; its later tiles are "dead"
 //             (processed without waiting, nothing written).  ALL_END_SAME_STEP: per-step flags, resolved by the
 //             finalize kernel, as in decode_persistent.cu.  Every spin is bounded (~2 s): on expiry an abort flag makes
-//             all remaining tiles dead, the kernel ends and the host call reports the failure instead of hanging.
+//             all remaining tiles dead, the kernel ends and the finalize kernel reports steps_run = -1 (an exception on the host side).
 #include "decode_kernels.cuh"
 #include "tc_common.cuh"
 #include "sample_select.cuh"
@@ -500,7 +500,14 @@ __global__ void wide_init_kernel(int64_t* tokens, int T1, int B, int start_id, i
 }
 
 __global__ void wide_finalize_kernel(const int* first_end, const unsigned char* allend, const int* block_steps, int MB, int B,
-                                     int T, int stop_rule, int32_t* lengths, int32_t* steps_out) {
+                                     int T, int stop_rule, int32_t* lengths, int32_t* steps_out, const int* abort_flag) {
+  if (abort_flag != nullptr && *abort_flag != 0) {
+    // a spin of the loop ran into its bound (a CTA that never became resident, a lost update): the tokens are garbage.
+    // steps_run = -1 is what the host side turns into an exception at its one synchronisation point.
+    if (threadIdx.x == 0 && steps_out) *steps_out = -1;
+    if (lengths) for (int i = threadIdx.x; i < B; i += blockDim.x) lengths[i] = -1;
+    return;
+  }
   // one block: steps_run = first step at which every 128-sequence block reported "all rows emitted END"
   // (ALL_END_SAME_STEP, seq2seq.py:220), or the last block to finish (sticky rule, predictor.py:343-347); then lengths
   __shared__ int steps_sh;
@@ -658,7 +665,8 @@ int wide_greedy(const i2l_dec_desc& d, const void* packed, const PackedDec& lay,
   } else {
     I2L_CUDA_OK(cudaMemsetAsync(w.block_steps, 0, (size_t)MB * 4, s));
   }
-  wide_finalize_kernel<<<1, 256, 0, s>>>(w.first_end, w.allend, w.block_steps, MB, batch, max_length, stop_rule, lengths, steps_run);
+  wide_finalize_kernel<<<1, 256, 0, s>>>(w.first_end, w.allend, w.block_steps, MB, batch, max_length, stop_rule, lengths, steps_run,
+                                         max_length > 0 ? w.abort_flag : nullptr);
   I2L_LAUNCH_OK();
   return I2L_OK;
 }

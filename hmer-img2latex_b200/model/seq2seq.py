@@ -15,6 +15,14 @@ from .decoder import LSTMDecoder
 from .encoder import CNNEncoder, ResNetEncoder, normalize_u8
 
 
+def _checked_steps(n: int) -> int:
+    """steps_run < 0 is the device-side report of a decode loop that aborted (decode_wide.cu: a bounded spin expired)"""
+    if n < 0:
+        raise RuntimeError("the persistent decode loop aborted on the device (a bounded flag wait expired); the tokens "
+                           "of this call are invalid")
+    return n
+
+
 class Seq2SeqModel(nn.Module):
     def __init__(self, model_type: str = "cnn_lstm", vocab_size: int = None, encoder_params: Dict = None,
                  decoder_params: Dict = None, precision: Optional[str] = None):
@@ -80,7 +88,7 @@ class Seq2SeqModel(nn.Module):
         """reference seq2seq.py:192-232 (top_k / top_p are ignored there too)."""
         tokens, _, steps = self.decoder.greedy(encoder_output, start_token_id, end_token_id, max_length,
                                                temperature, N.STOP_ALL_END_SAME_STEP)
-        n = int(steps.item())                       # the one host sync of the decode
+        n = _checked_steps(int(steps.item()))       # the one host sync of the decode
         rows = tokens[:, : n + 1].tolist()
         if len(rows) == 1:                          # seq2seq.py:224-231
             seq = rows[0]
@@ -182,7 +190,7 @@ class Seq2SeqModel(nn.Module):
 
         def collect(slot: int):
             done[slot].synchronize()                              # the one host sync of the batch
-            return out_tok[slot], out_len[slot], int(out_steps[slot])
+            return out_tok[slot], out_len[slot], _checked_steps(int(out_steps[slot]))
 
         # Two batches are in flight: batch i+1 is copied while batch i computes, and the kernels of batch
         # i+1 are enqueued BEFORE the host waits for the results of batch i, so the GPU never idles on the

@@ -145,6 +145,8 @@ class Predictor:
             tokens, lengths, steps = self.model.decoder.sample(enc, start, end, max_length, temperature, top_k, top_p,
                                                                seed=seed, offset=i * max_length, uniforms=u)
             toks, lens = tokens.tolist(), lengths.tolist()         # single host read per batch
+            if lens and lens[0] < 0:                               # decode_wide.cu: the loop aborted on the device
+                raise RuntimeError("the persistent decode loop aborted on the device (a bounded flag wait expired)")
             for row, ln in zip(toks, lens):
                 seq = row[:ln]                                     # cut at first END (predictor.py:350-358)
                 if seq and seq[0] == start:                        # predictor.py:384-385
