@@ -440,6 +440,7 @@ def run_ours(args):
                                "max_len 150, V=512, E=H=256, L=1, random init" % B,
                    "global_batch": B * world, "parallelism": "dp%d (batch-sharded, token all-gather)" % world,
                    "token_exchange": exchange_kind, "host_binding": binding,
+                   "untimed_steps_before_the_timed_region": max(args.warmup, 3) + (32 if world > 1 else 0),
                    "l2_policy": "%d input batches used in turn (%d x %.0f MB of images) exceed the 126 MB L2; "
                                 "the bf16 activations written per step (587 MB) flush it as well"
                                 % (NB, NB, x_dev[0].numel() * x_dev[0].element_size() / 1e6),
