@@ -287,16 +287,25 @@ def run_ours(args):
         lib.i2l_prof_reset(); lib.i2l_prof_enable(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        if world > 1:
+            # device-side start line: the ranks leave the host barrier up to a millisecond apart, and with the exchange every
+            # rank's region ends when the LAST rank's shard has arrived -- so the start events are recorded behind one
+            # more collective on the compute stream, whose kernels finish together on all GPUs
+            dist.all_reduce(torch.zeros(1, device=dev))
         # ---- device-resident timed region ------------------------------------------------
         l0 = lib.i2l_launch_count()
+        t_host = [time.perf_counter() * 1e3] * 4
         e0.record()
+        t_host[1] = time.perf_counter() * 1e3
         for i in range(args.steps):
             out = step(x_dev[i % NB])
+        t_host[2] = time.perf_counter() * 1e3
         if xchg is not None:
             fl = xchg.flush()                                 # the last steps' global results: inside the timed region
             out = fl[-1] if fl else out
         e1.record()
         barrier()
+        t_host[3] = time.perf_counter() * 1e3
         launches = lib.i2l_launch_count() - l0
         lib.i2l_prof_enable(0)
         ms = e0.elapsed_time(e1)
@@ -387,7 +396,9 @@ def run_ours(args):
             except Exception as e:
                 nxt = {"error": repr(e)[:300]}
     if world > 1 and os.environ.get("I2L_BENCH_RANK_DEBUG"):
-        print("rank %d: timed region %.3f ms, e2e %.3f ms, kernels %s" % (rank, ms, e2e_s * 1e3, {k: (v[0], round(v[1] / max(v[0], 1), 4)) for k, v in sorted(prof.items())}),
+        print("rank %d: timed region %.3f ms (host: start %.3f, enqueued %.3f, done %.3f ms after rank-local barrier exit), e2e %.3f ms, kernels %s"
+              % (rank, ms, t_host[1] - t_host[0], t_host[2] - t_host[0], t_host[3] - t_host[0], e2e_s * 1e3,
+                 {k: (v[0], round(v[1] / max(v[0], 1), 4)) for k, v in sorted(prof.items())}),
               file=sys.stderr, flush=True)
     tms = torch.tensor([ms, e2e_s * 1e3, beam[0] if beam else 0.0, h2d_s * 1e3, strong or 0.0], device=dev,
                        dtype=torch.float64)
