@@ -165,11 +165,12 @@ class Seq2SeqModel(nn.Module):
                     src.record_stream(out_stream)                 # the caching allocator must not recycle it under the copy
                 done[slot].record(out_stream)
 
-        bufs: List[Optional[torch.Tensor]] = [None, None]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]          # H2D copy of the slot has landed
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]       # the encoder has read the slot
-        done = [torch.cuda.Event(), torch.cuda.Event()]           # results of the slot are in host memory
-        used = [False, False]
+        NS = 3                                                    # input staging slots: two copies stay queued ahead of the compute
+        bufs: List[Optional[torch.Tensor]] = [None] * NS
+        ready = [torch.cuda.Event() for _ in range(NS)]           # H2D copy of the slot has landed
+        consumed = [torch.cuda.Event() for _ in range(NS)]        # the encoder has read the slot
+        done = [torch.cuda.Event(), torch.cuda.Event()]           # results of the (output) slot are in host memory
+        used = [False] * NS
         out_tok: List[Optional[torch.Tensor]] = [None, None]
         out_len: List[Optional[torch.Tensor]] = [None, None]
         out_steps: List[Optional[torch.Tensor]] = [None, None]
@@ -192,15 +193,26 @@ class Seq2SeqModel(nn.Module):
             done[slot].synchronize()                              # the one host sync of the batch
             return out_tok[slot], out_len[slot], _checked_steps(int(out_steps[slot]))
 
-        # Two batches are in flight: batch i+1 is copied while batch i computes, and the kernels of batch
-        # i+1 are enqueued BEFORE the host waits for the results of batch i, so the GPU never idles on the
-        # host.  A yielded triple lives in pinned buffers that are reused: it is valid until the generator is advanced.
+        # Three batches are in flight: the copies of batches i+1 and i+2 are queued while batch i computes (a host hiccup
+        # of up to a whole batch time then leaves the copy engine busy), and the kernels of batch i+1 are enqueued BEFORE
+        # the host waits for the results of batch i, so the GPU never idles on the host.  A yielded triple lives in
+        # pinned buffers that are reused: it is valid until the generator is advanced.
         it = iter(host_batches)
-        cur = next(it, None)
-        if cur is None:
+        queue: List[int] = []                                     # staged input slots, oldest first
+        n_in = 0
+
+        def stage_next() -> None:
+            nonlocal n_in
+            xb = next(it, None)
+            if xb is not None:
+                stage(n_in % NS, xb)
+                queue.append(n_in % NS)
+                n_in += 1
+
+        stage_next()
+        stage_next()
+        if not queue:
             return
-        stage(0, cur)
-        i = 0
         prev = -1
         nres = 0
 
@@ -211,11 +223,9 @@ class Seq2SeqModel(nn.Module):
                 tokens, lengths = tokens[lo: lo + exchange.shard], lengths[lo: lo + exchange.shard]
             return tokens, lengths, steps
 
-        while cur is not None:
-            nxt = next(it, None)
-            slot = i & 1
-            if nxt is not None:
-                stage(slot ^ 1, nxt)                              # overlaps with the compute below
+        while queue:
+            slot = queue.pop(0)
+            stage_next()                                          # overlaps with the compute below
             compute.wait_event(ready[slot])
             xin = bufs[slot]
             if xin.dtype == torch.uint8 and hasattr(self.encoder, "forward_u8"):
@@ -246,8 +256,6 @@ class Seq2SeqModel(nn.Module):
                 if prev >= 0:
                     yield collect(prev)
                 prev = oslot
-            cur = nxt
-            i += 1
         if exchange is not None:
             for res in exchange.flush():                          # the last two batches' global results
                 oslot = nres & 1
