@@ -59,10 +59,12 @@ __global__ void xchg_write_kernel(const int64_t* __restrict__ tokens, const int3
   }
 }
 
-// The flag wait is ONE warp: a reader that is ahead of its peers spins for up to a whole step, and 40 spinning blocks
-// beside the persistent one-CTA-per-SM encoder kernels of the next batch delay whole tile ranges of theirs (measured at
-// N = 8: +70 us of compute-stream gaps per 0.92 ms step).  The widening copy is a second kernel behind it.
-__global__ void xchg_wait_kernel(const uint32_t* __restrict__ flags, int world, int parity, uint32_t seq, int* timeout_flag) {
+__global__ void xchg_read_kernel(const int32_t* __restrict__ buf, const uint32_t* __restrict__ flags, int world, int cap,
+                                 int T1, int n_total, int parity, uint32_t seq, int64_t* __restrict__ tokens,
+                                 int32_t* __restrict__ lengths, int32_t* __restrict__ steps, int* timeout_flag) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
   if (threadIdx.x < (unsigned)world) {
     const uint32_t* f = flags + parity * world + threadIdx.x;
     const long long t0 = clock64();
@@ -70,16 +72,12 @@ __global__ void xchg_wait_kernel(const uint32_t* __restrict__ flags, int world, 
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
       if (v == seq) break;
-      if (clock64() - t0 > 8000000000LL) { atomicExch(timeout_flag, 1); break; }   // ~4 s at 1.9 GHz: report instead of hanging
+      if (clock64() - t0 > 8000000000LL) { ok = 0; break; }   // ~4 s at 1.9 GHz: report instead of hanging
       __nanosleep(200);
     } while (true);
   }
-}
-
-__global__ void xchg_read_kernel(const int32_t* __restrict__ buf, const uint32_t* __restrict__ flags, int world, int cap,
-                                 int T1, int n_total, int parity, uint32_t seq, int64_t* __restrict__ tokens,
-                                 int32_t* __restrict__ lengths, int32_t* __restrict__ steps, int* timeout_flag) {
-  if (*reinterpret_cast<volatile int*>(timeout_flag) != 0) return;   // the wait kernel gave up: nothing valid to widen
+  __syncthreads();
+  if (!ok) { if (threadIdx.x == 0) atomicExch(timeout_flag, 1); return; }
   const int W = T1 + 1;
   const size_t words = slot_words(cap, T1);
   const int base = n_total / world, rem = n_total % world;       // dist.shard_bounds: the first `rem` ranks hold one more
@@ -154,8 +152,6 @@ extern "C" int i2l_token_exchange_read(const void* local_buffer, int32_t world, 
   const size_t fo = flags_offset(world, n_total, T1);
   const int grid = min(cdiv(n_total, 16), 40);
   KernelTimer kt("xchg.read_wait", (cudaStream_t)stream);
-  xchg_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(base + fo), world, (int)(seq & 1), seq, timeout_flag);
-  I2L_LAUNCH_OK();
   xchg_read_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int32_t*>(base),
                                                            reinterpret_cast<const uint32_t*>(base + fo), world, cap, T1,
                                                            n_total, (int)(seq & 1), seq, tokens, lengths, steps, timeout_flag);

@@ -69,6 +69,7 @@ class TokenExchange:
     # 0.92 ms: 3 -> 0.997 ms per step, 32 -> 1.067 ms (the exchange kernels of many steps then pile up behind the
     # persistent compute kernels and spill into the encoders, whose one-CTA-per-SM tile ranges they delay).
     RUN_AHEAD = 3
+    fence_after_decode = True
 
     def __init__(self, n_total: int, T1: int, device: torch.device, group=None, rank: Optional[int] = None,
                  world: Optional[int] = None, buffers: Optional[List[torch.Tensor]] = None):
@@ -160,8 +161,17 @@ class TokenExchange:
         if self._staged is not None:
             raise RuntimeError("TokenExchange.stage: kick() the previous step first")
         side = self._side()
+        cur = torch.cuda.current_stream(self.device)
         ev = self._produced[self.seq & 1]
-        ev.record(torch.cuda.current_stream(self.device))
+        ev.record(cur)
+        if self.fence_after_decode and self._kicks > 0:
+            # The exchange released by the last kick() runs beside the decode kernel that has just been enqueued; whatever
+            # the current stream runs NEXT (the following batch's encoder: persistent kernels with one CTA per SM) must not
+            # share the GPU with it.  Normally the ~60 us of exchange are long over when the 390 us decode ends and this
+            # wait costs nothing; when a peer is late the encoder waits instead of being slowed down for its whole run --
+            # measured at N = 8: exchange kernels that slip under the encoders put every rank into a state where each
+            # step's exchange is late for the next one (1.42 ms per step instead of 1.00).
+            cur.wait_event(self._consumed[(self._kicks - 1) % self.RUN_AHEAD])
         self._staged = (tokens, lengths, steps, ev)
 
     def kick(self):
